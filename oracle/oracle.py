@@ -1,0 +1,360 @@
+"""ctypes front end of the CPU ORACLE (oracle/kmerlr_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (kmerlr_b200/) must never import it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libkmerlr_oracle.so")
+
+TIE_GO118, TIE_INDEX = 0, 1
+SUMMARY = {"": 0, "mean": 1, "product": 2, "min": 3, "max": 4}
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("kmerlr_oracle.c", "kmerlr_oracle.h")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libkmerlr_oracle.so"])
+    return _SO
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("M", "N", "complement", "reverse", "revcomp", "binarize", "alphabet", "max_ambiguous")]
+
+
+def make_config(M, N, complement=False, reverse=False, revcomp=False, binarize=False, alphabet="nucleotide",
+                max_ambiguous=-1):
+    return Config(M, N, int(complement), int(reverse), int(revcomp), int(binarize),
+                  {"nucleotide": 0, "gapped-nucleotide": 1}[alphabet], max_ambiguous)
+
+
+class HookState(C.Structure):
+    _fields_ = [("loss_old", C.c_double), ("loss_new", C.c_double)]
+
+
+class Estimator(C.Structure):
+    _fields_ = [("n_active", C.c_int64), ("active_idx", C.POINTER(C.c_int64)), ("theta", C.POINTER(C.c_double)),
+                ("state_cap", C.c_int64), ("hook", HookState), ("l1reg_over_n", C.c_double)]
+
+
+class Model(C.Structure):
+    _fields_ = [("cfg", Config), ("n_classes", C.c_int64), ("class_k", C.POINTER(C.c_int32)),
+                ("class_code", C.POINTER(C.c_uint64)), ("n_features", C.c_int64),
+                ("features", C.POINTER(C.c_int32)), ("n_members", C.c_int64), ("theta", C.POINTER(C.c_double)),
+                ("summary", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+        L.ko_extract.restype = vp
+        L.ko_extract.argtypes = [C.POINTER(Config), vp, vp, i64, vp, vp, i64, vp, i64, C.c_int, C.c_int]
+        L.ko_matrix_free.argtypes = [vp]
+        L.ko_matrix_info.argtypes = [vp] + [C.POINTER(i64)] * 4
+        L.ko_matrix_classes.argtypes = [vp, vp, vp]
+        L.ko_matrix_rows.argtypes = [vp, vp, vp, vp]
+        L.ko_matrix_from_csr.restype = vp
+        L.ko_matrix_from_csr.argtypes = [i64, i64, vp, vp, vp]
+        L.ko_class_name.restype = C.c_int
+        L.ko_class_name.argtypes = [C.POINTER(Config), i32, C.c_uint64, C.c_char_p, C.c_int]
+        L.ko_class_code.restype = C.c_uint64
+        L.ko_class_code.argtypes = [C.POINTER(Config), vp, i32]
+        L.ko_coeff_dim.restype = i64
+        L.ko_coeff_dim.argtypes = [i64]
+        L.ko_coeff_ind2sub.restype = i64
+        L.ko_coeff_ind2sub.argtypes = [i64, i64, i64]
+        L.ko_coeff_sub2ind.argtypes = [i64, i64, C.POINTER(i64), C.POINTER(i64)]
+        L.ko_linear_pdf.argtypes = [vp, vp, C.c_int, vp]
+        L.ko_log_pdf.argtypes = [vp, vp, C.c_int, vp]
+        L.ko_gradient.argtypes = [vp, vp, vp, i64, vp, dbl, C.c_int, vp]
+        L.ko_loss.restype = dbl
+        L.ko_loss.argtypes = [vp, vp, vp, i64, vp, dbl, C.c_int]
+        L.ko_class_weights.argtypes = [vp, i64, vp]
+        L.ko_nlargest_abs.argtypes = [vp, vp, i64, C.c_int]
+        L.ko_select.restype = C.c_int
+        L.ko_select.argtypes = [vp, vp, vp, C.c_int, i64, dbl, vp, vp, i64, C.c_int, dbl, dbl, vp, i64,
+                                C.POINTER(dbl), C.POINTER(i64), vp]
+        L.ko_reduce.restype = vp
+        L.ko_reduce.argtypes = [vp, vp, i64]
+        L.ko_step_size.restype = dbl
+        L.ko_step_size.argtypes = [vp, dbl, dbl]
+        L.ko_proxgrad.restype = i64
+        L.ko_proxgrad.argtypes = [vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, i64, C.POINTER(HookState), C.POINTER(dbl)]
+        L.ko_estimate_loop.restype = i64
+        L.ko_estimate_loop.argtypes = [vp, vp, vp, C.c_int, i64, C.c_int, dbl, dbl, dbl, dbl, dbl, i64, i64,
+                                       C.POINTER(Estimator), vp, vp, i64]
+        L.ko_window_slots.restype = i64
+        L.ko_window_slots.argtypes = [i64, i64, i64]
+        L.ko_score_windows.argtypes = [C.POINTER(Model), C.c_int, vp, vp, i64, i64, i64, vp, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def flatten(seqs):
+    """list of bytes/str -> (uint8 concatenation, int64 offsets[n+1])"""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(b) for b in bs])
+    buf = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if off[-1] else np.zeros(0, dtype=np.uint8)
+    return buf, off
+
+
+class Matrix:
+    """KmerDataSet restated: rows (CSR without the bias column) + class list."""
+
+    def __init__(self, handle, cfg=None):
+        self.h = handle
+        self.cfg = cfg
+        n, m, nnz, nc = (C.c_int64() for _ in range(4))
+        lib().ko_matrix_info(handle, n, m, nnz, nc)
+        self.n, self.m, self.nnz, self.n_classes = n.value, m.value, nnz.value, nc.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ko_matrix_free(self.h)
+            self.h = None
+
+    def classes(self):
+        k = np.zeros(self.n_classes, dtype=np.int32)
+        code = np.zeros(self.n_classes, dtype=np.uint64)
+        lib().ko_matrix_classes(self.h, _p(k), _p(code))
+        return k, code
+
+    def rows(self):
+        rowptr = np.zeros(self.n + 1, dtype=np.int64)
+        col = np.zeros(max(self.nnz, 1), dtype=np.int32)
+        val = np.zeros(max(self.nnz, 1), dtype=np.float64)
+        lib().ko_matrix_rows(self.h, _p(rowptr), _p(col), _p(val))
+        return rowptr, col[:self.nnz], val[:self.nnz]
+
+    def dense(self):
+        rowptr, col, val = self.rows()
+        d = np.zeros((self.n, self.m))
+        for i in range(self.n):
+            d[i, col[rowptr[i]:rowptr[i + 1]]] = val[rowptr[i]:rowptr[i + 1]]
+        return d
+
+    def class_names(self):
+        k, code = self.classes()
+        return [class_name(self.cfg, int(a), int(b)) for a, b in zip(k, code)]
+
+
+def class_name(cfg, k, code):
+    buf = C.create_string_buffer(256)
+    lib().ko_class_name(C.byref(cfg), k, code, buf, 256)
+    return buf.value.decode()
+
+
+def extract(cfg, seqs, frozen=None, features=None, threads=0, faithful=False):
+    buf, off = flatten(seqs) if not isinstance(seqs, tuple) else seqs
+    fk = fc = None
+    nf = 0
+    if frozen is not None:
+        fk = np.ascontiguousarray(frozen[0], dtype=np.int32)
+        fc = np.ascontiguousarray(frozen[1], dtype=np.uint64)
+        nf = len(fk)
+    ft = None
+    nft = 0
+    if features is not None and len(features):
+        ft = np.ascontiguousarray(features, dtype=np.int32).reshape(-1, 2)
+        nft = ft.shape[0]
+    h = lib().ko_extract(C.byref(cfg), _p(buf), _p(off), len(off) - 1, _p(fk), _p(fc), nf, _p(ft), nft,
+                         threads, int(faithful))
+    if not h:
+        raise ValueError("ko_extract: bad configuration")
+    return Matrix(h, cfg)
+
+
+def from_csr(n, m, rowptr, col, val):
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    return Matrix(lib().ko_matrix_from_csr(n, m, _p(rowptr), _p(col), _p(val)))
+
+
+def from_dense(d):
+    d = np.asarray(d, dtype=np.float64)
+    rowptr = [0]
+    col, val = [], []
+    for r in d:
+        nz = np.nonzero(r)[0]
+        col.extend(nz.tolist())
+        val.extend(r[nz].tolist())
+        rowptr.append(len(col))
+    return from_csr(d.shape[0], d.shape[1], rowptr, col or [0], val or [0.0])
+
+
+def coeff_dim(n):
+    return lib().ko_coeff_dim(n)
+
+
+def ind2sub(n, k1, k2):
+    return lib().ko_coeff_ind2sub(n, k1, k2)
+
+
+def sub2ind(n, i):
+    a, b = C.c_int64(), C.c_int64()
+    lib().ko_coeff_sub2ind(n, i, a, b)
+    return a.value, b.value
+
+
+def ntheta(mat, cooccurrence):
+    return coeff_dim(mat.m) if cooccurrence else mat.m + 1
+
+
+def _lab(labels):
+    return np.ascontiguousarray(labels, dtype=np.uint8)
+
+
+def _cw(cw):
+    return np.ascontiguousarray(cw, dtype=np.float64)
+
+
+def linear_pdf(mat, theta, cooccurrence=False):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    out = np.zeros(mat.n)
+    lib().ko_linear_pdf(mat.h, _p(theta), int(cooccurrence), _p(out))
+    return out
+
+
+def log_pdf(mat, theta, cooccurrence=False):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    out = np.zeros(mat.n)
+    lib().ko_log_pdf(mat.h, _p(theta), int(cooccurrence), _p(out))
+    return out
+
+
+def gradient(mat, labels, theta, cw=(1.0, 1.0), lam=0.0, cooccurrence=False):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    g = np.zeros(len(theta))
+    lab, cw = _lab(labels), _cw(cw)
+    lib().ko_gradient(mat.h, _p(lab), _p(theta), len(theta), _p(cw), lam, int(cooccurrence), _p(g))
+    return g
+
+
+def loss(mat, labels, theta, cw=(1.0, 1.0), lam=0.0, cooccurrence=False):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    lab, cw = _lab(labels), _cw(cw)
+    return lib().ko_loss(mat.h, _p(lab), _p(theta), len(theta), _p(cw), lam, int(cooccurrence))
+
+
+def class_weights(labels):
+    lab = _lab(labels)
+    cw = np.zeros(2)
+    lib().ko_class_weights(_p(lab), len(lab), _p(cw))
+    return cw
+
+
+def nlargest_abs(x, tie=TIE_GO118):
+    x = np.array(x, dtype=np.float64)
+    idx = np.zeros(len(x), dtype=np.int64)
+    lib().ko_nlargest_abs(_p(x), _p(idx), len(x), tie)
+    return x, idx
+
+
+def select(mat, labels, cw, N, theta0, active_idx, active_theta, cooccurrence=False, tie=TIE_GO118,
+           epsilon_lambda=0.0, prev_lambda=0.0):
+    nt = ntheta(mat, cooccurrence)
+    ai = np.ascontiguousarray(active_idx, dtype=np.int64)
+    at = np.ascontiguousarray(active_theta, dtype=np.float64)
+    mask = np.zeros(nt, dtype=np.uint8)
+    g = np.zeros(nt)
+    lam, c = C.c_double(), C.c_int64()
+    lab, cw = _lab(labels), _cw(cw)
+    ok = lib().ko_select(mat.h, _p(lab), _p(cw), int(cooccurrence), N, theta0, _p(ai), _p(at), len(ai), tie,
+                         epsilon_lambda, prev_lambda, _p(mask), nt, lam, c, _p(g))
+    return dict(ok=bool(ok), lam=lam.value, c=c.value, mask=mask.astype(bool), g=g)
+
+
+def reduce(mat, sel):
+    sel = np.ascontiguousarray(sel, dtype=np.int64)
+    return Matrix(lib().ko_reduce(mat.h, _p(sel), len(sel)))
+
+
+def step_size(mat, l2=0.0, step_factor=1.0):
+    return lib().ko_step_size(mat.h, l2, step_factor)
+
+
+def proxgrad(rmat, labels, theta, cw=(1.0, 1.0), lam=0.0, l2=0.0, step_factor=1.0, epsilon=0.0,
+             epsilon_loss=1e-8, max_iter=100000, hook=None):
+    theta = np.array(theta, dtype=np.float64)
+    lab, cw = _lab(labels), _cw(cw)
+    delta = C.c_double()
+    hk = hook if hook is not None else HookState(float("nan"), float("nan"))
+    it = lib().ko_proxgrad(rmat.h, _p(lab), _p(theta), _p(cw), lam, l2, step_factor, epsilon, epsilon_loss,
+                           max_iter, C.byref(hk), delta)
+    return theta, it, delta.value
+
+
+class EstimatorState:
+    """KmerLrEstimator state carried between leapfrog targets (warm start, kmerLr_estimator.go:263-267)."""
+
+    def __init__(self, cap=4096):
+        self.cap = cap
+        self.idx = np.zeros(cap, dtype=np.int64)
+        self.theta = np.zeros(cap + 1, dtype=np.float64)
+        self.c = Estimator(0, self.idx.ctypes.data_as(C.POINTER(C.c_int64)),
+                           self.theta.ctypes.data_as(C.POINTER(C.c_double)), cap,
+                           HookState(float("nan"), float("nan")), 0.0)
+
+    @property
+    def active_idx(self):
+        return self.idx[:self.c.n_active].copy()
+
+    @property
+    def active_theta(self):
+        return self.theta[:self.c.n_active + 1].copy()
+
+
+def estimate_loop(mat, labels, cw, N, est, cooccurrence=False, tie=TIE_GO118, epsilon_lambda=0.0, l2=0.0,
+                  step_factor=1.0, epsilon=0.0, epsilon_loss=1e-8, max_iter=100000, max_epochs=0, path_cap=256):
+    lab, cw = _lab(labels), _cw(cw)
+    pl = np.zeros(path_cap)
+    pi = np.zeros(path_cap, dtype=np.int64)
+    ep = lib().ko_estimate_loop(mat.h, _p(lab), _p(cw), int(cooccurrence), N, tie, epsilon_lambda, l2, step_factor,
+                                epsilon, epsilon_loss, max_iter, max_epochs, C.byref(est.c), _p(pl), _p(pi), path_cap)
+    if ep < 0:
+        raise RuntimeError("estimator state capacity exceeded")
+    k = min(ep, path_cap)
+    return dict(epochs=ep, lambdas=pl[:k].copy(), iters=pi[:k].copy())
+
+
+def window_slots(length, W, step):
+    return lib().ko_window_slots(length, W, step)
+
+
+def score_windows(models, regions, W, step, threads=0):
+    """models: list of dict(cfg, class_k, class_code, features, theta (members x F+1), summary)."""
+    keep = []
+    arr = (Model * len(models))()
+    for i, md in enumerate(models):
+        ck = np.ascontiguousarray(md["class_k"], dtype=np.int32)
+        cc = np.ascontiguousarray(md["class_code"], dtype=np.uint64)
+        ft = np.ascontiguousarray(md["features"], dtype=np.int32).reshape(-1, 2)
+        th = np.ascontiguousarray(md["theta"], dtype=np.float64).reshape(-1, ft.shape[0] + 1)
+        keep += [ck, cc, ft, th]
+        arr[i] = Model(md["cfg"], len(ck), ck.ctypes.data_as(C.POINTER(C.c_int32)),
+                       cc.ctypes.data_as(C.POINTER(C.c_uint64)), ft.shape[0],
+                       ft.ctypes.data_as(C.POINTER(C.c_int32)), th.shape[0],
+                       th.ctypes.data_as(C.POINTER(C.c_double)), SUMMARY[md.get("summary", "")])
+    buf, off = flatten(regions) if not isinstance(regions, tuple) else regions
+    total = sum(window_slots(int(off[i + 1] - off[i]), W, step) for i in range(len(off) - 1))
+    out = np.zeros(max(total, 1))
+    lib().ko_score_windows(arr, len(models), _p(buf), _p(off), len(off) - 1, W, step, _p(out), threads)
+    return out[:total]
