@@ -1,0 +1,444 @@
+"""Host-side mirror of the reference's interface for the hot path (names and argument meaning follow
+the Go seams of pbenner/kmerLr listed in SURVEY.md section 8b), on top of the C ABI.
+
+Go is not available in this image, so this module plays the part of the cgo shim's callers: the
+same control flow the Go code keeps (leapfrog epoch loop, estimator state) with every hot call going
+to libkmerlr_b200.so.  Nothing here computes on the CPU; no GPU -> KmerLrError.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, KmerLrError, check, lib, TIE_GO118, TIE_INDEX, FLAG_SHARDED  # noqa: F401
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---------------------------------------------------------------------------------------------------
+# lifecycle / communicator
+# ---------------------------------------------------------------------------------------------------
+def init(device=0):
+    check(lib().kmerlr_init(device))
+
+
+def shutdown():
+    check(lib().kmerlr_shutdown())
+
+
+def last_device_ms():
+    return lib().kmerlr_last_device_ms()
+
+
+def launch_count():
+    return lib().kmerlr_launch_count()
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib().kmerlr_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(rank, world, unique_id):
+    check(lib().kmerlr_comm_init(rank, world, C.create_string_buffer(unique_id, 128)))
+
+
+def comm_destroy():
+    check(lib().kmerlr_comm_destroy())
+
+
+def comm_init_torch():
+    """One process per GPU under torchrun: rank 0 creates the NCCL id, torch.distributed ships it."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    comm_init(rank, world, box[0])
+    return rank, world
+
+
+# ---------------------------------------------------------------------------------------------------
+# NewKmerCounter configuration (kmerLr_learn.go:94, kmerLr_classifier.go:96-103)
+# ---------------------------------------------------------------------------------------------------
+def NewKmerCounter(M, N, complement=False, reverse=False, revcomp=False, max_ambiguous=None,
+                   alphabet="nucleotide", binarize=False):
+    return Config(M, N, int(complement), int(reverse), int(revcomp), int(binarize),
+                  {"nucleotide": 0, "gapped-nucleotide": 1}[alphabet],
+                  -1 if max_ambiguous is None else int(max_ambiguous))
+
+
+def flatten(seqs):
+    """[]string -> (concatenated uint8 buffer, int64 offsets[n+1]); what the cgo shim passes down."""
+    if isinstance(seqs, tuple):
+        return np.ascontiguousarray(seqs[0], dtype=np.uint8), np.ascontiguousarray(seqs[1], dtype=np.int64)
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    buf = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if off[-1] else np.zeros(1, dtype=np.uint8)
+    return buf, off
+
+
+# ---------------------------------------------------------------------------------------------------
+# CoeffIndex (kmerLr_coefficients_index.go:26-54)
+# ---------------------------------------------------------------------------------------------------
+class CoeffIndex(int):
+    def Dim(self):
+        return lib().kmerlr_coeff_dim(int(self))
+
+    def Ind2Sub(self, k1, k2):
+        return lib().kmerlr_coeff_ind2sub(int(self), k1, k2)
+
+    def Sub2Ind(self, i):
+        a, b = C.c_int64(), C.c_int64()
+        lib().kmerlr_coeff_sub2ind(int(self), i, a, b)
+        return a.value, b.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# data (kmerLr_data.go)
+# ---------------------------------------------------------------------------------------------------
+class Sequences:
+    """2-bit packed sequences resident in HBM."""
+
+    def __init__(self, seqs):
+        buf, off = flatten(seqs)
+        self.n = len(off) - 1
+        self.total_bases = int(off[-1])
+        h = C.c_uint64()
+        check(lib().kmerlr_sequences_create(_p(buf), _p(off), self.n, h))
+        self.h = h.value
+
+    def free(self):
+        if getattr(self, "h", 0):
+            lib().kmerlr_free(self.h)
+            self.h = 0
+
+    __del__ = free
+
+
+class KmerDataSet:
+    """KmerDataSet{Data, Labels, Kmers} (kmerLr_data.go:34-38); Data stays in HBM behind a handle."""
+
+    def __init__(self, handle):
+        self.h = handle
+        n, m, nnz, nc = (C.c_int64() for _ in range(4))
+        check(lib().kmerlr_matrix_info(handle, n, m, nnz, nc))
+        self.n, self.m, self.nnz, self.n_classes = n.value, m.value, nnz.value, nc.value
+        self.Labels = None
+
+    def free(self):
+        if getattr(self, "h", 0):
+            try:
+                lib().kmerlr_free(self.h)
+            except Exception:
+                pass
+            self.h = 0
+
+    __del__ = free
+
+    def Dim(self):
+        return self.m + 1
+
+    def Kmers(self):
+        """class list as (k, code) arrays; the Go side rebuilds KmerClass names from them"""
+        k = np.zeros(max(self.n_classes, 1), dtype=np.int32)
+        code = np.zeros(max(self.n_classes, 1), dtype=np.uint64)
+        check(lib().kmerlr_matrix_classes(self.h, _p(k), _p(code)))
+        return k[:self.n_classes], code[:self.n_classes]
+
+    def rows(self):
+        """(rowptr, col, val): CSR without the bias column (Go sparse index = col + 1)"""
+        rowptr = np.zeros(self.n + 1, dtype=np.int64)
+        col = np.zeros(max(self.nnz, 1), dtype=np.int32)
+        val = np.zeros(max(self.nnz, 1), dtype=np.float64)
+        check(lib().kmerlr_matrix_rows(self.h, _p(rowptr), _p(col), _p(val)))
+        return rowptr, col[:self.nnz], val[:self.nnz]
+
+    def SetLabels(self, labels):
+        lab = np.ascontiguousarray(labels, dtype=np.uint8)
+        check(lib().kmerlr_matrix_set_labels(self.h, _p(lab), len(lab)))
+        self.Labels = lab.astype(bool)
+
+    def class_weights(self):
+        cw = np.zeros(2)
+        check(lib().kmerlr_class_weights(self.h, _p(cw)))
+        return cw
+
+
+def from_csr(n, m, rowptr, col, val, sharded=False):
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    h = C.c_uint64()
+    check(lib().kmerlr_matrix_from_csr(n, m, _p(rowptr), _p(col), _p(val), FLAG_SHARDED if sharded else 0, h))
+    return KmerDataSet(h.value)
+
+
+def from_dense(d, sharded=False):
+    d = np.asarray(d, dtype=np.float64)
+    rowptr, col, val = [0], [], []
+    for r in d:
+        nz = np.nonzero(r)[0]
+        col.extend(nz.tolist())
+        val.extend(r[nz].tolist())
+        rowptr.append(len(col))
+    return from_csr(d.shape[0], d.shape[1], rowptr, col or [0], val or [0.0], sharded)
+
+
+def _extract(config, seqs, kmers, features, sharded):
+    fk = fc = ft = None
+    nf = nft = 0
+    if kmers is not None and len(kmers[0]):
+        fk = np.ascontiguousarray(kmers[0], dtype=np.int32)
+        fc = np.ascontiguousarray(kmers[1], dtype=np.uint64)
+        nf = len(fk)
+    if features is not None and len(features):
+        ft = np.ascontiguousarray(features, dtype=np.int32).reshape(-1, 2)
+        nft = ft.shape[0]
+    h = C.c_uint64()
+    flags = FLAG_SHARDED if sharded else 0
+    if isinstance(seqs, Sequences):
+        check(lib().kmerlr_extract_resident(C.byref(config), seqs.h, _p(fk), _p(fc), nf, _p(ft), nft, flags, h))
+    else:
+        buf, off = flatten(seqs)
+        check(lib().kmerlr_extract(C.byref(config), _p(buf), _p(off), len(off) - 1, _p(fk), _p(fc), nf, _p(ft), nft,
+                                   flags, h))
+    return KmerDataSet(h.value)
+
+
+def compile_training_data(config, kmersCounter, kmers, features, generate_features, binarize, fg, bg,
+                          sharded=False):
+    """compile_training_data (kmerLr_data.go:306-325).  fg / bg are the sequences import_fasta returned
+    (lists of str/bytes, or (buffer, offsets)); labels = true for fg."""
+    del config, generate_features
+    cfg = Config.from_buffer_copy(kmersCounter)
+    cfg.binarize = int(binarize)
+    fb, fo = flatten(fg)
+    bb, bo = flatten(bg)
+    nfg, nbg = len(fo) - 1, len(bo) - 1
+    buf = np.concatenate([fb[:fo[-1]], bb[:bo[-1]]]) if (fo[-1] + bo[-1]) else np.zeros(1, dtype=np.uint8)
+    off = np.concatenate([fo, bo[1:] + fo[-1]])
+    data = _extract(cfg, (buf, off), kmers, features, sharded)
+    data.SetLabels(np.concatenate([np.ones(nfg, dtype=np.uint8), np.zeros(nbg, dtype=np.uint8)]))
+    return data
+
+
+def compile_test_data(config, kmersCounter, kmers, features, generate_features, binarize, sequences):
+    """compile_test_data (kmerLr_data.go:327-335): counter frozen to the classifier's k-mers."""
+    del config, generate_features
+    cfg = Config.from_buffer_copy(kmersCounter)
+    cfg.binarize = int(binarize)
+    return _extract(cfg, sequences, kmers, features, False)
+
+
+def compute_class_weights(c):
+    """compute_class_weights (kmerLr_data.go:178-193); pure arithmetic on the label counts"""
+    c = np.asarray(c, dtype=bool)
+    n1, n0 = int(c.sum()), int((~c).sum())
+    return np.array([(n0 + n1) / (2.0 * n0), (n0 + n1) / (2.0 * n1)])
+
+
+# ---------------------------------------------------------------------------------------------------
+# logisticRegression (kmerLr_logistic_regression.go:30-272)
+# ---------------------------------------------------------------------------------------------------
+class logisticRegression:
+    def __init__(self, Theta, ClassWeights=(1.0, 1.0), Lambda=0.0, Cooccurrence=False):
+        self.Theta = np.ascontiguousarray(Theta, dtype=np.float64)
+        self.ClassWeights = np.ascontiguousarray(ClassWeights, dtype=np.float64)
+        self.Lambda = float(Lambda)
+        self.Cooccurrence = bool(Cooccurrence)
+
+    def Dim(self):
+        return len(self.Theta) - 1
+
+    def LinearPdf(self, data):
+        out = np.zeros(max(data.n, 1))
+        check(lib().kmerlr_linear_pdf(data.h, _p(self.Theta), len(self.Theta), int(self.Cooccurrence), _p(out)))
+        return out[:data.n]
+
+    def LogPdf(self, data):
+        out = np.zeros(max(data.n, 1))
+        check(lib().kmerlr_logpdf(data.h, _p(self.Theta), len(self.Theta), int(self.Cooccurrence), _p(out)))
+        return out[:data.n]
+
+    def Gradient(self, g, data, labels=None):
+        if labels is not None:
+            data.SetLabels(labels)
+        if g is None or len(g) == 0:
+            g = np.zeros(len(self.Theta))
+        elif len(g) != len(self.Theta):
+            raise KmerLrError(_lib.ERR_INTERNAL, "internal error")
+        check(lib().kmerlr_gradient(data.h, _p(self.Theta), len(self.Theta), _p(self.ClassWeights), self.Lambda,
+                                    int(self.Cooccurrence), _p(g)))
+        return g
+
+    def Loss(self, data, c=None):
+        if c is not None:
+            data.SetLabels(c)
+        out = C.c_double()
+        check(lib().kmerlr_loss(data.h, _p(self.Theta), len(self.Theta), _p(self.ClassWeights), self.Lambda,
+                                int(self.Cooccurrence), out))
+        return out.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# featureSelector (kmerLr_feature_selection.go)
+# ---------------------------------------------------------------------------------------------------
+class featureSelection:
+    def __init__(self, selector, b, c, theta_full):
+        self.selector, self.b, self.c = selector, b, c
+        self.sel = np.nonzero(b)[0].astype(np.int64)     # k of featureSelection.Data (:313-318)
+        self._theta = theta_full[self.sel]
+
+    def Theta(self):
+        return self._theta.copy()
+
+    def Data(self, data):
+        return select_data(data, self.sel)
+
+
+def select_data(data, sel):
+    """featureSelection.Data (kmerLr_feature_selection.go:309-343) for an explicit, ascending list of
+    coefficient indices (sel[0] = 0 is the bias)"""
+    sel = np.ascontiguousarray(sel, dtype=np.int64)
+    h = C.c_uint64()
+    check(lib().kmerlr_reduce(data.h, _p(sel), len(sel), h))
+    r = KmerDataSet(h.value)
+    r.Labels = data.Labels
+    return r
+
+
+class featureSelector:
+    def __init__(self, ClassWeights, Cooccurrence, N, M, Epsilon=0.0, tie=TIE_GO118):
+        self.ClassWeights = np.ascontiguousarray(ClassWeights, dtype=np.float64)
+        self.Cooccurrence, self.N, self.M, self.Epsilon, self.tie = bool(Cooccurrence), int(N), int(M), Epsilon, tie
+
+    def Select(self, data, theta0, active_idx, active_theta, lambda_prev, want_gradient=False):
+        if self.M != data.Dim() - 1:
+            raise KmerLrError(_lib.ERR_INTERNAL, "internal error")
+        nt = CoeffIndex(self.M).Dim() if self.Cooccurrence else self.M + 1
+        ai = np.ascontiguousarray(active_idx, dtype=np.int64)
+        at = np.ascontiguousarray(active_theta, dtype=np.float64)
+        mask = np.zeros(nt, dtype=np.uint8)
+        g = np.zeros(nt) if want_gradient else None
+        lam, c, ok = C.c_double(), C.c_int64(), C.c_int()
+        check(lib().kmerlr_select(data.h, _p(self.ClassWeights), int(self.Cooccurrence), self.N, float(theta0),
+                                  _p(ai), _p(at), len(ai), self.tie, self.Epsilon, float(lambda_prev), _p(mask), nt,
+                                  lam, c, ok, _p(g)))
+        t = np.zeros(nt)
+        t[0] = theta0
+        nz = at != 0.0
+        t[ai[nz]] = at[nz]
+        s = featureSelection(self, mask.astype(bool), c.value, t)
+        s.g = g
+        return s, lam.value, bool(ok.value)
+
+
+# ---------------------------------------------------------------------------------------------------
+# estimator (kmerLr_estimator.go:209-255 control loop; kmerLr_estimator_proximal.go solver)
+# ---------------------------------------------------------------------------------------------------
+class KmerLrEstimator:
+    """State the Go estimator keeps between leapfrog targets: theta, active coefficient indices,
+    L1Reg, the hook's loss_old / loss_new."""
+
+    def __init__(self, Cooccurrence=False, Epsilon=0.0, EpsilonLoss=1e-8, EpsilonLambda=0.0, L2Reg=0.0,
+                 StepSizeFactor=1.0, MaxIterations=100000, MaxEpochs=0, tie=TIE_GO118):
+        self.Cooccurrence, self.Epsilon, self.EpsilonLoss = Cooccurrence, Epsilon, EpsilonLoss
+        self.EpsilonLambda, self.L2Reg, self.StepSizeFactor = EpsilonLambda, L2Reg, StepSizeFactor
+        self.MaxIterations, self.MaxEpochs, self.tie = MaxIterations, MaxEpochs, tie
+        self.Theta = np.zeros(1)
+        self.active_idx = np.zeros(0, dtype=np.int64)
+        self.L1Reg = 0.0
+        self.ClassWeights = np.ones(2)
+        self.hook_state = np.array([np.nan, np.nan])
+        self.path = []
+
+    def estimate_proximal(self, data_train, lam):
+        """estimate_proximal (kmerLr_estimator_proximal.go:78-120) on the (reduced) data set."""
+        theta = np.ascontiguousarray(self.Theta, dtype=np.float64).copy()
+        iters, delta = C.c_int64(), C.c_double()
+        check(lib().kmerlr_proxgrad(data_train.h, _p(theta), len(theta), _p(self.ClassWeights), float(lam),
+                                    self.L2Reg, self.StepSizeFactor, self.Epsilon, self.EpsilonLoss,
+                                    self.MaxIterations, _p(self.hook_state), iters, delta))
+        self.Theta = theta
+        return iters.value, delta.value
+
+    def estimate_loop(self, data, lambdaAuto, balance=False):
+        """estimate_loop (kmerLr_estimator.go:209-255): leapfrog epochs until Select returns !ok."""
+        n = data.n
+        self.ClassWeights = data.class_weights() if balance else np.ones(2)
+        s = featureSelector(self.ClassWeights, self.Cooccurrence, lambdaAuto, data.m, self.EpsilonLambda, self.tie)
+        r = False
+        epoch = 0
+        while self.MaxEpochs == 0 or epoch < self.MaxEpochs:
+            selection, lam, ok = s.Select(data, self.Theta[0], self.active_idx, self.Theta[1:], self.L1Reg)
+            if not ok and r:
+                break
+            self.L1Reg = lam * n
+            self.active_idx = selection.sel[1:].copy()
+            self.Theta = selection.Theta()
+            reduced = selection.Data(data)
+            reduced.SetLabels(data.Labels)
+            iters, _ = self.estimate_proximal(reduced, lam)
+            reduced.free()
+            self.path.append((lam, iters, len(self.active_idx)))
+            r = True
+            epoch += 1
+        return epoch
+
+    def Estimate(self, data, LambdaAuto, balance=False):
+        """Estimate (kmerLr_estimator.go:257-270): one warm-started loop per target."""
+        out = []
+        for n in LambdaAuto:
+            self.estimate_loop(data, n, balance)
+            out.append((self.active_idx.copy(), self.Theta.copy()))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# genomic scoring (kmerLr_predict_genomic.go:116-171)
+# ---------------------------------------------------------------------------------------------------
+class genomicKmerLr:
+    """models: list of dict(counter=Config, class_k, class_code, features, theta, summary)"""
+
+    def __init__(self, classifiers):
+        self.classifiers = classifiers
+        self._keep = []
+        self._arr = (_lib.Model * len(classifiers))()
+        for i, md in enumerate(classifiers):
+            ck = np.ascontiguousarray(md["class_k"], dtype=np.int32)
+            cc = np.ascontiguousarray(md["class_code"], dtype=np.uint64)
+            ft = np.ascontiguousarray(md["features"], dtype=np.int32).reshape(-1, 2)
+            th = np.ascontiguousarray(md["theta"], dtype=np.float64).reshape(-1, ft.shape[0] + 1)
+            self._keep += [ck, cc, ft, th]
+            self._arr[i] = _lib.Model(md["counter"], len(ck), ck.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      cc.ctypes.data_as(C.POINTER(C.c_uint64)), ft.shape[0],
+                                      ft.ctypes.data_as(C.POINTER(C.c_int32)), th.shape[0],
+                                      th.ctypes.data_as(C.POINTER(C.c_double)), _lib.SUMMARY[md.get("summary", "")])
+
+    def predict_window_genomic(self, sequences, window_size, window_step):
+        """predict_window_genomic (:147-171): returns predictions[i] per region (log scale)"""
+        L = lib()
+        if isinstance(sequences, Sequences):
+            raise KmerLrError(_lib.ERR_ARG, "use predict_resident for resident sequences")
+        buf, off = flatten(sequences)
+        slots = [L.kmerlr_window_slots(int(off[i + 1] - off[i]), window_size, window_step)
+                 for i in range(len(off) - 1)]
+        out = np.zeros(max(sum(slots), 1))
+        check(L.kmerlr_score_windows(self._arr, len(self.classifiers), _p(buf), _p(off), len(off) - 1, window_size,
+                                     window_step, _p(out)))
+        res, p = [], 0
+        for s in slots:
+            res.append(out[p:p + s].copy())
+            p += s
+        return res
+
+    def predict_resident(self, sequences, window_size, window_step, fetch=False, total_slots=0):
+        out = np.zeros(max(total_slots, 1)) if fetch else None
+        check(lib().kmerlr_score_windows_resident(self._arr, len(self.classifiers), sequences.h, window_size,
+                                                  window_step, _p(out), None))
+        return out

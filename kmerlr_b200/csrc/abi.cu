@@ -1,0 +1,278 @@
+// abi.cu -- the C ABI of libkmerlr_b200.so (include/kmerlr_b200.h): handle registry, error
+// conversion, per-call device timing.  No CPU fallback: without an sm_100 device every entry point
+// that computes returns KMERLR_ERR_NOGPU.
+#include <cmath>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace kl {
+
+namespace {
+Ctx g_ctx;
+std::mutex g_mutex;   // the library is re-entrant: one call at a time per process / device
+std::unordered_map<uint64_t, std::shared_ptr<Object>> g_objects;
+uint64_t g_next = 1;
+thread_local std::string g_error;
+}  // namespace
+
+Ctx &ctx() { return g_ctx; }
+
+void require_ready() {
+  if (!g_ctx.ready) fail(KMERLR_ERR_NOGPU, "kmerlr_init() has not succeeded: no usable sm_100 GPU (there is no CPU fallback)");
+}
+
+uint64_t register_object(std::shared_ptr<Object> o) {
+  uint64_t h = g_next++;
+  g_objects[h] = std::move(o);
+  return h;
+}
+std::shared_ptr<Object> lookup_object(uint64_t h) {
+  auto it = g_objects.find(h);
+  return it == g_objects.end() ? nullptr : it->second;
+}
+
+template <typename F>
+int guarded(F &&f, bool timed = true) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (timed && g_ctx.ready) KL_CUDA(cudaEventRecord(g_ctx.ev0, g_ctx.stream));
+    f();
+    if (timed && g_ctx.ready) {
+      KL_CUDA(cudaEventRecord(g_ctx.ev1, g_ctx.stream));
+      KL_CUDA(cudaEventSynchronize(g_ctx.ev1));
+      float ms = 0.f;
+      KL_CUDA(cudaEventElapsedTime(&ms, g_ctx.ev0, g_ctx.ev1));
+      g_ctx.last_ms = ms;
+    }
+    return KMERLR_OK;
+  } catch (const Error &e) {
+    g_error = e.msg;
+    if (g_ctx.ready) cudaGetLastError();
+    return e.code;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return KMERLR_ERR_INTERNAL;
+  }
+}
+
+}  // namespace kl
+
+using namespace kl;
+
+extern "C" {
+
+int kmerlr_version(void) { return 100; }
+
+const char *kmerlr_last_error(void) { return g_error.c_str(); }
+
+double kmerlr_last_device_ms(void) { return g_ctx.last_ms; }
+
+int64_t kmerlr_launch_count(void) { return g_ctx.launches; }
+
+int kmerlr_init(int device) {
+  return guarded([&] {
+    if (g_ctx.ready) {
+      KL_REQUIRE(device == g_ctx.device, "kmerlr_init: already initialised on another device");
+      return;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      fail(KMERLR_ERR_NOGPU, "no CUDA device visible (there is no CPU fallback)");
+    }
+    KL_REQUIRE(device >= 0 && device < count, "kmerlr_init: device index out of range");
+    cudaDeviceProp prop;
+    KL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) fail(KMERLR_ERR_NOGPU, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "); this library is built for sm_100a only");
+    KL_CUDA(cudaSetDevice(device));
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    KL_CUDA(cudaEventCreate(&g_ctx.ev0));
+    KL_CUDA(cudaEventCreate(&g_ctx.ev1));
+    g_ctx.ready = true;
+  }, false);
+}
+
+int kmerlr_shutdown(void) {
+  return guarded([&] {
+    g_objects.clear();
+    if (g_ctx.ready) {
+      comm_destroy();
+      cudaEventDestroy(g_ctx.ev0); cudaEventDestroy(g_ctx.ev1);
+      cudaStreamDestroy(g_ctx.stream);
+      g_ctx = Ctx();
+    }
+  }, false);
+}
+
+int kmerlr_comm_unique_id(void *id128) { return guarded([&] { comm_unique_id(id128); }, false); }
+int kmerlr_comm_init(int rank, int world, const void *id128) { return guarded([&] { comm_init(rank, world, id128); }, false); }
+int kmerlr_comm_destroy(void) { return guarded([&] { comm_destroy(); }, false); }
+
+int kmerlr_sequences_create(const uint8_t *seq, const int64_t *off, int64_t n, kmerlr_handle *out) {
+  return guarded([&] {
+    KL_REQUIRE(out, "null output handle");
+    *out = register_object(sequences_create(seq, off, n));
+  });
+}
+
+int kmerlr_extract_resident(const kmerlr_config *cfg, kmerlr_handle sequences, const int32_t *frozen_k,
+                            const uint64_t *frozen_code, int64_t n_frozen, const int32_t *features,
+                            int64_t n_features, int flags, kmerlr_handle *out) {
+  return guarded([&] {
+    KL_REQUIRE(cfg && out, "null argument");
+    auto s = lookup<SeqSet>(sequences, "sequences");
+    *out = register_object(extract(*cfg, *s, frozen_k, frozen_code, n_frozen, features, n_features, flags));
+  });
+}
+
+int kmerlr_extract(const kmerlr_config *cfg, const uint8_t *seq, const int64_t *off, int64_t n,
+                   const int32_t *frozen_k, const uint64_t *frozen_code, int64_t n_frozen,
+                   const int32_t *features, int64_t n_features, int flags, kmerlr_handle *out) {
+  return guarded([&] {
+    KL_REQUIRE(cfg && out, "null argument");
+    auto s = sequences_create(seq, off, n);
+    *out = register_object(extract(*cfg, *s, frozen_k, frozen_code, n_frozen, features, n_features, flags));
+  });
+}
+
+int kmerlr_matrix_info(kmerlr_handle h, int64_t *n, int64_t *m, int64_t *nnz, int64_t *n_classes) {
+  return guarded([&] {
+    auto M = lookup<Matrix>(h, "matrix");
+    if (n) *n = M->n;
+    if (m) *m = M->m;
+    if (nnz) *nnz = M->nnz;
+    if (n_classes) *n_classes = (int64_t)M->class_k.size();
+  }, false);
+}
+
+int kmerlr_matrix_classes(kmerlr_handle h, int32_t *k_out, uint64_t *code_out) {
+  return guarded([&] {
+    auto M = lookup<Matrix>(h, "matrix");
+    for (size_t j = 0; j < M->class_k.size(); j++) { k_out[j] = M->class_k[j]; code_out[j] = M->class_code[j]; }
+  }, false);
+}
+
+int kmerlr_matrix_rows(kmerlr_handle h, int64_t *rowptr, int32_t *col, double *val) {
+  return guarded([&] { matrix_rows(*lookup<Matrix>(h, "matrix"), rowptr, col, val); });
+}
+
+int kmerlr_matrix_set_labels(kmerlr_handle h, const uint8_t *labels, int64_t n) {
+  return guarded([&] { matrix_set_labels(*lookup<Matrix>(h, "matrix"), labels, n); });
+}
+
+int kmerlr_matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const int32_t *col, const double *val,
+                           int flags, kmerlr_handle *out) {
+  return guarded([&] {
+    KL_REQUIRE(out, "null output handle");
+    *out = register_object(matrix_from_csr(n, m, rowptr, col, val, flags));
+  });
+}
+
+int kmerlr_free(kmerlr_handle h) {
+  return guarded([&] {
+    KL_REQUIRE(g_objects.erase(h) == 1, "kmerlr_free: invalid handle");
+  }, false);
+}
+
+int64_t kmerlr_coeff_dim(int64_t n) { return (n + 1) * n / 2 + 1; }
+int64_t kmerlr_coeff_ind2sub(int64_t n, int64_t k1, int64_t k2) {
+  if (k1 == k2) return k1 + 1;
+  return n + (n * (n - 1) / 2) - (n - k1) * ((n - k1) - 1) / 2 + k2 - k1;
+}
+void kmerlr_coeff_sub2ind(int64_t n, int64_t i, int64_t *k1, int64_t *k2) {
+  if (i < n) { *k1 = i; *k2 = i; return; }
+  i = i - n;
+  int64_t a = n - 2 - (int64_t)std::floor(std::sqrt((double)(-8 * i + 4 * n * (n - 1) - 7)) / 2.0 - 0.5);
+  *k1 = a;
+  *k2 = i + a + 1 - n * (n - 1) / 2 + (n - a) * ((n - a) - 1) / 2;
+}
+
+int kmerlr_linear_pdf(kmerlr_handle h, const double *theta, int64_t ntheta, int cooccurrence, double *out_n) {
+  return guarded([&] { linear_pdf(*lookup<Matrix>(h, "matrix"), theta, ntheta, cooccurrence, out_n, false); });
+}
+int kmerlr_logpdf(kmerlr_handle h, const double *theta, int64_t ntheta, int cooccurrence, double *out_n) {
+  return guarded([&] { linear_pdf(*lookup<Matrix>(h, "matrix"), theta, ntheta, cooccurrence, out_n, true); });
+}
+int kmerlr_gradient(kmerlr_handle h, const double *theta, int64_t ntheta, const double class_w[2], double lambda,
+                    int cooccurrence, double *g_out) {
+  return guarded([&] { gradient(*lookup<Matrix>(h, "matrix"), theta, ntheta, class_w, lambda, cooccurrence, g_out); });
+}
+int kmerlr_loss(kmerlr_handle h, const double *theta, int64_t ntheta, const double class_w[2], double lambda,
+                int cooccurrence, double *loss_out) {
+  return guarded([&] { *loss_out = loss(*lookup<Matrix>(h, "matrix"), theta, ntheta, class_w, lambda, cooccurrence); });
+}
+int kmerlr_class_weights(kmerlr_handle h, double class_w_out[2]) {
+  return guarded([&] {
+    auto M = lookup<Matrix>(h, "matrix");
+    KL_REQUIRE(M->has_labels, "class_weights: the matrix has no labels");
+    double n0 = (double)M->n_neg, n1 = (double)M->n_pos;
+    class_w_out[0] = (n0 + n1) / (2.0 * n0);
+    class_w_out[1] = (n0 + n1) / (2.0 * n1);
+  }, false);
+}
+
+int kmerlr_select(kmerlr_handle h, const double class_w[2], int cooccurrence, int64_t N, double theta0,
+                  const int64_t *active_idx, const double *active_theta, int64_t n_active, int tie,
+                  double epsilon_lambda, double prev_lambda, uint8_t *mask_out, int64_t ntheta, double *lambda_out,
+                  int64_t *c_out, int *ok_out, double *g_out_or_null) {
+  return guarded([&] {
+    KL_REQUIRE(mask_out && lambda_out && c_out && ok_out, "null argument");
+    select(*lookup<Matrix>(h, "matrix"), class_w, cooccurrence, N, theta0, active_idx, active_theta, n_active, tie,
+           epsilon_lambda, prev_lambda, mask_out, ntheta, lambda_out, c_out, ok_out, g_out_or_null);
+  });
+}
+
+int kmerlr_reduce(kmerlr_handle h, const int64_t *sel, int64_t nsel, kmerlr_handle *out) {
+  return guarded([&] {
+    KL_REQUIRE(out, "null output handle");
+    *out = register_object(matrix_reduce(*lookup<Matrix>(h, "matrix"), sel, nsel));
+  });
+}
+
+int kmerlr_step_size(kmerlr_handle h, double l2, double step_factor, double *step_out) {
+  return guarded([&] {
+    auto M = lookup<Matrix>(h, "matrix");
+    KL_REQUIRE(M->n_global > 0, "step_size: empty data set");
+    double L = 0.25 * (matrix_maxsq(*M) + 1.0) + l2 / (double)M->n_global;
+    *step_out = 1.0 / (2.0 * L + std::fmin(2.0 * l2, L)) * step_factor;
+  });
+}
+
+int kmerlr_proxgrad(kmerlr_handle h, double *theta_inout, int64_t ntheta, const double class_w[2], double lambda,
+                    double l2, double step_factor, double epsilon, double epsilon_loss, int64_t max_iter,
+                    double hook_state[2], int64_t *iters_out, double *delta_out) {
+  return guarded([&] {
+    proxgrad(*lookup<Matrix>(h, "matrix"), theta_inout, ntheta, class_w, lambda, l2, step_factor, epsilon,
+             epsilon_loss, max_iter, hook_state, iters_out, delta_out);
+  });
+}
+
+int64_t kmerlr_window_slots(int64_t len, int64_t W, int64_t step) {
+  int64_t n = len - W;
+  return n > 0 ? n / step + 1 : 0;
+}
+
+int kmerlr_score_windows(const kmerlr_model *models, int n_models, const uint8_t *seq, const int64_t *region_off,
+                         int64_t n_regions, int64_t W, int64_t step, double *out) {
+  return guarded([&] {
+    auto s = sequences_create(seq, region_off, n_regions);
+    score_windows(models, n_models, *s, W, step, out, nullptr);
+  });
+}
+
+int kmerlr_score_windows_resident(const kmerlr_model *models, int n_models, kmerlr_handle sequences, int64_t W,
+                                  int64_t step, double *out_host_or_null, kmerlr_handle *out_dev_or_null) {
+  return guarded([&] {
+    auto s = lookup<SeqSet>(sequences, "sequences");
+    std::shared_ptr<Object> dev;
+    score_windows(models, n_models, *s, W, step, out_host_or_null, out_dev_or_null ? &dev : nullptr);
+    if (out_dev_or_null) *out_dev_or_null = register_object(dev);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+// common.cuh -- shared infrastructure of libkmerlr_b200.so (context, errors, device buffers,
+// matrix / sequence objects, small device helpers).  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/kmerlr_b200.h"
+
+namespace kl {
+
+// ---------------------------------------------------------------------------------------------
+// errors: C++ exceptions inside, status codes at the C ABI (reference style: log.Fatal for
+// argument / IO errors, panic("internal error") for invariants -- SURVEY 8b)
+// ---------------------------------------------------------------------------------------------
+struct Error {
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] inline void fail(int code, const std::string &msg) { throw Error{code, msg}; }
+
+#define KL_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      ::kl::fail(KMERLR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +      \
+                                      __FILE__ + ":" + std::to_string(__LINE__) + ")");            \
+  } while (0)
+
+#define KL_REQUIRE(cond, msg)                                                                      \
+  do {                                                                                             \
+    if (!(cond)) ::kl::fail(KMERLR_ERR_ARG, std::string(msg));                                     \
+  } while (0)
+
+#define KL_INVARIANT(cond)                                                                         \
+  do {                                                                                             \
+    if (!(cond)) ::kl::fail(KMERLR_ERR_INTERNAL, std::string("internal error: ") + #cond + " (" +  \
+                                                     __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context: one process drives one GPU
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+  bool ready = false;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  double last_ms = 0.0;
+  // communicator (NCCL via dlopen, see comm.cu)
+  void *comm = nullptr;
+  int rank = 0, world = 1;
+};
+Ctx &ctx();
+void require_ready();
+
+// launch helper: counts launches (bench.py reports gpu_launches) and checks the launch
+#define KL_LAUNCH(kernel, grid, block, smem, ...)                                                  \
+  do {                                                                                             \
+    kernel<<<(grid), (block), (smem), ::kl::ctx().stream>>>(__VA_ARGS__);                          \
+    ::kl::ctx().launches++;                                                                        \
+    KL_CUDA(cudaGetLastError());                                                                   \
+  } while (0)
+
+inline void sync_stream() { KL_CUDA(cudaStreamSynchronize(ctx().stream)); }
+
+// ---------------------------------------------------------------------------------------------
+// device buffer (RAII)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) KL_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void zero() { if (n) KL_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx().stream)); }
+  void upload(const T *h, size_t count) {
+    if (count) KL_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+  }
+  void download(T *h, size_t count) const {
+    if (count) KL_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// objects behind handles
+// ---------------------------------------------------------------------------------------------
+struct Object {
+  virtual ~Object() {}
+};
+
+// 2-bit packed sequences resident in HBM.  Every sequence starts on a 64-base block
+// (16 B of codes + 8 B of invalid mask); base j of sequence i is bits [2(j&15), 2(j&15)+1] of
+// bits2[blk[i]*4 + (j>>4)], its "not ACGT" flag is bit (j&15) of inv16[blk[i]*4 + (j>>4)].
+struct SeqSet : Object {
+  int64_t n = 0;
+  int64_t total_bases = 0;
+  int64_t total_blocks = 0;
+  int64_t max_len = 0;
+  DevBuf<int64_t> len;      // n
+  DevBuf<int64_t> blk;      // n+1, in 64-base blocks
+  DevBuf<uint32_t> bits2;   // total_blocks*4
+  DevBuf<uint16_t> inv16;   // total_blocks*4
+};
+
+enum ValType : int { VAL_ONE = 0, VAL_U32 = 1, VAL_F64 = 2 };
+
+// KmerDataSet in HBM: CSR rows (without the bias column) + lazily built CSC + labels + classes
+struct Matrix : Object {
+  int64_t n = 0, m = 0, nnz = 0;
+  ValType vt = VAL_U32;
+  DevBuf<int64_t> rowptr;    // n+1
+  DevBuf<uint32_t> col;      // nnz
+  DevBuf<uint32_t> val_u32;  // nnz (VAL_U32)
+  DevBuf<double> val_f64;    // nnz (VAL_F64)
+  // CSC view (built on first use by ensure_csc): entries of column c in ascending row order
+  bool has_csc = false;
+  DevBuf<int64_t> colptr;    // m+1
+  DevBuf<uint32_t> crow;     // nnz
+  DevBuf<uint32_t> cval_u32;
+  DevBuf<double> cval_f64;
+  // column-chunk task list of the deterministic X^T w reduction
+  int64_t n_tasks = 0;
+  DevBuf<int64_t> taskptr;   // m+1
+  DevBuf<uint32_t> taskcol;  // n_tasks
+  // labels
+  bool has_labels = false;
+  DevBuf<uint8_t> labels;    // n
+  int64_t n_pos = 0, n_neg = 0;   // global counts (all ranks)
+  // class list (host)
+  std::vector<int32_t> class_k;
+  std::vector<uint64_t> class_code;
+  // sample sharding
+  bool sharded = false;
+  int64_t n_global = 0;
+  // cached max_i ||x_i||^2 (without bias), global
+  bool has_maxsq = false;
+  double maxsq = 0.0;
+};
+
+// handle registry (abi.cu)
+uint64_t register_object(std::shared_ptr<Object> o);
+std::shared_ptr<Object> lookup_object(uint64_t h);
+template <typename T>
+std::shared_ptr<T> lookup(uint64_t h, const char *what) {
+  auto o = std::dynamic_pointer_cast<T>(lookup_object(h));
+  if (!o) fail(KMERLR_ERR_ARG, std::string("invalid ") + what + " handle");
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// module entry points (one .cu file each)
+// ---------------------------------------------------------------------------------------------
+// scan.cu
+void exclusive_scan_i64(const int64_t *in, int64_t *out, int64_t n);            // out[n] = total
+void exclusive_scan_u32_to_i64(const uint32_t *in, int64_t *out, int64_t n);    // out[n] = total
+void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n);          // out[n] = total
+// extract.cu
+std::shared_ptr<SeqSet> sequences_create(const uint8_t *seq, const int64_t *off, int64_t n);
+std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const int32_t *frozen_k,
+                                const uint64_t *frozen_code, int64_t n_frozen, const int32_t *features,
+                                int64_t n_features, int flags);
+// matrix.cu
+std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const int32_t *col,
+                                        const double *val, int flags);
+void matrix_rows(const Matrix &M, int64_t *rowptr, int32_t *col, double *val);
+void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n);
+void ensure_csc(Matrix &M);
+std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel);
+double matrix_maxsq(Matrix &M);
+// logistic.cu
+void linear_pdf(Matrix &M, const double *theta, int64_t ntheta, int cooc, double *out_host, bool logpdf);
+void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc,
+              double *g_host);
+double loss(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc);
+void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], double lambda, double l2,
+              double step_factor, double epsilon, double epsilon_loss, int64_t max_iter, double hook[2],
+              int64_t *iters, double *delta);
+// select.cu
+void select(Matrix &M, const double cw[2], int cooc, int64_t N, double theta0, const int64_t *active_idx,
+            const double *active_theta, int64_t n_active, int tie, double eps_lambda, double prev_lambda,
+            uint8_t *mask, int64_t ntheta, double *lambda_out, int64_t *c_out, int *ok_out, double *g_out);
+// score.cu
+void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, int64_t W, int64_t step,
+                   double *out_host, std::shared_ptr<Object> *out_dev);
+// comm.cu
+void comm_unique_id(void *id128);
+void comm_init(int rank, int world, const void *id128);
+void comm_destroy();
+void comm_allreduce_sum_f64(double *dev, int64_t count);
+void comm_allreduce_sum_i64(int64_t *dev, int64_t count);
+void comm_allreduce_max_f64(double *dev, int64_t count);
+void comm_allreduce_max_u8(uint8_t *dev, int64_t count);
+void comm_allgather_f64(const double *dev_in, double *dev_out, int64_t count_per_rank);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// reduction in a fixed order that depends only on the lane layout (deterministic)
+__device__ __forceinline__ double warp_sum_down(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// log(1+exp(x)) with a = 0: LogAdd(0, x) of autodiff's logarithmetic package, restated as
+// max(0,x) + log1p(exp(-|x|))  (kmerLr_logistic_regression.go:138-145)
+__device__ __forceinline__ double log_add0(double x) {
+  return x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x));
+}
+#endif
+
+}  // namespace kl

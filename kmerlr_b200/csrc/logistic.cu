@@ -1,0 +1,422 @@
+// logistic.cu -- stage 2 of the hot path: sparse logistic loss / gradient and the proximal-gradient
+// estimator.
+//
+// Replaces logisticRegression.LinearPdf / LogPdf / Gradient / Loss
+// (kmerLr_logistic_regression.go:47-272) and estimate_proximal + eval_stopping + estimate_step_size
+// (kmerLr_estimator_proximal.go:30-120, hook kmerLr_estimator_hook.go:46-99).
+//
+// Two passes over the matrix per gradient, both deterministic (no float atomics):
+//   rows pass  (CSR, warp per row):   z_i = theta_0 + sum_j v_ij theta_j, loss term, w_i
+//   cols pass  (CSC, warp per 1024-entry column chunk):  g_j = sum_i w_i v_ij
+// The reduction tree of a column depends only on the column's own entries, so two features with
+// identical columns get bit-identical gradients (what leapfrog tie handling needs).
+#include "common.cuh"
+
+#include <cmath>
+
+namespace kl {
+
+namespace {
+
+constexpr int TASK_CHUNK = 1024;
+constexpr int RED_BLOCKS = 256;
+
+struct PgState {
+  long long iter;
+  int done;          // 0 running, 1 stopped, 2 final loss evaluation pending
+  int first;
+  double delta, loss_old, loss_new, lossval;
+};
+
+__device__ __forceinline__ int64_t ind2sub(int64_t n, int64_t k1, int64_t k2) {
+  return n + (n * (n - 1) / 2) - (n - k1) * ((n - k1) - 1) / 2 + k2 - k1;
+}
+
+template <typename VT>
+__device__ __forceinline__ double valf(const VT *val, int64_t p) { return val ? (double)val[p] : 1.0; }
+
+// rows pass: MODE 0 = z only, 1 = log sigma(z), 2 = w_i and loss term
+template <typename VT, int MODE>
+__global__ void rows_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+                            const VT *__restrict__ val, int64_t n, int64_t m, const double *__restrict__ theta,
+                            int cooc, const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n,
+                            double *__restrict__ out, double *__restrict__ lossterm, const PgState *st) {
+  if (st && st->done == 1) return;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  unsigned lane = lane_id();
+  int64_t a = rowptr[row], b = rowptr[row + 1];
+  double s = 0.0;
+  for (int64_t p = a + lane; p < b; p += 32) s += valf(val, p) * __ldg(theta + col[p] + 1);
+  if (cooc) {
+    // pair terms (kmerLr_logistic_regression.go:69-84)
+    for (int64_t p1 = a; p1 < b; p1++) {
+      double v1 = valf(val, p1);
+      int64_t c1 = col[p1];
+      for (int64_t p2 = p1 + 1 + lane; p2 < b; p2 += 32)
+        s += v1 * valf(val, p2) * __ldg(theta + ind2sub(m, c1, (int64_t)col[p2]));
+    }
+  }
+  s = warp_sum_down(s);
+  if (lane == 0) {
+    double z = theta[0] + s;
+    if (MODE == 0) out[row] = z;
+    else if (MODE == 1) out[row] = -log_add0(-z);
+    else {
+      // Gradient weight (:166-178) and Loss term (:257-263)
+      double r = -log_add0(-z);
+      if (labels[row]) { out[row] = inv_n * cw1 * (exp(r) - 1.0); lossterm[row] = -cw1 * r; }
+      else             { out[row] = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
+    }
+  }
+}
+
+// deterministic sum of x[0..n): fixed grid, strided sequential sums, fixed tree
+__global__ void reduce_stage1(const double *__restrict__ x, int64_t n, double *__restrict__ part, const PgState *st) {
+  if (st && st->done == 1) return;
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+// out[0] = sum(part) in index order
+__global__ void reduce_stage2(const double *__restrict__ part, int np, double *__restrict__ out, const PgState *st) {
+  if (st && st->done == 1) return;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < np; i++) s += part[i];
+    out[0] = s;
+  }
+}
+
+// cols pass: one warp per column chunk
+template <typename VT>
+__global__ void cols_partial(const int64_t *__restrict__ colptr, const uint32_t *__restrict__ crow,
+                             const VT *__restrict__ cval, const int64_t *__restrict__ taskptr,
+                             const uint32_t *__restrict__ taskcol, int64_t n_tasks, const double *__restrict__ w,
+                             double *__restrict__ part, const PgState *st) {
+  if (st && st->done) return;
+  int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_tasks) return;
+  unsigned lane = lane_id();
+  uint32_t c = taskcol[t];
+  int64_t a = colptr[c] + (t - taskptr[c]) * TASK_CHUNK, b = a + TASK_CHUNK;
+  if (b > colptr[c + 1]) b = colptr[c + 1];
+  double s = 0.0;
+  for (int64_t p = a + lane; p < b; p += 32) s += __ldg(w + crow[p]) * valf(cval, p);
+  s = warp_sum_down(s);
+  if (lane == 0) part[t] = s;
+}
+
+// g[c+1] = sum of the column's chunk partials in chunk order, plus the L1 sign term (:237-246)
+__global__ void cols_finalize(const int64_t *__restrict__ taskptr, const double *__restrict__ part, int64_t m,
+                              const double *__restrict__ wsum, double *__restrict__ g, const PgState *st) {
+  if (st && st->done) return;
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) g[0] = wsum[0];
+  if (c >= m) return;
+  double s = 0.0;
+  for (int64_t t = taskptr[c]; t < taskptr[c + 1]; t++) s += part[t];
+  g[c + 1] = s;
+}
+
+// pair coefficients (kmerLr_logistic_regression.go:183-195): g[Ind2Sub(a,b)] = sum_i w_i v_ia v_ib,
+// one warp per pair, intersecting the two CSC columns
+template <typename VT>
+__global__ void pairs_gradient(const int64_t *__restrict__ colptr, const uint32_t *__restrict__ crow,
+                               const VT *__restrict__ cval, int64_t m, const double *__restrict__ w,
+                               double *__restrict__ g) {
+  int64_t npairs = m * (m - 1) / 2;
+  int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned lane = lane_id();
+  for (int64_t pi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pi < npairs; pi += warps) {
+    // pair index -> (a, b), a < b, row-major over the strict upper triangle
+    int64_t a = (int64_t)floor(((double)(2 * m - 1) - sqrt((double)(2 * m - 1) * (double)(2 * m - 1) - 8.0 * (double)pi)) / 2.0);
+    while (a > 0 && a * (2 * m - a - 1) / 2 > pi) a--;
+    while ((a + 1) * (2 * m - a - 2) / 2 <= pi) a++;
+    int64_t b = pi - a * (2 * m - a - 1) / 2 + a + 1;
+    int64_t a0 = colptr[a], a1 = colptr[a + 1], b0 = colptr[b], b1 = colptr[b + 1];
+    // iterate the shorter column, binary search the longer one
+    bool swap = (a1 - a0) > (b1 - b0);
+    int64_t s0 = swap ? b0 : a0, s1 = swap ? b1 : a1, l0 = swap ? a0 : b0, l1 = swap ? a1 : b1;
+    double s = 0.0;
+    for (int64_t p = s0 + lane; p < s1; p += 32) {
+      uint32_t r = crow[p];
+      int64_t lo = l0, hi = l1;
+      while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (crow[mid] < r) lo = mid + 1; else hi = mid; }
+      if (lo < l1 && crow[lo] == r) {
+        double va = valf(cval, swap ? lo : p), vb = valf(cval, swap ? p : lo);
+        s += w[r] * va * vb;
+      }
+    }
+    s = warp_sum_down(s);
+    if (lane == 0) g[ind2sub(m, a, b)] = s;
+  }
+}
+
+__global__ void add_l1_sign(const double *__restrict__ theta, double *__restrict__ g, int64_t ntheta, double lambda) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < 1 || j >= ntheta) return;
+  if (theta[j] < 0) g[j] -= lambda; else if (theta[j] > 0) g[j] += lambda;
+}
+
+// sum over ranks in rank order (deterministic, identical on every rank)
+__global__ void sum_ranks(const double *__restrict__ gathered, int world, int64_t count, double *__restrict__ out) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  double s = 0.0;
+  for (int r = 0; r < world; r++) s += gathered[(int64_t)r * count + j];
+  out[j] = s;
+}
+
+// hook (kmerLr_estimator_hook.go:46-99): loss = mean + lambda * sum_{j=1..m} |theta_j|
+__global__ void hook_kernel(PgState *st, const double *__restrict__ losssum, const double *__restrict__ theta,
+                            int64_t m, double inv_n, double lambda, double eps_loss) {
+  if (st->done == 1) return;
+  __shared__ double sh[256];
+  double s = 0.0;
+  if (!isnan(lambda) && lambda != 0.0)
+    for (int64_t j = 1 + threadIdx.x; j < m + 1; j += blockDim.x) s += lambda * fabs(theta[j]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double l = losssum[0] * inv_n + sh[0];
+    st->lossval = l;
+    if (st->first) { st->first = 0; return; }   // loss at the start point: no hook call yet
+    double t = st->loss_old; st->loss_old = st->loss_new; st->loss_new = t;
+    if (eps_loss != 0.0) {
+      st->loss_new = l;
+      if (st->done == 0 && fabs(st->loss_old - st->loss_new) < eps_loss) st->done = 1;
+    }
+    if (st->done == 2) st->done = 1;
+  }
+}
+
+// theta <- prox(theta - s g), eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98)
+__global__ void prox_kernel(PgState *st, double *__restrict__ theta, const double *__restrict__ g, int64_t ntheta,
+                            double step, double lambda, double eps, long long max_iter) {
+  if (st->done) return;
+  __shared__ double shx[256], shd[256];
+  __shared__ int shnan;
+  if (threadIdx.x == 0) shnan = 0;
+  __syncthreads();
+  double mx = 0.0, md = 0.0;
+  for (int64_t k = threadIdx.x; k < ntheta; k += blockDim.x) {
+    double t0 = theta[k], t1 = t0 - step * g[k];
+    if (k > 0) {
+      if (t1 >= 0.0) t1 = fmax(fabs(t1) - step * lambda, 0.0);
+      else           t1 = -fmax(fabs(t1) - step * lambda, 0.0);
+    }
+    theta[k] = t1;
+    if (isnan(t1)) shnan = 1;
+    mx = fmax(mx, fabs(t1));
+    md = fmax(md, fabs(t1 - t0));
+  }
+  shx[threadIdx.x] = mx; shd[threadIdx.x] = md;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      shx[threadIdx.x] = fmax(shx[threadIdx.x], shx[threadIdx.x + o]);
+      shd[threadIdx.x] = fmax(shd[threadIdx.x], shd[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double max_x = shx[0], max_delta = shd[0];
+    st->iter += 1;
+    if (shnan) { st->delta = nan(""); st->done = 1; return; }
+    st->delta = max_x != 0.0 ? max_delta / max_x : max_delta;
+    if ((max_x != 0.0 && max_delta / max_x <= eps) || (max_x == 0.0 && max_delta == 0.0)) st->done = 1;
+    else if (st->iter >= max_iter) st->done = 2;
+  }
+}
+
+struct Work {
+  DevBuf<double> theta, w, lossterm, part, g, red, scalars, gathered;
+};
+
+template <typename VT>
+const VT *csr_val(const Matrix &M);
+template <> const uint32_t *csr_val<uint32_t>(const Matrix &M) { return M.vt == VAL_U32 ? M.val_u32.p : nullptr; }
+template <> const double *csr_val<double>(const Matrix &M) { return M.val_f64.p; }
+template <typename VT>
+const VT *csc_val(const Matrix &M);
+template <> const uint32_t *csc_val<uint32_t>(const Matrix &M) { return M.vt == VAL_U32 ? M.cval_u32.p : nullptr; }
+template <> const double *csc_val<double>(const Matrix &M) { return M.cval_f64.p; }
+
+inline unsigned warp_grid(int64_t items, int threads) { return (unsigned)((items * 32 + threads - 1) / threads); }
+
+// deterministic sum of a device vector into out[0] (all ranks when sharded)
+void reduce_sum(const Matrix &M, const double *x, int64_t n, Work &wk, double *out, const PgState *st,
+                bool all_ranks = true) {
+  KL_LAUNCH(reduce_stage1, RED_BLOCKS, 256, 0, x, n, wk.red.p, st);
+  KL_LAUNCH(reduce_stage2, 1, 32, 0, wk.red.p, RED_BLOCKS, out, st);
+  if (M.sharded && all_ranks) {
+    comm_allgather_f64(out, wk.gathered.p, 1);
+    KL_LAUNCH(sum_ranks, 1, 32, 0, wk.gathered.p, ctx().world, (int64_t)1, out);
+  }
+}
+
+template <typename VT, int MODE>
+void launch_rows(const Matrix &M, const double *theta, int cooc, const double cw[2], double *out, double *lossterm,
+                 const PgState *st) {
+  if (M.n == 0) return;
+  double inv_n = 1.0 / (double)M.n_global;
+  KL_LAUNCH((rows_kernel<VT, MODE>), warp_grid(M.n, 256), 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m,
+            theta, cooc, M.labels.p, cw ? cw[0] : 1.0, cw ? cw[1] : 1.0, inv_n, out, lossterm, st);
+}
+
+// g (ntheta) from w; wk.scalars[1] receives sum(w)
+template <typename VT>
+void launch_cols(Matrix &M, Work &wk, int64_t ntheta, int cooc, const PgState *st) {
+  reduce_sum(M, wk.w.p, M.n, wk, wk.scalars.p + 1, nullptr, /*all_ranks=*/false);
+  if (M.n_tasks > 0)
+    KL_LAUNCH((cols_partial<VT>), warp_grid(M.n_tasks, 256), 256, 0, M.colptr.p, M.crow.p, csc_val<VT>(M), M.taskptr.p,
+              M.taskcol.p, M.n_tasks, wk.w.p, wk.part.p, st);
+  KL_LAUNCH(cols_finalize, (unsigned)((M.m + 1 + 255) / 256), 256, 0, M.taskptr.p, wk.part.p, M.m, wk.scalars.p + 1,
+            wk.g.p, st);
+  if (cooc && M.m > 1)
+    KL_LAUNCH((pairs_gradient<VT>), (unsigned)(ctx().sm_count * 8), 256, 0, M.colptr.p, M.crow.p, csc_val<VT>(M), M.m,
+              wk.w.p, wk.g.p);
+  if (M.sharded) {
+    // every rank sums the per-rank gradients in rank order: same bits everywhere, and identical
+    // columns keep identical gradients (an NCCL ring reduces different slices in different orders)
+    comm_allgather_f64(wk.g.p, wk.gathered.p, ntheta);
+    KL_LAUNCH(sum_ranks, (unsigned)((ntheta + 255) / 256), 256, 0, wk.gathered.p, ctx().world, ntheta, wk.g.p);
+  }
+}
+
+void alloc_work(const Matrix &M, int64_t ntheta, Work &wk) {
+  wk.theta.alloc((size_t)ntheta);
+  wk.w.alloc((size_t)(M.n ? M.n : 1));
+  wk.lossterm.alloc((size_t)(M.n ? M.n : 1));
+  wk.part.alloc((size_t)(M.n_tasks ? M.n_tasks : 1));
+  wk.g.alloc((size_t)ntheta);
+  wk.red.alloc(RED_BLOCKS);
+  wk.scalars.alloc(8);
+  wk.gathered.alloc((size_t)(M.sharded ? ntheta * ctx().world : 1));
+}
+
+void check_theta(const Matrix &M, int64_t ntheta, int cooc) {
+  if (cooc) KL_INVARIANT(ntheta == kmerlr_coeff_dim(M.m));
+  else KL_INVARIANT(ntheta == M.m + 1);
+}
+
+template <typename F>
+void dispatch_vt(const Matrix &M, F &&f) {
+  if (M.vt == VAL_F64) f((double *)nullptr);
+  else f((uint32_t *)nullptr);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+void linear_pdf(Matrix &M, const double *theta, int64_t ntheta, int cooc, double *out_host, bool logpdf) {
+  require_ready();
+  check_theta(M, ntheta, cooc);
+  DevBuf<double> dth((size_t)ntheta), out((size_t)(M.n ? M.n : 1));
+  dth.upload(theta, (size_t)ntheta);
+  dispatch_vt(M, [&](auto *tag) {
+    using VT = typename std::remove_pointer<decltype(tag)>::type;
+    if (logpdf) launch_rows<VT, 1>(M, dth.p, cooc, nullptr, out.p, nullptr, nullptr);
+    else launch_rows<VT, 0>(M, dth.p, cooc, nullptr, out.p, nullptr, nullptr);
+  });
+  out.download(out_host, (size_t)M.n);
+  sync_stream();
+}
+
+void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc,
+              double *g_host) {
+  require_ready();
+  check_theta(M, ntheta, cooc);
+  KL_REQUIRE(M.has_labels, "gradient: the matrix has no labels (kmerlr_matrix_set_labels)");
+  ensure_csc(M);
+  Work wk; alloc_work(M, ntheta, wk);
+  wk.theta.upload(theta, (size_t)ntheta);
+  wk.g.zero();
+  dispatch_vt(M, [&](auto *tag) {
+    using VT = typename std::remove_pointer<decltype(tag)>::type;
+    launch_rows<VT, 2>(M, wk.theta.p, cooc, cw, wk.w.p, wk.lossterm.p, nullptr);
+    launch_cols<VT>(M, wk, ntheta, cooc, nullptr);
+  });
+  if (!std::isnan(lambda) && lambda != 0.0)
+    KL_LAUNCH(add_l1_sign, (unsigned)((ntheta + 255) / 256), 256, 0, wk.theta.p, wk.g.p, ntheta, lambda);
+  wk.g.download(g_host, (size_t)ntheta);
+  sync_stream();
+}
+
+double loss(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc) {
+  require_ready();
+  check_theta(M, ntheta, cooc);
+  KL_REQUIRE(M.has_labels, "loss: the matrix has no labels (kmerlr_matrix_set_labels)");
+  if (M.n_global == 0) return 0.0;
+  Work wk; alloc_work(M, ntheta, wk);
+  wk.theta.upload(theta, (size_t)ntheta);
+  dispatch_vt(M, [&](auto *tag) {
+    using VT = typename std::remove_pointer<decltype(tag)>::type;
+    launch_rows<VT, 2>(M, wk.theta.p, cooc, cw, wk.w.p, wk.lossterm.p, nullptr);
+  });
+  reduce_sum(M, wk.lossterm.p, M.n, wk, wk.scalars.p, nullptr);
+  double s = 0.0;
+  wk.scalars.download(&s, 1);
+  sync_stream();
+  double r = s / (double)M.n_global;
+  // the L1 loop bound of the reference is data[0].Dim() = m+1, also in pair mode (:255,267)
+  if (!std::isnan(lambda) && lambda != 0.0)
+    for (int64_t j = 1; j < M.m + 1; j++) r += lambda * std::fabs(theta[j]);
+  return r;
+}
+
+void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], double lambda, double l2,
+              double step_factor, double epsilon, double epsilon_loss, int64_t max_iter, double hook[2],
+              int64_t *iters, double *delta) {
+  require_ready();
+  check_theta(M, ntheta, 0);
+  KL_REQUIRE(M.has_labels, "proxgrad: the matrix has no labels (kmerlr_matrix_set_labels)");
+  KL_REQUIRE(M.n_global > 0, "proxgrad: empty data set");
+  ensure_csc(M);
+  // estimate_step_size (kmerLr_estimator_proximal.go:54-76)
+  double L = 0.25 * (matrix_maxsq(M) + 1.0) + l2 / (double)M.n_global;
+  double step = 1.0 / (2.0 * L + std::fmin(2.0 * l2, L)) * step_factor;
+  Work wk; alloc_work(M, ntheta, wk);
+  wk.theta.upload(theta, (size_t)ntheta);
+  DevBuf<PgState> st(1);
+  PgState h{};
+  h.iter = 0; h.done = max_iter > 0 ? 0 : 1; h.first = 1; h.delta = 0.0;
+  h.loss_old = hook ? hook[0] : NAN; h.loss_new = hook ? hook[1] : NAN; h.lossval = NAN;
+  st.upload(&h, 1);
+  const double inv_n = 1.0 / (double)M.n_global;
+  const int BATCH = 16;
+  while (true) {
+    for (int it = 0; it < BATCH; it++) {
+      dispatch_vt(M, [&](auto *tag) {
+        using VT = typename std::remove_pointer<decltype(tag)>::type;
+        launch_rows<VT, 2>(M, wk.theta.p, 0, cw, wk.w.p, wk.lossterm.p, st.p);
+        reduce_sum(M, wk.lossterm.p, M.n, wk, wk.scalars.p, st.p);
+        KL_LAUNCH(hook_kernel, 1, 256, 0, st.p, wk.scalars.p, wk.theta.p, M.m, inv_n, lambda, epsilon_loss);
+        launch_cols<VT>(M, wk, ntheta, 0, st.p);
+        KL_LAUNCH(prox_kernel, 1, 256, 0, st.p, wk.theta.p, wk.g.p, ntheta, step, lambda, epsilon, (long long)max_iter);
+      });
+    }
+    st.download(&h, 1);
+    sync_stream();
+    if (h.done == 1) break;
+  }
+  wk.theta.download(theta, (size_t)ntheta);
+  sync_stream();
+  if (hook) { hook[0] = h.loss_old; hook[1] = h.loss_new; }
+  if (iters) *iters = (int64_t)h.iter;
+  if (delta) *delta = h.delta;
+}
+
+}  // namespace kl

@@ -1,0 +1,142 @@
+"""Stage 1 parity: CUDA k-mer extraction (through the C ABI) vs the CPU oracle -- bit exact counts,
+column indices and class lists (north_star).  Needs a B200."""
+import numpy as np
+import pytest
+
+from conftest import cat
+
+pytestmark = pytest.mark.gpu
+
+
+def same_matrix(d, ref):
+    assert (d.n, d.m, d.nnz) == (ref.n, ref.m, ref.nnz)
+    k, code = d.Kmers()
+    ok, ocode = ref.classes()
+    assert np.array_equal(k, ok) and np.array_equal(code, ocode)
+    for x, y in zip(d.rows(), ref.rows()):
+        assert np.array_equal(x, y)
+
+
+def cfg_pair(K, O, M, N, **kw):
+    return K.NewKmerCounter(M, N, **kw), O.make_config(M, N, **kw)
+
+
+@pytest.mark.parametrize("M,N,flags", [
+    (1, 6, dict(revcomp=True)), (2, 6, dict(revcomp=True)), (8, 8, dict(revcomp=True)), (1, 8, dict(revcomp=True)),
+    (1, 8, dict()), (3, 7, dict(complement=True)), (3, 7, dict(reverse=True)), (1, 4, dict(revcomp=True)),
+    (6, 6, dict()), (1, 1, dict(revcomp=True)), (2, 10, dict(revcomp=True, binarize=True)),
+])
+def test_reference_fixtures(K, oracle, fixtures, M, N, flags):
+    """C1: the bundled kmerLr_test_{fg,bg}.fa (11 + 11 x 1000 bp, mixed case)"""
+    kc, oc = cfg_pair(K, oracle, M, N, **flags)
+    buf, off, _ = cat(fixtures, "kmerLr_test_fg", "kmerLr_test_bg")
+    d = K.compile_test_data(None, kc, None, None, True, flags.get("binarize", False), (buf, off))
+    same_matrix(d, oracle.extract(oc, (buf, off)))
+
+
+def test_cooccurrence_fixture(K, oracle, fixtures):
+    """C1: kmerLr_test_co_{fg,bg}.fa, 2 6 --binarize --revcomp (TestKmers6 data): m = 70"""
+    kc, oc = cfg_pair(K, oracle, 2, 6, revcomp=True, binarize=True)
+    buf, off, y = cat(fixtures, "kmerLr_test_co_fg", "kmerLr_test_co_bg")
+    d = K.compile_training_data(None, kc, None, None, True, True, (buf[:off[10]], off[:11]),
+                                (buf[off[10]:], off[10:] - off[10]))
+    assert d.m == 70
+    same_matrix(d, oracle.extract(oc, (buf, off)))
+    assert np.all(d.rows()[2] == 1.0)
+
+
+@pytest.mark.parametrize("L,M,N,flags", [
+    (500, 1, 8, dict(revcomp=True)), (200, 1, 10, dict(revcomp=True, binarize=True)), (37, 1, 8, dict(revcomp=True)),
+    (64, 5, 9, dict()), (300, 6, 12, dict(revcomp=True)), (120, 1, 13, dict(revcomp=True)), (500, 1, 5, dict(revcomp=True)),
+    (3000, 1, 5, dict(revcomp=True)), (1900, 6, 7, dict()),
+])
+def test_synthetic(K, oracle, L, M, N, flags):
+    from kmerlr_b200 import synth
+    kc, oc = cfg_pair(K, oracle, M, N, **flags)
+    buf, off, _ = synth.training_set(150, 150, L)
+    d = K.compile_test_data(None, kc, None, None, True, flags.get("binarize", False), (buf, off))
+    same_matrix(d, oracle.extract(oc, (buf, off)))
+
+
+def test_ragged_empty_and_invalid(K, oracle):
+    """ragged lengths, empty sequences, sequences shorter than k, lower case, N and other bytes"""
+    rng = np.random.default_rng(7)
+    seqs = []
+    for L in [0, 1, 2, 5, 7, 8, 9, 31, 32, 33, 63, 64, 65, 100, 257, 400, 0, 3]:
+        s = rng.choice(list("ACGTacgt"), size=L)
+        seqs.append("".join(s))
+    seqs[9] = seqs[9][:10] + "N" + seqs[9][11:]
+    seqs[13] = "NNNN" + seqs[13][4:50] + "nX-" + seqs[13][53:]
+    seqs[14] = seqs[14][:100] + "N" * 30 + seqs[14][130:]
+    seqs.append("N" * 40)
+    for M, N, flags in [(1, 8, dict(revcomp=True)), (2, 7, dict()), (1, 3, dict(revcomp=True)), (6, 9, dict(reverse=True)),
+                        (4, 8, dict(complement=True, binarize=True))]:
+        kc, oc = cfg_pair(K, oracle, M, N, **flags)
+        d = K.compile_test_data(None, kc, None, None, True, flags.get("binarize", False), seqs)
+        same_matrix(d, oracle.extract(oc, seqs))
+    # no sequences at all
+    d = K.compile_test_data(None, K.NewKmerCounter(1, 6, revcomp=True), None, None, True, False, [])
+    assert (d.n, d.m, d.nnz) == (0, 0, 0)
+
+
+def test_frozen_counter_and_features(K, oracle, fixtures):
+    """TestKmers2 property on the nucleotide alphabet + explicit feature lists with pair products
+    (kmerLr_data.go:210-229, the shape of kmerLr_test.go:36-66)"""
+    kc, oc = cfg_pair(K, oracle, 2, 7, revcomp=True)
+    buf, off, _ = cat(fixtures, "kmerLr_test_fg", "kmerLr_test_bg")
+    a = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    classes = a.Kmers()
+    b = K.compile_test_data(None, kc, classes, None, True, False, (buf, off))
+    for x, y in zip(a.rows(), b.rows()):
+        assert np.array_equal(x, y)
+    # frozen to a subset, applied to other sequences
+    sub = (classes[0][::3], classes[1][::3])
+    from kmerlr_b200 import synth
+    sbuf, soff, _ = synth.training_set(20, 20, 300)
+    c = K.compile_test_data(None, kc, sub, None, True, False, (sbuf, soff))
+    same_matrix(c, oracle.extract(oc, (sbuf, soff), frozen=sub))
+    # explicit features: every 5th single plus some pairs
+    m = len(sub[0])
+    rng = np.random.default_rng(3)
+    feats = [(i, i) for i in range(0, m, 5)] + [tuple(sorted(rng.choice(m, 2, replace=False))) for _ in range(300)]
+    e = K.compile_test_data(None, kc, sub, feats, False, False, (sbuf, soff))
+    ref = oracle.extract(oc, (sbuf, soff), frozen=sub, features=feats)
+    assert (e.n, e.m, e.nnz) == (ref.n, ref.m, ref.nnz)
+    for x, y in zip(e.rows(), ref.rows()):
+        assert np.array_equal(x, y)
+
+
+def test_unsupported_configurations_fail_loudly(K):
+    with pytest.raises(K.KmerLrError):
+        K.compile_test_data(None, K.NewKmerCounter(4, 8, revcomp=True, alphabet="gapped-nucleotide"), None, None, True,
+                            False, ["ACGTACGTACGT"])
+    with pytest.raises(K.KmerLrError):
+        K.compile_test_data(None, K.NewKmerCounter(1, 14), None, None, True, False, ["ACGTACGTACGTACGT"])
+    with pytest.raises(K.KmerLrError):
+        K.compile_test_data(None, K.NewKmerCounter(6, 8, revcomp=True), None, None, True, False, ["ACGT" * 2000])
+
+
+def test_full_size_properties(K):
+    """C2-shaped rows at a reduced count: size independent properties (sortedness, no explicit zeros,
+    row sums = number of k-mer instances, revcomp invariance)"""
+    from kmerlr_b200 import synth
+    buf, off, _ = synth.training_set(2048, 2048, 500)
+    kc = K.NewKmerCounter(1, 8, revcomp=True)
+    d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    rp, col, val = d.rows()
+    assert d.m == 43860 or d.m <= 43860
+    assert np.all(val >= 1)
+    inst = sum(500 - k + 1 for k in range(1, 9))
+    sums = np.add.reduceat(val, rp[:-1])
+    assert np.all(sums == inst)
+    for i in (0, 17, 4095):
+        c = col[rp[i]:rp[i + 1]]
+        assert np.all(np.diff(c) > 0)
+    # reverse complementing every sequence leaves the revcomp-merged rows unchanged
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    rc = comp[buf.reshape(-1, 500)[:, ::-1]].reshape(-1)
+    d2 = K.compile_test_data(None, kc, d.Kmers(), None, True, False, (rc, off))
+    for x, y in zip(d.rows(), d2.rows()):
+        assert np.array_equal(x, y)

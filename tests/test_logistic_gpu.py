@@ -1,0 +1,176 @@
+"""Stage 2 parity: sparse logistic loss / gradient, leapfrog selection, reduced matrices and the
+proximal-gradient estimator (through the C ABI) vs the CPU oracle.  Needs a B200.
+
+Tolerances (north_star): loss <= 1e-6 relative, theta <= 1e-5; selected feature sets, indices
+and the first lambda are exact.  The observed agreement is far tighter and asserted as such."""
+import numpy as np
+import pytest
+
+from conftest import cat
+
+pytestmark = pytest.mark.gpu
+
+RTOL_G = 1e-10      # gradient entries, relative to max |g|
+RTOL_LOSS = 1e-12
+
+
+def build(K, O, fixtures, M, N, fg="kmerLr_test_fg", bg="kmerLr_test_bg", **flags):
+    buf, off, y = cat(fixtures, fg, bg)
+    nfg = int(y.sum())
+    kc, oc = K.NewKmerCounter(M, N, **flags), O.make_config(M, N, **flags)
+    d = K.compile_training_data(None, kc, None, None, True, flags.get("binarize", False), (buf[:off[nfg]], off[:nfg + 1]),
+                                (buf[off[nfg]:], off[nfg:] - off[nfg]))
+    return d, O.extract(oc, (buf, off)), y
+
+
+def close_g(g, og):
+    scale = max(np.max(np.abs(og)), 1e-300)
+    assert np.max(np.abs(g - og)) <= RTOL_G * scale
+
+
+def test_linear_logpdf_gradient_loss(K, oracle, fixtures):
+    d, ref, y = build(K, oracle, fixtures, 1, 6, revcomp=True)
+    rng = np.random.default_rng(1)
+    for cw, lam in [((1.0, 1.0), 0.0), ((0.7, 1.9), 0.05), ((1.0, 1.0), float("nan"))]:
+        theta = rng.normal(scale=0.01, size=d.m + 1)
+        theta[rng.integers(1, d.m + 1, size=d.m // 2)] = 0.0
+        lr = K.logisticRegression(theta, cw, lam)
+        assert np.allclose(lr.LinearPdf(d), oracle.linear_pdf(ref, theta), rtol=1e-12, atol=1e-13)
+        assert np.allclose(lr.LogPdf(d), oracle.log_pdf(ref, theta), rtol=1e-12, atol=1e-13)
+        close_g(lr.Gradient(None, d), oracle.gradient(ref, y, theta, cw, lam))
+        lo, olo = lr.Loss(d), oracle.loss(ref, y, theta, cw, lam)
+        assert abs(lo - olo) <= RTOL_LOSS * abs(olo)
+    with pytest.raises(K.KmerLrError):       # panic("internal error") on a theta of the wrong length
+        K.logisticRegression(np.zeros(d.m), (1, 1)).LinearPdf(d)
+
+
+def test_identical_columns_get_identical_gradients(K, oracle, fixtures):
+    """what leapfrog tie handling rests on: the column reduction depends on the column only"""
+    d, ref, y = build(K, oracle, fixtures, 2, 6, fg="kmerLr_test_co_fg", bg="kmerLr_test_co_bg", revcomp=True, binarize=True)
+    X = ref.dense()
+    g = K.logisticRegression(np.zeros(d.m + 1)).Gradient(None, d)[1:]
+    groups = {}
+    for j in range(d.m):
+        groups.setdefault(X[:, j].tobytes(), []).append(j)
+    assert any(len(v) > 1 for v in groups.values())
+    for cols in groups.values():
+        assert len({g[j] for j in cols}) == 1
+
+
+def test_cooccurrence_gradient_and_select_go118(K, oracle, fixtures):
+    """TestKmers6 data (kmerLr_test.go:192-268) on the GPU: 57-way tie, lambda, the golden pair"""
+    O = oracle
+    d, ref, y = build(K, O, fixtures, 2, 6, fg="kmerLr_test_co_fg", bg="kmerLr_test_co_bg", revcomp=True, binarize=True)
+    nt = K.CoeffIndex(d.m).Dim()
+    assert nt == 2486
+    rng = np.random.default_rng(5)
+    theta = np.zeros(nt)
+    theta[rng.integers(0, nt, 40)] = rng.normal(scale=0.05, size=40)
+    lr = K.logisticRegression(theta, (1, 1), 0.0, Cooccurrence=True)
+    assert np.allclose(lr.LinearPdf(d), O.linear_pdf(ref, theta, True), rtol=1e-12, atol=1e-13)
+    close_g(lr.Gradient(None, d), O.gradient(ref, y, theta, cooccurrence=True))
+    assert abs(lr.Loss(d) - O.loss(ref, y, theta, cooccurrence=True)) < 1e-13
+    s = K.featureSelector((1, 1), True, 2, d.m, tie=K.TIE_GO118)
+    sel, lam, ok = s.Select(d, 0.0, [], [], 0.0, want_gradient=True)
+    r = O.select(ref, y, (1, 1), 2, 0.0, [], [], cooccurrence=True, tie=O.TIE_GO118)
+    assert ok and lam == 0.2375 and np.array_equal(sel.b, r["mask"])
+    assert np.sum(np.abs(sel.g[1:]) == np.max(np.abs(sel.g[1:]))) == 57
+    pairs = [K.CoeffIndex(d.m).Sub2Ind(int(j) - 1) for j in sel.sel[1:]]
+    cls = sorted({k for p in pairs for k in p})
+    assert [[cls.index(a), cls.index(b)] for a, b in pairs] == [[0, 1], [1, 2]]     # kmerLr_test.go:205-206
+    # loss / predictions at the golden theta (kmerLr_test.go:201-204,224,228,248)
+    red = sel.Data(d)
+    red.SetLabels(y)
+    th = np.array([-0.1000970529629098, 0.09995715710821684, 0.09995715710821684])
+    lrr = K.logisticRegression(th)
+    assert abs(lrr.Loss(red) - 0.644417014007959) < 1e-14
+    lp = lrr.LogPdf(red)
+    assert np.allclose(lp[:10], -0.6444834689451768, atol=1e-14) and np.allclose(lp[10:], -0.744447612033651, atol=1e-14)
+    # the index tie rule agrees with the oracle in the same mode
+    s2 = K.featureSelector((1, 1), True, 2, d.m, tie=K.TIE_INDEX)
+    sel2, lam2, _ = s2.Select(d, 0.0, [], [], 0.0)
+    r2 = O.select(ref, y, (1, 1), 2, 0.0, [], [], cooccurrence=True, tie=O.TIE_INDEX)
+    assert lam2 == r2["lam"] and np.array_equal(sel2.b, r2["mask"])
+
+
+def test_scores_lambda_from_csr(K, oracle, fixtures):
+    """README.md:39: first leapfrog lambda of the 16 x 7 example, features {1,6} (scoresLr_test.go:47-56)"""
+    X = np.vstack([fixtures["scoresLr_test_fg"], fixtures["scoresLr_test_bg"]])
+    y = np.array([1] * 8 + [0] * 8, dtype=np.uint8)
+    d = K.from_dense(X)
+    d.SetLabels(y)
+    s = K.featureSelector((1, 1), False, 2, d.m, tie=K.TIE_GO118)
+    sel, lam, ok = s.Select(d, 0.0, [], [], 0.0)
+    assert "%e" % lam == "2.496875e+00" and sel.sel.tolist() == [0, 2, 7] and ok
+    red = sel.Data(d)
+    red.SetLabels(y)
+    th = np.array([0.842178566751775, -0.05466291047449, -0.03026279836545])
+    assert abs(K.logisticRegression(th, (1, 1), 4.647556e+00).Loss(red) - 0.813659729805629) < 1e-9
+
+
+def test_reduce_matches_oracle(K, oracle, fixtures):
+    d, ref, y = build(K, oracle, fixtures, 1, 5, revcomp=True)
+    sel = np.array([0, 1, 3, 10, 50, 200, d.m], dtype=np.int64)
+    red = K.select_data(d, sel)
+    oref = oracle.reduce(ref, sel)
+    assert (red.n, red.m, red.nnz) == (oref.n, oref.m, oref.nnz)
+    for x, z in zip(red.rows(), oref.rows()):
+        assert np.array_equal(x, z)
+
+
+@pytest.mark.parametrize("tie", ["go118", "index"])
+def test_leapfrog_path_fixtures(K, oracle, fixtures, tie):
+    """C1: kmerLr learn on the bundled fixtures, k=1..6 revcomp, --lambda-auto=2,5,10: same selected
+    sets, same lambda sequence, theta within 1e-5, loss within 1e-6 of the CPU oracle"""
+    O = oracle
+    d, ref, y = build(K, O, fixtures, 1, 6, revcomp=True)
+    kt, ot = (K.TIE_GO118, O.TIE_GO118) if tie == "go118" else (K.TIE_INDEX, O.TIE_INDEX)
+    est = K.KmerLrEstimator(EpsilonLoss=1e-8, tie=kt, MaxIterations=20000)
+    oest = O.EstimatorState()
+    for N in (2, 5, 10):
+        est.path = []
+        est.estimate_loop(d, N)
+        res = O.estimate_loop(ref, y, (1, 1), N, oest, tie=ot, epsilon_loss=1e-8, max_iter=20000)
+        assert len(est.path) == res["epochs"]
+        assert np.array_equal(est.active_idx, oest.active_idx)
+        lams = np.array([p[0] for p in est.path])
+        assert np.allclose(lams, res["lambdas"], rtol=1e-9, atol=0)
+        assert lams[0] == res["lambdas"][0] or abs(lams[0] - res["lambdas"][0]) <= 1e-15 * abs(lams[0])
+        assert [p[1] for p in est.path] == res["iters"].tolist()
+        assert np.max(np.abs(est.Theta - oest.active_theta)) <= 1e-5 * max(1.0, np.max(np.abs(oest.active_theta)))
+    # loss of the final model on the reduced data
+    sel = np.concatenate([[0], est.active_idx])
+    rm = O.reduce(ref, sel)
+    red = K.select_data(d, sel)
+    red.SetLabels(y)
+    lo = K.logisticRegression(est.Theta, (1, 1), est.L1Reg / d.n).Loss(red)
+    olo = O.loss(rm, y, oest.active_theta, (1, 1), est.L1Reg / d.n)
+    assert abs(lo - olo) <= 1e-6 * abs(olo)
+
+
+def test_proxgrad_matches_oracle_iteration_by_iteration(K, oracle):
+    """same step size, update, stopping rule (kmerLr_estimator_proximal.go:30-120): same iteration count"""
+    from kmerlr_b200 import synth
+    O = oracle
+    buf, off, y = synth.training_set(300, 300, 200)
+    kc, oc = K.NewKmerCounter(1, 5, revcomp=True), O.make_config(1, 5, revcomp=True)
+    d = K.compile_training_data(None, kc, None, None, True, False, (buf[:off[300]], off[:301]), (buf[off[300]:], off[300:] - off[300]))
+    ref = O.extract(oc, (buf, off))
+    cw = K.compute_class_weights(y)
+    assert np.allclose(cw, d.class_weights()) and np.allclose(cw, O.class_weights(y))
+    step = 0.0
+    import ctypes as C
+    out = C.c_double()
+    from kmerlr_b200 import _lib
+    _lib.check(_lib.lib().kmerlr_step_size(d.h, 0.0, 1.0, out))
+    step = out.value
+    assert step == O.step_size(ref)
+    for eps, eps_loss, lam, cap in [(0.0, 1e-7, 0.002, 5000), (1e-4, 0.0, 0.0005, 5000), (0.0, 1e-300, 0.001, 37)]:
+        est = K.KmerLrEstimator(Epsilon=eps, EpsilonLoss=eps_loss, MaxIterations=cap)
+        est.Theta = np.zeros(d.m + 1)
+        iters, delta = est.estimate_proximal(d, lam)
+        oth, oit, odelta = O.proxgrad(ref, y, np.zeros(d.m + 1), (1, 1), lam, epsilon=eps, epsilon_loss=eps_loss, max_iter=cap)
+        assert iters == oit
+        assert np.max(np.abs(est.Theta - oth)) <= 1e-9
+        assert np.array_equal(est.Theta == 0.0, oth == 0.0)
+        assert abs(delta - odelta) <= 1e-6 * max(abs(odelta), 1e-300)

@@ -1,0 +1,83 @@
+"""Stage 3 parity: sliding-window genomic scoring (through the C ABI) vs the CPU oracle, which
+restates genomicKmerLr.Predict per window (kmerLr_predict_genomic.go:134-171).  Needs a B200."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make_model(K, O, seqs, M, N, n_feat, members=1, pairs=0, summary="", seed=0, **flags):
+    """a model over classes observed in seqs: n_feat singles (+ pairs), random theta"""
+    rng = np.random.default_rng(seed)
+    ref = O.extract(O.make_config(M, N, **flags), seqs)
+    k, code = ref.classes()
+    pick = np.sort(rng.choice(ref.m, size=min(n_feat, ref.m), replace=False))
+    ck, cc = k[pick], code[pick]
+    feats = [(i, i) for i in range(len(pick))]
+    for _ in range(pairs):
+        a, b = sorted(rng.choice(len(pick), 2, replace=False))
+        feats.append((int(a), int(b)))
+    theta = rng.normal(scale=0.3, size=(members, len(feats) + 1))
+    kmd = dict(counter=K.NewKmerCounter(M, N, **flags), class_k=ck, class_code=cc, features=feats, theta=theta, summary=summary)
+    omd = dict(cfg=O.make_config(M, N, **flags), class_k=ck, class_code=cc, features=feats, theta=theta, summary=summary)
+    return kmd, omd
+
+
+def regions(seed=3):
+    from kmerlr_b200 import synth
+    rng = np.random.default_rng(seed)
+    lens = [1000, 200, 201, 150, 777, 4096, 0, 210, 5000]
+    seqs = []
+    for i, L in enumerate(lens):
+        s = bytes(synth.random_bases(L, 3, offset=100000 * i)).decode()
+        seqs.append(s)
+    s = list(seqs[4])
+    for p in rng.choice(777, 12, replace=False):
+        s[p] = "N"
+    seqs[4] = "".join(s).lower()
+    return seqs
+
+
+def check(K, O, kms, oms, seqs, W, step, tol=1e-12):
+    out = K.genomicKmerLr(kms).predict_window_genomic(seqs, W, step)
+    ref = O.score_windows(oms, seqs, W, step)
+    flat = np.concatenate(out) if len(out) else np.zeros(0)
+    assert len(flat) == len(ref)
+    assert np.allclose(flat, ref, rtol=tol, atol=tol)
+    # slots the strict loop bound never writes stay exactly 0.0 (kmerLr_predict_genomic.go:153-159)
+    assert np.array_equal(flat == 0.0, ref == 0.0)
+    return flat
+
+
+def test_linear_models(K, oracle):
+    """count features, singles only: the prefix-sum kernel"""
+    seqs = regions()
+    km, om = make_model(K, oracle, seqs[:1], 1, 8, 100, seed=1, revcomp=True)
+    f = check(K, oracle, [km], [om], seqs, 200, 10)
+    assert len(f) == sum(oracle.window_slots(len(s), 200, 10) for s in seqs) and np.all(f <= 0)
+    km2, om2 = make_model(K, oracle, seqs[:1], 3, 6, 40, seed=2)
+    check(K, oracle, [km2], [om2], seqs, 100, 1)
+    check(K, oracle, [km, km2], [om, om2], seqs, 200, 7)       # two models are summed
+    km3, om3 = make_model(K, oracle, seqs[:1], 2, 5, 30, seed=4, complement=True)
+    check(K, oracle, [km3], [om3], seqs, 64, 3)
+
+
+def test_generic_models(K, oracle):
+    """binarized counts, pair features, ensembles with a summary: one warp per window"""
+    seqs = regions()[:5]
+    km, om = make_model(K, oracle, seqs[:1], 2, 6, 60, pairs=20, seed=5, revcomp=True, binarize=True)
+    check(K, oracle, [km], [om], seqs, 200, 10)
+    km, om = make_model(K, oracle, seqs[:1], 1, 7, 50, pairs=10, seed=6, revcomp=True)
+    check(K, oracle, [km], [om], seqs, 120, 5)
+    for summary in ("mean", "product", "min", "max"):
+        km, om = make_model(K, oracle, seqs[:1], 2, 5, 30, members=3, summary=summary, seed=7, revcomp=True)
+        check(K, oracle, [km], [om], seqs, 150, 25)
+    km2, om2 = make_model(K, oracle, seqs[:1], 4, 4, 20, seed=8)
+    check(K, oracle, [km, km2], [om, om2], seqs, 150, 25)
+
+
+def test_ensemble_without_summary_fails(K, oracle):
+    seqs = regions()[:1]
+    km, _ = make_model(K, oracle, seqs, 2, 4, 10, members=2, summary="")
+    with pytest.raises(K.KmerLrError):
+        K.genomicKmerLr([km]).predict_window_genomic(seqs, 100, 10)
