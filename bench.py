@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- the kmerLr hot path on B200: k-mer sequences/sec (+ prox-grad iterations/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port)
+
+One STEP = one pass of the hot path over one batch of synthetic input of the BASELINE.json
+configs[1] shape (C2): extract 100 000 fg + 100 000 bg sequences x 500 bp, k = 1..8, revcomp-merged,
+into the sparse count matrix, then one full-space proximal-gradient iteration on it (rows pass:
+z, loss, weights; columns pass: X^T w; prox update).  N > 1: every rank (GPU) gets its own
+200 000-sequence shard (weak scaling); the class union and the gradient are reduced over NCCL.
+
+`value` is timed on the device (CUDA events on the library's stream) with the packed sequences
+already resident in HBM; `e2e` is the same step through the host-buffer C-ABI calls
+(kmerlr_extract + kmerlr_proxgrad) with the H2D / D2H copies inside a wall-clock region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (n_fg, n_bg, L, M, N, binarize)
+    "c2": (100000, 100000, 500, 1, 8, False),
+    "c3": (1000000, 1000000, 200, 1, 10, True),
+    "small": (2000, 2000, 500, 1, 8, False),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes_extract(n, L, nnz, binarize):
+    """SURVEY 8d / BASELINE.md 4: ceil(L/4) + q (4 + v) + 8 per sequence"""
+    return n * ((L + 3) // 4) + nnz * (4 + (0 if binarize else 4)) + n * 8
+
+
+def algorithmic_bytes_iter(n, m, nnz, binarize):
+    """nnz (4 + v) + (n+1) 8 + n + 3 (m+1) 8 per full-space prox-grad iteration"""
+    return nnz * (4 + (0 if binarize else 4)) + (n + 1) * 8 + n + 3 * (m + 1) * 8
+
+
+def run_reference(args, rank, world):
+    """the reference's own CPU algorithm (oracle port: per-sequence hash-map counting, union + sort,
+    O(n m) convert_counts walk, serial-over-samples gradient / loss) on the box's host cores"""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from kmerlr_b200 import synth
+    n_fg, n_bg, L, M, N, binarize = CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    s_fg = s_bg = max(1, min(n_fg, args.ref_sample // 2))
+    cfg = O.make_config(M, N, revcomp=True, binarize=binarize)
+    times = []
+    for it in range(args.warmup + args.steps):
+        buf, off, labels = synth.training_set(s_fg, s_bg, L, first_fg=it * s_fg, first_bg=it * s_bg)
+        t0 = time.perf_counter()
+        mat = O.extract(cfg, (buf, off), threads=cores, faithful=True)
+        theta = np.zeros(mat.m + 1)
+        O.proxgrad(mat, labels, theta, (1.0, 1.0), lam=1e-3, epsilon=0.0, epsilon_loss=1e-300, max_iter=1)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = (s_fg + s_bg) / (ms / 1e3)
+    sample = "%d fg + %d bg sequences x %d bp per step (of %d + %d), k=%d..%d revcomp" % (s_fg, s_bg, L, n_fg, n_bg, M, N)
+    line = {
+        "impl": "reference", "metric": "kmer_sequences_per_sec", "value": value, "unit": "sequences/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "sequences/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    n_fg, n_bg, L, M, N, binarize = CONFIGS[args.config]
+    return {"workload": "%s: %d fg + %d bg sequences x %d bp per GPU, k=%d..%d, revcomp-merged%s; step = k-mer "
+                        "extraction + one full-space proximal-gradient iteration" %
+                        (args.config.upper(), n_fg, n_bg, L, M, N, ", binarized" if binarize else ""),
+            "sequences_per_gpu": n_fg + n_bg, "seq_len": L, "k_min": M, "k_max": N,
+            "parallelism": "sample-sharded x%d" % world,
+            "l2": "working set per step (CSR + CSC + staging, > 6 GB at C2) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--ref-sample", type=int, default=8000, help="sequences per step of the CPU arm")
+    ap.add_argument("--iters", type=int, default=20, help="full-space prox-grad iterations timed back to back")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--short", action="store_true", help="profiling runs only: allow fewer than 3 warm-up steps")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not args.short:
+        args.warmup = 3
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import kmerlr_b200 as K
+    from kmerlr_b200 import api, synth
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K.init(local_rank)
+    if world > 1:
+        K.comm_init_torch()
+    sharded = world > 1
+
+    n_fg, n_bg, L, M, N, binarize = CONFIGS[args.config]
+    n = n_fg + n_bg
+    buf, off, labels = synth.training_set(n_fg, n_bg, L, first_fg=rank * n_fg, first_bg=rank * n_bg)
+    # pinned host copies (the e2e arm copies from pinned memory)
+    pin = torch.empty(len(buf), dtype=torch.uint8).pin_memory()
+    pin.numpy()[:] = buf
+    hbuf = pin.numpy()
+    counter = K.NewKmerCounter(M, N, revcomp=True, binarize=binarize)
+    seqs = K.Sequences((hbuf, off))
+    lam = 1e-3
+    cw = np.ones(2)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        """returns (device ms, matrix info)"""
+        ms = 0.0
+        data = api._extract(counter, seqs, None, None, sharded)
+        ms += K.last_device_ms()
+        data.SetLabels(labels)
+        ms += K.last_device_ms()
+        est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-300, MaxIterations=1)
+        est.Theta = np.zeros(data.m + 1)
+        est.ClassWeights = cw
+        est.estimate_proximal(data, lam)
+        ms += K.last_device_ms()
+        info = (data.n, data.m, data.nnz)
+        data.free()
+        return ms, info
+
+    def step_e2e():
+        """the same step through the host-buffer C-ABI calls; returns wall seconds"""
+        t0 = time.perf_counter()
+        data = api._extract(counter, (hbuf, off), None, None, sharded)
+        data.SetLabels(labels)
+        est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-300, MaxIterations=1)
+        est.Theta = np.zeros(data.m + 1)
+        est.ClassWeights = cw
+        est.estimate_proximal(data, lam)
+        checksum = float(est.Theta[0])          # the step's result, read on the host
+        dt = time.perf_counter() - t0
+        m = data.m
+        data.free()
+        return dt, m, checksum
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    K.api.profile(True)
+    launches0 = K.launch_count()
+    dev_ms, info = [], None
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ms, info = step_resident()
+        dev_ms.append(ms)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = K.launch_count() - launches0
+    prof = K.api.profile_dump()
+    K.api.profile(False)
+    clocks = sampler.stop() if sampler else None
+
+    # full-space prox-grad iterations back to back on a resident matrix
+    data = api._extract(counter, seqs, None, None, sharded)
+    data.SetLabels(labels)
+    est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-300, MaxIterations=2)
+    est.Theta = np.zeros(data.m + 1)
+    est.ClassWeights = cw
+    est.estimate_proximal(data, lam)             # builds the CSC view, warms up
+    est.MaxIterations = args.iters
+    K.api.profile(True)
+    barrier()
+    est.estimate_proximal(data, lam)
+    iter_ms = K.last_device_ms()
+    prof_it = K.api.profile_dump()
+    K.api.profile(False)
+    n_rows, m_cols, nnz = data.n, data.m, data.nnz
+    data.free()
+
+    # e2e through host buffers
+    e2e_s = []
+    for i in range(1 + min(3, args.steps)):
+        dt, m_e2e, _ = step_e2e()
+        if i > 0:
+            e2e_s.append(dt)
+    barrier()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_step = allmax(float(np.mean(dev_ms)))
+    ms_e2e = allmax(1e3 * float(np.mean(e2e_s)))
+    ms_iter = allmax(iter_ms / args.iters)
+    wall_ms_step = allmax(1e3 * t_wall / args.steps)
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    # dominant kernel of the step
+    per_kernel = {k: v[0] / args.steps for k, v in prof.items()}
+    top = max(per_kernel, key=per_kernel.get)
+    top_ms_total, top_launches = prof[top]
+    if "extract_kernel" in top:
+        abytes = algorithmic_bytes_extract(n_rows, L, nnz, binarize)
+        what = "extraction: ceil(L/4) + q(4+v) + 8 bytes per sequence x %d sequences per launch" % n_rows
+    else:
+        abytes = algorithmic_bytes_iter(n_rows, m_cols, nnz, binarize)
+        what = "one prox-grad pass"
+    ach = abytes / (top_ms_total / top_launches * 1e-3) / 1e9
+    ext_ms = sum(v for k, v in per_kernel.items() if "extract_kernel" in k)
+    roof = {"bound": "hbm", "kernel": top.split("<")[0].strip("()"), "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
+            "what": what, "kernel_ms_per_launch": top_ms_total / top_launches,
+            "kernel_share_of_step": per_kernel[top] / sum(per_kernel.values())}
+    it_bytes = algorithmic_bytes_iter(n_rows, m_cols, nnz, binarize)
+    it_rows = sum(v[0] for k, v in prof_it.items() if "rows_kernel" in k) / args.iters
+    it_cols = sum(v[0] for k, v in prof_it.items() if "cols_partial" in k) / args.iters
+    line = {
+        "metric": "kmer_sequences_per_sec", "value": world * n / (ms_step * 1e-3), "unit": "sequences/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "matrix": {"n": n_rows, "m": m_cols, "nnz": nnz},
+        "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": "sequences/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(len(hbuf) + off.nbytes + labels.nbytes + 8 * (m_e2e + 1) + 64),
+                "d2h_bytes_per_step": int(8 * (m_e2e + 1) + 64)},
+        "gpu_launches": int(launches),
+        "wall_ms_per_step": wall_ms_step,
+        "extract_sequences_per_sec": world * n / (ext_ms * 1e-3) if ext_ms > 0 else None,
+        "proxgrad_iters_per_sec": 1e3 / ms_iter,
+        "proxgrad": {"ms_per_iter": ms_iter, "rows_pass_ms": it_rows, "cols_pass_ms": it_cols,
+                     "algorithmic_bytes_per_iter": it_bytes, "achieved_gbs": it_bytes / (ms_iter * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": it_bytes / (ms_iter * 1e-3) / 1e9 / peak},
+        "kernels_ms_per_step": {k.split("<")[0].strip("()"): round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])[:12]},
+        "roofline": roof,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        s_half = max(1, min(n_fg, args.ref_sample // 2))
+        sb, so, sl = synth.training_set(s_half, s_half, L)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or time.perf_counter() - t0 < 10.0:
+            mat = O.extract(O.make_config(M, N, revcomp=True, binarize=binarize), (sb, so), threads=cores, faithful=True)
+            O.proxgrad(mat, sl, np.zeros(mat.m + 1), (1.0, 1.0), lam=lam, epsilon=0.0, epsilon_loss=1e-300, max_iter=1)
+            reps += 1
+            if time.perf_counter() - t0 > 30.0:
+                break
+        dt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = {"value": 2 * s_half / dt, "unit": "sequences/s", "cores": cores, "kind": "port",
+                                "sample": "%d fg + %d bg sequences x %d bp (of %d + %d), %d repetitions, all host "
+                                          "threads; Go is not installed, so this is the C oracle port" %
+                                          (s_half, s_half, L, n_fg, n_bg, reps)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

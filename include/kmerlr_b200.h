@@ -58,6 +58,11 @@ int         kmerlr_version(void);
 double      kmerlr_last_device_ms(void);
 /* number of kernels the library has launched since kmerlr_init (bench.py reports gpu_launches) */
 int64_t     kmerlr_launch_count(void);
+/* per-kernel device time: CUDA events around every launch while enabled (enable clears the totals);
+ * read sums the kernels whose name contains the substring; dump = "name\tms\tlaunches\n" lines */
+int         kmerlr_profile(int enable);
+int         kmerlr_profile_read(const char *kernel_substr, double *ms_total, int64_t *launches);
+int         kmerlr_profile_dump(char *buf, int64_t buflen);
 
 /* ---- sample sharding over the GPUs of one box ------------------------------------ */
 int kmerlr_comm_unique_id(void *id128);                       /* ncclGetUniqueId, 128 bytes       */

@@ -36,6 +36,24 @@ def launch_count():
     return lib().kmerlr_launch_count()
 
 
+def profile(enable):
+    check(lib().kmerlr_profile(int(enable)))
+
+
+def profile_read(kernel_substr):
+    """(total device ms, launches) of the kernels whose name contains kernel_substr"""
+    ms, n = C.c_double(), C.c_int64()
+    check(lib().kmerlr_profile_read(kernel_substr.encode(), ms, n))
+    return ms.value, n.value
+
+
+def profile_dump():
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().kmerlr_profile_dump(buf, len(buf)))
+    rows = [r.split("\t") for r in buf.value.decode().splitlines()]
+    return {r[0]: (float(r[1]), int(r[2])) for r in rows}
+
+
 def comm_unique_id():
     buf = C.create_string_buffer(128)
     check(lib().kmerlr_comm_unique_id(buf))

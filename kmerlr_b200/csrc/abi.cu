@@ -4,6 +4,7 @@
 #include <cmath>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -18,6 +19,39 @@ thread_local std::string g_error;
 }  // namespace
 
 Ctx &ctx() { return g_ctx; }
+
+// ---- per-kernel profiling ---------------------------------------------------------------------------
+namespace {
+struct ProfRec { std::string name; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof_pending;
+std::vector<cudaEvent_t> g_prof_pool;
+std::unordered_map<std::string, std::pair<double, int64_t>> g_prof_totals;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  KL_CUDA(cudaEventCreate(&e));
+  return e;
+}
+void prof_resolve() {
+  if (g_prof_pending.empty()) return;
+  KL_CUDA(cudaStreamSynchronize(g_ctx.stream));
+  for (auto &r : g_prof_pending) {
+    float ms = 0.f;
+    KL_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    auto &t = g_prof_totals[r.name];
+    t.first += ms; t.second += 1;
+    g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+  }
+  g_prof_pending.clear();
+}
+}  // namespace
+void profile_begin(const char *name) {
+  if (g_prof_pending.size() > 8192) prof_resolve();
+  ProfRec r{name, prof_event(), prof_event()};
+  KL_CUDA(cudaEventRecord(r.e0, g_ctx.stream));
+  g_prof_pending.push_back(r);
+}
+void profile_end() { KL_CUDA(cudaEventRecord(g_prof_pending.back().e1, g_ctx.stream)); }
 
 void require_ready() {
   if (!g_ctx.ready) fail(KMERLR_ERR_NOGPU, "kmerlr_init() has not succeeded: no usable sm_100 GPU (there is no CPU fallback)");
@@ -70,6 +104,35 @@ const char *kmerlr_last_error(void) { return g_error.c_str(); }
 double kmerlr_last_device_ms(void) { return g_ctx.last_ms; }
 
 int64_t kmerlr_launch_count(void) { return g_ctx.launches; }
+
+int kmerlr_profile(int enable) {
+  return guarded([&] {
+    prof_resolve();
+    if (enable) g_prof_totals.clear();
+    g_ctx.profiling = enable != 0;
+  }, false);
+}
+
+int kmerlr_profile_read(const char *kernel_substr, double *ms_total, int64_t *launches) {
+  return guarded([&] {
+    prof_resolve();
+    double ms = 0.0; int64_t n = 0;
+    for (auto &kv : g_prof_totals)
+      if (kv.first.find(kernel_substr) != std::string::npos) { ms += kv.second.first; n += kv.second.second; }
+    *ms_total = ms; *launches = n;
+  }, false);
+}
+
+int kmerlr_profile_dump(char *buf, int64_t buflen) {
+  return guarded([&] {
+    prof_resolve();
+    std::string out;
+    for (auto &kv : g_prof_totals)
+      out += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+    KL_REQUIRE((int64_t)out.size() + 1 <= buflen, "profile_dump: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+  }, false);
+}
 
 int kmerlr_init(int device) {
   return guarded([&] {

@@ -57,6 +57,7 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   double last_ms = 0.0;
+  bool profiling = false;
   // communicator (NCCL via dlopen, see comm.cu)
   void *comm = nullptr;
   int rank = 0, world = 1;
@@ -64,10 +65,17 @@ struct Ctx {
 Ctx &ctx();
 void require_ready();
 
+// per-kernel device timing (bench.py: roofline of the dominant kernel, measured with CUDA events on
+// the launching stream); off by default
+void profile_begin(const char *name);
+void profile_end();
+
 // launch helper: counts launches (bench.py reports gpu_launches) and checks the launch
 #define KL_LAUNCH(kernel, grid, block, smem, ...)                                                  \
   do {                                                                                             \
+    if (::kl::ctx().profiling) ::kl::profile_begin(#kernel);                                       \
     kernel<<<(grid), (block), (smem), ::kl::ctx().stream>>>(__VA_ARGS__);                          \
+    if (::kl::ctx().profiling) ::kl::profile_end();                                                \
     ::kl::ctx().launches++;                                                                        \
     KL_CUDA(cudaGetLastError());                                                                   \
   } while (0)

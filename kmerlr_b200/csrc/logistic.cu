@@ -396,9 +396,15 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   h.loss_old = hook ? hook[0] : NAN; h.loss_new = hook ? hook[1] : NAN; h.lossval = NAN;
   st.upload(&h, 1);
   const double inv_n = 1.0 / (double)M.n_global;
-  const int BATCH = 16;
+  const int64_t BATCH = 16;
+  int64_t issued = 0;
   while (true) {
-    for (int it = 0; it < BATCH; it++) {
+    // max_iter prox steps need max_iter + 1 row passes (the last one only evaluates the hook)
+    int64_t nb = max_iter + 1 - issued;
+    if (nb > BATCH) nb = BATCH;
+    if (nb < 1) nb = 1;
+    issued += nb;
+    for (int64_t it = 0; it < nb; it++) {
       dispatch_vt(M, [&](auto *tag) {
         using VT = typename std::remove_pointer<decltype(tag)>::type;
         launch_rows<VT, 2>(M, wk.theta.p, 0, cw, wk.w.p, wk.lossterm.p, st.p);
