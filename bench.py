@@ -315,6 +315,7 @@ def main():
                 "h2d_bytes_per_step": int(len(hbuf) + off.nbytes + labels.nbytes + 8 * (m_e2e + 1) + 64),
                 "d2h_bytes_per_step": int(8 * (m_e2e + 1) + 64)},
         "gpu_launches": int(launches),
+        "ms_steps": [round(x, 3) for x in dev_ms],
         "wall_ms_per_step": wall_ms_step,
         "extract_sequences_per_sec": world * n / (ext_ms * 1e-3) if ext_ms > 0 else None,
         "proxgrad_iters_per_sec": 1e3 / ms_iter,

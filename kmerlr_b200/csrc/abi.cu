@@ -154,6 +154,10 @@ int kmerlr_init(int device) {
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    KL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    KL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     KL_CUDA(cudaEventCreate(&g_ctx.ev0));
     KL_CUDA(cudaEventCreate(&g_ctx.ev1));
     g_ctx.ready = true;
@@ -164,6 +168,7 @@ int kmerlr_shutdown(void) {
   return guarded([&] {
     g_objects.clear();
     if (g_ctx.ready) {
+      cudaStreamSynchronize(g_ctx.stream);
       comm_destroy();
       cudaEventDestroy(g_ctx.ev0); cudaEventDestroy(g_ctx.ev1);
       cudaStreamDestroy(g_ctx.stream);

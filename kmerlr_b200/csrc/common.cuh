@@ -99,13 +99,15 @@ struct DevBuf {
     return *this;
   }
   ~DevBuf() { release(); }
+  // stream-ordered allocation from the device's default pool (release threshold = keep everything):
+  // after the first step no call reaches the driver's allocator
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) KL_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    if (count) KL_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), ctx().stream));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, ctx().stream);
     p = nullptr; n = 0;
   }
   void zero() { if (n) KL_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx().stream)); }

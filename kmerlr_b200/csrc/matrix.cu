@@ -8,53 +8,112 @@ namespace kl {
 
 namespace {
 
-// ---- stable transpose ---------------------------------------------------------------------------
-// Rows are split into B contiguous blocks.  cnt[b][c] = entries of column c in block b (integer
-// atomics: order independent).  A scan over b gives every block its slice of every column, and each
-// block then fills its slices walking its rows in ascending order, so the entries of a column end
-// up in ascending row order -- the order the reference accumulates a gradient entry in
-// (kmerLr_logistic_regression.go:166-181) -- independent of scheduling.
-__global__ void csc_count(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, int64_t n,
-                          int64_t rows_per_block, int64_t m, uint32_t *__restrict__ cnt) {
-  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= n) return;
-  unsigned lane = lane_id();
-  uint32_t *c = cnt + (row / rows_per_block) * m;
-  for (int64_t p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32) atomicAdd(c + col[p], 1u);
-}
+// ---- stable transpose: LSD radix sort of the entries by column ---------------------------------------
+// The CSC view must list the entries of a column in ascending row order (the order the reference
+// accumulates a gradient entry in, kmerLr_logistic_regression.go:166-181) and must not depend on
+// scheduling.  Entries start in row order (CSR), so a STABLE sort by column gives exactly that:
+// 8-bit digits, least significant first; every pass = per-tile digit histogram, one scan, and a
+// scatter whose local ranks come from warp match (no atomics in the ranking, fully deterministic).
+constexpr int RS_THREADS = 256;
+constexpr int RS_GROUPS = 32;                       // 32 consecutive entries per lane-group
+constexpr int RS_WARP_ITEMS = 32 * RS_GROUPS;       // 1024 consecutive entries per warp
+constexpr int RS_TILE = (RS_THREADS / 32) * RS_WARP_ITEMS;   // 8192 entries per CTA
 
-__global__ void csc_block_scan(uint32_t *__restrict__ cnt, int64_t B, int64_t m, uint32_t *__restrict__ colcnt) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= m) return;
-  uint32_t run = 0;
-  for (int64_t b = 0; b < B; b++) {
-    uint32_t t = cnt[b * m + c];
-    cnt[b * m + c] = run;
-    run += t;
+__global__ void __launch_bounds__(RS_THREADS) radix_hist(const uint32_t *__restrict__ keys, int64_t nnz, int shift,
+                                                         uint32_t *__restrict__ hist, int64_t ntiles) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 8
+  for (int i = 0; i < RS_TILE / RS_THREADS; i++) {
+    int64_t p = base + (int64_t)i * RS_THREADS + threadIdx.x;
+    if (p < nnz) atomicAdd(&h[(keys[p] >> shift) & 255u], 1u);
   }
-  colcnt[c] = run;
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];   // digit-major: one flat scan gives offsets
 }
 
-template <typename VT>
-__global__ void csc_fill(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
-                         const VT *__restrict__ val, int64_t n, int64_t rows_per_block, int64_t m,
-                         uint32_t *__restrict__ cnt, const int64_t *__restrict__ colptr,
-                         uint32_t *__restrict__ crow, VT *__restrict__ cval) {
-  int64_t b = blockIdx.x;
-  int64_t r0 = b * rows_per_block, r1 = r0 + rows_per_block;
-  if (r1 > n) r1 = n;
-  uint32_t *cur = cnt + b * m;
-  for (int64_t row = r0; row < r1; row++) {
-    // columns are distinct inside a row: no two threads touch the same cursor between barriers
-    for (int64_t p = rowptr[row] + threadIdx.x; p < rowptr[row + 1]; p += blockDim.x) {
-      uint32_t c = col[p];
-      int64_t pos = colptr[c] + cur[c];
-      cur[c] = cur[c] + 1;
-      crow[pos] = (uint32_t)row;
-      if (val) cval[pos] = val[p];
+template <typename VT, bool FIRST>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint32_t *__restrict__ keys,
+                                                            const uint32_t *__restrict__ rows_in,
+                                                            const int64_t *__restrict__ rowptr, int64_t nrows,
+                                                            const VT *__restrict__ vals, int64_t nnz, int shift,
+                                                            const int64_t *__restrict__ offs, int64_t ntiles,
+                                                            uint32_t *__restrict__ keys_out,
+                                                            uint32_t *__restrict__ rows_out,
+                                                            VT *__restrict__ vals_out) {
+  __shared__ uint32_t wcnt[RS_THREADS / 32][256];
+  __shared__ int64_t goff[256];
+  const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WARP_ITEMS;
+  for (int i = lane; i < 256; i += 32) wcnt[w][i] = 0;
+  __syncwarp();
+  // sub-pass 1: rank of every entry among the earlier entries of its warp with the same digit
+  uint32_t lr[RS_GROUPS];
+#pragma unroll
+  for (int g = 0; g < RS_GROUPS; g++) {
+    int64_t p = wbase + g * 32 + lane;
+    bool valid = p < nnz;
+    uint32_t d = valid ? ((keys[p] >> shift) & 255u) : 256u;
+    unsigned mask = __match_any_sync(0xffffffffu, d);
+    uint32_t old = valid ? wcnt[w][d] : 0u;
+    __syncwarp();
+    if (valid && (unsigned)(__ffs(mask) - 1) == lane) wcnt[w][d] = old + __popc(mask);
+    __syncwarp();
+    lr[g] = old + __popc(mask & lanemask_lt());
+  }
+  __syncthreads();
+  // bases: digit = threadIdx.x; earlier warps of the tile come first
+  {
+    uint32_t run = 0;
+#pragma unroll
+    for (int ww = 0; ww < RS_THREADS / 32; ww++) {
+      uint32_t c = wcnt[ww][threadIdx.x];
+      wcnt[ww][threadIdx.x] = run;
+      run += c;
     }
-    __syncthreads();
+    goff[threadIdx.x] = offs[(int64_t)threadIdx.x * ntiles + blockIdx.x];
   }
+  __syncthreads();
+  // row of the warp's first entry (first pass: rows are implicit in the CSR row pointers)
+  int64_t rcur = 0;
+  if (FIRST) {
+    if (wbase < nnz) {
+      int64_t lo = 0, hi = nrows;   // last row with rowptr[row] <= wbase
+      while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (rowptr[mid] <= wbase) lo = mid; else hi = mid; }
+      rcur = lo;
+    }
+  }
+  // sub-pass 2: scatter
+#pragma unroll
+  for (int g = 0; g < RS_GROUPS; g++) {
+    int64_t p = wbase + g * 32 + lane;
+    bool valid = p < nnz;
+    uint32_t row = 0;
+    if (FIRST) {
+      int64_t r = rcur;
+      if (valid) while (rowptr[r + 1] <= p) r++;
+      row = (uint32_t)r;
+      rcur = __shfl_sync(0xffffffffu, r, 0);
+    }
+    if (valid) {
+      uint32_t key = keys[p], d = (key >> shift) & 255u;
+      int64_t dst = goff[d] + wcnt[w][d] + lr[g];
+      keys_out[dst] = key;
+      rows_out[dst] = FIRST ? row : rows_in[p];
+      if (vals) vals_out[dst] = vals[p];
+    }
+  }
+}
+
+// colptr[c] = first position of a key >= c in the sorted key array
+__global__ void lower_bounds(const uint32_t *__restrict__ sorted, int64_t nnz, int64_t m, int64_t *__restrict__ colptr) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > m) return;
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((int64_t)sorted[mid] < c) lo = mid + 1; else hi = mid; }
+  colptr[c] = lo;
 }
 
 constexpr int TASK_CHUNK = 1024;   // CSC entries per warp task of the X^T w reduction
@@ -206,22 +265,35 @@ void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n) {
 
 template <typename VT>
 static void build_csc(Matrix &M, const VT *val, VT *cval) {
-  // number of row blocks: bounded by the 1 GiB budget of the count table
-  int64_t B = (int64_t)ctx().sm_count * 4;
-  int64_t cap = ((int64_t)1 << 28) / (M.m > 0 ? M.m : 1);
-  if (B > cap) B = cap;
-  if (B > M.n) B = M.n;
-  if (B < 1) B = 1;
-  int64_t rpb = (M.n + B - 1) / B;
-  B = (M.n + rpb - 1) / rpb;
-  DevBuf<uint32_t> cnt((size_t)(B * M.m)), colcnt((size_t)M.m);
-  cnt.zero();
-  unsigned wgrid = (unsigned)((M.n * 32 + 255) / 256);
-  KL_LAUNCH(csc_count, wgrid, 256, 0, M.rowptr.p, M.col.p, M.n, rpb, M.m, cnt.p);
-  KL_LAUNCH(csc_block_scan, (unsigned)((M.m + 255) / 256), 256, 0, cnt.p, B, M.m, colcnt.p);
-  exclusive_scan_u32_to_i64(colcnt.p, M.colptr.p, M.m);
-  KL_LAUNCH((csc_fill<VT>), (unsigned)B, 256, 0, M.rowptr.p, M.col.p, val, M.n, rpb, M.m, cnt.p, M.colptr.p,
-            M.crow.p, cval);
+  const int64_t nnz = M.nnz, ntiles = (nnz + RS_TILE - 1) / RS_TILE;
+  int bits = 1;
+  while (((int64_t)1 << bits) < M.m) bits++;
+  const int passes = (bits + 7) / 8;
+  DevBuf<uint32_t> hist((size_t)(256 * ntiles));
+  DevBuf<int64_t> offs((size_t)(256 * ntiles) + 1);
+  // ping-pong buffers; the last pass writes straight into the CSC arrays
+  DevBuf<uint32_t> kA((size_t)nnz), kB(passes > 1 ? (size_t)nnz : 1), rA(passes > 1 ? (size_t)nnz : 1),
+      rB(passes > 2 ? (size_t)nnz : 1);
+  DevBuf<VT> vA(val && passes > 1 ? (size_t)nnz : 1), vB(val && passes > 2 ? (size_t)nnz : 1);
+  const uint32_t *kin = M.col.p, *rin = nullptr;
+  const VT *vin = val;
+  for (int ps = 0; ps < passes; ps++) {
+    const bool last = ps == passes - 1;
+    uint32_t *kout = (ps & 1) ? kB.p : kA.p;
+    if (passes == 1) kout = kA.p;
+    uint32_t *rout = last ? M.crow.p : ((ps & 1) ? rB.p : rA.p);
+    VT *vout = val ? (last ? cval : ((ps & 1) ? vB.p : vA.p)) : nullptr;
+    KL_LAUNCH(radix_hist, (unsigned)ntiles, RS_THREADS, 0, kin, nnz, 8 * ps, hist.p, ntiles);
+    exclusive_scan_u32_to_i64(hist.p, offs.p, 256 * ntiles);
+    if (ps == 0)
+      KL_LAUNCH((radix_scatter<VT, true>), (unsigned)ntiles, RS_THREADS, 0, kin, rin, M.rowptr.p, M.n, vin, nnz, 8 * ps,
+                offs.p, ntiles, kout, rout, vout);
+    else
+      KL_LAUNCH((radix_scatter<VT, false>), (unsigned)ntiles, RS_THREADS, 0, kin, rin, M.rowptr.p, M.n, vin, nnz, 8 * ps,
+                offs.p, ntiles, kout, rout, vout);
+    kin = kout; rin = rout; vin = vout;
+  }
+  KL_LAUNCH(lower_bounds, (unsigned)((M.m + 1 + 255) / 256), 256, 0, kin, nnz, M.m, M.colptr.p);
   sync_stream();
 }
 
@@ -229,7 +301,7 @@ void ensure_csc(Matrix &M) {
   if (M.has_csc) return;
   M.colptr.alloc((size_t)M.m + 1);
   M.crow.alloc((size_t)(M.nnz ? M.nnz : 1));
-  if (M.m == 0 || M.n == 0) {
+  if (M.m == 0 || M.n == 0 || M.nnz == 0) {
     M.colptr.zero();
   } else if (M.vt == VAL_U32) {
     M.cval_u32.alloc((size_t)(M.nnz ? M.nnz : 1));
