@@ -288,6 +288,10 @@ def main():
     peak, peak_src = peaks()
     # dominant kernel of the step
     per_kernel = {k: v[0] / args.steps for k, v in prof.items()}
+    merged = {}
+    for k, v in per_kernel.items():
+        nm = k.split("<")[0].strip("()")
+        merged[nm] = round(merged.get(nm, 0.0) + v, 4)
     top = max(per_kernel, key=per_kernel.get)
     top_ms_total, top_launches = prof[top]
     if "extract_kernel" in top:
@@ -322,7 +326,7 @@ def main():
         "proxgrad": {"ms_per_iter": ms_iter, "rows_pass_ms": it_rows, "cols_pass_ms": it_cols,
                      "algorithmic_bytes_per_iter": it_bytes, "achieved_gbs": it_bytes / (ms_iter * 1e-3) / 1e9,
                      "frac_of_hbm_peak": it_bytes / (ms_iter * 1e-3) / 1e9 / peak},
-        "kernels_ms_per_step": {k.split("<")[0].strip("()"): round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])[:12]},
+        "kernels_ms_per_step": dict(sorted(merged.items(), key=lambda kv: -kv[1])[:14]),
         "roofline": roof,
         "clocks": clocks,
     }

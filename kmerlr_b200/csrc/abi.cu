@@ -2,6 +2,7 @@
 // conversion, per-call device timing.  No CPU fallback: without an sm_100 device every entry point
 // that computes returns KMERLR_ERR_NOGPU.
 #include <cmath>
+#include <map>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -19,6 +20,45 @@ thread_local std::string g_error;
 }  // namespace
 
 Ctx &ctx() { return g_ctx; }
+
+// ---- caching arena ------------------------------------------------------------------------------------
+namespace {
+std::multimap<size_t, void *> g_free_blocks;            // size -> block
+std::unordered_map<void *, size_t> g_block_size;        // every block we own
+constexpr size_t ARENA_GRAIN = (size_t)2 << 20;         // 2 MiB
+}  // namespace
+void *arena_alloc(size_t bytes) {
+  size_t want = (bytes + ARENA_GRAIN - 1) / ARENA_GRAIN * ARENA_GRAIN;
+  auto it = g_free_blocks.lower_bound(want);
+  // reuse a cached block unless it would waste more than half of itself
+  if (it != g_free_blocks.end() && it->first <= 2 * want + 8 * ARENA_GRAIN) {
+    void *p = it->second;
+    g_free_blocks.erase(it);
+    return p;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    // out of memory: give the cache back to the driver and retry once
+    cudaGetLastError();
+    cudaStreamSynchronize(g_ctx.stream);
+    for (auto &kv : g_free_blocks) { cudaFree(kv.second); g_block_size.erase(kv.second); }
+    g_free_blocks.clear();
+    KL_CUDA(cudaMalloc(&p, want));
+  }
+  g_block_size[p] = want;
+  return p;
+}
+void arena_free(void *p) {
+  auto it = g_block_size.find(p);
+  if (it == g_block_size.end()) return;
+  g_free_blocks.emplace(it->second, p);
+}
+void arena_release_all() {
+  for (auto &kv : g_block_size) cudaFree(kv.first);
+  g_block_size.clear();
+  g_free_blocks.clear();
+}
 
 // ---- per-kernel profiling ---------------------------------------------------------------------------
 namespace {
@@ -154,10 +194,7 @@ int kmerlr_init(int device) {
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    cudaMemPool_t pool;
-    KL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = UINT64_MAX;
-    KL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+
     KL_CUDA(cudaEventCreate(&g_ctx.ev0));
     KL_CUDA(cudaEventCreate(&g_ctx.ev1));
     g_ctx.ready = true;
@@ -169,6 +206,7 @@ int kmerlr_shutdown(void) {
     g_objects.clear();
     if (g_ctx.ready) {
       cudaStreamSynchronize(g_ctx.stream);
+      arena_release_all();
       comm_destroy();
       cudaEventDestroy(g_ctx.ev0); cudaEventDestroy(g_ctx.ev1);
       cudaStreamDestroy(g_ctx.stream);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,9 +83,35 @@ void profile_end();
 
 inline void sync_stream() { KL_CUDA(cudaStreamSynchronize(ctx().stream)); }
 
+// KMERLR_TRACE=1: host-side phase timestamps on stderr (where does a call spend its wall time)
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  const char *what;
+  explicit Trace(const char *w) : what(w) {
+    static int env = -1;
+    if (env < 0) { const char *e = getenv("KMERLR_TRACE"); env = (e && *e == '1') ? 1 : 0; }
+    on = env == 1;
+    if (on) t0 = last = std::chrono::steady_clock::now();
+  }
+  void mark(const char *phase, bool sync = true) {
+    if (!on) return;
+    if (sync) cudaStreamSynchronize(ctx().stream);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[trace %s] %-28s %8.3f ms (total %8.3f)\n", what, phase,
+            std::chrono::duration<double, std::milli>(t - last).count(),
+            std::chrono::duration<double, std::milli>(t - t0).count());
+    last = t;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // device buffer (RAII)
 // ---------------------------------------------------------------------------------------------
+void *arena_alloc(size_t bytes);
+void arena_free(void *p);
+void arena_release_all();
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -99,15 +126,16 @@ struct DevBuf {
     return *this;
   }
   ~DevBuf() { release(); }
-  // stream-ordered allocation from the device's default pool (release threshold = keep everything):
-  // after the first step no call reaches the driver's allocator
+  // device memory comes from a caching arena (abi.cu): freed blocks are kept and handed out again,
+  // so that after the first step no call reaches the driver's allocator.  Everything runs on one
+  // stream, which makes reuse safe without events.
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) KL_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), ctx().stream));
+    if (count) p = (T *)arena_alloc(count * sizeof(T));
   }
   void release() {
-    if (p) cudaFreeAsync(p, ctx().stream);
+    if (p) arena_free(p);
     p = nullptr; n = 0;
   }
   void zero() { if (n) KL_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx().stream)); }

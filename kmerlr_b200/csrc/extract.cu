@@ -3,19 +3,21 @@
 // Replaces scan_sequences + NewKmerCountsList/SetKmers + convert_counts_list
 // (kmerLr_data.go:197-284,306-357; k-mer semantics of gonetics restated in SURVEY.md 8c).
 //
-// Design (one warp per sequence, no hash tables, no float atomics):
-//   * sequences are 2-bit packed in HBM (+1 invalid bit per base), see SeqSet;
-//   * "two strand suffix sort": the k-mer class counts of ALL k in [M,N] follow from ONE sort of
-//     the 2L suffix keys (N-prefix of every suffix of S and of op(S), op = revcomp / complement /
-//     reverse): the k-mers of level k are the distinct k-prefixes of the sorted keys, the class
-//     count of canonical u is #forward keys with prefix u + #op-strand keys with prefix u
-//     (op-strand keys are ignored when u == op(u));
-//   * the sort is a bitonic network over 32*E keys held in registers (E per lane), in-register
-//     compare-exchanges for distances < E and warp shuffles above;
-//   * levels k <= 5 never touch the sort: per-warp direct-address count tables in shared memory;
-//   * run boundaries / counts / output slots come from warp ballots, so rows leave the kernel
-//     already sorted by (k, code) = by final column index;
-//   * columns are ranks in the bitmap of observed (or frozen) classes.
+// Design (one warp per sequence, no hash tables, no float atomics).  Sequences are 2-bit packed in
+// HBM (+1 invalid bit per base, see SeqSet); every lane rolls the forward code and the image under
+// the strand operation (revcomp / complement / reverse) over its stretch of positions, so the
+// canonical code min(u, op(u)) of the k-mer starting at a position costs a shift and a min.  Levels:
+//   * k <= 5   "table levels": forward counts of the deepest table level in a per-warp shared
+//              memory table (one atomic per position), shallower levels are sums of 4 children;
+//   * k = 6..8 "bitmap levels": one bit per canonical code in a per-warp shared memory bitmap
+//              (4^k bits), set with atomicOr; the rare repeats go to a small list and are added to
+//              the counts afterwards.  Walking the bitmap emits the row in code order;
+//   * k >= 9   "sorted levels" (two strand suffix sort): ONE bitonic sort of the 2L suffix keys
+//              (N-prefix of every suffix of S and of op(S)) in registers -- in-register
+//              compare-exchanges below distance E, warp shuffles above; the classes of level k are
+//              the distinct k-prefixes of the sorted keys, found with warp ballots.
+// Rows leave the kernel sorted by (k, code) = by final column index; columns are ranks in the
+// bitmap of observed (or frozen) classes, which the kernel marks one 32-bit word at a time.
 #include "common.cuh"
 
 namespace kl {
@@ -23,22 +25,31 @@ namespace kl {
 namespace {
 
 constexpr uint32_t SENT = 0xFFFFFFFFu;
-constexpr int KS_MAX = 5;          // levels <= KS_MAX use direct tables
+constexpr int KT_MAX = 5;          // levels <= KT_MAX use direct tables
+constexpr int KB_MAX = 8;          // levels KT_MAX < k <= KB_MAX use per-row bitmaps
 constexpr int MAX_N = 13;          // 2*13 code bits + strand + 4 len bits = 31 bits
 constexpr int TAB_WORDS = 688;     // (4+16+64+256+1024)/2 = 682 packed u16 pairs, padded
 
 struct XParams {
   int M, N, op, binarize;
-  int ks_lo, ks_hi;                // table levels (empty if ks_lo > ks_hi)
-  int big_lo;                      // sorted levels [big_lo, N] (empty if big_lo > N)
+  int t_lo, t_hi;                  // table levels (empty if t_lo > t_hi)
+  int b_lo, b_hi;                  // bitmap levels (empty if b_lo > b_hi)
+  int s_lo;                        // sorted levels [s_lo, N] (empty if s_lo > N)
   int mark;                        // mark observed classes in the bitmap
-  uint32_t level_off[MAX_N + 2];   // dense id of (k, code 0)
+  uint32_t level_off[MAX_N + 2];   // dense id of (k, code 0), multiples of 32
+  uint32_t bm_off[KB_MAX + 2];     // word offset of level k's bitmap inside the per-warp bitmap area
+  uint32_t pf_off[KB_MAX + 2];     // word offset of level k's prefix array (one entry per 4 words)
+  int bm_words, pf_words, dup_cap; // per-warp shared memory areas, in 32-bit words
+  int warp_words;                  // total per-warp shared memory, in 32-bit words
   int64_t stride, n;
   const int64_t *len, *blk;
   const uint32_t *bits2;
   const uint16_t *inv16;
   uint32_t *st_id, *st_cnt, *rowcnt, *bitmap;
 };
+
+// image of code u under the strand operation for the table levels, index tab_off(k) + u
+__constant__ uint16_t c_img[1368];
 
 __device__ __forceinline__ uint32_t swap_pairs(uint32_t y) {
   return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
@@ -135,80 +146,101 @@ __device__ __forceinline__ void warp_sort(uint32_t (&K)[E], unsigned lane) {
 struct BaseReader {
   const uint32_t *bits2;
   const uint16_t *inv16;
-  int64_t L;
-  int64_t cur_word;
+  int L, cur_word;
   uint32_t w, iv;
-  __device__ __forceinline__ void init(const uint32_t *b, const uint16_t *m, int64_t len) {
+  __device__ __forceinline__ void init(const uint32_t *b, const uint16_t *m, int len) {
     bits2 = b; inv16 = m; L = len; cur_word = -1; w = 0; iv = 0;
   }
   // base idx -> (code, invalid); out of range = invalid
-  __device__ __forceinline__ void get(int64_t idx, uint32_t &x, uint32_t &inv) {
-    if (idx < 0 || idx >= L) { x = 0; inv = 1; return; }
-    int64_t wi = idx >> 4;
+  __device__ __forceinline__ void get(int idx, uint32_t &x, uint32_t &inv) {
+    if ((unsigned)idx >= (unsigned)L) { x = 0; inv = 1; return; }
+    int wi = idx >> 4;
     if (wi != cur_word) { cur_word = wi; w = __ldg(bits2 + wi); iv = __ldg(inv16 + wi); }
-    int sh = (int)(idx & 15);
+    int sh = idx & 15;
     x = (w >> (2 * sh)) & 3u;
     inv = (iv >> sh) & 1u;
   }
 };
 
 struct Emitter {
-  uint32_t *st_id, *st_cnt, *bitmap;
-  int64_t rowbase;
+  uint32_t *sid, *scnt, *bitmap;   // sid / scnt already point at this row's staging slice
   uint32_t cursor;
   int binarize, mark;
-  __device__ __forceinline__ void emit(bool flag, uint32_t id, uint32_t cnt) {
+  // ballot-compacted emission; returns the ballot (bit i = lane i emitted)
+  __device__ __forceinline__ unsigned emit(bool flag, uint32_t id, uint32_t cnt) {
     unsigned em = __ballot_sync(0xffffffffu, flag);
     if (flag) {
-      int64_t pos = rowbase + cursor + __popc(em & lanemask_lt());
-      st_id[pos] = id;
-      if (!binarize) st_cnt[pos] = cnt;
-      if (mark) {
-        uint32_t bit = 1u << (id & 31);
-        if (!(bitmap[id >> 5] & bit)) atomicOr(bitmap + (id >> 5), bit);
-      }
+      uint32_t pos = cursor + __popc(em & lanemask_lt());
+      sid[pos] = id;
+      if (!binarize) scnt[pos] = cnt;
     }
     cursor += __popc(em);
+    return em;
+  }
+  // the same for entries that are not aligned with bitmap words (sorted levels)
+  __device__ __forceinline__ void emit_mark(bool flag, uint32_t id, uint32_t cnt) {
+    emit(flag, id, cnt);
+    if (flag && mark) {
+      uint32_t bit = 1u << (id & 31);
+      if (!(bitmap[id >> 5] & bit)) atomicOr(bitmap + (id >> 5), bit);
+    }
+  }
+  // OR a word of 32 consecutive class ids into the global bitmap of observed classes
+  __device__ __forceinline__ void mark_word(uint32_t word_index, uint32_t bits) {
+    if (mark && bits && (bits & ~bitmap[word_index])) atomicOr(bitmap + word_index, bits);
   }
 };
 
 // ---- the extraction kernel: one warp per sequence ------------------------------------------------
-// E = keys per lane (0: no sorted levels, sequences of any length)
+// E = keys per lane of the register sort (0: no sorted levels, sequences of any length)
 template <int E>
-__global__ void __launch_bounds__(128) extract_kernel(XParams P) {
+__global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
   constexpr int EE = E > 0 ? E : 1;
-  extern __shared__ uint32_t smem[];
+  constexpr int KEYW = 33 * E;
+  extern __shared__ __align__(16) uint32_t smem[];
   const unsigned lane = lane_id();
   const int warp_in_block = threadIdx.x >> 5;
-  constexpr int KEYW = E > 0 ? 32 * (E + 1) : 0;
-  uint32_t *sk = smem + (size_t)warp_in_block * (KEYW + TAB_WORDS);
-  uint32_t *tab = sk + KEYW;
+  // per-warp areas: [bitmaps][prefix][tables][sort keys][dup count + dups]
+  uint32_t *bm = smem + (size_t)warp_in_block * P.warp_words;
+  uint32_t *pf = bm + P.bm_words;
+  uint32_t *tab = pf + P.pf_words;
+  uint32_t *sk = tab + TAB_WORDS;
+  uint32_t *dupn = sk + KEYW;
+  uint32_t *dups = dupn + 4;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int N = P.N, M = P.M, op = P.op;
   const bool two = op != 0;
-  const uint32_t maskN = (N == 16) ? 0xFFFFFFFFu : ((1u << (2 * N)) - 1u);
+  const uint32_t maskN = (1u << (2 * N)) - 1u;
   const uint32_t maskNb = (1u << N) - 1u;
+  const bool has_tab = P.t_lo <= P.t_hi, has_bm = P.b_lo <= P.b_hi, has_sort = E > 0 && P.s_lo <= N;
+
+  // shared memory starts clean; every row leaves it clean again
+  for (int i = lane; i < P.bm_words; i += 32) bm[i] = 0;
+  if (lane == 0) dupn[0] = 0;
+  __syncwarp();
 
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block; row < P.n; row += nwarps) {
-    const int64_t L = P.len[row];
+    const int L = (int)P.len[row];
     const uint32_t *b2 = P.bits2 + P.blk[row] * 4;
     const uint16_t *iv16 = P.inv16 + P.blk[row] * 4;
-    // reset count tables
-    if (P.ks_lo <= P.ks_hi)
+    if (has_tab)
       for (int i = lane; i < TAB_WORDS; i += 32) tab[i] = 0;
     __syncwarp();
 
     // ---- key generation: lane handles steps u in [u0, u0+steps) of [0, L+N-1) -------------------
-    const int64_t total_steps = L + N - 1;
-    const int64_t steps = (total_steps + 31) / 32;
-    const int64_t u0 = (int64_t)lane * steps;
+    // after consuming base u the window is [u-N+1, u]: FW = its forward code (the k-mers STARTING
+    // at p = u-N+1 are its prefixes), S2 = its image under revcomp / reverse (the images of those
+    // k-mers are its SUFFIXES), IV = invalid flags of the window
+    const int total_steps = L + N - 1;
+    const int steps = (total_steps + 31) / 32;
+    const int u0 = (int)lane * steps;
     uint32_t K[EE];
 #pragma unroll
     for (int r = 0; r < EE; r++) K[r] = SENT;
     {
       BaseReader rd; rd.init(b2, iv16, L);
       uint32_t FW = 0, S2 = 0, IV = 0xFFFFFFFFu;
-      auto consume = [&](int64_t idx) {
+      auto consume = [&](int idx) {
         uint32_t x, inv; rd.get(idx, x, inv);
         FW = ((FW << 2) | x) & maskN;
         if (op == 1) S2 = (S2 >> 2) | ((3u - x) << (2 * (N - 1)));
@@ -216,44 +248,62 @@ __global__ void __launch_bounds__(128) extract_kernel(XParams P) {
         IV = (IV << 1) | inv;
       };
       auto produce = [&](uint32_t &kf, uint32_t &k2) {
-        uint32_t xw = IV & maskNb;
-        int len_f = N - 32 + __clz(xw);                 // valid bases forward from window start
-        int len_r = xw ? (__ffs(xw) - 1) : N;           // valid bases backward from window end
+        const uint32_t xw = IV & maskNb;
+        const int len_f = N - 32 + __clz(xw);           // valid bases forward from the window start
         kf = SENT; k2 = SENT;
         if (len_f >= M) {
-          uint32_t code = FW & ~((1u << (2 * (N - len_f))) - 1u);
-          kf = (code << 5) | (uint32_t)len_f;
-          if (op == 2) k2 = ((((~FW) & maskN) & ~((1u << (2 * (N - len_f))) - 1u)) << 5) | 16u | (uint32_t)len_f;
-          // direct tables for the small levels (forward strand only)
-          for (int k = P.ks_lo; k <= P.ks_hi; k++) {
-            if (len_f >= k) {
-              uint32_t idx = tab_off(k) + (FW >> (2 * (N - k)));
+          // table levels: one count at the deepest table level this suffix reaches
+          if (has_tab) {
+            int kk = len_f < P.t_hi ? len_f : P.t_hi;
+            if (kk >= P.t_lo) {
+              uint32_t idx = tab_off(kk) + (FW >> (2 * (N - kk)));
               atomicAdd(tab + (idx >> 1), 1u << (16 * (idx & 1)));
             }
           }
+          // bitmap levels: canonical code = min(prefix, image)
+          if (has_bm) {
+            for (int k = P.b_lo; k <= P.b_hi; k++) {
+              if (len_f < k) break;
+              const uint32_t mk = (1u << (2 * k)) - 1u;
+              uint32_t c = FW >> (2 * (N - k));
+              if (op == 1 || op == 3) c = min(c, S2 & mk);
+              else if (op == 2) c = min(c, (~c) & mk);
+              const uint32_t bit = 1u << (c & 31);
+              const uint32_t old = atomicOr(bm + P.bm_off[k] + (c >> 5), bit);
+              if ((old & bit) && !P.binarize) {
+                uint32_t at = atomicAdd(dupn, 1u);
+                if ((int)at < P.dup_cap) dups[at] = ((uint32_t)k << 26) | c;
+              }
+            }
+          }
+          if (has_sort) {
+            uint32_t code = FW & ~((1u << (2 * (N - len_f))) - 1u);
+            kf = (code << 5) | (uint32_t)len_f;
+            if (op == 2) k2 = ((((~FW) & maskN) & ~((1u << (2 * (N - len_f))) - 1u)) << 5) | 16u | (uint32_t)len_f;
+          }
         }
-        if ((op == 1 || op == 3) && len_r >= M) {
-          uint32_t code = S2 & ~((1u << (2 * (N - len_r))) - 1u);
-          k2 = (code << 5) | 16u | (uint32_t)len_r;
+        if (has_sort && (op == 1 || op == 3)) {
+          const int len_r = xw ? (__ffs(xw) - 1) : N;   // valid bases backward from the window end
+          if (len_r >= M) {
+            uint32_t code = S2 & ~((1u << (2 * (N - len_r))) - 1u);
+            k2 = (code << 5) | 16u | (uint32_t)len_r;
+          }
         }
       };
-      for (int64_t idx = u0 - N + 1; idx < u0; idx++) consume(idx);
+      for (int idx = u0 - N + 1; idx < u0; idx++) consume(idx);
       if (E > 0) {
-        constexpr int PMAX = EE;   // slots: two strands -> 2 per step, else 1
 #pragma unroll
-        for (int i = 0; i < PMAX; i++) {
+        for (int i = 0; i < EE; i++) {
           bool active = two ? (2 * i + 1 < EE) : true;
           if (active && i < steps && u0 + i < total_steps) {
             consume(u0 + i);
             uint32_t kf, k2; produce(kf, k2);
-            if (P.big_lo <= N) {
-              if (two) { if (2 * i + 1 < EE) { K[(2 * i) % EE] = k2; K[(2 * i + 1) % EE] = kf; } }
-              else K[i] = kf;
-            }
+            if (two) { if (2 * i + 1 < EE) { K[(2 * i) % EE] = k2; K[(2 * i + 1) % EE] = kf; } }
+            else K[i] = kf;
           }
         }
       } else {
-        for (int64_t i = 0; i < steps && u0 + i < total_steps; i++) {
+        for (int i = 0; i < steps && u0 + i < total_steps; i++) {
           consume(u0 + i);
           uint32_t kf, k2; produce(kf, k2);
         }
@@ -262,41 +312,110 @@ __global__ void __launch_bounds__(128) extract_kernel(XParams P) {
     __syncwarp();
 
     Emitter em;
-    em.st_id = P.st_id; em.st_cnt = P.st_cnt; em.bitmap = P.bitmap;
-    em.rowbase = row * P.stride; em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
+    em.sid = P.st_id + row * P.stride; em.scnt = P.st_cnt + (P.binarize ? 0 : row * P.stride);
+    em.bitmap = P.bitmap; em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
 
-    // ---- small levels from the tables ---------------------------------------------------------
-    for (int k = P.ks_lo; k <= P.ks_hi; k++) {
-      const uint32_t nk = 1u << (2 * k), toff = tab_off(k);
-      for (uint32_t base = 0; base < nk; base += 32) {
-        uint32_t u = base + lane;
-        bool flag = false; uint32_t cnt = 0;
-        if (u < nk) {
-          uint32_t i1 = toff + u;
-          cnt = (tab[i1 >> 1] >> (16 * (i1 & 1))) & 0xFFFFu;
-          if (two) {
-            uint32_t ru = kmer_op(u, k, op);
-            if (u > ru) cnt = 0;
-            else if (u < ru) { uint32_t i2 = toff + ru; cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu; }
-          }
-          flag = cnt > 0;
+    // ---- table levels ---------------------------------------------------------------------------
+    if (has_tab) {
+      // a k-mer count is the sum of its 4 extensions plus the suffixes that end right after it
+      for (int k = P.t_hi - 1; k >= P.t_lo; k--) {
+        const uint32_t nk = 1u << (2 * k), toff = tab_off(k), coff = tab_off(k + 1);
+        for (uint32_t u = lane; u < nk; u += 32) {
+          uint32_t c0 = coff + 4 * u;                 // 4 children = two aligned words
+          uint32_t w0 = tab[c0 >> 1], w1 = tab[(c0 >> 1) + 1];
+          uint32_t sum = (w0 & 0xFFFFu) + (w0 >> 16) + (w1 & 0xFFFFu) + (w1 >> 16);
+          uint32_t idx = toff + u;
+          if (sum) atomicAdd(tab + (idx >> 1), sum << (16 * (idx & 1)));
         }
-        em.emit(flag, P.level_off[k] + u, cnt);
+        __syncwarp();
+      }
+      for (int k = P.t_lo; k <= P.t_hi; k++) {
+        const uint32_t nk = 1u << (2 * k), toff = tab_off(k);
+        for (uint32_t base = 0; base < nk; base += 32) {
+          uint32_t u = base + lane, cnt = 0;
+          if (u < nk) {
+            uint32_t i1 = toff + u;
+            cnt = (tab[i1 >> 1] >> (16 * (i1 & 1))) & 0xFFFFu;
+            if (two) {
+              uint32_t ru = c_img[i1];
+              if (u > ru) cnt = 0;
+              else if (u < ru) { uint32_t i2 = toff + ru; cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu; }
+            }
+          }
+          unsigned word = em.emit(cnt > 0, P.level_off[k] + u, cnt);
+          if (lane == 0) em.mark_word((P.level_off[k] + base) >> 5, word);
+        }
       }
     }
 
-    // ---- sorted levels ---------------------------------------------------------------------------
-    if (E > 0 && P.big_lo <= N) {
-      warp_sort<EE>(K, lane);
+    // ---- bitmap levels: walk the bitmap 128 words at a time (4 consecutive words per lane) ---------
+    if (has_bm) {
+      for (int k = P.b_lo; k <= P.b_hi; k++) {
+        const int W = 1 << (2 * k - 5);
+        const uint32_t *bk = bm + P.bm_off[k];
+        uint32_t *pk = pf + P.pf_off[k];
+        const uint32_t idbase = P.level_off[k], gword = P.level_off[k] >> 5;
+        for (int it = 0; it * 128 < W; it++) {
+          const int wi = it * 128 + (int)lane * 4;
+          uint4 w4 = make_uint4(0, 0, 0, 0);
+          if (wi < W) w4 = *reinterpret_cast<const uint4 *>(bk + wi);
+          em.mark_word(gword + wi, w4.x); em.mark_word(gword + wi + 1, w4.y);
+          em.mark_word(gword + wi + 2, w4.z); em.mark_word(gword + wi + 3, w4.w);
+          const uint32_t c = __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
+          uint32_t incl = c;
 #pragma unroll
-      for (int r = 0; r < EE; r++) sk[lane * (EE + 1) + r] = K[r];
+          for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += y;
+          }
+          uint32_t pos = em.cursor + incl - c;
+          if (wi < W) pk[wi >> 2] = pos;               // staging slot of this lane's first class
+          const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            uint32_t w = ws[j];
+            while (w) {
+              int b = __ffs(w) - 1;
+              w &= w - 1;
+              em.sid[pos] = idbase + (uint32_t)(wi + j) * 32u + (uint32_t)b;
+              if (!P.binarize) em.scnt[pos] = 1;
+              pos++;
+            }
+          }
+          em.cursor += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      }
       __syncwarp();
-      for (int k = P.big_lo; k <= N; k++) {
+      __threadfence_block();
+      // repeats: add one to the count of the class, found by its rank in the bitmap
+      if (!P.binarize) {
+        const uint32_t nd = min(dupn[0], (uint32_t)P.dup_cap);
+        for (uint32_t i = lane; i < nd; i += 32) {
+          const uint32_t e = dups[i], k = e >> 26, c = e & 0x3FFFFFFu, wi = c >> 5;
+          const uint32_t *bk = bm + P.bm_off[k];
+          uint32_t slot = pf[P.pf_off[k] + (wi >> 2)] + __popc(bk[wi] & ((1u << (c & 31)) - 1u));
+          for (uint32_t j = wi & ~3u; j < wi; j++) slot += __popc(bk[j]);
+          atomicAdd(em.scnt + slot, 1u);
+        }
+        __syncwarp();
+        if (lane == 0) dupn[0] = 0;
+      }
+      for (int i = (int)lane * 4; i < P.bm_words; i += 128) *reinterpret_cast<uint4 *>(bm + i) = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+    }
+
+    // ---- sorted levels ---------------------------------------------------------------------------
+    if (has_sort) {
+      warp_sort<EE>(K, lane);
+      // sorted index s = lane*EE + r lives at sk[s + s/32]: conflict free both ways
+#pragma unroll
+      for (int r = 0; r < EE; r++) { unsigned si = lane * EE + r; sk[si + (si >> 5)] = K[r]; }
+      __syncwarp();
+      for (int k = P.s_lo; k <= N; k++) {
         const int s = 2 * (N - k) + 5;
         uint32_t carry_f = 0, carry_r = 0, last_key = 0;
         for (int g = 0; g < EE; g++) {
-          const unsigned sidx = (unsigned)g * 32u + lane;
-          const uint32_t key = sk[(sidx / EE) * (EE + 1) + (sidx % EE)];
+          const uint32_t key = sk[g * 33 + lane];
           uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
           if (lane == 0) kprev = last_key;
           const uint32_t p = key >> s, pp = kprev >> s;
@@ -325,7 +444,7 @@ __global__ void __launch_bounds__(128) extract_kernel(XParams P) {
             } else cnt = cf;
             flag = cnt > 0;
           }
-          em.emit(flag, P.level_off[k] + pp, cnt);
+          em.emit_mark(flag, P.level_off[k] + pp, cnt);
           // carry of the run that is still open at the end of this group
           if (hm) {
             int hl = 31 - __clz(hm);
@@ -465,17 +584,20 @@ __global__ void features_rows(const int64_t *__restrict__ rowptr, const uint32_t
 
 template <int E>
 void launch_extract(const XParams &P) {
-  constexpr int KEYW = E > 0 ? 32 * (E + 1) : 0;
-  size_t smem = (size_t)4 * (KEYW + TAB_WORDS) * sizeof(uint32_t);
+  // warps per block: as many as fit the shared memory of one block (the dup list grows with L)
+  int wpb = 4;
+  while (wpb > 1 && (size_t)wpb * P.warp_words * 4 > (size_t)160 * 1024) wpb >>= 1;
+  size_t smem = (size_t)wpb * P.warp_words * sizeof(uint32_t);
+  KL_REQUIRE(smem <= (size_t)220 * 1024, "sequence too long for the shared-memory working set of one warp");
   KL_CUDA(cudaFuncSetAttribute(extract_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_kernel<E>, 128, smem));
+  KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_kernel<E>, 32 * wpb, smem));
   if (per_sm < 1) per_sm = 1;
   int64_t blocks = (int64_t)ctx().sm_count * per_sm;
-  int64_t need = (P.n + 3) / 4;
+  int64_t need = (P.n + wpb - 1) / wpb;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  KL_LAUNCH((extract_kernel<E>), (unsigned)blocks, 128, smem, P);
+  KL_LAUNCH((extract_kernel<E>), (unsigned)blocks, 32 * wpb, smem, P);
 }
 
 }  // namespace
@@ -567,12 +689,17 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   XParams P{};
   P.M = cfg.M; P.N = cfg.N; P.binarize = cfg.binarize != 0;
   P.op = cfg.revcomp ? 1 : (cfg.complement ? 2 : (cfg.reverse ? 3 : 0));
-  P.ks_lo = cfg.M; P.ks_hi = cfg.N < KS_MAX ? cfg.N : KS_MAX;
-  P.big_lo = cfg.M > KS_MAX + 1 ? cfg.M : KS_MAX + 1;
+  P.t_lo = cfg.M; P.t_hi = cfg.N < KT_MAX ? cfg.N : KT_MAX;
+  P.b_lo = cfg.M > KT_MAX + 1 ? cfg.M : KT_MAX + 1; P.b_hi = cfg.N < KB_MAX ? cfg.N : KB_MAX;
+  P.s_lo = cfg.M > KB_MAX + 1 ? cfg.M : KB_MAX + 1;
   P.n = s.n;
   P.len = s.len.p; P.blk = s.blk.p; P.bits2 = s.bits2.p; P.inv16 = s.inv16.p;
+  // dense class ids: every level starts on a multiple of 32 so that bitmap words never straddle levels
   uint64_t dense = 0;
-  for (int k = cfg.M; k <= cfg.N; k++) { P.level_off[k] = (uint32_t)dense; dense += 1ull << (2 * k); }
+  for (int k = cfg.M; k <= cfg.N; k++) {
+    P.level_off[k] = (uint32_t)dense;
+    dense += ((1ull << (2 * k)) + 31) / 32 * 32;
+  }
   P.level_off[cfg.N + 1] = (uint32_t)dense;
   const int64_t nbits = (int64_t)dense, nw = (nbits + 31) / 32;
   // staging stride: upper bound on distinct classes of one sequence
@@ -584,16 +711,52 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   }
   if (stride < 1) stride = 1;
   P.stride = stride;
-  KL_REQUIRE(s.max_len < 65536 || P.ks_lo > P.ks_hi, "sequences of 65536 bp or more need M > 5 on the GPU path");
-  // keys per lane
+  KL_REQUIRE(s.max_len < 65536 || P.t_lo > P.t_hi, "sequences of 65536 bp or more need M > 5 on the GPU path");
+  KL_REQUIRE(s.max_len < ((int64_t)1 << 30), "sequence too long");
+  // keys per lane of the register sort (levels above KB_MAX only)
   int E = 0;
-  if (P.big_lo <= cfg.N) {
+  if (P.s_lo <= cfg.N) {
     int64_t steps = (s.max_len + cfg.N - 1 + 31) / 32;
     int64_t slots = P.op ? 2 * steps : steps;
     E = 2; while (E < slots && E < 128) E <<= 1;
-    KL_REQUIRE(E <= 64, "sequence too long for the register sort path (k > 5 needs L <= ~1000 bp with an "
+    KL_REQUIRE(E <= 64, "sequence too long for the register sort path (k > 8 needs L <= ~1000 bp with an "
                         "equivalence flag, ~2000 bp without)");
   }
+  // per-warp shared memory
+  P.bm_words = 0; P.pf_words = 0; P.dup_cap = 0;
+  int nbl = 0;
+  for (int k = P.b_lo; k <= P.b_hi; k++) {
+    P.bm_off[k] = (uint32_t)P.bm_words; P.pf_off[k] = (uint32_t)P.pf_words;
+    P.bm_words += 1 << (2 * k - 5); P.pf_words += 1 << (2 * k - 7);
+    nbl++;
+  }
+  if (nbl && !P.binarize) {
+    int64_t cap = (int64_t)nbl * (s.max_len > 0 ? s.max_len : 1);
+    P.dup_cap = (int)((cap + 3) / 4 * 4);
+  }
+  P.warp_words = P.bm_words + P.pf_words + TAB_WORDS + 33 * E + 4 + P.dup_cap;
+  P.warp_words = (P.warp_words + 3) / 4 * 4;
+  // images of the table-level codes under the strand operation
+  if (P.op && P.t_lo <= P.t_hi) {
+    std::vector<uint16_t> img(1368, 0);
+    for (int k = 1; k <= KT_MAX; k++) {
+      uint32_t off = ((1u << (2 * k)) - 4u) / 3u;
+      for (uint32_t u = 0; u < (1u << (2 * k)); u++) {
+        uint32_t r = 0;
+        for (int i = 0; i < k; i++) {
+          uint32_t d = (u >> (2 * i)) & 3u;               // digit i from the right
+          if (P.op == 1) r |= (3u - d) << (2 * (k - 1 - i));
+          else if (P.op == 2) r |= (3u - d) << (2 * i);
+          else r |= d << (2 * (k - 1 - i));
+        }
+        img[off + u] = (uint16_t)r;
+      }
+    }
+    KL_CUDA(cudaMemcpyToSymbolAsync(c_img, img.data(), img.size() * sizeof(uint16_t), 0, cudaMemcpyHostToDevice,
+                                    ctx().stream));
+    sync_stream();
+  }
+  Trace tr("extract");
   DevBuf<uint32_t> st_id((size_t)(s.n ? s.n * stride : 1));
   DevBuf<uint32_t> st_cnt((size_t)(P.binarize ? 1 : (s.n ? s.n * stride : 1)));
   DevBuf<uint32_t> rowcnt((size_t)(s.n ? s.n : 1));
@@ -601,6 +764,7 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   bitmap.zero();
   P.st_id = st_id.p; P.st_cnt = st_cnt.p; P.rowcnt = rowcnt.p; P.bitmap = bitmap.p;
   P.mark = n_frozen == 0;
+  tr.mark("alloc staging");
 
   if (s.n > 0) {
     switch (E) {
@@ -613,6 +777,7 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
       default: launch_extract<64>(P); break;
     }
   }
+  tr.mark("extract_kernel");
   // class set: observed union (all ranks) or the frozen list
   if (n_frozen > 0) {
     std::vector<uint32_t> hb((size_t)nw, 0u);
@@ -667,6 +832,7 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
       out->class_k[j] = k; out->class_code[j] = hid[j] - P.level_off[k];
     }
   }
+  tr.mark("ranks + class list");
   // final CSR
   out->rowptr.alloc((size_t)s.n + 1);
   DevBuf<uint32_t> kept;
@@ -684,8 +850,10 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   } else {
     out->rowptr.zero(); out->nnz = 0;
   }
+  tr.mark("rowptr scan");
   out->col.alloc((size_t)(out->nnz ? out->nnz : 1));
   if (out->vt == VAL_U32) out->val_u32.alloc((size_t)(out->nnz ? out->nnz : 1));
+  tr.mark("alloc csr");
   if (s.n > 0) {
     uint32_t *vp = out->vt == VAL_U32 ? out->val_u32.p : nullptr;
     if (n_frozen > 0)
@@ -696,6 +864,7 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
                 out->rowptr.p, out->col.p, vp);
   }
   sync_stream();
+  tr.mark("compact");
   if (n_features > 0) return apply_features(*out, features, n_features);
   return out;
 }

@@ -384,7 +384,9 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   check_theta(M, ntheta, 0);
   KL_REQUIRE(M.has_labels, "proxgrad: the matrix has no labels (kmerlr_matrix_set_labels)");
   KL_REQUIRE(M.n_global > 0, "proxgrad: empty data set");
+  Trace tr("proxgrad");
   ensure_csc(M);
+  tr.mark("ensure_csc");
   // estimate_step_size (kmerLr_estimator_proximal.go:54-76)
   double L = 0.25 * (matrix_maxsq(M) + 1.0) + l2 / (double)M.n_global;
   double step = 1.0 / (2.0 * L + std::fmin(2.0 * l2, L)) * step_factor;
@@ -420,6 +422,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   }
   wk.theta.download(theta, (size_t)ntheta);
   sync_stream();
+  tr.mark("iterations");
   if (hook) { hook[0] = h.loss_old; hook[1] = h.loss_new; }
   if (iters) *iters = (int64_t)h.iter;
   if (delta) *delta = h.delta;

@@ -43,10 +43,17 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint32_t *__re
                                                             uint32_t *__restrict__ keys_out,
                                                             uint32_t *__restrict__ rows_out,
                                                             VT *__restrict__ vals_out) {
+  // dynamic smem: the tile in sorted order (keys, rows, values), written out as coalesced runs
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  uint32_t *skey = (uint32_t *)rs_smem;
+  uint32_t *srow = skey + RS_TILE;
+  VT *sval = (VT *)(srow + RS_TILE);
   __shared__ uint32_t wcnt[RS_THREADS / 32][256];
+  __shared__ uint32_t tdig[257];
   __shared__ int64_t goff[256];
   const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WARP_ITEMS;
+  const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
+  const int64_t wbase = tbase + (int64_t)w * RS_WARP_ITEMS;
   for (int i = lane; i < 256; i += 32) wcnt[w][i] = 0;
   __syncwarp();
   // sub-pass 1: rank of every entry among the earlier entries of its warp with the same digit
@@ -55,8 +62,14 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint32_t *__re
   for (int g = 0; g < RS_GROUPS; g++) {
     int64_t p = wbase + g * 32 + lane;
     bool valid = p < nnz;
-    uint32_t d = valid ? ((keys[p] >> shift) & 255u) : 256u;
-    unsigned mask = __match_any_sync(0xffffffffu, d);
+    uint32_t d = valid ? ((keys[p] >> shift) & 255u) : 0u;
+    // lanes holding the same digit: 8 ballots (match.any serialises over the distinct values)
+    unsigned mask = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+      mask &= ((d >> b) & 1u) ? bal : ~bal;
+    }
     uint32_t old = valid ? wcnt[w][d] : 0u;
     __syncwarp();
     if (valid && (unsigned)(__ffs(mask) - 1) == lane) wcnt[w][d] = old + __popc(mask);
@@ -73,6 +86,20 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint32_t *__re
       wcnt[ww][threadIdx.x] = run;
       run += c;
     }
+    // exclusive scan of the tile's digit counts (256 threads = 256 digits)
+    uint32_t x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (unsigned)o) x += y;
+    }
+    __shared__ uint32_t wtot[RS_THREADS / 32];
+    if (lane == 31) wtot[w] = x;
+    __syncthreads();
+    uint32_t before = 0;
+    for (unsigned ww = 0; ww < w; ww++) before += wtot[ww];
+    tdig[threadIdx.x] = before + x - run;
+    if (threadIdx.x == 255) tdig[256] = before + x;
     goff[threadIdx.x] = offs[(int64_t)threadIdx.x * ntiles + blockIdx.x];
   }
   __syncthreads();
@@ -85,7 +112,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint32_t *__re
       rcur = lo;
     }
   }
-  // sub-pass 2: scatter
+  // sub-pass 2: place every entry at its sorted position inside the tile
 #pragma unroll
   for (int g = 0; g < RS_GROUPS; g++) {
     int64_t p = wbase + g * 32 + lane;
@@ -99,11 +126,21 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter(const uint32_t *__re
     }
     if (valid) {
       uint32_t key = keys[p], d = (key >> shift) & 255u;
-      int64_t dst = goff[d] + wcnt[w][d] + lr[g];
-      keys_out[dst] = key;
-      rows_out[dst] = FIRST ? row : rows_in[p];
-      if (vals) vals_out[dst] = vals[p];
+      uint32_t slot = tdig[d] + wcnt[w][d] + lr[g];
+      skey[slot] = key;
+      srow[slot] = FIRST ? row : rows_in[p];
+      if (vals) sval[slot] = vals[p];
     }
+  }
+  __syncthreads();
+  // write out: consecutive threads -> consecutive slots -> consecutive addresses inside a digit run
+  const uint32_t tile_n = tdig[256];
+  for (uint32_t i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+    uint32_t key = skey[i], d = (key >> shift) & 255u;
+    int64_t dst = goff[d] + (i - tdig[d]);
+    keys_out[dst] = key;
+    rows_out[dst] = srow[i];
+    if (vals) vals_out[dst] = sval[i];
   }
 }
 
@@ -269,6 +306,7 @@ static void build_csc(Matrix &M, const VT *val, VT *cval) {
   int bits = 1;
   while (((int64_t)1 << bits) < M.m) bits++;
   const int passes = (bits + 7) / 8;
+  Trace tr("csc");
   DevBuf<uint32_t> hist((size_t)(256 * ntiles));
   DevBuf<int64_t> offs((size_t)(256 * ntiles) + 1);
   // ping-pong buffers; the last pass writes straight into the CSC arrays
@@ -277,6 +315,7 @@ static void build_csc(Matrix &M, const VT *val, VT *cval) {
   DevBuf<VT> vA(val && passes > 1 ? (size_t)nnz : 1), vB(val && passes > 2 ? (size_t)nnz : 1);
   const uint32_t *kin = M.col.p, *rin = nullptr;
   const VT *vin = val;
+  tr.mark("alloc");
   for (int ps = 0; ps < passes; ps++) {
     const bool last = ps == passes - 1;
     uint32_t *kout = (ps & 1) ? kB.p : kA.p;
@@ -285,13 +324,18 @@ static void build_csc(Matrix &M, const VT *val, VT *cval) {
     VT *vout = val ? (last ? cval : ((ps & 1) ? vB.p : vA.p)) : nullptr;
     KL_LAUNCH(radix_hist, (unsigned)ntiles, RS_THREADS, 0, kin, nnz, 8 * ps, hist.p, ntiles);
     exclusive_scan_u32_to_i64(hist.p, offs.p, 256 * ntiles);
-    if (ps == 0)
-      KL_LAUNCH((radix_scatter<VT, true>), (unsigned)ntiles, RS_THREADS, 0, kin, rin, M.rowptr.p, M.n, vin, nnz, 8 * ps,
+    const size_t smem = (size_t)RS_TILE * (8 + (val ? sizeof(VT) : 0));
+    if (ps == 0) {
+      KL_CUDA(cudaFuncSetAttribute(radix_scatter<VT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      KL_LAUNCH((radix_scatter<VT, true>), (unsigned)ntiles, RS_THREADS, smem, kin, rin, M.rowptr.p, M.n, vin, nnz, 8 * ps,
                 offs.p, ntiles, kout, rout, vout);
-    else
-      KL_LAUNCH((radix_scatter<VT, false>), (unsigned)ntiles, RS_THREADS, 0, kin, rin, M.rowptr.p, M.n, vin, nnz, 8 * ps,
+    } else {
+      KL_CUDA(cudaFuncSetAttribute(radix_scatter<VT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      KL_LAUNCH((radix_scatter<VT, false>), (unsigned)ntiles, RS_THREADS, smem, kin, rin, M.rowptr.p, M.n, vin, nnz, 8 * ps,
                 offs.p, ntiles, kout, rout, vout);
+    }
     kin = kout; rin = rout; vin = vout;
+    tr.mark("pass");
   }
   KL_LAUNCH(lower_bounds, (unsigned)((M.m + 1 + 255) / 256), 256, 0, kin, nnz, M.m, M.colptr.p);
   sync_stream();
