@@ -171,7 +171,8 @@ struct SeqSet : Object {
 
 enum ValType : int { VAL_ONE = 0, VAL_U32 = 1, VAL_F64 = 2 };
 
-// KmerDataSet in HBM: CSR rows (without the bias column) + lazily built CSC + labels + classes
+// KmerDataSet in HBM: CSR rows (without the bias column) + labels + classes; a CSC view is built
+// lazily for the pair-feature (co-occurrence) gradient only
 struct Matrix : Object {
   int64_t n = 0, m = 0, nnz = 0;
   ValType vt = VAL_U32;
@@ -185,10 +186,6 @@ struct Matrix : Object {
   DevBuf<uint32_t> crow;     // nnz
   DevBuf<uint32_t> cval_u32;
   DevBuf<double> cval_f64;
-  // column-chunk task list of the deterministic X^T w reduction
-  int64_t n_tasks = 0;
-  DevBuf<int64_t> taskptr;   // m+1
-  DevBuf<uint32_t> taskcol;  // n_tasks
   // labels
   bool has_labels = false;
   DevBuf<uint8_t> labels;    // n
@@ -199,9 +196,11 @@ struct Matrix : Object {
   // sample sharding
   bool sharded = false;
   int64_t n_global = 0;
-  // cached max_i ||x_i||^2 (without bias), global
+  // cached max_i ||x_i||^2 (without bias) and max |x_ij|, global
   bool has_maxsq = false;
   double maxsq = 0.0;
+  bool has_vmax = false;
+  double vmax = 0.0;
 };
 
 // handle registry (abi.cu)
@@ -234,6 +233,7 @@ void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n);
 void ensure_csc(Matrix &M);
 std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel);
 double matrix_maxsq(Matrix &M);
+double matrix_vmax(Matrix &M);
 // logistic.cu
 void linear_pdf(Matrix &M, const double *theta, int64_t ntheta, int cooc, double *out_host, bool logpdf);
 void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc,

@@ -5,11 +5,13 @@
 // (kmerLr_logistic_regression.go:47-272) and estimate_proximal + eval_stopping + estimate_step_size
 // (kmerLr_estimator_proximal.go:30-120, hook kmerLr_estimator_hook.go:46-99).
 //
-// Two passes over the matrix per gradient, both deterministic (no float atomics):
-//   rows pass  (CSR, warp per row):   z_i = theta_0 + sum_j v_ij theta_j, loss term, w_i
-//   cols pass  (CSC, warp per 1024-entry column chunk):  g_j = sum_i w_i v_ij
-// The reduction tree of a column depends only on the column's own entries, so two features with
-// identical columns get bit-identical gradients (what leapfrog tie handling needs).
+// ONE pass over the matrix per gradient (CSR, warp per row): z_i = theta_0 + sum_j v_ij theta_j, the
+// loss term and the weight w_i, then the row's contributions w_i v_ij are added to the gradient in
+// 64-bit FIXED POINT (scale 2^e, e chosen so that the worst case sum fits): integer addition is
+// associative, so the result does not depend on the order of the atomics -- it is deterministic,
+// two features with identical columns get bit-identical gradients (what leapfrog tie handling
+// needs), and an int64 all-reduce over the ranks gives the same bits as one GPU.
+// The first columns (the dense low-k classes) accumulate in shared memory, the rest in L2.
 #include "common.cuh"
 
 #include <cmath>
@@ -95,35 +97,73 @@ __global__ void reduce_stage2(const double *__restrict__ part, int np, double *_
   }
 }
 
-// cols pass: one warp per column chunk
+// the fused pass: persistent blocks, one warp per row
+//   G[0]    += round(w_i * S)                 (bias, Go index 0)
+//   G[c+1]  += round(w_i * v_ic * S)          for every entry of the row
+constexpr int HOT_COLS = 4096;   // columns < HOT_COLS accumulate in shared memory (32 KB)
+
 template <typename VT>
-__global__ void cols_partial(const int64_t *__restrict__ colptr, const uint32_t *__restrict__ crow,
-                             const VT *__restrict__ cval, const int64_t *__restrict__ taskptr,
-                             const uint32_t *__restrict__ taskcol, int64_t n_tasks, const double *__restrict__ w,
-                             double *__restrict__ part, const PgState *st) {
-  if (st && st->done) return;
-  int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (t >= n_tasks) return;
-  unsigned lane = lane_id();
-  uint32_t c = taskcol[t];
-  int64_t a = colptr[c] + (t - taskptr[c]) * TASK_CHUNK, b = a + TASK_CHUNK;
-  if (b > colptr[c + 1]) b = colptr[c + 1];
-  double s = 0.0;
-  for (int64_t p = a + lane; p < b; p += 32) s += __ldg(w + crow[p]) * valf(cval, p);
-  s = warp_sum_down(s);
-  if (lane == 0) part[t] = s;
+__global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+                                                    const VT *__restrict__ val, int64_t n, int64_t m,
+                                                    const double *__restrict__ theta,
+                                                    const uint8_t *__restrict__ labels, double cw0, double cw1,
+                                                    double inv_n, double scale, unsigned long long *__restrict__ G,
+                                                    double *__restrict__ lossterm, const PgState *st) {
+  if (st && st->done == 1) return;
+  __shared__ unsigned long long hot[HOT_COLS];
+  const int64_t hot_cols = m < HOT_COLS ? m : HOT_COLS;
+  for (int i = threadIdx.x; i < hot_cols; i += blockDim.x) hot[i] = 0ull;
+  __syncthreads();
+  const unsigned lane = lane_id();
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  long long bias_acc = 0;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
+    const int64_t a = rowptr[row], b = rowptr[row + 1];
+    double s = 0.0;
+    for (int64_t p = a + lane; p < b; p += 32) s += valf(val, p) * __ldg(theta + col[p] + 1);
+    s = warp_sum_down(s);
+    double w = 0.0;
+    if (lane == 0) {
+      // Gradient weight (:166-178) and Loss term (:257-263)
+      double z = theta[0] + s, r = -log_add0(-z);
+      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lossterm[row] = -cw1 * r; }
+      else             { w = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
+      bias_acc += __double2ll_rn(w * scale);
+    }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    const double ws = w * scale;          // scale is a power of two: exact
+    for (int64_t p = a + lane; p < b; p += 32) {
+      const uint32_t c = col[p];
+      const unsigned long long q = (unsigned long long)__double2ll_rn(ws * valf(val, p));
+      if (c < (uint32_t)hot_cols) atomicAdd(&hot[c], q);
+      else atomicAdd(&G[c + 1], q);
+    }
+  }
+  if (lane == 0 && bias_acc != 0) atomicAdd(&G[0], (unsigned long long)bias_acc);
+  __syncthreads();
+  for (int i = threadIdx.x; i < hot_cols; i += blockDim.x)
+    if (hot[i]) atomicAdd(&G[i + 1], hot[i]);
 }
 
-// g[c+1] = sum of the column's chunk partials in chunk order, plus the L1 sign term (:237-246)
-__global__ void cols_finalize(const int64_t *__restrict__ taskptr, const double *__restrict__ part, int64_t m,
-                              const double *__restrict__ wsum, double *__restrict__ g, const PgState *st) {
-  if (st && st->done) return;
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0) g[0] = wsum[0];
-  if (c >= m) return;
-  double s = 0.0;
-  for (int64_t t = taskptr[c]; t < taskptr[c + 1]; t++) s += part[t];
-  g[c + 1] = s;
+// pair mode: the weights come from the pair-aware rows kernel; same fixed-point accumulation
+template <typename VT>
+__global__ void scatter_w(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+                          const VT *__restrict__ val, int64_t n, const double *__restrict__ w, double scale,
+                          unsigned long long *__restrict__ G) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  unsigned lane = lane_id();
+  const double ws = w[row] * scale;
+  if (lane == 0) atomicAdd(&G[0], (unsigned long long)__double2ll_rn(ws));
+  for (int64_t p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32)
+    atomicAdd(&G[col[p] + 1], (unsigned long long)__double2ll_rn(ws * valf(val, p)));
+}
+
+// g[j] = G[j] / S for the single-feature coefficients
+__global__ void finalize_g(const unsigned long long *__restrict__ G, int64_t count, double inv_scale,
+                           double *__restrict__ g) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < count) g[j] = (double)(long long)G[j] * inv_scale;
 }
 
 // pair coefficients (kmerLr_logistic_regression.go:183-195): g[Ind2Sub(a,b)] = sum_i w_i v_ia v_ib,
@@ -202,47 +242,65 @@ __global__ void hook_kernel(PgState *st, const double *__restrict__ losssum, con
   }
 }
 
-// theta <- prox(theta - s g), eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98)
-__global__ void prox_kernel(PgState *st, double *__restrict__ theta, const double *__restrict__ g, int64_t ntheta,
-                            double step, double lambda, double eps, long long max_iter) {
+// theta <- prox(theta - s g), eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98).
+// prox_update: grid-wide update + per-block max |theta|, max |delta|; prox_finish: the decision.
+__global__ void prox_update(const PgState *st, double *__restrict__ theta, const unsigned long long *__restrict__ G,
+                            double inv_scale, int64_t ntheta, double step, double lambda,
+                            double *__restrict__ blockmax) {
   if (st->done) return;
-  __shared__ double shx[256], shd[256];
-  __shared__ int shnan;
-  if (threadIdx.x == 0) shnan = 0;
-  __syncthreads();
-  double mx = 0.0, md = 0.0;
-  for (int64_t k = threadIdx.x; k < ntheta; k += blockDim.x) {
-    double t0 = theta[k], t1 = t0 - step * g[k];
+  __shared__ double shx[256], shd[256], shn[256];
+  double mx = 0.0, md = 0.0, nn = 0.0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < ntheta; k += (int64_t)gridDim.x * blockDim.x) {
+    double g = (double)(long long)G[k] * inv_scale;
+    double t0 = theta[k], t1 = t0 - step * g;
     if (k > 0) {
       if (t1 >= 0.0) t1 = fmax(fabs(t1) - step * lambda, 0.0);
       else           t1 = -fmax(fabs(t1) - step * lambda, 0.0);
     }
     theta[k] = t1;
-    if (isnan(t1)) shnan = 1;
+    if (isnan(t1)) nn = 1.0;
     mx = fmax(mx, fabs(t1));
     md = fmax(md, fabs(t1 - t0));
   }
-  shx[threadIdx.x] = mx; shd[threadIdx.x] = md;
+  shx[threadIdx.x] = mx; shd[threadIdx.x] = md; shn[threadIdx.x] = nn;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) {
       shx[threadIdx.x] = fmax(shx[threadIdx.x], shx[threadIdx.x + o]);
       shd[threadIdx.x] = fmax(shd[threadIdx.x], shd[threadIdx.x + o]);
+      shn[threadIdx.x] = fmax(shn[threadIdx.x], shn[threadIdx.x + o]);
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0) { blockmax[3 * blockIdx.x] = shx[0]; blockmax[3 * blockIdx.x + 1] = shd[0]; blockmax[3 * blockIdx.x + 2] = shn[0]; }
+}
+__global__ void prox_finish(PgState *st, const double *__restrict__ blockmax, int nblocks, double eps, long long max_iter) {
+  if (st->done) return;
+  double mx = 0.0, md = 0.0, nn = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 32) {
+    mx = fmax(mx, blockmax[3 * i]); md = fmax(md, blockmax[3 * i + 1]); nn = fmax(nn, blockmax[3 * i + 2]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    nn = fmax(nn, __shfl_xor_sync(0xffffffffu, nn, o));
+  }
   if (threadIdx.x == 0) {
-    double max_x = shx[0], max_delta = shd[0];
     st->iter += 1;
-    if (shnan) { st->delta = nan(""); st->done = 1; return; }
-    st->delta = max_x != 0.0 ? max_delta / max_x : max_delta;
-    if ((max_x != 0.0 && max_delta / max_x <= eps) || (max_x == 0.0 && max_delta == 0.0)) st->done = 1;
+    if (nn != 0.0) { st->delta = nan(""); st->done = 1; return; }
+    st->delta = mx != 0.0 ? md / mx : md;
+    if ((mx != 0.0 && md / mx <= eps) || (mx == 0.0 && md == 0.0)) st->done = 1;
     else if (st->iter >= max_iter) st->done = 2;
   }
 }
 
+constexpr int PROX_BLOCKS = 64;
+
 struct Work {
-  DevBuf<double> theta, w, lossterm, part, g, red, scalars, gathered;
+  DevBuf<double> theta, w, lossterm, g, red, scalars, gathered, blockmax;
+  DevBuf<unsigned long long> G;
+  double scale = 1.0, inv_scale = 1.0;
 };
 
 template <typename VT>
@@ -276,34 +334,41 @@ void launch_rows(const Matrix &M, const double *theta, int cooc, const double cw
             theta, cooc, M.labels.p, cw ? cw[0] : 1.0, cw ? cw[1] : 1.0, inv_n, out, lossterm, st);
 }
 
-// g (ntheta) from w; wk.scalars[1] receives sum(w)
+// fixed-point scale: sum_i |w_i v_ic| <= max(cw) * max|v|, kept below 2^60
+void set_scale(Matrix &M, Work &wk, const double cw[2]) {
+  double bound = std::fmax(std::fabs(cw[0]), std::fabs(cw[1])) * std::fmax(matrix_vmax(M), 1.0);
+  if (!(bound > 0.0) || !std::isfinite(bound)) bound = 1.0;
+  int e = 60 - (int)std::ceil(std::log2(bound));
+  if (e > 1000) e = 1000;
+  wk.scale = std::ldexp(1.0, e);
+  wk.inv_scale = std::ldexp(1.0, -e);
+}
+
+// the fused pass: loss terms + fixed-point gradient of the single-feature coefficients (all ranks)
 template <typename VT>
-void launch_cols(Matrix &M, Work &wk, int64_t ntheta, int cooc, const PgState *st) {
-  reduce_sum(M, wk.w.p, M.n, wk, wk.scalars.p + 1, nullptr, /*all_ranks=*/false);
-  if (M.n_tasks > 0)
-    KL_LAUNCH((cols_partial<VT>), warp_grid(M.n_tasks, 256), 256, 0, M.colptr.p, M.crow.p, csc_val<VT>(M), M.taskptr.p,
-              M.taskcol.p, M.n_tasks, wk.w.p, wk.part.p, st);
-  KL_LAUNCH(cols_finalize, (unsigned)((M.m + 1 + 255) / 256), 256, 0, M.taskptr.p, wk.part.p, M.m, wk.scalars.p + 1,
-            wk.g.p, st);
-  if (cooc && M.m > 1)
-    KL_LAUNCH((pairs_gradient<VT>), (unsigned)(ctx().sm_count * 8), 256, 0, M.colptr.p, M.crow.p, csc_val<VT>(M), M.m,
-              wk.w.p, wk.g.p);
-  if (M.sharded) {
-    // every rank sums the per-rank gradients in rank order: same bits everywhere, and identical
-    // columns keep identical gradients (an NCCL ring reduces different slices in different orders)
-    comm_allgather_f64(wk.g.p, wk.gathered.p, ntheta);
-    KL_LAUNCH(sum_ranks, (unsigned)((ntheta + 255) / 256), 256, 0, wk.gathered.p, ctx().world, ntheta, wk.g.p);
+void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
+  KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
+  if (M.n > 0) {
+    int per_sm = 0;
+    KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
+    if (blocks > need) blocks = need;
+    KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
+              M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st);
   }
+  if (M.sharded) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
 }
 
 void alloc_work(const Matrix &M, int64_t ntheta, Work &wk) {
   wk.theta.alloc((size_t)ntheta);
   wk.w.alloc((size_t)(M.n ? M.n : 1));
   wk.lossterm.alloc((size_t)(M.n ? M.n : 1));
-  wk.part.alloc((size_t)(M.n_tasks ? M.n_tasks : 1));
   wk.g.alloc((size_t)ntheta);
+  wk.G.alloc((size_t)M.m + 1);
   wk.red.alloc(RED_BLOCKS);
   wk.scalars.alloc(8);
+  wk.blockmax.alloc(3 * PROX_BLOCKS);
   wk.gathered.alloc((size_t)(M.sharded ? ntheta * ctx().world : 1));
 }
 
@@ -340,15 +405,38 @@ void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2]
   require_ready();
   check_theta(M, ntheta, cooc);
   KL_REQUIRE(M.has_labels, "gradient: the matrix has no labels (kmerlr_matrix_set_labels)");
-  ensure_csc(M);
   Work wk; alloc_work(M, ntheta, wk);
+  set_scale(M, wk, cw);
   wk.theta.upload(theta, (size_t)ntheta);
   wk.g.zero();
   dispatch_vt(M, [&](auto *tag) {
     using VT = typename std::remove_pointer<decltype(tag)>::type;
-    launch_rows<VT, 2>(M, wk.theta.p, cooc, cw, wk.w.p, wk.lossterm.p, nullptr);
-    launch_cols<VT>(M, wk, ntheta, cooc, nullptr);
+    if (!cooc) {
+      launch_fused<VT>(M, wk, cw, nullptr);
+    } else {
+      // pair mode: z needs the pair terms, so the weights come from the general rows kernel; the
+      // single-feature part still goes through the fixed-point pass with theta restricted to it
+      // being irrelevant: w is what matters.  Reuse the fused kernel's scatter by running the pair
+      // aware rows kernel for w and the CSC kernels for the pairs.
+      launch_rows<VT, 2>(M, wk.theta.p, cooc, cw, wk.w.p, wk.lossterm.p, nullptr);
+      ensure_csc(M);
+      KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
+      if (M.n > 0)
+        KL_LAUNCH((scatter_w<VT>), warp_grid(M.n, 256), 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, wk.w.p,
+                  wk.scale, wk.G.p);
+      if (M.sharded) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
+      if (M.m > 1) {
+        KL_LAUNCH((pairs_gradient<VT>), (unsigned)(ctx().sm_count * 8), 256, 0, M.colptr.p, M.crow.p, csc_val<VT>(M),
+                  M.m, wk.w.p, wk.g.p);
+        if (M.sharded) {
+          // pair entries: every rank sums the per-rank values in rank order
+          comm_allgather_f64(wk.g.p, wk.gathered.p, ntheta);
+          KL_LAUNCH(sum_ranks, (unsigned)((ntheta + 255) / 256), 256, 0, wk.gathered.p, ctx().world, ntheta, wk.g.p);
+        }
+      }
+    }
   });
+  KL_LAUNCH(finalize_g, (unsigned)((M.m + 1 + 255) / 256), 256, 0, wk.G.p, M.m + 1, wk.inv_scale, wk.g.p);
   if (!std::isnan(lambda) && lambda != 0.0)
     KL_LAUNCH(add_l1_sign, (unsigned)((ntheta + 255) / 256), 256, 0, wk.theta.p, wk.g.p, ntheta, lambda);
   wk.g.download(g_host, (size_t)ntheta);
@@ -385,12 +473,11 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   KL_REQUIRE(M.has_labels, "proxgrad: the matrix has no labels (kmerlr_matrix_set_labels)");
   KL_REQUIRE(M.n_global > 0, "proxgrad: empty data set");
   Trace tr("proxgrad");
-  ensure_csc(M);
-  tr.mark("ensure_csc");
   // estimate_step_size (kmerLr_estimator_proximal.go:54-76)
   double L = 0.25 * (matrix_maxsq(M) + 1.0) + l2 / (double)M.n_global;
   double step = 1.0 / (2.0 * L + std::fmin(2.0 * l2, L)) * step_factor;
   Work wk; alloc_work(M, ntheta, wk);
+  set_scale(M, wk, cw);
   wk.theta.upload(theta, (size_t)ntheta);
   DevBuf<PgState> st(1);
   PgState h{};
@@ -409,11 +496,12 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
     for (int64_t it = 0; it < nb; it++) {
       dispatch_vt(M, [&](auto *tag) {
         using VT = typename std::remove_pointer<decltype(tag)>::type;
-        launch_rows<VT, 2>(M, wk.theta.p, 0, cw, wk.w.p, wk.lossterm.p, st.p);
+        launch_fused<VT>(M, wk, cw, st.p);
         reduce_sum(M, wk.lossterm.p, M.n, wk, wk.scalars.p, st.p);
         KL_LAUNCH(hook_kernel, 1, 256, 0, st.p, wk.scalars.p, wk.theta.p, M.m, inv_n, lambda, epsilon_loss);
-        launch_cols<VT>(M, wk, ntheta, 0, st.p);
-        KL_LAUNCH(prox_kernel, 1, 256, 0, st.p, wk.theta.p, wk.g.p, ntheta, step, lambda, epsilon, (long long)max_iter);
+        KL_LAUNCH(prox_update, PROX_BLOCKS, 256, 0, st.p, wk.theta.p, wk.G.p, wk.inv_scale, ntheta, step, lambda,
+                  wk.blockmax.p);
+        KL_LAUNCH(prox_finish, 1, 32, 0, st.p, wk.blockmax.p, PROX_BLOCKS, epsilon, (long long)max_iter);
       });
     }
     st.download(&h, 1);

@@ -153,18 +153,6 @@ __global__ void lower_bounds(const uint32_t *__restrict__ sorted, int64_t nnz, i
   colptr[c] = lo;
 }
 
-constexpr int TASK_CHUNK = 1024;   // CSC entries per warp task of the X^T w reduction
-
-__global__ void task_counts(const int64_t *__restrict__ colptr, int64_t m, uint32_t *__restrict__ nt) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < m) nt[c] = (uint32_t)((colptr[c + 1] - colptr[c] + TASK_CHUNK - 1) / TASK_CHUNK);
-}
-__global__ void task_fill(const int64_t *__restrict__ taskptr, int64_t m, uint32_t *__restrict__ taskcol) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= m) return;
-  for (int64_t t = taskptr[c]; t < taskptr[c + 1]; t++) taskcol[t] = (uint32_t)c;
-}
-
 // ---- featureSelection.Data (kmerLr_feature_selection.go:309-343) ----------------------------------
 template <typename VT>
 __device__ __forceinline__ double row_value(const uint32_t *col, const VT *val, int64_t a, int64_t b, uint32_t c) {
@@ -223,6 +211,16 @@ __global__ void row_sqnorm_max(const int64_t *__restrict__ rowptr, const VT *__r
   }
   // non-negative doubles compare like their bit patterns
   if (lane == 0) atomicMax(out, (unsigned long long)__double_as_longlong(s));
+}
+
+template <typename VT>
+__global__ void abs_max(const VT *__restrict__ val, int64_t nnz, unsigned long long *__restrict__ out) {
+  double mx = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
+    mx = fmax(mx, fabs((double)val[p]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane_id() == 0 && mx > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
 }
 
 }  // namespace
@@ -356,20 +354,6 @@ void ensure_csc(Matrix &M) {
   } else {
     build_csc<uint32_t>(M, nullptr, nullptr);
   }
-  // task list
-  M.taskptr.alloc((size_t)M.m + 1);
-  if (M.m > 0) {
-    DevBuf<uint32_t> nt((size_t)M.m);
-    KL_LAUNCH(task_counts, (unsigned)((M.m + 255) / 256), 256, 0, M.colptr.p, M.m, nt.p);
-    exclusive_scan_u32_to_i64(nt.p, M.taskptr.p, M.m);
-    KL_CUDA(cudaMemcpyAsync(&M.n_tasks, M.taskptr.p + M.m, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
-    sync_stream();
-    M.taskcol.alloc((size_t)(M.n_tasks ? M.n_tasks : 1));
-    KL_LAUNCH(task_fill, (unsigned)((M.m + 255) / 256), 256, 0, M.taskptr.p, M.m, M.taskcol.p);
-  } else {
-    M.taskptr.zero(); M.n_tasks = 0;
-    M.taskcol.alloc(1);
-  }
   sync_stream();
   M.has_csc = true;
 }
@@ -446,6 +430,32 @@ double matrix_maxsq(Matrix &M) {
   double v;
   memcpy(&v, &bits, sizeof(v));
   M.maxsq = v; M.has_maxsq = true;
+  return v;
+}
+
+// max |x_ij| over the stored entries (fixed-point scale of the gradient accumulation)
+double matrix_vmax(Matrix &M) {
+  if (M.has_vmax) return M.vmax;
+  DevBuf<unsigned long long> d(1);
+  d.zero();
+  if (M.nnz > 0) {
+    if (M.vt == VAL_U32) KL_LAUNCH((abs_max<uint32_t>), 1024, 256, 0, M.val_u32.p, M.nnz, d.p);
+    else if (M.vt == VAL_F64) KL_LAUNCH((abs_max<double>), 1024, 256, 0, M.val_f64.p, M.nnz, d.p);
+  }
+  unsigned long long bits = 0;
+  d.download(&bits, 1);
+  sync_stream();
+  double v;
+  memcpy(&v, &bits, sizeof(v));
+  if (M.vt == VAL_ONE) v = M.nnz > 0 ? 1.0 : 0.0;
+  if (M.sharded) {
+    DevBuf<double> t(1);
+    t.upload(&v, 1);
+    comm_allreduce_max_f64(t.p, 1);
+    t.download(&v, 1);
+    sync_stream();
+  }
+  M.vmax = v; M.has_vmax = true;
   return v;
 }
 

@@ -48,7 +48,7 @@ def test_cooccurrence_fixture(K, oracle, fixtures):
 @pytest.mark.parametrize("L,M,N,flags", [
     (500, 1, 8, dict(revcomp=True)), (200, 1, 10, dict(revcomp=True, binarize=True)), (37, 1, 8, dict(revcomp=True)),
     (64, 5, 9, dict()), (300, 6, 12, dict(revcomp=True)), (120, 1, 13, dict(revcomp=True)), (500, 1, 5, dict(revcomp=True)),
-    (3000, 1, 5, dict(revcomp=True)), (1900, 6, 7, dict()),
+    (3000, 1, 5, dict(revcomp=True)), (1900, 6, 7, dict()), (2500, 1, 8, dict(revcomp=True)), (700, 4, 9, dict(revcomp=True)),
 ])
 def test_synthetic(K, oracle, L, M, N, flags):
     from kmerlr_b200 import synth
@@ -113,7 +113,7 @@ def test_unsupported_configurations_fail_loudly(K):
     with pytest.raises(K.KmerLrError):
         K.compile_test_data(None, K.NewKmerCounter(1, 14), None, None, True, False, ["ACGTACGTACGTACGT"])
     with pytest.raises(K.KmerLrError):
-        K.compile_test_data(None, K.NewKmerCounter(6, 8, revcomp=True), None, None, True, False, ["ACGT" * 2000])
+        K.compile_test_data(None, K.NewKmerCounter(6, 9, revcomp=True), None, None, True, False, ["ACGT" * 2000])
 
 
 def test_full_size_properties(K):
