@@ -307,8 +307,7 @@ def main():
             "what": what, "kernel_ms_per_launch": top_ms_total / top_launches,
             "kernel_share_of_step": per_kernel[top] / sum(per_kernel.values())}
     it_bytes = algorithmic_bytes_iter(n_rows, m_cols, nnz, binarize)
-    it_rows = sum(v[0] for k, v in prof_it.items() if "rows_kernel" in k) / args.iters
-    it_cols = sum(v[0] for k, v in prof_it.items() if "cols_partial" in k) / args.iters
+    it_fused = sum(v[0] for k, v in prof_it.items() if "fused_kernel" in k) / max(1, sum(v[1] for k, v in prof_it.items() if "fused_kernel" in k))
     line = {
         "metric": "kmer_sequences_per_sec", "value": world * n / (ms_step * 1e-3), "unit": "sequences/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -323,7 +322,7 @@ def main():
         "wall_ms_per_step": wall_ms_step,
         "extract_sequences_per_sec": world * n / (ext_ms * 1e-3) if ext_ms > 0 else None,
         "proxgrad_iters_per_sec": 1e3 / ms_iter,
-        "proxgrad": {"ms_per_iter": ms_iter, "rows_pass_ms": it_rows, "cols_pass_ms": it_cols,
+        "proxgrad": {"ms_per_iter": ms_iter, "fused_pass_ms": it_fused,
                      "algorithmic_bytes_per_iter": it_bytes, "achieved_gbs": it_bytes / (ms_iter * 1e-3) / 1e9,
                      "frac_of_hbm_peak": it_bytes / (ms_iter * 1e-3) / 1e9 / peak},
         "kernels_ms_per_step": dict(sorted(merged.items(), key=lambda kv: -kv[1])[:14]),

@@ -110,9 +110,12 @@ __global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ 
                                                     double inv_n, double scale, unsigned long long *__restrict__ G,
                                                     double *__restrict__ lossterm, const PgState *st) {
   if (st && st->done == 1) return;
-  __shared__ unsigned long long hot[HOT_COLS];
+  // 64-bit accumulators as two 32-bit words: shared memory has native 32-bit atomic adds only
+  // (a 64-bit add would be a compare-and-swap loop); the carry out of the low word is added to
+  // the high word by the thread whose add wrapped, so the pair is an exact 64-bit sum
+  __shared__ uint32_t hot_lo[HOT_COLS], hot_hi[HOT_COLS];
   const int64_t hot_cols = m < HOT_COLS ? m : HOT_COLS;
-  for (int i = threadIdx.x; i < hot_cols; i += blockDim.x) hot[i] = 0ull;
+  for (int i = threadIdx.x; i < hot_cols; i += blockDim.x) { hot_lo[i] = 0u; hot_hi[i] = 0u; }
   __syncthreads();
   const unsigned lane = lane_id();
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -135,14 +138,20 @@ __global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ 
     for (int64_t p = a + lane; p < b; p += 32) {
       const uint32_t c = col[p];
       const unsigned long long q = (unsigned long long)__double2ll_rn(ws * valf(val, p));
-      if (c < (uint32_t)hot_cols) atomicAdd(&hot[c], q);
-      else atomicAdd(&G[c + 1], q);
+      if (c < (uint32_t)hot_cols) {
+        const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
+        const uint32_t old = atomicAdd(&hot_lo[c], lo);
+        const uint32_t add_hi = hi + ((old + lo) < old ? 1u : 0u);
+        if (add_hi) atomicAdd(&hot_hi[c], add_hi);
+      } else atomicAdd(&G[c + 1], q);
     }
   }
   if (lane == 0 && bias_acc != 0) atomicAdd(&G[0], (unsigned long long)bias_acc);
   __syncthreads();
-  for (int i = threadIdx.x; i < hot_cols; i += blockDim.x)
-    if (hot[i]) atomicAdd(&G[i + 1], hot[i]);
+  for (int i = threadIdx.x; i < hot_cols; i += blockDim.x) {
+    unsigned long long v = ((unsigned long long)hot_hi[i] << 32) | hot_lo[i];
+    if (v) atomicAdd(&G[i + 1], v);
+  }
 }
 
 // pair mode: the weights come from the pair-aware rows kernel; same fixed-point accumulation
