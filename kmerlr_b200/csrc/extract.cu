@@ -24,11 +24,15 @@ namespace kl {
 
 namespace {
 
-constexpr uint32_t SENT = 0xFFFFFFFFu;
-constexpr int KT_MAX = 5;          // levels <= KT_MAX use direct tables
-constexpr int KB_MAX = 8;          // levels KT_MAX < k <= KB_MAX use per-row bitmaps
-constexpr int MAX_N = 13;          // 2*13 code bits + strand + 4 len bits = 31 bits
+constexpr uint32_t SENT = 0xFFFFFFFFu;    // sort key of a position without a valid k-mer (sorts last)
+constexpr uint32_t NOKEY = 0xFFFFFFFEu;   // "no previous key" in front of the sorted array
+constexpr int KT_MAX = 5;          // levels <= KT_MAX use direct count tables
+constexpr int KB_MAX = 8;          // highest level that can use a per-row bitmap
+constexpr int KB_DEFAULT = 7;      // ... level 8 does so only when the rows are too long for the register sort
+constexpr int MAX_N = 13;          // 2*13 code bits + 4 length bits per position
 constexpr int TAB_WORDS = 688;     // (4+16+64+256+1024)/2 = 682 packed u16 pairs, padded
+constexpr int DUP_SMEM = 108;      // repeats of the bitmap levels kept in shared memory (the rest: global list)
+constexpr int OBS_MAX_LEVEL = 8;   // marks of observed classes of levels <= 8 are gathered per block in smem
 
 struct XParams {
   int M, N, op, binarize;
@@ -39,17 +43,17 @@ struct XParams {
   uint32_t level_off[MAX_N + 2];   // dense id of (k, code 0), multiples of 32
   uint32_t bm_off[KB_MAX + 2];     // word offset of level k's bitmap inside the per-warp bitmap area
   uint32_t pf_off[KB_MAX + 2];     // word offset of level k's prefix array (one entry per 4 words)
-  int bm_words, pf_words, dup_cap; // per-warp shared memory areas, in 32-bit words
+  uint32_t cl_off[KT_MAX + 2];     // canonical code list of table level k: offset and length
+  uint32_t cl_cnt[KT_MAX + 2];
+  int bm_words, pf_words, ts_words;// per-warp shared memory areas, in 32-bit words
   int warp_words;                  // total per-warp shared memory, in 32-bit words
-  int64_t stride, n;
+  int obs_words;                   // per-block bitmap of observed classes (levels <= OBS_MAX_LEVEL)
+  int64_t stride, n, ovf_stride;
   const int64_t *len, *blk;
   const uint32_t *bits2;
-  const uint16_t *inv16;
-  uint32_t *st_id, *st_cnt, *rowcnt, *bitmap;
+  const uint16_t *inv16, *canon;
+  uint32_t *st_id, *st_cnt, *rowcnt, *bitmap, *ovf;
 };
-
-// image of code u under the strand operation for the table levels, index tab_off(k) + u
-__constant__ uint16_t c_img[1368];
 
 __device__ __forceinline__ uint32_t swap_pairs(uint32_t y) {
   return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
@@ -93,7 +97,7 @@ __global__ void pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__re
   inv16[w] = (uint16_t)inv;
 }
 
-// ---- bitonic sort of 32*E keys, index = lane*E + r, ascending ----------------------------------
+// ---- bitonic sort of 32*E keys in registers, index = lane*E + r, ascending ----------------------
 __device__ __forceinline__ void ce(uint32_t &a, uint32_t &b) {
   uint32_t lo = min(a, b), hi = max(a, b);
   a = lo; b = hi;
@@ -163,63 +167,130 @@ struct BaseReader {
 };
 
 struct Emitter {
-  uint32_t *sid, *scnt, *bitmap;   // sid / scnt already point at this row's staging slice
+  uint32_t *sid, *scnt;            // this row's staging slices
+  uint32_t *obs, *bitmap;          // observed classes: per-block (shared) and global bitmap
+  uint32_t obs_bits;               // ids below this are marked in obs
   uint32_t cursor;
   int binarize, mark;
-  // ballot-compacted emission; returns the ballot (bit i = lane i emitted)
-  __device__ __forceinline__ unsigned emit(bool flag, uint32_t id, uint32_t cnt) {
+  // mark one class id as observed
+  __device__ __forceinline__ void mark_id(uint32_t id) {
+    if (!mark) return;
+    const uint32_t bit = 1u << (id & 31), w = id >> 5;
+    if (id < obs_bits) { if (!(obs[w] & bit)) atomicOr(obs + w, bit); }
+    else if (!(bitmap[w] & bit)) atomicOr(bitmap + w, bit);
+  }
+  // OR a word of 32 consecutive class ids (a level <= OBS_MAX_LEVEL) into the block's bitmap
+  __device__ __forceinline__ void mark_word(uint32_t word_index, uint32_t bits) {
+    if (mark && (bits & ~obs[word_index])) atomicOr(obs + word_index, bits);
+  }
+  // ballot-compacted emission (coalesced stores)
+  __device__ __forceinline__ void emit(bool flag, uint32_t id, uint32_t cnt) {
     unsigned em = __ballot_sync(0xffffffffu, flag);
     if (flag) {
       uint32_t pos = cursor + __popc(em & lanemask_lt());
       sid[pos] = id;
       if (!binarize) scnt[pos] = cnt;
+      mark_id(id);
     }
     cursor += __popc(em);
-    return em;
-  }
-  // the same for entries that are not aligned with bitmap words (sorted levels)
-  __device__ __forceinline__ void emit_mark(bool flag, uint32_t id, uint32_t cnt) {
-    emit(flag, id, cnt);
-    if (flag && mark) {
-      uint32_t bit = 1u << (id & 31);
-      if (!(bitmap[id >> 5] & bit)) atomicOr(bitmap + (id >> 5), bit);
-    }
-  }
-  // OR a word of 32 consecutive class ids into the global bitmap of observed classes
-  __device__ __forceinline__ void mark_word(uint32_t word_index, uint32_t bits) {
-    if (mark && bits && (bits & ~bitmap[word_index])) atomicOr(bitmap + word_index, bits);
   }
 };
+
+__host__ __device__ constexpr int ext_threads(int E) { return E <= 16 ? 512 : (E == 32 ? 256 : 128); }
+
+// ---- sorted level: the canonical codes of one level, sorted in registers -----------------------------
+// K[r] sits at sorted index lane*E + r.  A run (equal keys) is one class, its length the count; a run
+// is emitted by the lane holding the position right after it.  Ids and counts go through the warp's
+// shared-memory buffer so that the global stores are coalesced.
+template <int E>
+__device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lane, uint32_t *sbuf, Emitter &em,
+                                            uint32_t idbase) {
+  uint32_t prevlast = __shfl_up_sync(0xffffffffu, K[E - 1], 1);
+  if (lane == 0) prevlast = NOKEY;
+  int c = 0, lastb = -1;
+  {
+    uint32_t prev = prevlast;
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      if (K[r] != prev) { c++; lastb = (int)lane * E + r; }
+      prev = K[r];
+    }
+  }
+  if (lane == 0) c -= 1;                     // sorted index 0 opens the first run and closes none
+  int incl = c, mx = lastb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o), z = __shfl_up_sync(0xffffffffu, mx, o);
+    if (lane >= (unsigned)o) { incl += y; mx = max(mx, z); }
+  }
+  const int base = incl - c, total = __shfl_sync(0xffffffffu, incl, 31);
+  int start0 = __shfl_up_sync(0xffffffffu, mx, 1);   // last boundary before this lane's keys
+  if (lane == 0) start0 = 0;
+  // round 1: ids
+  {
+    uint32_t prev = prevlast; int j = base;
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      if (K[r] != prev && !(r == 0 && lane == 0)) { sbuf[j] = idbase + prev; j++; }
+      prev = K[r];
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < total; i += 32) {
+    const uint32_t id = sbuf[i];
+    em.sid[em.cursor + i] = id;
+    em.mark_id(id);
+  }
+  __syncwarp();
+  // round 2: counts = distance to the previous boundary
+  if (!em.binarize) {
+    uint32_t prev = prevlast; int j = base, st = start0;
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      const int gi = (int)lane * E + r;
+      if (K[r] != prev) {
+        if (!(r == 0 && lane == 0)) { sbuf[j] = (uint32_t)(gi - st); j++; }
+        st = gi;
+      }
+      prev = K[r];
+    }
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) em.scnt[em.cursor + i] = sbuf[i];
+    __syncwarp();
+  }
+  em.cursor += (uint32_t)total;
+}
 
 // ---- the extraction kernel: one warp per sequence ------------------------------------------------
 // E = keys per lane of the register sort (0: no sorted levels, sequences of any length)
 template <int E>
-__global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
+__global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParams P) {
   constexpr int EE = E > 0 ? E : 1;
-  constexpr int KEYW = 33 * E;
   extern __shared__ __align__(16) uint32_t smem[];
   const unsigned lane = lane_id();
-  const int warp_in_block = threadIdx.x >> 5;
-  // per-warp areas: [bitmaps][prefix][tables][sort keys][dup count + dups]
-  uint32_t *bm = smem + (size_t)warp_in_block * P.warp_words;
+  const int warp_in_block = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  // block: [observed classes]; per warp: [bitmaps][prefix][count tables | sort buffer][dup count + dups]
+  uint32_t *obs = smem;
+  uint32_t *bm = smem + P.obs_words + (size_t)warp_in_block * P.warp_words;
   uint32_t *pf = bm + P.bm_words;
   uint32_t *tab = pf + P.pf_words;
-  uint32_t *sk = tab + TAB_WORDS;
-  uint32_t *dupn = sk + KEYW;
+  uint32_t *dupn = tab + P.ts_words;
   uint32_t *dups = dupn + 4;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gwarp = (int64_t)blockIdx.x * wpb + warp_in_block, nwarps = (int64_t)gridDim.x * wpb;
+  uint32_t *ovf = P.ovf ? P.ovf + gwarp * P.ovf_stride : nullptr;
   const int N = P.N, M = P.M, op = P.op;
   const bool two = op != 0;
   const uint32_t maskN = (1u << (2 * N)) - 1u;
   const uint32_t maskNb = (1u << N) - 1u;
   const bool has_tab = P.t_lo <= P.t_hi, has_bm = P.b_lo <= P.b_hi, has_sort = E > 0 && P.s_lo <= N;
 
-  // shared memory starts clean; every row leaves it clean again
+  // shared memory starts clean; every row leaves its bitmaps clean again
+  for (int i = threadIdx.x; i < P.obs_words; i += blockDim.x) obs[i] = 0;
   for (int i = lane; i < P.bm_words; i += 32) bm[i] = 0;
   if (lane == 0) dupn[0] = 0;
-  __syncwarp();
+  __syncthreads();
 
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_in_block; row < P.n; row += nwarps) {
+  for (int64_t row = gwarp; row < P.n; row += nwarps) {
     const int L = (int)P.len[row];
     const uint32_t *b2 = P.bits2 + P.blk[row] * 4;
     const uint16_t *iv16 = P.inv16 + P.blk[row] * 4;
@@ -227,16 +298,16 @@ __global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
       for (int i = lane; i < TAB_WORDS; i += 32) tab[i] = 0;
     __syncwarp();
 
-    // ---- key generation: lane handles steps u in [u0, u0+steps) of [0, L+N-1) -------------------
+    // ---- pass over the positions: lane handles steps u in [u0, u0+steps) of [0, L+N-1) -----------
     // after consuming base u the window is [u-N+1, u]: FW = its forward code (the k-mers STARTING
     // at p = u-N+1 are its prefixes), S2 = its image under revcomp / reverse (the images of those
     // k-mers are its SUFFIXES), IV = invalid flags of the window
     const int total_steps = L + N - 1;
     const int steps = (total_steps + 31) / 32;
     const int u0 = (int)lane * steps;
-    uint32_t K[EE];
+    uint32_t FWL[EE];                 // (forward code << 4) | valid length, per position of this lane
 #pragma unroll
-    for (int r = 0; r < EE; r++) K[r] = SENT;
+    for (int r = 0; r < EE; r++) FWL[r] = 0;
     {
       BaseReader rd; rd.init(b2, iv16, L);
       uint32_t FW = 0, S2 = 0, IV = 0xFFFFFFFFu;
@@ -247,10 +318,9 @@ __global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
         else if (op == 3) S2 = (S2 >> 2) | (x << (2 * (N - 1)));
         IV = (IV << 1) | inv;
       };
-      auto produce = [&](uint32_t &kf, uint32_t &k2) {
+      auto produce = [&]() -> uint32_t {
         const uint32_t xw = IV & maskNb;
         const int len_f = N - 32 + __clz(xw);           // valid bases forward from the window start
-        kf = SENT; k2 = SENT;
         if (len_f >= M) {
           // table levels: one count at the deepest table level this suffix reaches
           if (has_tab) {
@@ -271,41 +341,27 @@ __global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
               const uint32_t bit = 1u << (c & 31);
               const uint32_t old = atomicOr(bm + P.bm_off[k] + (c >> 5), bit);
               if ((old & bit) && !P.binarize) {
-                uint32_t at = atomicAdd(dupn, 1u);
-                if ((int)at < P.dup_cap) dups[at] = ((uint32_t)k << 26) | c;
+                const uint32_t at = atomicAdd(dupn, 1u), e = ((uint32_t)k << 26) | c;
+                if (at < (uint32_t)DUP_SMEM) dups[at] = e; else ovf[at - DUP_SMEM] = e;
               }
             }
           }
-          if (has_sort) {
-            uint32_t code = FW & ~((1u << (2 * (N - len_f))) - 1u);
-            kf = (code << 5) | (uint32_t)len_f;
-            if (op == 2) k2 = ((((~FW) & maskN) & ~((1u << (2 * (N - len_f))) - 1u)) << 5) | 16u | (uint32_t)len_f;
-          }
         }
-        if (has_sort && (op == 1 || op == 3)) {
-          const int len_r = xw ? (__ffs(xw) - 1) : N;   // valid bases backward from the window end
-          if (len_r >= M) {
-            uint32_t code = S2 & ~((1u << (2 * (N - len_r))) - 1u);
-            k2 = (code << 5) | 16u | (uint32_t)len_r;
-          }
-        }
+        return (FW << 4) | (uint32_t)len_f;
       };
       for (int idx = u0 - N + 1; idx < u0; idx++) consume(idx);
       if (E > 0) {
 #pragma unroll
         for (int i = 0; i < EE; i++) {
-          bool active = two ? (2 * i + 1 < EE) : true;
-          if (active && i < steps && u0 + i < total_steps) {
+          if (i < steps && u0 + i < total_steps) {
             consume(u0 + i);
-            uint32_t kf, k2; produce(kf, k2);
-            if (two) { if (2 * i + 1 < EE) { K[(2 * i) % EE] = k2; K[(2 * i + 1) % EE] = kf; } }
-            else K[i] = kf;
+            FWL[i] = produce();
           }
         }
       } else {
         for (int i = 0; i < steps && u0 + i < total_steps; i++) {
           consume(u0 + i);
-          uint32_t kf, k2; produce(kf, k2);
+          produce();
         }
       }
     }
@@ -313,7 +369,8 @@ __global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
 
     Emitter em;
     em.sid = P.st_id + row * P.stride; em.scnt = P.st_cnt + (P.binarize ? 0 : row * P.stride);
-    em.bitmap = P.bitmap; em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
+    em.obs = obs; em.bitmap = P.bitmap; em.obs_bits = (uint32_t)P.obs_words * 32u;
+    em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
 
     // ---- table levels ---------------------------------------------------------------------------
     if (has_tab) {
@@ -329,23 +386,26 @@ __global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
         }
         __syncwarp();
       }
+      // walk the classes of every level in code order (canon = the codes u <= image(u))
       for (int k = P.t_lo; k <= P.t_hi; k++) {
-        const uint32_t nk = 1u << (2 * k), toff = tab_off(k);
-        for (uint32_t base = 0; base < nk; base += 32) {
-          uint32_t u = base + lane, cnt = 0;
-          if (u < nk) {
-            uint32_t i1 = toff + u;
+        const uint32_t nc = P.cl_cnt[k], toff = tab_off(k);
+        const uint16_t *cl = P.canon + P.cl_off[k];
+        for (uint32_t base = 0; base < nc; base += 32) {
+          const uint32_t j = base + lane;
+          uint32_t u = 0, cnt = 0;
+          if (j < nc) {
+            u = two ? (uint32_t)__ldg(cl + j) : j;
+            const uint32_t i1 = toff + u;
             cnt = (tab[i1 >> 1] >> (16 * (i1 & 1))) & 0xFFFFu;
             if (two) {
-              uint32_t ru = c_img[i1];
-              if (u > ru) cnt = 0;
-              else if (u < ru) { uint32_t i2 = toff + ru; cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu; }
+              const uint32_t ru = kmer_op(u, k, op);
+              if (ru != u) { const uint32_t i2 = toff + ru; cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu; }
             }
           }
-          unsigned word = em.emit(cnt > 0, P.level_off[k] + u, cnt);
-          if (lane == 0) em.mark_word((P.level_off[k] + base) >> 5, word);
+          em.emit(cnt > 0, P.level_off[k] + u, cnt);
         }
       }
+      __syncwarp();
     }
 
     // ---- bitmap levels: walk the bitmap 128 words at a time (4 consecutive words per lane) ---------
@@ -359,8 +419,10 @@ __global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
           const int wi = it * 128 + (int)lane * 4;
           uint4 w4 = make_uint4(0, 0, 0, 0);
           if (wi < W) w4 = *reinterpret_cast<const uint4 *>(bk + wi);
-          em.mark_word(gword + wi, w4.x); em.mark_word(gword + wi + 1, w4.y);
-          em.mark_word(gword + wi + 2, w4.z); em.mark_word(gword + wi + 3, w4.w);
+          if (w4.x | w4.y | w4.z | w4.w) {
+            em.mark_word(gword + wi, w4.x); em.mark_word(gword + wi + 1, w4.y);
+            em.mark_word(gword + wi + 2, w4.z); em.mark_word(gword + wi + 3, w4.w);
+          }
           const uint32_t c = __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
           uint32_t incl = c;
 #pragma unroll
@@ -389,9 +451,10 @@ __global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
       __threadfence_block();
       // repeats: add one to the count of the class, found by its rank in the bitmap
       if (!P.binarize) {
-        const uint32_t nd = min(dupn[0], (uint32_t)P.dup_cap);
+        const uint32_t nd = dupn[0];
         for (uint32_t i = lane; i < nd; i += 32) {
-          const uint32_t e = dups[i], k = e >> 26, c = e & 0x3FFFFFFu, wi = c >> 5;
+          const uint32_t e = i < (uint32_t)DUP_SMEM ? dups[i] : ovf[i - DUP_SMEM];
+          const uint32_t k = e >> 26, c = e & 0x3FFFFFFu, wi = c >> 5;
           const uint32_t *bk = bm + P.bm_off[k];
           uint32_t slot = pf[P.pf_off[k] + (wi >> 2)] + __popc(bk[wi] & ((1u << (c & 31)) - 1u));
           for (uint32_t j = wi & ~3u; j < wi; j++) slot += __popc(bk[j]);
@@ -404,63 +467,30 @@ __global__ void __launch_bounds__(128) extract_kernel(const XParams P) {
       __syncwarp();
     }
 
-    // ---- sorted levels ---------------------------------------------------------------------------
+    // ---- sorted levels: one register sort of the canonical codes per level ---------------------------
     if (has_sort) {
-      warp_sort<EE>(K, lane);
-      // sorted index s = lane*EE + r lives at sk[s + s/32]: conflict free both ways
-#pragma unroll
-      for (int r = 0; r < EE; r++) { unsigned si = lane * EE + r; sk[si + (si >> 5)] = K[r]; }
-      __syncwarp();
       for (int k = P.s_lo; k <= N; k++) {
-        const int s = 2 * (N - k) + 5;
-        uint32_t carry_f = 0, carry_r = 0, last_key = 0;
-        for (int g = 0; g < EE; g++) {
-          const uint32_t key = sk[g * 33 + lane];
-          uint32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
-          if (lane == 0) kprev = last_key;
-          const uint32_t p = key >> s, pp = kprev >> s;
-          const bool first = (g == 0 && lane == 0);
-          const bool head = first || (p != pp);
-          const unsigned hm = __ballot_sync(0xffffffffu, head);
-          const bool valid = key != SENT && (int)(key & 15u) >= k;
-          const unsigned vf = __ballot_sync(0xffffffffu, valid && !(key & 16u));
-          const unsigned vr = __ballot_sync(0xffffffffu, valid && (key & 16u));
-          // a head closes the run that ended just before it
-          bool flag = false; uint32_t cnt = 0;
-          if (head && !first) {
-            unsigned below = hm & lanemask_lt();
-            unsigned range; uint32_t cf, cr;
-            if (below) {
-              int lower = 31 - __clz(below);
-              range = lanemask_lt() & ~((1u << lower) - 1u);
-              cf = __popc(vf & range); cr = __popc(vr & range);
-            } else {
-              range = lanemask_lt();
-              cf = __popc(vf & range) + carry_f; cr = __popc(vr & range) + carry_r;
-            }
-            if (two) {
-              uint32_t ru = kmer_op(pp, k, op);
-              if (pp > ru) cnt = 0; else if (pp == ru) cnt = cf; else cnt = cf + cr;
-            } else cnt = cf;
-            flag = cnt > 0;
-          }
-          em.emit_mark(flag, P.level_off[k] + pp, cnt);
-          // carry of the run that is still open at the end of this group
-          if (hm) {
-            int hl = 31 - __clz(hm);
-            unsigned range = ~((1u << hl) - 1u);
-            carry_f = __popc(vf & range); carry_r = __popc(vr & range);
-          } else {
-            carry_f += __popc(vf); carry_r += __popc(vr);
-          }
-          last_key = __shfl_sync(0xffffffffu, key, 31);
+        uint32_t K[EE];
+#pragma unroll
+        for (int r = 0; r < EE; r++) {
+          const uint32_t f = FWL[r];
+          uint32_t c = (f >> 4) >> (2 * (N - k));
+          if (two) c = min(c, kmer_op(c, k, op));
+          K[r] = (int)(f & 15u) >= k ? c : SENT;
         }
-        // the last run of the array is the sentinel run (at least 2(N-1) slots are never valid)
+        warp_sort<EE>(K, lane);
+        emit_sorted<EE>(K, lane, tab, em, P.level_off[k]);
       }
-      __syncwarp();
     }
     if (lane == 0) P.rowcnt[row] = em.cursor;
   }
+  // flush the block's observed classes
+  __syncthreads();
+  if (P.mark)
+    for (int i = threadIdx.x; i < P.obs_words; i += blockDim.x) {
+      const uint32_t w = obs[i];
+      if (w && (w & ~P.bitmap[i])) atomicOr(P.bitmap + i, w);
+    }
 }
 
 // ---- bitmap helpers -------------------------------------------------------------------------------
@@ -584,20 +614,54 @@ __global__ void features_rows(const int64_t *__restrict__ rowptr, const uint32_t
 
 template <int E>
 void launch_extract(const XParams &P) {
-  // warps per block: as many as fit the shared memory of one block (the dup list grows with L)
-  int wpb = 4;
-  while (wpb > 1 && (size_t)wpb * P.warp_words * 4 > (size_t)160 * 1024) wpb >>= 1;
-  size_t smem = (size_t)wpb * P.warp_words * sizeof(uint32_t);
-  KL_REQUIRE(smem <= (size_t)220 * 1024, "sequence too long for the shared-memory working set of one warp");
-  KL_CUDA(cudaFuncSetAttribute(extract_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_kernel<E>, 32 * wpb, smem));
-  if (per_sm < 1) per_sm = 1;
-  int64_t blocks = (int64_t)ctx().sm_count * per_sm;
+  // warps per block: the choice that keeps the most warps resident per SM (the block shares one
+  // bitmap of observed classes, every warp brings its own working set)
+  KL_CUDA(cudaFuncSetAttribute(extract_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  int best_wpb = 0, best_per_sm = 0;
+  for (int wpb = ext_threads(E) / 32; wpb >= 1; wpb--) {
+    size_t smem = ((size_t)P.obs_words + (size_t)wpb * P.warp_words) * sizeof(uint32_t);
+    if (smem > (size_t)227 * 1024) continue;
+    int per_sm = 0;
+    KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_kernel<E>, 32 * wpb, smem));
+    if (per_sm * wpb > best_per_sm * best_wpb) { best_wpb = wpb; best_per_sm = per_sm; }
+  }
+  KL_REQUIRE(best_wpb > 0, "sequence too long for the shared-memory working set of one warp");
+  const int wpb = best_wpb;
+  size_t smem = ((size_t)P.obs_words + (size_t)wpb * P.warp_words) * sizeof(uint32_t);
+  int64_t blocks = (int64_t)ctx().sm_count * best_per_sm;
   int64_t need = (P.n + wpb - 1) / wpb;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   KL_LAUNCH((extract_kernel<E>), (unsigned)blocks, 32 * wpb, smem, P);
+}
+
+// codes u <= image(u) of the table levels, level after level, for the three strand operations
+const uint16_t *canon_lists(int op, uint32_t (&off)[KT_MAX + 2], uint32_t (&cnt)[KT_MAX + 2]) {
+  static DevBuf<uint16_t> dev[4];
+  static std::vector<uint32_t> offs[4], cnts[4];
+  if (!dev[op].p) {
+    std::vector<uint16_t> list;
+    offs[op].assign(KT_MAX + 2, 0); cnts[op].assign(KT_MAX + 2, 0);
+    for (int k = 1; k <= KT_MAX; k++) {
+      offs[op][k] = (uint32_t)list.size();
+      for (uint32_t u = 0; u < (1u << (2 * k)); u++) {
+        uint32_t r = 0;
+        for (int i = 0; i < k; i++) {
+          uint32_t d = (u >> (2 * i)) & 3u;               // digit i from the right
+          if (op == 1) r |= (3u - d) << (2 * (k - 1 - i));
+          else if (op == 2) r |= (3u - d) << (2 * i);
+          else r |= d << (2 * (k - 1 - i));
+        }
+        if (op == 0 || u <= r) list.push_back((uint16_t)u);   // op 0: every code is its own class
+      }
+      cnts[op][k] = (uint32_t)list.size() - offs[op][k];
+    }
+    dev[op].alloc(list.size());
+    dev[op].upload(list.data(), list.size());
+    sync_stream();
+  }
+  for (int k = 0; k < KT_MAX + 2; k++) { off[k] = offs[op][k]; cnt[k] = cnts[op][k]; }
+  return dev[op].p;
 }
 
 }  // namespace
@@ -690,8 +754,12 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   P.M = cfg.M; P.N = cfg.N; P.binarize = cfg.binarize != 0;
   P.op = cfg.revcomp ? 1 : (cfg.complement ? 2 : (cfg.reverse ? 3 : 0));
   P.t_lo = cfg.M; P.t_hi = cfg.N < KT_MAX ? cfg.N : KT_MAX;
-  P.b_lo = cfg.M > KT_MAX + 1 ? cfg.M : KT_MAX + 1; P.b_hi = cfg.N < KB_MAX ? cfg.N : KB_MAX;
-  P.s_lo = cfg.M > KB_MAX + 1 ? cfg.M : KB_MAX + 1;
+  // levels above the tables: per-row bitmaps up to level 7, a register sort per level above that;
+  // rows too long for the register sort (more than 64 positions per lane) keep level 8 on a bitmap
+  const int64_t steps = (s.max_len + cfg.N - 1 + 31) / 32;
+  const int kb = steps > 64 ? KB_MAX : KB_DEFAULT;
+  P.b_lo = cfg.M > KT_MAX + 1 ? cfg.M : KT_MAX + 1; P.b_hi = cfg.N < kb ? cfg.N : kb;
+  P.s_lo = cfg.M > kb + 1 ? cfg.M : kb + 1;
   P.n = s.n;
   P.len = s.len.p; P.blk = s.blk.p; P.bits2 = s.bits2.p; P.inv16 = s.inv16.p;
   // dense class ids: every level starts on a multiple of 32 so that bitmap words never straddle levels
@@ -713,49 +781,32 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   P.stride = stride;
   KL_REQUIRE(s.max_len < 65536 || P.t_lo > P.t_hi, "sequences of 65536 bp or more need M > 5 on the GPU path");
   KL_REQUIRE(s.max_len < ((int64_t)1 << 30), "sequence too long");
-  // keys per lane of the register sort (levels above KB_MAX only)
+  // keys per lane of the register sort
   int E = 0;
   if (P.s_lo <= cfg.N) {
-    int64_t steps = (s.max_len + cfg.N - 1 + 31) / 32;
-    int64_t slots = P.op ? 2 * steps : steps;
-    E = 2; while (E < slots && E < 128) E <<= 1;
-    KL_REQUIRE(E <= 64, "sequence too long for the register sort path (k > 8 needs L <= ~1000 bp with an "
-                        "equivalence flag, ~2000 bp without)");
+    E = 2; while (E < steps && E < 128) E <<= 1;
+    KL_REQUIRE(E <= 64, "sequence too long for the register sort path (k > 8 needs L <= ~2000 bp)");
   }
   // per-warp shared memory
-  P.bm_words = 0; P.pf_words = 0; P.dup_cap = 0;
+  P.bm_words = 0; P.pf_words = 0;
   int nbl = 0;
   for (int k = P.b_lo; k <= P.b_hi; k++) {
     P.bm_off[k] = (uint32_t)P.bm_words; P.pf_off[k] = (uint32_t)P.pf_words;
     P.bm_words += 1 << (2 * k - 5); P.pf_words += 1 << (2 * k - 7);
     nbl++;
   }
-  if (nbl && !P.binarize) {
-    int64_t cap = (int64_t)nbl * (s.max_len > 0 ? s.max_len : 1);
-    P.dup_cap = (int)((cap + 3) / 4 * 4);
-  }
-  P.warp_words = P.bm_words + P.pf_words + TAB_WORDS + 33 * E + 4 + P.dup_cap;
+  P.pf_words = (P.pf_words + 3) / 4 * 4;
+  P.ts_words = 32 * E > TAB_WORDS ? 32 * E : TAB_WORDS;
+  P.warp_words = P.bm_words + P.pf_words + P.ts_words + 4 + DUP_SMEM;
   P.warp_words = (P.warp_words + 3) / 4 * 4;
-  // images of the table-level codes under the strand operation
-  if (P.op && P.t_lo <= P.t_hi) {
-    std::vector<uint16_t> img(1368, 0);
-    for (int k = 1; k <= KT_MAX; k++) {
-      uint32_t off = ((1u << (2 * k)) - 4u) / 3u;
-      for (uint32_t u = 0; u < (1u << (2 * k)); u++) {
-        uint32_t r = 0;
-        for (int i = 0; i < k; i++) {
-          uint32_t d = (u >> (2 * i)) & 3u;               // digit i from the right
-          if (P.op == 1) r |= (3u - d) << (2 * (k - 1 - i));
-          else if (P.op == 2) r |= (3u - d) << (2 * i);
-          else r |= d << (2 * (k - 1 - i));
-        }
-        img[off + u] = (uint16_t)r;
-      }
-    }
-    KL_CUDA(cudaMemcpyToSymbolAsync(c_img, img.data(), img.size() * sizeof(uint16_t), 0, cudaMemcpyHostToDevice,
-                                    ctx().stream));
-    sync_stream();
+  // the block's bitmap of observed classes covers the levels up to OBS_MAX_LEVEL
+  {
+    int top = cfg.N < OBS_MAX_LEVEL ? cfg.N : OBS_MAX_LEVEL;
+    P.obs_words = top >= cfg.M ? (int)(P.level_off[top + 1] / 32) : 0;
+    P.obs_words = (P.obs_words + 3) / 4 * 4;
   }
+  // canonical code lists of the table levels
+  if (P.t_lo <= P.t_hi) P.canon = canon_lists(P.op, P.cl_off, P.cl_cnt);
   Trace tr("extract");
   DevBuf<uint32_t> st_id((size_t)(s.n ? s.n * stride : 1));
   DevBuf<uint32_t> st_cnt((size_t)(P.binarize ? 1 : (s.n ? s.n * stride : 1)));
@@ -764,6 +815,13 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   bitmap.zero();
   P.st_id = st_id.p; P.st_cnt = st_cnt.p; P.rowcnt = rowcnt.p; P.bitmap = bitmap.p;
   P.mark = n_frozen == 0;
+  // repeats beyond the shared-memory list of a warp (low-complexity rows): one global list per warp
+  DevBuf<uint32_t> ovf;
+  P.ovf_stride = nbl * (s.max_len > 0 ? s.max_len : 1);
+  if (nbl && !P.binarize && s.n > 0) {
+    ovf.alloc((size_t)ctx().sm_count * 64 * (size_t)P.ovf_stride);
+    P.ovf = ovf.p;
+  }
   tr.mark("alloc staging");
 
   if (s.n > 0) {

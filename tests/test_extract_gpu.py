@@ -79,6 +79,22 @@ def test_ragged_empty_and_invalid(K, oracle):
     assert (d.n, d.m, d.nnz) == (0, 0, 0)
 
 
+def test_low_complexity_repeats(K, oracle):
+    """homopolymers and short tandem repeats: almost every k-mer instance repeats an earlier one (the
+    repeat lists of the bitmap levels overflow their shared-memory part), counts up to L"""
+    rng = np.random.default_rng(11)
+    seqs = ["A" * 600, "AC" * 300, "ACG" * 333, "T" * 2100, "ACGTTGCA" * 250, "G" * 9,
+            "".join(rng.choice(list("AC"), size=800)), "AAAAAAAAC" * 100 + "N" + "GT" * 200]
+    for M, N, flags in [(1, 8, dict(revcomp=True)), (6, 7, dict()), (5, 8, dict(reverse=True)), (1, 8, dict(revcomp=True, binarize=True))]:
+        kc, oc = cfg_pair(K, oracle, M, N, **flags)
+        d = K.compile_test_data(None, kc, None, None, True, flags.get("binarize", False), seqs)
+        same_matrix(d, oracle.extract(oc, seqs))
+    short = [s[:900] for s in seqs]
+    kc, oc = cfg_pair(K, oracle, 7, 10, revcomp=True)
+    d = K.compile_test_data(None, kc, None, None, True, False, short)
+    same_matrix(d, oracle.extract(oc, short))
+
+
 def test_frozen_counter_and_features(K, oracle, fixtures):
     """TestKmers2 property on the nucleotide alphabet + explicit feature lists with pair products
     (kmerLr_data.go:210-229, the shape of kmerLr_test.go:36-66)"""
