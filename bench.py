@@ -307,7 +307,7 @@ def main():
             "what": what, "kernel_ms_per_launch": top_ms_total / top_launches,
             "kernel_share_of_step": per_kernel[top] / sum(per_kernel.values())}
     it_bytes = algorithmic_bytes_iter(n_rows, m_cols, nnz, binarize)
-    it_fused = sum(v[0] for k, v in prof_it.items() if "fused_kernel" in k) / max(1, sum(v[1] for k, v in prof_it.items() if "fused_kernel" in k))
+    it_fused = sum(v[0] for k, v in prof_it.items() if "fused_" in k) / max(1, sum(v[1] for k, v in prof_it.items() if "fused_" in k))
     line = {
         "metric": "kmer_sequences_per_sec", "value": world * n / (ms_step * 1e-3), "unit": "sequences/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,

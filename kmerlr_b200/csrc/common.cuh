@@ -201,6 +201,9 @@ struct Matrix : Object {
   double maxsq = 0.0;
   bool has_vmax = false;
   double vmax = 0.0;
+  // the same two numbers over this rank's rows, when the kernel that wrote the rows computed them
+  bool has_local_stats = false;
+  double local_maxsq = 0.0, local_vmax = 0.0;
 };
 
 // handle registry (abi.cu)

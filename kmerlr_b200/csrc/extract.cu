@@ -541,17 +541,20 @@ __global__ void count_kept(const uint32_t *__restrict__ st_id, const uint32_t *_
   if (lane == 0) kept[row] = tot;
 }
 
+// stats[0] = max_i sum_j v_ij^2, stats[1] = max v_ij over the rows written (exact integers): what the
+// step size (kmerLr_estimator_proximal.go:54-69) and the fixed-point scale of the gradient need
 template <bool FILTER>
 __global__ void compact_rows(const uint32_t *__restrict__ st_id, const uint32_t *__restrict__ st_cnt,
                              const uint32_t *__restrict__ rowcnt, int64_t stride, int64_t n,
                              const uint32_t *__restrict__ bm, const uint32_t *__restrict__ rank,
                              const int64_t *__restrict__ rowptr, uint32_t *__restrict__ col,
-                             uint32_t *__restrict__ val) {
+                             uint32_t *__restrict__ val, unsigned long long *__restrict__ stats) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
   unsigned lane = lane_id();
   uint32_t c = rowcnt[row];
   int64_t outp = rowptr[row];
+  unsigned long long sq = 0; uint32_t vm = 0;
   for (uint32_t j0 = 0; j0 < c; j0 += 32) {
     uint32_t j = j0 + lane;
     bool keep = false; uint32_t id = 0, w = 0;
@@ -564,9 +567,20 @@ __global__ void compact_rows(const uint32_t *__restrict__ st_id, const uint32_t 
     if (keep) {
       int64_t pos = outp + __popc(km & lanemask_lt());
       col[pos] = __ldg(rank + (id >> 5)) + __popc(w & ((1u << (id & 31)) - 1u));
-      if (val) val[pos] = st_cnt[row * stride + j];
+      uint32_t v = 1;
+      if (val) { v = st_cnt[row * stride + j]; val[pos] = v; }
+      sq += (unsigned long long)v * v; vm = max(vm, v);
     }
     outp += __popc(km);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    vm = max(vm, __shfl_xor_sync(0xffffffffu, vm, o));
+  }
+  if (lane == 0) {
+    if (sq > stats[0]) atomicMax(stats, sq);
+    if ((unsigned long long)vm > stats[1]) atomicMax(stats + 1, (unsigned long long)vm);
   }
 }
 
@@ -912,16 +926,22 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   out->col.alloc((size_t)(out->nnz ? out->nnz : 1));
   if (out->vt == VAL_U32) out->val_u32.alloc((size_t)(out->nnz ? out->nnz : 1));
   tr.mark("alloc csr");
+  DevBuf<unsigned long long> stats(2);
+  stats.zero();
   if (s.n > 0) {
     uint32_t *vp = out->vt == VAL_U32 ? out->val_u32.p : nullptr;
     if (n_frozen > 0)
       KL_LAUNCH((compact_rows<true>), wgrid, 128, 0, st_id.p, st_cnt.p, rowcnt.p, stride, s.n, bitmap.p, rank.p,
-                out->rowptr.p, out->col.p, vp);
+                out->rowptr.p, out->col.p, vp, stats.p);
     else
       KL_LAUNCH((compact_rows<false>), wgrid, 128, 0, st_id.p, st_cnt.p, rowcnt.p, stride, s.n, bitmap.p, rank.p,
-                out->rowptr.p, out->col.p, vp);
+                out->rowptr.p, out->col.p, vp, stats.p);
   }
+  unsigned long long hstats[2] = {0, 0};
+  stats.download(hstats, 2);
   sync_stream();
+  out->has_local_stats = true;
+  out->local_maxsq = (double)hstats[0]; out->local_vmax = (double)hstats[1];
   tr.mark("compact");
   if (n_features > 0) return apply_features(*out, features, n_features);
   return out;

@@ -154,6 +154,91 @@ __global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ 
   }
 }
 
+// The fused pass for long rows: ONE BLOCK PER ROW.  All threads of the block work on the same row, and
+// the columns of a row are distinct, so the block's shared-memory accumulators take plain 64-bit
+// read-modify-writes (no atomics: two block barriers per row order the rows); the columns below `cs`
+// live in shared memory, the rest goes to L2 with RED.64.  The first FB_EPT*T entries of the NEXT row
+// are loaded into registers while the current row is processed.
+constexpr int FB_EPT = 4;
+constexpr uint32_t FB_NONE = 0xFFFFFFFFu;
+
+template <typename VT, int T>
+__global__ void __launch_bounds__(T, (T <= 512 ? 2 : 1))
+fused_block_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const VT *__restrict__ val,
+                   int64_t n, int64_t m, const double *__restrict__ theta, const uint8_t *__restrict__ labels,
+                   double cw0, double cw1, double inv_n, double scale, unsigned long long *__restrict__ G,
+                   double *__restrict__ lossterm, const PgState *st, int cs) {
+  if (st && st->done == 1) return;
+  extern __shared__ unsigned long long acc[];
+  __shared__ double red[2][T / 32];
+  __shared__ double wsh[2];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned lane = lane_id();
+  for (int i = tid; i < cs; i += T) acc[i] = 0ull;
+  __syncthreads();
+  long long bias_acc = 0;
+  int par = 0;
+  uint32_t c[FB_EPT], cn[FB_EPT];
+  double v[FB_EPT], vn[FB_EPT];
+  int64_t a = 0, b = 0, an = 0, bn = 0;
+  auto load_chunk = [&](int64_t r, uint32_t (&cc)[FB_EPT], double (&vv)[FB_EPT], int64_t &ra, int64_t &rb) {
+    ra = rowptr[r]; rb = rowptr[r + 1];
+#pragma unroll
+    for (int j = 0; j < FB_EPT; j++) {
+      const int64_t p = ra + (int64_t)j * T + tid;
+      if (p < rb) { cc[j] = col[p]; vv[j] = valf(val, p); } else { cc[j] = FB_NONE; vv[j] = 0.0; }
+    }
+  };
+  int64_t row = blockIdx.x;
+  if (row < n) load_chunk(row, c, v, a, b);
+  for (; row < n; row += gridDim.x) {
+    const int64_t rn = row + gridDim.x;
+    if (rn < n) load_chunk(rn, cn, vn, an, bn);
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < FB_EPT; j++)
+      if (c[j] != FB_NONE) s += v[j] * __ldg(theta + c[j] + 1);
+    for (int64_t p = a + (int64_t)FB_EPT * T + tid; p < b; p += T) s += valf(val, p) * __ldg(theta + col[p] + 1);
+    s = warp_sum_down(s);
+    if (lane == 0) red[par][warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      // Gradient weight (:166-178) and Loss term (:257-263)
+      double z = theta[0];
+#pragma unroll
+      for (int w8 = 0; w8 < T / 32; w8++) z += red[par][w8];
+      const double r = -log_add0(-z);
+      double w;
+      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lossterm[row] = -cw1 * r; }
+      else             { w = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
+      wsh[par] = w * scale;               // scale is a power of two: exact
+      bias_acc += __double2ll_rn(w * scale);
+    }
+    __syncthreads();
+    const double ws = wsh[par];
+#pragma unroll
+    for (int j = 0; j < FB_EPT; j++) {
+      if (c[j] != FB_NONE) {
+        const unsigned long long q = (unsigned long long)__double2ll_rn(ws * v[j]);
+        if (c[j] < (uint32_t)cs) acc[c[j]] += q; else atomicAdd(&G[c[j] + 1], q);
+      }
+    }
+    for (int64_t p = a + (int64_t)FB_EPT * T + tid; p < b; p += T) {
+      const uint32_t cc = col[p];
+      const unsigned long long q = (unsigned long long)__double2ll_rn(ws * valf(val, p));
+      if (cc < (uint32_t)cs) acc[cc] += q; else atomicAdd(&G[cc + 1], q);
+    }
+    par ^= 1;
+#pragma unroll
+    for (int j = 0; j < FB_EPT; j++) { c[j] = cn[j]; v[j] = vn[j]; }
+    a = an; b = bn;
+  }
+  if (tid == 0 && bias_acc != 0) atomicAdd(&G[0], (unsigned long long)bias_acc);
+  __syncthreads();
+  for (int i = tid; i < cs; i += T)
+    if (acc[i]) atomicAdd(&G[i + 1], acc[i]);
+}
+
 // pair mode: the weights come from the pair-aware rows kernel; same fixed-point accumulation
 template <typename VT>
 __global__ void scatter_w(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
@@ -354,17 +439,49 @@ void set_scale(Matrix &M, Work &wk, const double cw[2]) {
 }
 
 // the fused pass: loss terms + fixed-point gradient of the single-feature coefficients (all ranks)
+// which kernel runs the fused pass: rows with hundreds of entries go one block per row
+// (KMERLR_FUSED = warp | b512 | b1024 overrides the choice; for experiments)
+int fused_mode(const Matrix &M) {
+  static int env = -1;
+  if (env < 0) {
+    const char *e = getenv("KMERLR_FUSED");
+    env = 0;
+    if (e && !strcmp(e, "warp")) env = 1; else if (e && !strcmp(e, "b512")) env = 2; else if (e && !strcmp(e, "b1024")) env = 3;
+  }
+  if (env) return env;
+  return (M.n > 0 && M.nnz / M.n >= 384) ? 2 : 1;
+}
+
+template <typename VT, int T>
+void launch_fused_block(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
+  const int per_sm = T <= 512 ? 2 : 1;
+  int64_t cs = ((int64_t)(per_sm == 2 ? 112000 : 224000)) / 8;
+  if (cs > M.m) cs = M.m;
+  const size_t smem = (size_t)cs * sizeof(unsigned long long);
+  KL_CUDA(cudaFuncSetAttribute((fused_block_kernel<VT, T>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = (int64_t)ctx().sm_count * per_sm;
+  if (blocks > M.n) blocks = M.n;
+  KL_LAUNCH((fused_block_kernel<VT, T>), (unsigned)blocks, T, smem, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m,
+            wk.theta.p, M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, (int)cs);
+}
+
+// the fused pass: loss terms + fixed-point gradient of the single-feature coefficients (all ranks)
 template <typename VT>
 void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
   KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
   if (M.n > 0) {
-    int per_sm = 0;
-    KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, 0));
-    if (per_sm < 1) per_sm = 1;
-    int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
-    if (blocks > need) blocks = need;
-    KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
-              M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st);
+    const int mode = fused_mode(M);
+    if (mode == 2) launch_fused_block<VT, 512>(M, wk, cw, st);
+    else if (mode == 3) launch_fused_block<VT, 1024>(M, wk, cw, st);
+    else {
+      int per_sm = 0;
+      KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, 0));
+      if (per_sm < 1) per_sm = 1;
+      int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
+      if (blocks > need) blocks = need;
+      KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
+                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st);
+    }
   }
   if (M.sharded) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
 }

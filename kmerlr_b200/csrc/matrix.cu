@@ -415,20 +415,30 @@ std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nse
 // max_i ||x_i||^2 without the bias (estimate_step_size, kmerLr_estimator_proximal.go:54-69)
 double matrix_maxsq(Matrix &M) {
   if (M.has_maxsq) return M.maxsq;
-  DevBuf<unsigned long long> d(1);
-  d.zero();
-  if (M.n > 0) {
-    unsigned wgrid = (unsigned)((M.n * 32 + 127) / 128);
-    if (M.vt == VAL_U32) KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rowptr.p, M.val_u32.p, M.n, d.p);
-    else if (M.vt == VAL_F64) KL_LAUNCH((row_sqnorm_max<double>), wgrid, 128, 0, M.rowptr.p, M.val_f64.p, M.n, d.p);
-    else KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rowptr.p, (const uint32_t *)nullptr, M.n, d.p);
+  double v = 0.0;
+  if (M.has_local_stats) {
+    v = M.local_maxsq;
+  } else {
+    DevBuf<unsigned long long> d(1);
+    d.zero();
+    if (M.n > 0) {
+      unsigned wgrid = (unsigned)((M.n * 32 + 127) / 128);
+      if (M.vt == VAL_U32) KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rowptr.p, M.val_u32.p, M.n, d.p);
+      else if (M.vt == VAL_F64) KL_LAUNCH((row_sqnorm_max<double>), wgrid, 128, 0, M.rowptr.p, M.val_f64.p, M.n, d.p);
+      else KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rowptr.p, (const uint32_t *)nullptr, M.n, d.p);
+    }
+    unsigned long long bits = 0;
+    d.download(&bits, 1);
+    sync_stream();
+    memcpy(&v, &bits, sizeof(v));
   }
-  if (M.sharded) comm_allreduce_max_f64((double *)d.p, 1);
-  unsigned long long bits = 0;
-  d.download(&bits, 1);
-  sync_stream();
-  double v;
-  memcpy(&v, &bits, sizeof(v));
+  if (M.sharded) {
+    DevBuf<double> t(1);
+    t.upload(&v, 1);
+    comm_allreduce_max_f64(t.p, 1);
+    t.download(&v, 1);
+    sync_stream();
+  }
   M.maxsq = v; M.has_maxsq = true;
   return v;
 }
@@ -436,18 +446,22 @@ double matrix_maxsq(Matrix &M) {
 // max |x_ij| over the stored entries (fixed-point scale of the gradient accumulation)
 double matrix_vmax(Matrix &M) {
   if (M.has_vmax) return M.vmax;
-  DevBuf<unsigned long long> d(1);
-  d.zero();
-  if (M.nnz > 0) {
-    if (M.vt == VAL_U32) KL_LAUNCH((abs_max<uint32_t>), 1024, 256, 0, M.val_u32.p, M.nnz, d.p);
-    else if (M.vt == VAL_F64) KL_LAUNCH((abs_max<double>), 1024, 256, 0, M.val_f64.p, M.nnz, d.p);
+  double v = 0.0;
+  if (M.has_local_stats) {
+    v = M.local_vmax;
+  } else {
+    DevBuf<unsigned long long> d(1);
+    d.zero();
+    if (M.nnz > 0) {
+      if (M.vt == VAL_U32) KL_LAUNCH((abs_max<uint32_t>), 1024, 256, 0, M.val_u32.p, M.nnz, d.p);
+      else if (M.vt == VAL_F64) KL_LAUNCH((abs_max<double>), 1024, 256, 0, M.val_f64.p, M.nnz, d.p);
+    }
+    unsigned long long bits = 0;
+    d.download(&bits, 1);
+    sync_stream();
+    memcpy(&v, &bits, sizeof(v));
+    if (M.vt == VAL_ONE) v = M.nnz > 0 ? 1.0 : 0.0;
   }
-  unsigned long long bits = 0;
-  d.download(&bits, 1);
-  sync_stream();
-  double v;
-  memcpy(&v, &bits, sizeof(v));
-  if (M.vt == VAL_ONE) v = M.nnz > 0 ? 1.0 : 0.0;
   if (M.sharded) {
     DevBuf<double> t(1);
     t.upload(&v, 1);
