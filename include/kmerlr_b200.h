@@ -64,6 +64,10 @@ int         kmerlr_profile(int enable);
 int         kmerlr_profile_read(const char *kernel_substr, double *ms_total, int64_t *launches);
 int         kmerlr_profile_dump(char *buf, int64_t buflen);
 
+/* run-time switches (tests and experiments): "implicit" = 1 (default) lets count matrices that came
+ * straight from kmerlr_extract use the matrix-free logistic pass, 0 forces the CSR kernels */
+int         kmerlr_option(const char *name, int64_t value);
+
 /* ---- sample sharding over the GPUs of one box ------------------------------------ */
 int kmerlr_comm_unique_id(void *id128);                       /* ncclGetUniqueId, 128 bytes       */
 int kmerlr_comm_init(int rank, int world, const void *id128); /* ncclCommInitRank                 */

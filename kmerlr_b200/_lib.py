@@ -17,7 +17,7 @@ SUMMARY = {"": 0, "mean": 1, "product": 2, "min": 3, "max": 4}
 # every symbol include/kmerlr_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "kmerlr_init", "kmerlr_shutdown", "kmerlr_last_error", "kmerlr_version", "kmerlr_last_device_ms",
-    "kmerlr_launch_count", "kmerlr_profile", "kmerlr_profile_read", "kmerlr_profile_dump", "kmerlr_comm_unique_id", "kmerlr_comm_init", "kmerlr_comm_destroy",
+    "kmerlr_launch_count", "kmerlr_option", "kmerlr_profile", "kmerlr_profile_read", "kmerlr_profile_dump", "kmerlr_comm_unique_id", "kmerlr_comm_init", "kmerlr_comm_destroy",
     "kmerlr_sequences_create", "kmerlr_extract_resident", "kmerlr_extract", "kmerlr_matrix_info",
     "kmerlr_matrix_classes", "kmerlr_matrix_rows", "kmerlr_matrix_set_labels", "kmerlr_matrix_from_csr",
     "kmerlr_free", "kmerlr_coeff_dim", "kmerlr_coeff_ind2sub", "kmerlr_coeff_sub2ind", "kmerlr_linear_pdf",
@@ -64,6 +64,7 @@ def lib():
     L.kmerlr_last_error.restype = C.c_char_p
     L.kmerlr_last_device_ms.restype = dbl
     L.kmerlr_launch_count.restype = i64
+    L.kmerlr_option.argtypes = [C.c_char_p, i64]
     L.kmerlr_profile.argtypes = [C.c_int]
     L.kmerlr_profile_read.argtypes = [C.c_char_p, pdbl, pi64]
     L.kmerlr_profile_dump.argtypes = [C.c_char_p, i64]

@@ -36,6 +36,11 @@ def launch_count():
     return lib().kmerlr_launch_count()
 
 
+def option(name, value):
+    """run-time switches of the library (kmerlr_option): "implicit" 0/1"""
+    check(lib().kmerlr_option(name.encode(), int(value)))
+
+
 def profile(enable):
     check(lib().kmerlr_profile(int(enable)))
 

@@ -174,6 +174,14 @@ int kmerlr_profile_dump(char *buf, int64_t buflen) {
   }, false);
 }
 
+int kmerlr_option(const char *name, int64_t value) {
+  return guarded([&] {
+    KL_REQUIRE(name != nullptr, "option: null name");
+    if (!strcmp(name, "implicit")) g_ctx.implicit_ok = value != 0;
+    else fail(KMERLR_ERR_ARG, std::string("unknown option ") + name);
+  }, false);
+}
+
 int kmerlr_init(int device) {
   return guarded([&] {
     if (g_ctx.ready) {
@@ -232,7 +240,7 @@ int kmerlr_extract_resident(const kmerlr_config *cfg, kmerlr_handle sequences, c
   return guarded([&] {
     KL_REQUIRE(cfg && out, "null argument");
     auto s = lookup<SeqSet>(sequences, "sequences");
-    *out = register_object(extract(*cfg, *s, frozen_k, frozen_code, n_frozen, features, n_features, flags));
+    *out = register_object(extract(*cfg, s, frozen_k, frozen_code, n_frozen, features, n_features, flags));
   });
 }
 
@@ -242,7 +250,7 @@ int kmerlr_extract(const kmerlr_config *cfg, const uint8_t *seq, const int64_t *
   return guarded([&] {
     KL_REQUIRE(cfg && out, "null argument");
     auto s = sequences_create(seq, off, n);
-    *out = register_object(extract(*cfg, *s, frozen_k, frozen_code, n_frozen, features, n_features, flags));
+    *out = register_object(extract(*cfg, s, frozen_k, frozen_code, n_frozen, features, n_features, flags));
   });
 }
 

@@ -59,6 +59,7 @@ struct Ctx {
   int64_t launches = 0;
   double last_ms = 0.0;
   bool profiling = false;
+  bool implicit_ok = true;   // kmerlr_option("implicit")
   // communicator (NCCL via dlopen, see comm.cu)
   void *comm = nullptr;
   int rank = 0, world = 1;
@@ -171,6 +172,19 @@ struct SeqSet : Object {
 
 enum ValType : int { VAL_ONE = 0, VAL_U32 = 1, VAL_F64 = 2 };
 
+// What the matrix-free logistic pass needs (logistic.cu): a count matrix that came straight out of the
+// extraction (one column per observed / frozen class, counts not binarized) is a linear function of
+// the k-mer occurrences, so X theta and X^T w can be evaluated from the packed sequences.
+constexpr int IMP_MAX_N = 10;      // forward-code tables of 4^1 + ... + 4^N entries
+struct Implicit {
+  std::shared_ptr<SeqSet> seqs;
+  int M = 0, N = 0, op = 0;
+  uint32_t level_off[16] = {0};    // dense class id of (k, code 0)
+  uint32_t fo[16] = {0};           // offset of level j in the forward-code tables, fo[N+1] = total
+  DevBuf<uint32_t> bitmap, rank;   // class set over dense ids: column = rank[id>>5] + popc(bits below)
+  DevBuf<uint32_t> col_id;         // dense class id of every column
+};
+
 // KmerDataSet in HBM: CSR rows (without the bias column) + labels + classes; a CSC view is built
 // lazily for the pair-feature (co-occurrence) gradient only
 struct Matrix : Object {
@@ -201,6 +215,8 @@ struct Matrix : Object {
   double maxsq = 0.0;
   bool has_vmax = false;
   double vmax = 0.0;
+  // matrix-free view (count matrices produced by extract() without an explicit feature list)
+  std::shared_ptr<Implicit> imp;
   // the same two numbers over this rank's rows, when the kernel that wrote the rows computed them
   bool has_local_stats = false;
   double local_maxsq = 0.0, local_vmax = 0.0;
@@ -225,7 +241,7 @@ void exclusive_scan_u32_to_i64(const uint32_t *in, int64_t *out, int64_t n);    
 void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n);          // out[n] = total
 // extract.cu
 std::shared_ptr<SeqSet> sequences_create(const uint8_t *seq, const int64_t *off, int64_t n);
-std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const int32_t *frozen_k,
+std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs, const int32_t *frozen_k,
                                 const uint64_t *frozen_code, int64_t n_frozen, const int32_t *features,
                                 int64_t n_features, int flags);
 // matrix.cu
@@ -271,6 +287,15 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+}
+__device__ __forceinline__ uint32_t swap_pairs(uint32_t y) {
+  return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+}
+// image of the k-mer code u under the strand operation (1 revcomp, 2 complement, 3 reverse)
+__device__ __forceinline__ uint32_t kmer_op(uint32_t u, int k, int op) {
+  if (op == 1) return swap_pairs(__brev(~u)) >> (32 - 2 * k);
+  if (op == 2) return (~u) & ((1u << (2 * k)) - 1u);
+  return swap_pairs(__brev(u)) >> (32 - 2 * k);
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

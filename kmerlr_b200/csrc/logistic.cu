@@ -154,89 +154,160 @@ __global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ 
   }
 }
 
-// The fused pass for long rows: ONE BLOCK PER ROW.  All threads of the block work on the same row, and
-// the columns of a row are distinct, so the block's shared-memory accumulators take plain 64-bit
-// read-modify-writes (no atomics: two block barriers per row order the rows); the columns below `cs`
-// live in shared memory, the rest goes to L2 with RED.64.  The first FB_EPT*T entries of the NEXT row
-// are loaded into registers while the current row is processed.
-constexpr int FB_EPT = 4;
-constexpr uint32_t FB_NONE = 0xFFFFFFFFu;
+// ---- matrix-free pass (count matrices straight from the extraction, Matrix::imp) --------------------
+// The count of class c in row i is the number of positions p of sequence i whose k-mer belongs to c, so
+//   z_i = theta_0 + sum_p T[len_p][code_p],   T[j][u] = sum_{k=M..j} theta[class of the k-prefix of u]
+//   g_c = sum over the codes u of c and the levels j >= k of F_k, F_k[u] = H_k[u] + sum_x F_{k+1}[4u+x]
+// where (len_p, code_p) = the longest valid k-mer (<= N bases) starting at p and H[len_p][code_p]
+// collects round(w_i S) of every position.  One gather and one RED.64 per POSITION instead of one per
+// stored entry per level, no CSR traffic at all; the integer sums are exact, so the result equals
+// sum_i round(w_i S) count_ic bit for bit in any order.
+struct ImpParams {
+  int M, N, op;
+  uint32_t level_off[16], fo[16];
+};
 
-template <typename VT, int T>
-__global__ void __launch_bounds__(T, (T <= 512 ? 2 : 1))
-fused_block_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const VT *__restrict__ val,
-                   int64_t n, int64_t m, const double *__restrict__ theta, const uint8_t *__restrict__ labels,
-                   double cw0, double cw1, double inv_n, double scale, unsigned long long *__restrict__ G,
-                   double *__restrict__ lossterm, const PgState *st, int cs) {
+__global__ void imp_build_T(const ImpParams P, const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ rank,
+                            const double *__restrict__ theta, double *__restrict__ T, int64_t total,
+                            const PgState *st) {
   if (st && st->done == 1) return;
-  extern __shared__ unsigned long long acc[];
-  __shared__ double red[2][T / 32];
-  __shared__ double wsh[2];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int j = P.M;
+  while (j < P.N && t >= (int64_t)P.fo[j + 1]) j++;
+  const uint32_t u = (uint32_t)(t - P.fo[j]);
+  double s = 0.0;
+  for (int k = P.M; k <= j; k++) {
+    uint32_t c = u >> (2 * (j - k));
+    if (P.op) c = min(c, kmer_op(c, k, P.op));
+    const uint32_t id = P.level_off[k] + c, w = bitmap[id >> 5], bit = 1u << (id & 31);
+    if (w & bit) s += theta[rank[id >> 5] + __popc(w & (bit - 1u)) + 1];
+  }
+  T[t] = s;
+}
+
+// rolling window over the packed bases of one sequence (forward code + invalid mask)
+struct ImpRoller {
+  const uint32_t *b2;
+  const uint16_t *iv;
+  int L, N, M, cw;
+  uint32_t FW, IV, word, ivw, maskN, maskNb;
+  __device__ __forceinline__ void init(const uint32_t *b, const uint16_t *v, int len, int n, int m) {
+    b2 = b; iv = v; L = len; N = n; M = m; cw = -1; FW = 0; IV = 0xFFFFFFFFu; word = 0; ivw = 0;
+    maskN = (1u << (2 * n)) - 1u; maskNb = (1u << n) - 1u;
+  }
+  __device__ __forceinline__ void consume(int idx) {
+    uint32_t x = 0, inv = 1;
+    if ((unsigned)idx < (unsigned)L) {
+      if ((idx >> 4) != cw) { cw = idx >> 4; word = __ldg(b2 + cw); ivw = __ldg(iv + cw); }
+      x = (word >> (2 * (idx & 15))) & 3u; inv = (ivw >> (idx & 15)) & 1u;
+    }
+    FW = ((FW << 2) | x) & maskN;
+    IV = (IV << 1) | inv;
+  }
+  // table index of the longest valid k-mer starting at the first base of the window, or NOIDX
+  __device__ __forceinline__ uint32_t index(const uint32_t *fo) const {
+    const int lf = N - 32 + __clz(IV & maskNb);
+    return lf >= M ? fo[lf] + (FW >> (2 * (N - lf))) : 0xFFFFFFFFu;
+  }
+};
+
+// one warp per sequence; lane = a contiguous stretch of positions.  CACHE > 0: the table index of every
+// position stays in registers between the gather and the scatter (rows of up to 32*CACHE-N+1 bases);
+// CACHE = 0: the window is rolled twice (rows of any length)
+template <int CACHE>
+__global__ void __launch_bounds__(256) imp_pass(const ImpParams P, int64_t n, const int64_t *__restrict__ len,
+                                                const int64_t *__restrict__ blk, const uint32_t *__restrict__ bits2,
+                                                const uint16_t *__restrict__ inv16, const double *__restrict__ T,
+                                                const double *__restrict__ theta, const uint8_t *__restrict__ labels,
+                                                double cw0, double cw1, double inv_n, double scale,
+                                                unsigned long long *__restrict__ H, unsigned long long *__restrict__ G,
+                                                double *__restrict__ lossterm, const PgState *st) {
+  if (st && st->done == 1) return;
+  constexpr int CC = CACHE > 0 ? CACHE : 1;
+  constexpr uint32_t NOIDX = 0xFFFFFFFFu;
   const unsigned lane = lane_id();
-  for (int i = tid; i < cs; i += T) acc[i] = 0ull;
-  __syncthreads();
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int N = P.N;
   long long bias_acc = 0;
-  int par = 0;
-  uint32_t c[FB_EPT], cn[FB_EPT];
-  double v[FB_EPT], vn[FB_EPT];
-  int64_t a = 0, b = 0, an = 0, bn = 0;
-  auto load_chunk = [&](int64_t r, uint32_t (&cc)[FB_EPT], double (&vv)[FB_EPT], int64_t &ra, int64_t &rb) {
-    ra = rowptr[r]; rb = rowptr[r + 1];
-#pragma unroll
-    for (int j = 0; j < FB_EPT; j++) {
-      const int64_t p = ra + (int64_t)j * T + tid;
-      if (p < rb) { cc[j] = col[p]; vv[j] = valf(val, p); } else { cc[j] = FB_NONE; vv[j] = 0.0; }
-    }
-  };
-  int64_t row = blockIdx.x;
-  if (row < n) load_chunk(row, c, v, a, b);
-  for (; row < n; row += gridDim.x) {
-    const int64_t rn = row + gridDim.x;
-    if (rn < n) load_chunk(rn, cn, vn, an, bn);
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
+    const int L = (int)len[row];
+    const uint32_t *b2 = bits2 + blk[row] * 4;
+    const uint16_t *iv = inv16 + blk[row] * 4;
+    // the window after base u is [u-N+1, u]; the k-mers starting at its first base are its prefixes
+    const int total_steps = L + N - 1, steps = (total_steps + 31) / 32, u0 = (int)lane * steps;
+    uint32_t IDX[CC];
     double s = 0.0;
+    {
+      ImpRoller R; R.init(b2, iv, L, N, P.M);
+      for (int idx = u0 - N + 1; idx < u0; idx++) R.consume(idx);
+      if (CACHE > 0) {
 #pragma unroll
-    for (int j = 0; j < FB_EPT; j++)
-      if (c[j] != FB_NONE) s += v[j] * __ldg(theta + c[j] + 1);
-    for (int64_t p = a + (int64_t)FB_EPT * T + tid; p < b; p += T) s += valf(val, p) * __ldg(theta + col[p] + 1);
-    s = warp_sum_down(s);
-    if (lane == 0) red[par][warp] = s;
-    __syncthreads();
-    if (tid == 0) {
-      // Gradient weight (:166-178) and Loss term (:257-263)
-      double z = theta[0];
-#pragma unroll
-      for (int w8 = 0; w8 < T / 32; w8++) z += red[par][w8];
-      const double r = -log_add0(-z);
-      double w;
-      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lossterm[row] = -cw1 * r; }
-      else             { w = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
-      wsh[par] = w * scale;               // scale is a power of two: exact
-      bias_acc += __double2ll_rn(w * scale);
-    }
-    __syncthreads();
-    const double ws = wsh[par];
-#pragma unroll
-    for (int j = 0; j < FB_EPT; j++) {
-      if (c[j] != FB_NONE) {
-        const unsigned long long q = (unsigned long long)__double2ll_rn(ws * v[j]);
-        if (c[j] < (uint32_t)cs) acc[c[j]] += q; else atomicAdd(&G[c[j] + 1], q);
+        for (int i = 0; i < CC; i++) {
+          uint32_t ix = NOIDX;
+          if (i < steps && u0 + i < total_steps) { R.consume(u0 + i); ix = R.index(P.fo); }
+          IDX[i] = ix;
+          if (ix != NOIDX) s += __ldg(T + ix);
+        }
+      } else {
+        for (int i = 0; i < steps && u0 + i < total_steps; i++) {
+          R.consume(u0 + i);
+          const uint32_t ix = R.index(P.fo);
+          if (ix != NOIDX) s += __ldg(T + ix);
+        }
       }
     }
-    for (int64_t p = a + (int64_t)FB_EPT * T + tid; p < b; p += T) {
-      const uint32_t cc = col[p];
-      const unsigned long long q = (unsigned long long)__double2ll_rn(ws * valf(val, p));
-      if (cc < (uint32_t)cs) acc[cc] += q; else atomicAdd(&G[cc + 1], q);
+    s = warp_sum_down(s);
+    double w = 0.0;
+    if (lane == 0) {
+      // Gradient weight (:166-178) and Loss term (:257-263)
+      double z = theta[0] + s, r = -log_add0(-z);
+      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lossterm[row] = -cw1 * r; }
+      else             { w = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
     }
-    par ^= 1;
+    w = __shfl_sync(0xffffffffu, w, 0);
+    const unsigned long long q = (unsigned long long)__double2ll_rn(w * scale);
+    if (lane == 0) bias_acc += (long long)q;
+    if (CACHE > 0) {
 #pragma unroll
-    for (int j = 0; j < FB_EPT; j++) { c[j] = cn[j]; v[j] = vn[j]; }
-    a = an; b = bn;
+      for (int i = 0; i < CC; i++)
+        if (IDX[i] != NOIDX) atomicAdd(H + IDX[i], q);
+    } else {
+      ImpRoller R; R.init(b2, iv, L, N, P.M);
+      for (int idx = u0 - N + 1; idx < u0; idx++) R.consume(idx);
+      for (int i = 0; i < steps && u0 + i < total_steps; i++) {
+        R.consume(u0 + i);
+        const uint32_t ix = R.index(P.fo);
+        if (ix != NOIDX) atomicAdd(H + ix, q);
+      }
+    }
   }
-  if (tid == 0 && bias_acc != 0) atomicAdd(&G[0], (unsigned long long)bias_acc);
-  __syncthreads();
-  for (int i = tid; i < cs; i += T)
-    if (acc[i]) atomicAdd(&G[i + 1], acc[i]);
+  if (lane == 0 && bias_acc != 0) atomicAdd(&G[0], (unsigned long long)bias_acc);
+}
+
+// F_j[u] = H_j[u] + F_{j+1}[4u .. 4u+3], in place, one launch per level from N-1 down to M
+__global__ void imp_fold_level(const ImpParams P, int j, unsigned long long *__restrict__ H, const PgState *st) {
+  if (st && st->done == 1) return;
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= (1u << (2 * j))) return;
+  const unsigned long long *c = H + P.fo[j + 1] + 4ull * u;
+  H[P.fo[j] + u] += c[0] + c[1] + c[2] + c[3];
+}
+
+// G[col + 1] = F_k[code] + F_k[image(code)]
+__global__ void imp_columns(const ImpParams P, const uint32_t *__restrict__ col_id, int64_t m,
+                            const unsigned long long *__restrict__ F, unsigned long long *__restrict__ G,
+                            const PgState *st) {
+  if (st && st->done == 1) return;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const uint32_t id = col_id[j];
+  int k = P.M;
+  while (k < P.N && id >= P.level_off[k + 1]) k++;
+  const uint32_t c = id - P.level_off[k];
+  unsigned long long g = F[P.fo[k] + c];
+  if (P.op) { const uint32_t r = kmer_op(c, k, P.op); if (r != c) g += F[P.fo[k] + r]; }
+  G[j + 1] = g;
 }
 
 // pair mode: the weights come from the pair-aware rows kernel; same fixed-point accumulation
@@ -393,7 +464,8 @@ constexpr int PROX_BLOCKS = 64;
 
 struct Work {
   DevBuf<double> theta, w, lossterm, g, red, scalars, gathered, blockmax;
-  DevBuf<unsigned long long> G;
+  DevBuf<unsigned long long> G, H;     // H: forward-code tables of the matrix-free pass
+  DevBuf<double> T;
   double scale = 1.0, inv_scale = 1.0;
 };
 
@@ -438,31 +510,36 @@ void set_scale(Matrix &M, Work &wk, const double cw[2]) {
   wk.inv_scale = std::ldexp(1.0, -e);
 }
 
-// the fused pass: loss terms + fixed-point gradient of the single-feature coefficients (all ranks)
-// which kernel runs the fused pass: rows with hundreds of entries go one block per row
-// (KMERLR_FUSED = warp | b512 | b1024 overrides the choice; for experiments)
-int fused_mode(const Matrix &M) {
+// kmerlr_option("implicit", 0) or KMERLR_IMPLICIT=0 forces the CSR kernel (tests compare the two)
+bool use_implicit(const Matrix &M) {
   static int env = -1;
-  if (env < 0) {
-    const char *e = getenv("KMERLR_FUSED");
-    env = 0;
-    if (e && !strcmp(e, "warp")) env = 1; else if (e && !strcmp(e, "b512")) env = 2; else if (e && !strcmp(e, "b1024")) env = 3;
-  }
-  if (env) return env;
-  return (M.n > 0 && M.nnz / M.n >= 384) ? 2 : 1;
+  if (env < 0) { const char *e = getenv("KMERLR_IMPLICIT"); env = (e && *e == '0') ? 0 : 1; }
+  return env == 1 && ctx().implicit_ok && M.imp && M.vt == VAL_U32 && M.n > 0;
 }
 
-template <typename VT, int T>
-void launch_fused_block(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
-  const int per_sm = T <= 512 ? 2 : 1;
-  int64_t cs = ((int64_t)(per_sm == 2 ? 112000 : 224000)) / 8;
-  if (cs > M.m) cs = M.m;
-  const size_t smem = (size_t)cs * sizeof(unsigned long long);
-  KL_CUDA(cudaFuncSetAttribute((fused_block_kernel<VT, T>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int64_t blocks = (int64_t)ctx().sm_count * per_sm;
-  if (blocks > M.n) blocks = M.n;
-  KL_LAUNCH((fused_block_kernel<VT, T>), (unsigned)blocks, T, smem, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m,
-            wk.theta.p, M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, (int)cs);
+void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
+  const Implicit &I = *M.imp;
+  const SeqSet &S = *I.seqs;
+  ImpParams P{};
+  P.M = I.M; P.N = I.N; P.op = I.op;
+  for (int k = 0; k < 16; k++) { P.level_off[k] = I.level_off[k]; P.fo[k] = I.fo[k]; }
+  const int64_t total = I.fo[I.N + 1];
+  if (!wk.T.p) { wk.T.alloc((size_t)total); wk.H.alloc((size_t)total); }
+  KL_CUDA(cudaMemsetAsync(wk.H.p, 0, (size_t)total * sizeof(unsigned long long), ctx().stream));
+  KL_LAUNCH(imp_build_T, (unsigned)((total + 255) / 256), 256, 0, P, I.bitmap.p, I.rank.p, wk.theta.p, wk.T.p, total, st);
+  const int64_t steps = (S.max_len + I.N - 1 + 31) / 32;
+  int64_t blocks = (int64_t)ctx().sm_count * 8, need = (M.n + 7) / 8;
+  if (blocks > need) blocks = need;
+  const double inv_n = 1.0 / (double)M.n_global;
+  if (steps <= 16)
+    KL_LAUNCH((imp_pass<16>), (unsigned)blocks, 256, 0, P, M.n, S.len.p, S.blk.p, S.bits2.p, S.inv16.p, wk.T.p, wk.theta.p,
+              M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st);
+  else
+    KL_LAUNCH((imp_pass<0>), (unsigned)blocks, 256, 0, P, M.n, S.len.p, S.blk.p, S.bits2.p, S.inv16.p, wk.T.p, wk.theta.p,
+              M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st);
+  for (int j = I.N - 1; j >= I.M; j--)
+    KL_LAUNCH(imp_fold_level, (unsigned)(((1u << (2 * j)) + 255) / 256), 256, 0, P, j, wk.H.p, st);
+  KL_LAUNCH(imp_columns, (unsigned)((M.m + 255) / 256), 256, 0, P, I.col_id.p, M.m, wk.H.p, wk.G.p, st);
 }
 
 // the fused pass: loss terms + fixed-point gradient of the single-feature coefficients (all ranks)
@@ -470,10 +547,9 @@ template <typename VT>
 void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
   KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
   if (M.n > 0) {
-    const int mode = fused_mode(M);
-    if (mode == 2) launch_fused_block<VT, 512>(M, wk, cw, st);
-    else if (mode == 3) launch_fused_block<VT, 1024>(M, wk, cw, st);
-    else {
+    if (use_implicit(M)) {
+      launch_implicit(M, wk, cw, st);
+    } else {
       int per_sm = 0;
       KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, 0));
       if (per_sm < 1) per_sm = 1;

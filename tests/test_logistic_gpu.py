@@ -44,6 +44,57 @@ def test_linear_logpdf_gradient_loss(K, oracle, fixtures):
         K.logisticRegression(np.zeros(d.m), (1, 1)).LinearPdf(d)
 
 
+@pytest.mark.parametrize("M,N,L,flags", [
+    (1, 8, 500, dict(revcomp=True)), (2, 6, 120, dict()), (3, 7, 333, dict(complement=True)),
+    (4, 9, 64, dict(reverse=True)), (1, 8, 700, dict(revcomp=True)), (6, 10, 200, dict(revcomp=True)),
+])
+def test_matrix_free_pass_equals_csr_pass(K, oracle, M, N, L, flags):
+    """count matrices straight from the extraction take the matrix-free pass (positions instead of stored
+    entries); it must agree with the CSR kernel and the oracle -- ragged rows, invalid bases, frozen subsets"""
+    from kmerlr_b200 import synth
+    buf, off, y = synth.training_set(70, 58, L)
+    buf = buf.copy()
+    buf[off[3] + 10] = ord("N")
+    buf[off[5]:off[5] + min(L, 40)] = ord("n")
+    buf[off[7]:off[8]] = ord("A")                      # a homopolymer row
+    kc, oc = K.NewKmerCounter(M, N, **flags), oracle.make_config(M, N, **flags)
+    d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    ref = oracle.extract(oc, (buf, off))
+    d.SetLabels(y)
+    rng = np.random.default_rng(M * 100 + N)
+    theta = rng.normal(scale=0.02, size=d.m + 1)
+    theta[rng.integers(1, d.m + 1, size=d.m // 3)] = 0.0
+    cw = (0.8, 1.3)
+    lr = K.logisticRegression(theta, cw, 0.0)
+    K.option("implicit", 1)
+    g1, l1 = lr.Gradient(None, d), lr.Loss(d)
+    K.option("implicit", 0)
+    try:
+        g0, l0 = lr.Gradient(None, d), lr.Loss(d)
+    finally:
+        K.option("implicit", 1)
+    og = oracle.gradient(ref, y, theta, cw)
+    close_g(g1, og)
+    close_g(g0, og)
+    assert np.max(np.abs(g1 - g0)) <= 1e-13 * np.max(np.abs(og))
+    assert abs(l1 - l0) <= 1e-13 * abs(l0)
+    # frozen subset of the classes: absent classes contribute nothing
+    k, code = d.Kmers()
+    sub = (k[::2], code[::2])
+    ds = K.compile_test_data(None, kc, sub, None, True, False, (buf, off))
+    ds.SetLabels(y)
+    refs = oracle.extract(oc, (buf, off), frozen=sub)
+    ths = rng.normal(scale=0.02, size=ds.m + 1)
+    close_g(K.logisticRegression(ths, cw).Gradient(None, ds), oracle.gradient(refs, y, ths, cw))
+    # proximal-gradient iterations on the full space follow the oracle's
+    est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=5)
+    est.Theta = np.zeros(d.m + 1)
+    est.ClassWeights = np.array(cw)
+    est.estimate_proximal(d, 1e-3)
+    oth, _, _ = oracle.proxgrad(ref, y, np.zeros(ref.m + 1), cw, lam=1e-3, epsilon=0.0, epsilon_loss=0.0, max_iter=5)
+    assert np.allclose(est.Theta, oth, rtol=1e-9, atol=1e-13)
+
+
 def test_identical_columns_get_identical_gradients(K, oracle, fixtures):
     """what leapfrog tie handling rests on: the column reduction depends on the column only"""
     d, ref, y = build(K, oracle, fixtures, 2, 6, fg="kmerLr_test_co_fg", bg="kmerLr_test_co_bg", revcomp=True, binarize=True)
