@@ -20,6 +20,8 @@
 // bitmap of observed (or frozen) classes, which the kernel marks one 32-bit word at a time.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace kl {
 
 namespace {
@@ -43,27 +45,17 @@ struct XParams {
   uint32_t level_off[MAX_N + 2];   // dense id of (k, code 0), multiples of 32
   uint32_t bm_off[KB_MAX + 2];     // word offset of level k's bitmap inside the per-warp bitmap area
   uint32_t pf_off[KB_MAX + 2];     // word offset of level k's prefix array (one entry per 4 words)
-  uint32_t cl_off[KT_MAX + 2];     // canonical code list of table level k: offset and length
-  uint32_t cl_cnt[KT_MAX + 2];
+  uint32_t tl_cnt;                 // classes of the table levels (flat list tl, in (k, code) order)
   int bm_words, pf_words, ts_words;// per-warp shared memory areas, in 32-bit words
   int warp_words;                  // total per-warp shared memory, in 32-bit words
   int obs_words;                   // per-block bitmap of observed classes (levels <= OBS_MAX_LEVEL)
   int64_t stride, n, ovf_stride;
   const int64_t *len, *blk;
   const uint32_t *bits2;
-  const uint16_t *inv16, *canon;
+  const uint16_t *inv16;
+  const uint2 *tl;                 // x = table index of the code | table index of its image << 16, y = class id
   uint32_t *st_id, *st_cnt, *rowcnt, *bitmap, *ovf;
 };
-
-__device__ __forceinline__ uint32_t swap_pairs(uint32_t y) {
-  return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
-}
-// image of the k-mer code u under the strand operation
-__device__ __forceinline__ uint32_t kmer_op(uint32_t u, int k, int op) {
-  if (op == 1) return swap_pairs(__brev(~u)) >> (32 - 2 * k);   // reverse complement
-  if (op == 2) return (~u) & ((1u << (2 * k)) - 1u);            // complement
-  return swap_pairs(__brev(u)) >> (32 - 2 * k);                 // reverse
-}
 
 __device__ __forceinline__ uint32_t tab_off(int k) {  // sum_{j=1}^{k-1} 4^j
   return ((1u << (2 * k)) - 4u) / 3u;
@@ -205,18 +197,17 @@ __host__ __device__ constexpr int ext_threads(int E) { return E <= 16 ? 512 : (E
 template <int E>
 __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lane, uint32_t *sbuf, Emitter &em,
                                             uint32_t idbase) {
+  using MaskT = typename std::conditional<(E <= 32), uint32_t, unsigned long long>::type;
   uint32_t prevlast = __shfl_up_sync(0xffffffffu, K[E - 1], 1);
   if (lane == 0) prevlast = NOKEY;
-  int c = 0, lastb = -1;
-  {
-    uint32_t prev = prevlast;
+  // bit r of bnd: a run starts at this lane's key r (sorted index lane*E + r)
+  MaskT bnd = (MaskT)(K[0] != prevlast);
 #pragma unroll
-    for (int r = 0; r < E; r++) {
-      if (K[r] != prev) { c++; lastb = (int)lane * E + r; }
-      prev = K[r];
-    }
-  }
-  if (lane == 0) c -= 1;                     // sorted index 0 opens the first run and closes none
+  for (int r = 1; r < E; r++) bnd |= (MaskT)(K[r] != K[r - 1]) << r;
+  // a run is emitted by the position right after it: every boundary but sorted index 0
+  const MaskT cls = lane == 0 ? (bnd & ~(MaskT)1) : bnd;
+  const int c = sizeof(MaskT) == 4 ? __popc((uint32_t)cls) : __popcll(cls);
+  const int lastb = bnd ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bnd) : 63 - __clzll(bnd)) : -1;
   int incl = c, mx = lastb;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -227,12 +218,12 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
   int start0 = __shfl_up_sync(0xffffffffu, mx, 1);   // last boundary before this lane's keys
   if (lane == 0) start0 = 0;
   // round 1: ids
-  {
-    uint32_t prev = prevlast; int j = base;
 #pragma unroll
-    for (int r = 0; r < E; r++) {
-      if (K[r] != prev && !(r == 0 && lane == 0)) { sbuf[j] = idbase + prev; j++; }
-      prev = K[r];
+  for (int r = 0; r < E; r++) {
+    if ((cls >> r) & 1) {
+      const MaskT below = cls & (((MaskT)1 << r) - 1);
+      const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
+      sbuf[j] = idbase + (r == 0 ? prevlast : K[r > 0 ? r - 1 : 0]);
     }
   }
   __syncwarp();
@@ -244,15 +235,15 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
   __syncwarp();
   // round 2: counts = distance to the previous boundary
   if (!em.binarize) {
-    uint32_t prev = prevlast; int j = base, st = start0;
 #pragma unroll
     for (int r = 0; r < E; r++) {
-      const int gi = (int)lane * E + r;
-      if (K[r] != prev) {
-        if (!(r == 0 && lane == 0)) { sbuf[j] = (uint32_t)(gi - st); j++; }
-        st = gi;
+      if ((cls >> r) & 1) {
+        const MaskT below = cls & (((MaskT)1 << r) - 1), bbelow = bnd & (((MaskT)1 << r) - 1);
+        const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
+        const int st = bbelow ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bbelow) : 63 - __clzll(bbelow))
+                              : start0;
+        sbuf[j] = (uint32_t)((int)lane * E + r - st);
       }
-      prev = K[r];
     }
     __syncwarp();
     for (int i = lane; i < total; i += 32) em.scnt[em.cursor + i] = sbuf[i];
@@ -386,24 +377,18 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         }
         __syncwarp();
       }
-      // walk the classes of every level in code order (canon = the codes u <= image(u))
-      for (int k = P.t_lo; k <= P.t_hi; k++) {
-        const uint32_t nc = P.cl_cnt[k], toff = tab_off(k);
-        const uint16_t *cl = P.canon + P.cl_off[k];
-        for (uint32_t base = 0; base < nc; base += 32) {
-          const uint32_t j = base + lane;
-          uint32_t u = 0, cnt = 0;
-          if (j < nc) {
-            u = two ? (uint32_t)__ldg(cl + j) : j;
-            const uint32_t i1 = toff + u;
-            cnt = (tab[i1 >> 1] >> (16 * (i1 & 1))) & 0xFFFFu;
-            if (two) {
-              const uint32_t ru = kmer_op(u, k, op);
-              if (ru != u) { const uint32_t i2 = toff + ru; cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu; }
-            }
-          }
-          em.emit(cnt > 0, P.level_off[k] + u, cnt);
+      // walk the classes of the table levels in (k, code) order: count = code + image
+      for (uint32_t base = 0; base < P.tl_cnt; base += 32) {
+        const uint32_t j = base + lane;
+        uint32_t id = 0, cnt = 0;
+        if (j < P.tl_cnt) {
+          const uint2 e = __ldg(P.tl + j);
+          const uint32_t i1 = e.x & 0xFFFFu, i2 = e.x >> 16;
+          cnt = (tab[i1 >> 1] >> (16 * (i1 & 1))) & 0xFFFFu;
+          if (i2 != i1) cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu;
+          id = e.y;
         }
+        em.emit(cnt > 0, id, cnt);
       }
       __syncwarp();
     }
@@ -430,21 +415,42 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
             uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= (unsigned)o) incl += y;
           }
-          uint32_t pos = em.cursor + incl - c;
-          if (wi < W) pk[wi >> 2] = pos;               // staging slot of this lane's first class
+          const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+          if (wi < W) pk[wi >> 2] = em.cursor + incl - c;   // staging slot of this lane's first class
           const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+          if (tot <= (uint32_t)P.ts_words) {
+            // ids through the warp's shared buffer: coalesced global stores
+            uint32_t pos = incl - c;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            uint32_t w = ws[j];
-            while (w) {
-              int b = __ffs(w) - 1;
-              w &= w - 1;
-              em.sid[pos] = idbase + (uint32_t)(wi + j) * 32u + (uint32_t)b;
-              if (!P.binarize) em.scnt[pos] = 1;
-              pos++;
+            for (int j = 0; j < 4; j++) {
+              uint32_t w = ws[j];
+              const uint32_t id0 = idbase + (uint32_t)(wi + j) * 32u;
+              while (w) {
+                tab[pos++] = id0 + (uint32_t)(__ffs(w) - 1);
+                w &= w - 1;
+              }
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < tot; i += 32) {
+              em.sid[em.cursor + i] = tab[i];
+              if (!P.binarize) em.scnt[em.cursor + i] = 1;
+            }
+            __syncwarp();
+          } else {
+            uint32_t pos = em.cursor + incl - c;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              uint32_t w = ws[j];
+              while (w) {
+                int b = __ffs(w) - 1;
+                w &= w - 1;
+                em.sid[pos] = idbase + (uint32_t)(wi + j) * 32u + (uint32_t)b;
+                if (!P.binarize) em.scnt[pos] = 1;
+                pos++;
+              }
             }
           }
-          em.cursor += __shfl_sync(0xffffffffu, incl, 31);
+          em.cursor += tot;
         }
       }
       __syncwarp();
@@ -555,23 +561,35 @@ __global__ void compact_rows(const uint32_t *__restrict__ st_id, const uint32_t 
   uint32_t c = rowcnt[row];
   int64_t outp = rowptr[row];
   unsigned long long sq = 0; uint32_t vm = 0;
-  for (uint32_t j0 = 0; j0 < c; j0 += 32) {
-    uint32_t j = j0 + lane;
-    bool keep = false; uint32_t id = 0, w = 0;
-    if (j < c) {
-      id = st_id[row * stride + j];
-      w = __ldg(bm + (id >> 5));
-      keep = FILTER ? ((w >> (id & 31)) & 1u) : true;
+  const uint32_t *rid = st_id + row * stride, *rcnt = val ? st_cnt + row * stride : nullptr;
+  // four chunks of 32 entries per iteration: all loads of the iteration are in flight together
+  for (uint32_t j0 = 0; j0 < c; j0 += 128) {
+    uint32_t id[4], v[4], w[4], rk[4];
+    bool in[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t j = j0 + 32 * u + lane;
+      in[u] = j < c;
+      id[u] = in[u] ? rid[j] : 0u;
+      v[u] = (in[u] && rcnt) ? rcnt[j] : 1u;
     }
-    unsigned km = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      int64_t pos = outp + __popc(km & lanemask_lt());
-      col[pos] = __ldg(rank + (id >> 5)) + __popc(w & ((1u << (id & 31)) - 1u));
-      uint32_t v = 1;
-      if (val) { v = st_cnt[row * stride + j]; val[pos] = v; }
-      sq += (unsigned long long)v * v; vm = max(vm, v);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      w[u] = in[u] ? __ldg(bm + (id[u] >> 5)) : 0u;
+      rk[u] = in[u] ? __ldg(rank + (id[u] >> 5)) : 0u;
     }
-    outp += __popc(km);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const bool keep = in[u] && (FILTER ? ((w[u] >> (id[u] & 31)) & 1u) : true);
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int64_t pos = outp + __popc(km & lanemask_lt());
+        col[pos] = rk[u] + __popc(w[u] & ((1u << (id[u] & 31)) - 1u));
+        if (val) val[pos] = v[u];
+        sq += (unsigned long long)v[u] * v[u]; vm = max(vm, v[u]);
+      }
+      outp += __popc(km);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -649,33 +667,38 @@ void launch_extract(const XParams &P) {
   KL_LAUNCH((extract_kernel<E>), (unsigned)blocks, 32 * wpb, smem, P);
 }
 
-// codes u <= image(u) of the table levels, level after level, for the three strand operations
-const uint16_t *canon_lists(int op, uint32_t (&off)[KT_MAX + 2], uint32_t (&cnt)[KT_MAX + 2]) {
-  static DevBuf<uint16_t> dev[4];
-  static std::vector<uint32_t> offs[4], cnts[4];
-  if (!dev[op].p) {
-    std::vector<uint16_t> list;
-    offs[op].assign(KT_MAX + 2, 0); cnts[op].assign(KT_MAX + 2, 0);
-    for (int k = 1; k <= KT_MAX; k++) {
-      offs[op][k] = (uint32_t)list.size();
-      for (uint32_t u = 0; u < (1u << (2 * k)); u++) {
-        uint32_t r = 0;
+// the classes of the table levels [t_lo, t_hi] in (k, code) order: table index of the code, table
+// index of its image under the strand operation (the same index when the code is its own image), id
+const uint2 *table_classes(int op, int t_lo, int t_hi, const uint32_t *level_off, uint32_t *count) {
+  struct Entry { int op, lo, hi; uint32_t off0; DevBuf<uint2> dev; uint32_t cnt; };
+  static std::vector<std::unique_ptr<Entry>> cache;
+  for (auto &e : cache)
+    if (e->op == op && e->lo == t_lo && e->hi == t_hi && e->off0 == level_off[t_lo]) { *count = e->cnt; return e->dev.p; }
+  std::vector<uint2> list;
+  for (int k = t_lo; k <= t_hi; k++) {
+    const uint32_t toff = ((1u << (2 * k)) - 4u) / 3u;
+    for (uint32_t u = 0; u < (1u << (2 * k)); u++) {
+      uint32_t r = u;
+      if (op) {
+        r = 0;
         for (int i = 0; i < k; i++) {
           uint32_t d = (u >> (2 * i)) & 3u;               // digit i from the right
           if (op == 1) r |= (3u - d) << (2 * (k - 1 - i));
           else if (op == 2) r |= (3u - d) << (2 * i);
           else r |= d << (2 * (k - 1 - i));
         }
-        if (op == 0 || u <= r) list.push_back((uint16_t)u);   // op 0: every code is its own class
       }
-      cnts[op][k] = (uint32_t)list.size() - offs[op][k];
+      if (u <= r) list.push_back(make_uint2((toff + u) | ((toff + r) << 16), level_off[k] + u));
     }
-    dev[op].alloc(list.size());
-    dev[op].upload(list.data(), list.size());
-    sync_stream();
   }
-  for (int k = 0; k < KT_MAX + 2; k++) { off[k] = offs[op][k]; cnt[k] = cnts[op][k]; }
-  return dev[op].p;
+  auto e = std::make_unique<Entry>();
+  e->op = op; e->lo = t_lo; e->hi = t_hi; e->off0 = level_off[t_lo]; e->cnt = (uint32_t)list.size();
+  e->dev.alloc(list.size());
+  e->dev.upload(list.data(), list.size());
+  sync_stream();
+  *count = e->cnt;
+  cache.push_back(std::move(e));
+  return cache.back()->dev.p;
 }
 
 }  // namespace
@@ -752,10 +775,11 @@ static std::shared_ptr<Matrix> apply_features(Matrix &cls, const int32_t *featur
   return out;
 }
 
-std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const int32_t *frozen_k,
+std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs, const int32_t *frozen_k,
                                 const uint64_t *frozen_code, int64_t n_frozen, const int32_t *features,
                                 int64_t n_features, int flags) {
   require_ready();
+  const SeqSet &s = *seqs;
   KL_REQUIRE(cfg.alphabet == 0, "only the nucleotide alphabet is implemented on the GPU path (gapped: SURVEY 8f-3)");
   KL_REQUIRE(cfg.M >= 1 && cfg.M <= cfg.N, "need 1 <= M <= N");
   KL_REQUIRE(cfg.N <= MAX_N, "k-mer length above 13 is not supported on the GPU path");
@@ -819,8 +843,8 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
     P.obs_words = top >= cfg.M ? (int)(P.level_off[top + 1] / 32) : 0;
     P.obs_words = (P.obs_words + 3) / 4 * 4;
   }
-  // canonical code lists of the table levels
-  if (P.t_lo <= P.t_hi) P.canon = canon_lists(P.op, P.cl_off, P.cl_cnt);
+  // classes of the table levels
+  if (P.t_lo <= P.t_hi) P.tl = table_classes(P.op, P.t_lo, P.t_hi, P.level_off, &P.tl_cnt);
   Trace tr("extract");
   DevBuf<uint32_t> st_id((size_t)(s.n ? s.n * stride : 1));
   DevBuf<uint32_t> st_cnt((size_t)(P.binarize ? 1 : (s.n ? s.n * stride : 1)));
@@ -891,8 +915,8 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
     out->n_global = nn;
   }
   // class list
+  DevBuf<uint32_t> ids((size_t)(m32 ? m32 : 1));
   {
-    DevBuf<uint32_t> ids((size_t)(m32 ? m32 : 1));
     KL_LAUNCH(enumerate_bits, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, rank.p, nw, ids.p);
     std::vector<uint32_t> hid((size_t)m32);
     ids.download(hid.data(), (size_t)m32);
@@ -944,6 +968,19 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, const SeqSet &s, const
   out->local_maxsq = (double)hstats[0]; out->local_vmax = (double)hstats[1];
   tr.mark("compact");
   if (n_features > 0) return apply_features(*out, features, n_features);
+  // count matrices with one column per class keep what the matrix-free logistic pass needs
+  if (!P.binarize && cfg.N <= IMP_MAX_N && s.n > 0 && m32 > 0) {
+    auto imp = std::make_shared<Implicit>();
+    imp->seqs = seqs; imp->M = cfg.M; imp->N = cfg.N; imp->op = P.op;
+    uint32_t fo = 0;
+    for (int k = cfg.M; k <= cfg.N + 1; k++) {
+      imp->level_off[k] = P.level_off[k];
+      imp->fo[k] = fo;
+      if (k <= cfg.N) fo += 1u << (2 * k);
+    }
+    imp->bitmap = std::move(bitmap); imp->rank = std::move(rank); imp->col_id = std::move(ids);
+    out->imp = imp;
+  }
   return out;
 }
 
