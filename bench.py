@@ -95,6 +95,50 @@ def algorithmic_bytes_iter(n, m, nnz, binarize):
     return nnz * (4 + (0 if binarize else 4)) + (n + 1) * 8 + n + 3 * (m + 1) * 8
 
 
+def canonical_classes(n_classes, M, N, seed=5):
+    """n_classes random revcomp classes (k, min(code, revcomp code)), sorted by (k, code)"""
+    rng = np.random.default_rng(seed)
+    out = set()
+    while len(out) < n_classes:
+        k = int(rng.integers(max(M, 4), N + 1))
+        u = int(rng.integers(0, 4 ** k))
+        r, x = 0, u
+        for _ in range(k):
+            r = (r << 2) | (3 - (x & 3))
+            x >>= 2
+        out.add((k, min(u, r)))
+    cl = sorted(out)
+    return np.array([c[0] for c in cl], dtype=np.int32), np.array([c[1] for c in cl], dtype=np.uint64)
+
+
+def bench_scoring(K, mbp, rank, reps=3):
+    """stage 3 (C5 shape at a bounded size): sliding-window scoring, W = 200, step = 10, of `mbp` Mbp in 24
+    contigs with a 100-feature k = 1..8 revcomp count model; sequences resident in HBM, scores stay in HBM"""
+    from kmerlr_b200 import synth
+    W, step, ncontig = 200, 10, 24
+    clen = int(mbp * 1e6) // ncontig
+    buf = synth.random_bases(clen * ncontig, 3, offset=rank * clen * ncontig)
+    off = np.arange(ncontig + 1, dtype=np.int64) * clen
+    ck, cc = canonical_classes(100, 1, 8)
+    rng = np.random.default_rng(9)
+    theta = rng.normal(scale=0.05, size=(1, len(ck) + 1))
+    model = dict(counter=K.NewKmerCounter(1, 8, revcomp=True), class_k=ck, class_code=cc,
+                 features=[(i, i) for i in range(len(ck))], theta=theta, summary="")
+    g = K.genomicKmerLr([model])
+    seqs = K.Sequences((buf, off))
+    windows = ncontig * ((clen - W + step - 1) // step)
+    ms = []
+    for i in range(reps + 1):
+        g.predict_resident(seqs, W, step)
+        if i > 0:
+            ms.append(K.last_device_ms())
+    seqs.free()
+    t = float(np.mean(ms)) * 1e-3
+    return {"windows_per_sec": windows / t, "bases_per_sec": clen * ncontig / t, "ms": 1e3 * t, "genome_mbp": mbp,
+            "window": W, "step": step, "model_features": int(len(ck)), "algorithmic_bytes_per_window": step / 4 + 8,
+            "achieved_gbs": windows * (step / 4 + 8) / t / 1e9, "model": model, "sample": (buf, off)}
+
+
 def run_reference(args, rank, world):
     """the reference's own CPU algorithm (oracle port: per-sequence hash-map counting, union + sort,
     O(n m) convert_counts walk, serial-over-samples gradient / loss) on the box's host cores"""
@@ -150,6 +194,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=8000, help="sequences per step of the CPU arm")
     ap.add_argument("--iters", type=int, default=20, help="full-space prox-grad iterations timed back to back")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--score-mbp", type=float, default=96.0, help="genome size of the window-scoring leg (0 = skip)")
     ap.add_argument("--short", action="store_true", help="profiling runs only: allow fewer than 3 warm-up steps")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.short:
@@ -260,6 +305,9 @@ def main():
     n_rows, m_cols, nnz = data.n, data.m, data.nnz
     data.free()
 
+    # stage 3: sliding-window scoring on a bounded genome
+    genomic = bench_scoring(K, args.score_mbp, rank) if args.score_mbp > 0 else None
+
     # e2e through host buffers
     e2e_s = []
     for i in range(1 + min(3, args.steps)):
@@ -279,6 +327,11 @@ def main():
     ms_e2e = allmax(1e3 * float(np.mean(e2e_s)))
     ms_iter = allmax(iter_ms / args.iters)
     wall_ms_step = allmax(1e3 * t_wall / args.steps)
+    if genomic is not None:
+        gms = allmax(genomic["ms"])                  # slowest rank
+        for key in ("windows_per_sec", "bases_per_sec", "achieved_gbs"):
+            genomic[key] *= genomic["ms"] / gms
+        genomic["ms"] = gms
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -329,9 +382,27 @@ def main():
         "roofline": roof,
         "clocks": clocks,
     }
+    if genomic is not None:
+        gmodel, gsample = genomic.pop("model"), genomic.pop("sample")
+        if world > 1:
+            genomic["windows_per_sec"] *= world       # every rank scores its own contigs, no collective
+            genomic["bases_per_sec"] *= world
+            genomic["achieved_gbs"] *= world
+        genomic["frac_of_hbm_peak"] = genomic["achieved_gbs"] / world / peak
+        line["genomic_scoring"] = genomic
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
+        if genomic is not None:
+            # the reference's per-window recount on a bounded slice of the same genome
+            nb = 400000
+            omd = dict(cfg=O.make_config(1, 8, revcomp=True), class_k=gmodel["class_k"], class_code=gmodel["class_code"],
+                       features=gmodel["features"], theta=gmodel["theta"], summary="")
+            t0 = time.perf_counter()
+            O.score_windows([omd], (gsample[0][:nb], np.array([0, nb], dtype=np.int64)), 200, 10, threads=cores)
+            dtc = time.perf_counter() - t0
+            genomic["cpu_baseline"] = {"windows_per_sec": ((nb - 200 + 9) // 10) / dtc, "cores": cores, "kind": "port",
+                                       "sample": "%d bp of the same genome, all host threads" % nb}
         s_half = max(1, min(n_fg, args.ref_sample // 2))
         sb, so, sl = synth.training_set(s_half, s_half, L)
         t0 = time.perf_counter()
