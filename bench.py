@@ -181,7 +181,8 @@ def workload_config(args, world):
                         (args.config.upper(), n_fg, n_bg, L, M, N, ", binarized" if binarize else ""),
             "sequences_per_gpu": n_fg + n_bg, "seq_len": L, "k_min": M, "k_max": N,
             "parallelism": "sample-sharded x%d" % world,
-            "l2": "working set per step (CSR + CSC + staging, > 6 GB at C2) exceeds the 126 MB L2"}
+            "l2": "inputs larger than L2: every step streams the staged rows and the CSR matrix (3 GB each at C2), "
+                  "the 126 MB L2 holds none of it across steps"}
 
 
 def main():

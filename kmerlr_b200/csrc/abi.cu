@@ -202,6 +202,8 @@ int kmerlr_init(int device) {
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < CTX_COPY_EVENTS; i++) KL_CUDA(cudaEventCreateWithFlags(&g_ctx.copy_ev[i], cudaEventDisableTiming));
 
     KL_CUDA(cudaEventCreate(&g_ctx.ev0));
     KL_CUDA(cudaEventCreate(&g_ctx.ev1));
@@ -217,6 +219,9 @@ int kmerlr_shutdown(void) {
       arena_release_all();
       comm_destroy();
       cudaEventDestroy(g_ctx.ev0); cudaEventDestroy(g_ctx.ev1);
+      cudaStreamSynchronize(g_ctx.copy_stream);
+      for (int i = 0; i < CTX_COPY_EVENTS; i++) cudaEventDestroy(g_ctx.copy_ev[i]);
+      cudaStreamDestroy(g_ctx.copy_stream);
       cudaStreamDestroy(g_ctx.stream);
       g_ctx = Ctx();
     }
@@ -249,8 +254,7 @@ int kmerlr_extract(const kmerlr_config *cfg, const uint8_t *seq, const int64_t *
                    const int32_t *features, int64_t n_features, int flags, kmerlr_handle *out) {
   return guarded([&] {
     KL_REQUIRE(cfg && out, "null argument");
-    auto s = sequences_create(seq, off, n);
-    *out = register_object(extract(*cfg, s, frozen_k, frozen_code, n_frozen, features, n_features, flags));
+    *out = register_object(extract_host(*cfg, seq, off, n, frozen_k, frozen_code, n_frozen, features, n_features, flags));
   });
 }
 

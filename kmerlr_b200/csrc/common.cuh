@@ -50,11 +50,14 @@ struct Error {
 // ---------------------------------------------------------------------------------------------
 // context: one process drives one GPU
 // ---------------------------------------------------------------------------------------------
+constexpr int CTX_COPY_EVENTS = 5;   // chunks of a pipelined host feed + 1
 struct Ctx {
   bool ready = false;
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;            // host -> device feeds overlapping the kernels
+  cudaEvent_t copy_ev[CTX_COPY_EVENTS] = {nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   double last_ms = 0.0;
@@ -244,6 +247,9 @@ std::shared_ptr<SeqSet> sequences_create(const uint8_t *seq, const int64_t *off,
 std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs, const int32_t *frozen_k,
                                 const uint64_t *frozen_code, int64_t n_frozen, const int32_t *features,
                                 int64_t n_features, int flags);
+std::shared_ptr<Matrix> extract_host(const kmerlr_config &cfg, const uint8_t *seq, const int64_t *off, int64_t n,
+                                     const int32_t *frozen_k, const uint64_t *frozen_code, int64_t n_frozen,
+                                     const int32_t *features, int64_t n_features, int flags);
 // matrix.cu
 std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const int32_t *col,
                                         const double *val, int flags);

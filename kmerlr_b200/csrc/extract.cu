@@ -49,7 +49,7 @@ struct XParams {
   int bm_words, pf_words, ts_words;// per-warp shared memory areas, in 32-bit words
   int warp_words;                  // total per-warp shared memory, in 32-bit words
   int obs_words;                   // per-block bitmap of observed classes (levels <= OBS_MAX_LEVEL)
-  int64_t stride, n, ovf_stride;
+  int64_t stride, n, row0, ovf_stride;   // the launch covers the rows [row0, n)
   const int64_t *len, *blk;
   const uint32_t *bits2;
   const uint16_t *inv16;
@@ -63,10 +63,10 @@ __device__ __forceinline__ uint32_t tab_off(int k) {  // sum_{j=1}^{k-1} 4^j
 
 // ---- pack: ASCII -> 2 bit codes + invalid mask --------------------------------------------------
 __global__ void pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off,
-                            const int64_t *__restrict__ blk, int64_t n, int64_t total_words,
+                            const int64_t *__restrict__ blk, int64_t n, int64_t w0, int64_t w1,
                             uint32_t *__restrict__ bits2, uint16_t *__restrict__ inv16) {
-  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= total_words) return;
+  int64_t w = w0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= w1) return;
   // sequence owning word w: last i with blk[i]*4 <= w
   int64_t lo = 0, hi = n;
   while (hi - lo > 1) {
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
   if (lane == 0) dupn[0] = 0;
   __syncthreads();
 
-  for (int64_t row = gwarp; row < P.n; row += nwarps) {
+  for (int64_t row = P.row0 + gwarp; row < P.n; row += nwarps) {
     const int L = (int)P.len[row];
     const uint32_t *b2 = P.bits2 + P.blk[row] * 4;
     const uint16_t *iv16 = P.inv16 + P.blk[row] * 4;
@@ -661,7 +661,7 @@ void launch_extract(const XParams &P) {
   const int wpb = best_wpb;
   size_t smem = ((size_t)P.obs_words + (size_t)wpb * P.warp_words) * sizeof(uint32_t);
   int64_t blocks = (int64_t)ctx().sm_count * best_per_sm;
-  int64_t need = (P.n + wpb - 1) / wpb;
+  int64_t need = (P.n - P.row0 + wpb - 1) / wpb;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   KL_LAUNCH((extract_kernel<E>), (unsigned)blocks, 32 * wpb, smem, P);
@@ -704,18 +704,22 @@ const uint2 *table_classes(int op, int t_lo, int t_hi, const uint32_t *level_off
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
-std::shared_ptr<SeqSet> sequences_create(const uint8_t *seq, const int64_t *off, int64_t n) {
+// lengths and block offsets on the device, packed arrays allocated but not filled yet; the host copies
+// of the block offsets and of the offsets relative to the first base come back for the feeding loop
+static std::shared_ptr<SeqSet> sequences_alloc(const int64_t *off, int64_t n, std::vector<int64_t> &blk,
+                                               std::vector<int64_t> &rel) {
   require_ready();
   KL_REQUIRE(n >= 0 && off != nullptr, "sequences: bad arguments");
   auto s = std::make_shared<SeqSet>();
   s->n = n;
-  std::vector<int64_t> len((size_t)n), blk((size_t)n + 1);
-  blk[0] = 0;
+  std::vector<int64_t> len((size_t)n);
+  blk.assign((size_t)n + 1, 0); rel.assign((size_t)n + 1, 0);
   for (int64_t i = 0; i < n; i++) {
     len[i] = off[i + 1] - off[i];
     KL_REQUIRE(len[i] >= 0, "sequences: offsets must be non-decreasing");
     if (len[i] > s->max_len) s->max_len = len[i];
     blk[i + 1] = blk[i] + (len[i] + 63) / 64;
+    rel[i + 1] = off[i + 1] - off[0];
   }
   s->total_bases = n ? off[n] - off[0] : 0;
   s->total_blocks = blk[n];
@@ -726,19 +730,49 @@ std::shared_ptr<SeqSet> sequences_create(const uint8_t *seq, const int64_t *off,
   int64_t words = s->total_blocks * 4;
   s->bits2.alloc((size_t)(words ? words : 1));
   s->inv16.alloc((size_t)(words ? words : 1));
-  if (words > 0) {
-    DevBuf<uint8_t> raw((size_t)s->total_bases);
-    DevBuf<int64_t> doff((size_t)n + 1);
-    std::vector<int64_t> rel((size_t)n + 1);
-    for (int64_t i = 0; i <= n; i++) rel[i] = off[i] - off[0];
-    raw.upload(seq + off[0], (size_t)s->total_bases);
-    doff.upload(rel.data(), (size_t)n + 1);
-    KL_LAUNCH(pack_kernel, (unsigned)((words + 255) / 256), 256, 0, raw.p, doff.p, s->blk.p, n, words,
-              s->bits2.p, s->inv16.p);
-    sync_stream();
-  } else {
-    sync_stream();
+  sync_stream();                  // len / blk are stack vectors of this call
+  return s;
+}
+
+// Host sequences feeding an extraction: the ASCII bytes go to the device in chunks on the copy stream
+// while the previous chunk is packed and extracted on the main stream.
+struct HostFeed {
+  const uint8_t *seq = nullptr;   // first base of sequence 0
+  std::vector<int64_t> blk, rel;
+  DevBuf<uint8_t> raw;
+  DevBuf<int64_t> doff;
+  // copy the bases of the sequences [r0, r1) and pack them (main stream waits for the copy)
+  void feed(SeqSet &s, int64_t r0, int64_t r1, int slot) {
+    const int64_t b0 = rel[r0], b1 = rel[r1];
+    if (b1 > b0) {
+      KL_CUDA(cudaMemcpyAsync(raw.p + b0, seq + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, ctx().copy_stream));
+      KL_CUDA(cudaEventRecord(ctx().copy_ev[slot], ctx().copy_stream));
+      KL_CUDA(cudaStreamWaitEvent(ctx().stream, ctx().copy_ev[slot], 0));
+    }
+    const int64_t w0 = blk[r0] * 4, w1 = blk[r1] * 4;
+    if (w1 > w0)
+      KL_LAUNCH(pack_kernel, (unsigned)((w1 - w0 + 255) / 256), 256, 0, raw.p, doff.p, s.blk.p, s.n, w0, w1, s.bits2.p,
+                s.inv16.p);
   }
+};
+
+static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t *off, int64_t n, HostFeed &hf) {
+  auto s = sequences_alloc(off, n, hf.blk, hf.rel);
+  hf.seq = seq + (n ? off[0] : 0);
+  hf.raw.alloc((size_t)(s->total_bases ? s->total_bases : 1));
+  hf.doff.alloc((size_t)n + 1);
+  hf.doff.upload(hf.rel.data(), (size_t)n + 1);
+  // the copy stream must not run ahead of the allocation / earlier work on the main stream
+  KL_CUDA(cudaEventRecord(ctx().copy_ev[CTX_COPY_EVENTS - 1], ctx().stream));
+  KL_CUDA(cudaStreamWaitEvent(ctx().copy_stream, ctx().copy_ev[CTX_COPY_EVENTS - 1], 0));
+  return s;
+}
+
+std::shared_ptr<SeqSet> sequences_create(const uint8_t *seq, const int64_t *off, int64_t n) {
+  HostFeed hf;
+  auto s = sequences_begin(seq, off, n, hf);
+  if (n > 0) hf.feed(*s, 0, n, 0);
+  sync_stream();
   return s;
 }
 
@@ -775,9 +809,9 @@ static std::shared_ptr<Matrix> apply_features(Matrix &cls, const int32_t *featur
   return out;
 }
 
-std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs, const int32_t *frozen_k,
-                                const uint64_t *frozen_code, int64_t n_frozen, const int32_t *features,
-                                int64_t n_features, int flags) {
+static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs,
+                                            const int32_t *frozen_k, const uint64_t *frozen_code, int64_t n_frozen,
+                                            const int32_t *features, int64_t n_features, int flags, HostFeed *feed) {
   require_ready();
   const SeqSet &s = *seqs;
   KL_REQUIRE(cfg.alphabet == 0, "only the nucleotide alphabet is implemented on the GPU path (gapped: SURVEY 8f-3)");
@@ -863,15 +897,23 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet
   tr.mark("alloc staging");
 
   if (s.n > 0) {
-    switch (E) {
-      case 0: launch_extract<0>(P); break;
-      case 2: launch_extract<2>(P); break;
-      case 4: launch_extract<4>(P); break;
-      case 8: launch_extract<8>(P); break;
-      case 16: launch_extract<16>(P); break;
-      case 32: launch_extract<32>(P); break;
-      default: launch_extract<64>(P); break;
+    // host sequences arrive in chunks: copy of chunk c+1 overlaps pack + extraction of chunk c
+    const int nchunks = (feed && s.n >= 4096) ? CTX_COPY_EVENTS - 1 : 1;
+    for (int c = 0; c < nchunks; c++) {
+      const int64_t r0 = s.n * c / nchunks, r1 = s.n * (c + 1) / nchunks;
+      if (feed) feed->feed(*seqs, r0, r1, c);
+      P.row0 = r0; P.n = r1;
+      switch (E) {
+        case 0: launch_extract<0>(P); break;
+        case 2: launch_extract<2>(P); break;
+        case 4: launch_extract<4>(P); break;
+        case 8: launch_extract<8>(P); break;
+        case 16: launch_extract<16>(P); break;
+        case 32: launch_extract<32>(P); break;
+        default: launch_extract<64>(P); break;
+      }
     }
+    P.row0 = 0; P.n = s.n;
   }
   tr.mark("extract_kernel");
   // class set: observed union (all ranks) or the frozen list
@@ -981,6 +1023,23 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet
     imp->bitmap = std::move(bitmap); imp->rank = std::move(rank); imp->col_id = std::move(ids);
     out->imp = imp;
   }
+  return out;
+}
+
+std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs, const int32_t *frozen_k,
+                                const uint64_t *frozen_code, int64_t n_frozen, const int32_t *features,
+                                int64_t n_features, int flags) {
+  return extract_impl(cfg, seqs, frozen_k, frozen_code, n_frozen, features, n_features, flags, nullptr);
+}
+
+// kmerlr_extract: sequences in host memory; upload, packing and extraction are pipelined
+std::shared_ptr<Matrix> extract_host(const kmerlr_config &cfg, const uint8_t *seq, const int64_t *off, int64_t n,
+                                     const int32_t *frozen_k, const uint64_t *frozen_code, int64_t n_frozen,
+                                     const int32_t *features, int64_t n_features, int flags) {
+  HostFeed hf;
+  auto s = sequences_begin(seq, off, n, hf);
+  auto out = extract_impl(cfg, s, frozen_k, frozen_code, n_frozen, features, n_features, flags, &hf);
+  sync_stream();
   return out;
 }
 

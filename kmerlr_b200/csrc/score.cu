@@ -47,6 +47,16 @@ __device__ __forceinline__ int model_lookup(const DevModel &md, int k, uint32_t 
     h = (h + 1) & md.hmask;
   }
 }
+// the same probe sequence over a copy of the table (shared memory)
+__device__ __forceinline__ int table_lookup(const uint32_t *keys, const int32_t *vals, uint32_t hmask, int k, uint32_t code) {
+  uint32_t key = ((uint32_t)k << 26) | code, h = hash_u32(key) & hmask;
+  while (true) {
+    uint32_t kk = keys[h];
+    if (kk == key) return vals[h];
+    if (kk == HEMPTY) return -1;
+    h = (h + 1) & hmask;
+  }
+}
 
 __device__ __forceinline__ double summarize(int summary, const double *x, int n) {
   double r;
@@ -141,8 +151,8 @@ __global__ void __launch_bounds__(256) score_linear(const DevModel *__restrict__
                                                     const uint16_t *__restrict__ inv16,
                                                     const LinearTile *__restrict__ tiles,
                                                     const int64_t *__restrict__ slot_off, int64_t W, int64_t step,
-                                                    int TP, int model_index, double *__restrict__ out) {
-  extern __shared__ double q[];   // nlev x (TP + 1), q[.][0] = 0
+                                                    int TP, int model_index, int hs_smem, double *__restrict__ out) {
+  extern __shared__ double q[];   // nlev x (TP + 1), q[.][0] = 0; then a copy of the class table
   __shared__ double warp_tot[8];
   const DevModel md = models[model_index];
   const LinearTile tl = tiles[blockIdx.x];
@@ -155,6 +165,11 @@ __global__ void __launch_bounds__(256) score_linear(const DevModel *__restrict__
   int lev_slot[16], nlev = 0;
   for (int k = 0; k < 16; k++) lev_slot[k] = ((md.levels >> k) & 1u) ? nlev++ : -1;
   const int stride = TP + 1;
+  // small class tables are probed in shared memory (most probes miss: one LDS instead of one LDG each)
+  uint32_t *skeys = reinterpret_cast<uint32_t *>(q + (size_t)nlev * stride);
+  int32_t *svals = reinterpret_cast<int32_t *>(skeys + hs_smem);
+  for (int i = threadIdx.x; i < hs_smem; i += blockDim.x) { skeys[i] = md.hkeys[i]; svals[i] = md.hvals[i]; }
+  if (hs_smem) __syncthreads();
   // phase 1: t_k(p) for p in [p0, p0 + TP): thread handles a contiguous run of positions
   const int per = (TP + blockDim.x - 1) / blockDim.x;
   {
@@ -187,7 +202,7 @@ __global__ void __launch_bounds__(256) score_linear(const DevModel *__restrict__
             uint32_t fw = FW >> (2 * (N - k)), code = fw;
             if (md.op == 1 || md.op == 3) code = min(fw, RC & ((1u << (2 * k)) - 1u));
             else if (md.op == 2) code = min(fw, (~fw) & ((1u << (2 * k)) - 1u));
-            int ci = model_lookup(md, k, code);
+            int ci = hs_smem ? table_lookup(skeys, svals, md.hmask, k, code) : model_lookup(md, k, code);
             if (ci >= 0) t = __ldg(md.cweight + (int64_t)member * md.n_classes + ci);
           }
           q[sl * stride + 1 + i] = t;
@@ -332,7 +347,9 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
         int nlev = __builtin_popcount(d.levels);
         if (nlev == 0) nlev = 1;
         // tile: as many positions as 200 KB of prefix sums allow, at least W + step
-        int64_t TP = (200 * 1024) / (8 * nlev) - 1;
+        const int64_t hs = (int64_t)d.hmask + 1;
+        const int hs_smem = hs * 8 <= 16 * 1024 ? (int)hs : 0;
+        int64_t TP = (200 * 1024 - hs_smem * 8) / (8 * nlev) - 1;
         if (TP > 16384) TP = 16384;
         KL_REQUIRE(TP >= W + step, "score_windows: window too large for the shared-memory tile");
         // windows per tile: starts a with a + W <= TP  ->  advance = number of such starts * step
@@ -345,10 +362,10 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
         (void)adv;
         DevBuf<LinearTile> dt(tiles.size() ? tiles.size() : 1);
         dt.upload(tiles.data(), tiles.size());
-        size_t smem = (size_t)nlev * (size_t)(TP + 1) * sizeof(double);
+        size_t smem = (size_t)nlev * (size_t)(TP + 1) * sizeof(double) + (size_t)hs_smem * 8;
         KL_CUDA(cudaFuncSetAttribute(score_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KL_LAUNCH(score_linear, (unsigned)tiles.size(), 256, smem, dmodels.p, n_models, 0, mi > 0 ? 1 : 0, s.len.p,
-                  s.blk.p, s.bits2.p, s.inv16.p, dt.p, dslot.p, W, step, (int)TP, mi, outbuf->val_f64.p);
+                  s.blk.p, s.bits2.p, s.inv16.p, dt.p, dslot.p, W, step, (int)TP, mi, hs_smem, outbuf->val_f64.p);
         sync_stream();
       }
     } else {
