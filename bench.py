@@ -311,9 +311,9 @@ def main():
 
     # e2e through host buffers
     e2e_s = []
-    for i in range(1 + min(3, args.steps)):
+    for i in range(2 + max(3, args.steps)):          # 2 untimed (the arena settles), then the timed ones
         dt, m_e2e, _ = step_e2e()
-        if i > 0:
+        if i > 1:
             e2e_s.append(dt)
     barrier()
 

@@ -264,13 +264,14 @@ int kmerlr_matrix_info(kmerlr_handle h, int64_t *n, int64_t *m, int64_t *nnz, in
     if (n) *n = M->n;
     if (m) *m = M->m;
     if (nnz) *nnz = M->nnz;
-    if (n_classes) *n_classes = (int64_t)M->class_k.size();
+    if (n_classes) *n_classes = M->n_classes;
   }, false);
 }
 
 int kmerlr_matrix_classes(kmerlr_handle h, int32_t *k_out, uint64_t *code_out) {
   return guarded([&] {
     auto M = lookup<Matrix>(h, "matrix");
+    matrix_class_list(*M);
     for (size_t j = 0; j < M->class_k.size(); j++) { k_out[j] = M->class_k[j]; code_out[j] = M->class_code[j]; }
   }, false);
 }

@@ -185,8 +185,7 @@ struct Implicit {
   uint32_t level_off[16] = {0};    // dense class id of (k, code 0)
   uint32_t fo[16] = {0};           // offset of level j in the forward-code tables, fo[N+1] = total
   DevBuf<uint32_t> bitmap, rank;   // class set over dense ids: column = rank[id>>5] + popc(bits below)
-  DevBuf<uint32_t> col_id;         // dense class id of every column
-};
+};                                 // (the dense class id of every column is Matrix::class_ids)
 
 // KmerDataSet in HBM: CSR rows (without the bias column) + labels + classes; a CSC view is built
 // lazily for the pair-feature (co-occurrence) gradient only
@@ -207,7 +206,13 @@ struct Matrix : Object {
   bool has_labels = false;
   DevBuf<uint8_t> labels;    // n
   int64_t n_pos = 0, n_neg = 0;   // global counts (all ranks)
-  // class list (host)
+  // class list: dense class ids on the device (extraction), decoded to (k, code) on the host the first
+  // time somebody asks (matrix_class_list)
+  int64_t n_classes = 0;
+  DevBuf<uint32_t> class_ids;
+  int class_M = 0, class_N = 0;
+  uint32_t class_level_off[16] = {0};
+  bool classes_on_host = true;
   std::vector<int32_t> class_k;
   std::vector<uint64_t> class_code;
   // sample sharding
@@ -250,6 +255,7 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet
 std::shared_ptr<Matrix> extract_host(const kmerlr_config &cfg, const uint8_t *seq, const int64_t *off, int64_t n,
                                      const int32_t *frozen_k, const uint64_t *frozen_code, int64_t n_frozen,
                                      const int32_t *features, int64_t n_features, int flags);
+void matrix_class_list(Matrix &M);   // fills class_k / class_code if they are still on the device
 // matrix.cu
 std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const int32_t *col,
                                         const double *val, int flags);

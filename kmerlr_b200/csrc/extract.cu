@@ -783,7 +783,8 @@ static std::shared_ptr<Matrix> apply_features(Matrix &cls, const int32_t *featur
   }
   auto out = std::make_shared<Matrix>();
   out->n = cls.n; out->m = nf; out->vt = cls.vt;
-  out->class_k = cls.class_k; out->class_code = cls.class_code;
+  matrix_class_list(cls);
+  out->class_k = cls.class_k; out->class_code = cls.class_code; out->n_classes = cls.n_classes;
   out->sharded = cls.sharded; out->n_global = cls.n_global;
   DevBuf<int32_t> dfeat((size_t)(2 * nf));
   dfeat.upload(features, (size_t)(2 * nf));
@@ -884,7 +885,22 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   DevBuf<uint32_t> st_cnt((size_t)(P.binarize ? 1 : (s.n ? s.n * stride : 1)));
   DevBuf<uint32_t> rowcnt((size_t)(s.n ? s.n : 1));
   DevBuf<uint32_t> bitmap((size_t)nw);
-  bitmap.zero();
+  std::vector<uint32_t> frozen_bits;       // host image of the frozen class set (alive until the next sync)
+  if (n_frozen > 0) {
+    frozen_bits.assign((size_t)nw, 0u);
+    uint64_t prev = 0;
+    for (int64_t j = 0; j < n_frozen; j++) {
+      int k = frozen_k[j];
+      KL_REQUIRE(k >= cfg.M && k <= cfg.N && frozen_code[j] < (1ull << (2 * k)), "frozen class outside [M,N]");
+      uint64_t id = (uint64_t)P.level_off[k] + frozen_code[j];
+      KL_REQUIRE(j == 0 || id > prev, "frozen class list must be sorted by (k, code) without duplicates");
+      prev = id;
+      frozen_bits[id >> 5] |= 1u << (id & 31);
+    }
+    bitmap.upload(frozen_bits.data(), (size_t)nw);
+  } else {
+    bitmap.zero();
+  }
   P.st_id = st_id.p; P.st_cnt = st_cnt.p; P.rowcnt = rowcnt.p; P.bitmap = bitmap.p;
   P.mark = n_frozen == 0;
   // repeats beyond the shared-memory list of a warp (low-complexity rows): one global list per warp
@@ -916,62 +932,20 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
     P.row0 = 0; P.n = s.n;
   }
   tr.mark("extract_kernel");
-  // class set: observed union (all ranks) or the frozen list
-  if (n_frozen > 0) {
-    std::vector<uint32_t> hb((size_t)nw, 0u);
-    uint64_t prev = 0;
-    for (int64_t j = 0; j < n_frozen; j++) {
-      int k = frozen_k[j];
-      KL_REQUIRE(k >= cfg.M && k <= cfg.N && frozen_code[j] < (1ull << (2 * k)), "frozen class outside [M,N]");
-      uint64_t id = (uint64_t)P.level_off[k] + frozen_code[j];
-      KL_REQUIRE(j == 0 || id > prev, "frozen class list must be sorted by (k, code) without duplicates");
-      prev = id;
-      hb[id >> 5] |= 1u << (id & 31);
-    }
-    bitmap.upload(hb.data(), (size_t)nw);
-    sync_stream();
-  } else if (sharded) {
+  // class set: observed union (all ranks; the frozen list was uploaded before the kernel)
+  if (n_frozen == 0 && sharded) {
     DevBuf<uint8_t> bytes((size_t)nbits);
     KL_LAUNCH(bitmap_to_bytes, (unsigned)((nbits + 255) / 256), 256, 0, bitmap.p, nbits, bytes.p);
     comm_allreduce_max_u8(bytes.p, nbits);
     KL_LAUNCH(bytes_to_bitmap, (unsigned)((nw + 255) / 256), 256, 0, bytes.p, nbits, bitmap.p, nw);
-    sync_stream();
   }
   DevBuf<uint32_t> pc((size_t)nw), rank((size_t)nw + 1);
   KL_LAUNCH(popc_words, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, nw, pc.p);
   exclusive_scan_u32(pc.p, rank.p, nw);
-  uint32_t m32 = 0;
-  KL_CUDA(cudaMemcpyAsync(&m32, rank.p + nw, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
-  sync_stream();
-
   auto out = std::make_shared<Matrix>();
-  out->n = s.n; out->m = (int64_t)m32; out->vt = P.binarize ? VAL_ONE : VAL_U32;
+  out->n = s.n; out->vt = P.binarize ? VAL_ONE : VAL_U32;
   out->sharded = sharded; out->n_global = s.n;
-  if (sharded) {
-    DevBuf<int64_t> tmp(1);
-    int64_t nn = s.n;
-    tmp.upload(&nn, 1);
-    comm_allreduce_sum_i64(tmp.p, 1);
-    tmp.download(&nn, 1);
-    sync_stream();
-    out->n_global = nn;
-  }
-  // class list
-  DevBuf<uint32_t> ids((size_t)(m32 ? m32 : 1));
-  {
-    KL_LAUNCH(enumerate_bits, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, rank.p, nw, ids.p);
-    std::vector<uint32_t> hid((size_t)m32);
-    ids.download(hid.data(), (size_t)m32);
-    sync_stream();
-    out->class_k.resize((size_t)m32); out->class_code.resize((size_t)m32);
-    int k = cfg.M;
-    for (size_t j = 0; j < (size_t)m32; j++) {
-      while (k < cfg.N && hid[j] >= P.level_off[k + 1]) k++;
-      out->class_k[j] = k; out->class_code[j] = hid[j] - P.level_off[k];
-    }
-  }
-  tr.mark("ranks + class list");
-  // final CSR
+  // row pointers of the final CSR
   out->rowptr.alloc((size_t)s.n + 1);
   DevBuf<uint32_t> kept;
   const uint32_t *cnt_final = rowcnt.p;
@@ -983,15 +957,32 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
       cnt_final = kept.p;
     }
     exclusive_scan_u32_to_i64(cnt_final, out->rowptr.p, s.n);
-    KL_CUDA(cudaMemcpyAsync(&out->nnz, out->rowptr.p + s.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
-    sync_stream();
   } else {
-    out->rowptr.zero(); out->nnz = 0;
+    out->rowptr.zero();
   }
-  tr.mark("rowptr scan");
+  // one round trip for the three sizes: classes, stored entries, global number of rows
+  DevBuf<int64_t> nglob(1);
+  int64_t nn = s.n;
+  if (sharded) {
+    nglob.upload(&nn, 1);
+    comm_allreduce_sum_i64(nglob.p, 1);
+    nglob.download(&nn, 1);
+  }
+  uint32_t m32 = 0;
+  KL_CUDA(cudaMemcpyAsync(&m32, rank.p + nw, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
+  KL_CUDA(cudaMemcpyAsync(&out->nnz, out->rowptr.p + s.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
+  sync_stream();
+  out->m = (int64_t)m32; out->n_global = nn;
+  tr.mark("ranks + rowptr");
+  // class list: dense ids stay on the device, (k, code) pairs are decoded on demand
+  out->n_classes = (int64_t)m32;
+  out->class_ids.alloc((size_t)(m32 ? m32 : 1));
+  KL_LAUNCH(enumerate_bits, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, rank.p, nw, out->class_ids.p);
+  out->class_M = cfg.M; out->class_N = cfg.N; out->classes_on_host = false;
+  for (int k = cfg.M; k <= cfg.N + 1; k++) out->class_level_off[k] = P.level_off[k];
+  // final CSR
   out->col.alloc((size_t)(out->nnz ? out->nnz : 1));
   if (out->vt == VAL_U32) out->val_u32.alloc((size_t)(out->nnz ? out->nnz : 1));
-  tr.mark("alloc csr");
   DevBuf<unsigned long long> stats(2);
   stats.zero();
   if (s.n > 0) {
@@ -1020,10 +1011,24 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
       imp->fo[k] = fo;
       if (k <= cfg.N) fo += 1u << (2 * k);
     }
-    imp->bitmap = std::move(bitmap); imp->rank = std::move(rank); imp->col_id = std::move(ids);
+    imp->bitmap = std::move(bitmap); imp->rank = std::move(rank);
     out->imp = imp;
   }
   return out;
+}
+
+void matrix_class_list(Matrix &M) {
+  if (M.classes_on_host) return;
+  std::vector<uint32_t> hid((size_t)M.n_classes);
+  M.class_ids.download(hid.data(), (size_t)M.n_classes);
+  sync_stream();
+  M.class_k.resize((size_t)M.n_classes); M.class_code.resize((size_t)M.n_classes);
+  int k = M.class_M;
+  for (size_t j = 0; j < hid.size(); j++) {
+    while (k < M.class_N && hid[j] >= M.class_level_off[k + 1]) k++;
+    M.class_k[j] = k; M.class_code[j] = hid[j] - M.class_level_off[k];
+  }
+  M.classes_on_host = true;
 }
 
 std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs, const int32_t *frozen_k,

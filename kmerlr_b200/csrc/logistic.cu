@@ -539,7 +539,7 @@ void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st)
               M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st);
   for (int j = I.N - 1; j >= I.M; j--)
     KL_LAUNCH(imp_fold_level, (unsigned)(((1u << (2 * j)) + 255) / 256), 256, 0, P, j, wk.H.p, st);
-  KL_LAUNCH(imp_columns, (unsigned)((M.m + 255) / 256), 256, 0, P, I.col_id.p, M.m, wk.H.p, wk.G.p, st);
+  KL_LAUNCH(imp_columns, (unsigned)((M.m + 255) / 256), 256, 0, P, M.class_ids.p, M.m, wk.H.p, wk.G.p, st);
 }
 
 // the fused pass: loss terms + fixed-point gradient of the single-feature coefficients (all ranks)
