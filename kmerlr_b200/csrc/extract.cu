@@ -8,16 +8,19 @@
 // the strand operation (revcomp / complement / reverse) over its stretch of positions, so the
 // canonical code min(u, op(u)) of the k-mer starting at a position costs a shift and a min.  Levels:
 //   * k <= 5   "table levels": forward counts of the deepest table level in a per-warp shared
-//              memory table (one atomic per position), shallower levels are sums of 4 children;
-//   * k = 6..8 "bitmap levels": one bit per canonical code in a per-warp shared memory bitmap
+//              memory table (one atomic per position), shallower levels are sums of 4 children; the
+//              classes are walked through a precomputed list (code, image, id);
+//   * k = 6, 7 "bitmap levels": one bit per canonical code in a per-warp shared memory bitmap
 //              (4^k bits), set with atomicOr; the rare repeats go to a small list and are added to
-//              the counts afterwards.  Walking the bitmap emits the row in code order;
-//   * k >= 9   "sorted levels" (two strand suffix sort): ONE bitonic sort of the 2L suffix keys
-//              (N-prefix of every suffix of S and of op(S)) in registers -- in-register
-//              compare-exchanges below distance E, warp shuffles above; the classes of level k are
-//              the distinct k-prefixes of the sorted keys, found with warp ballots.
+//              the counts afterwards.  Walking the bitmap emits the row in code order.  Level 8 is a
+//              bitmap level too when the rows are too long for the register sort;
+//   * k >= 8   "sorted levels": per level ONE bitonic sort of the canonical codes in registers --
+//              in-register compare-exchanges below distance E, warp shuffles above; a run of equal
+//              keys is a class, its length the count.
 // Rows leave the kernel sorted by (k, code) = by final column index; columns are ranks in the
-// bitmap of observed (or frozen) classes, which the kernel marks one 32-bit word at a time.
+// bitmap of observed (or frozen) classes; observed classes are gathered per block in shared memory.
+// Host sequences (kmerlr_extract) arrive in chunks on a copy stream while earlier chunks are
+// packed and extracted.
 #include "common.cuh"
 
 #include <type_traits>
