@@ -356,8 +356,15 @@ def main():
         what = "one prox-grad pass"
     ach = abytes / (top_ms_total / top_launches * 1e-3) / 1e9
     ext_ms = sum(v for k, v in per_kernel.items() if "extract_kernel" in k)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.config == "c2":
+            traffic = tj.get(top.split("<")[0].strip("()"), {}).get("bytes")
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": top.split("<")[0].strip("()"), "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
+            "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
             "what": what, "kernel_ms_per_launch": top_ms_total / top_launches,
             "kernel_share_of_step": per_kernel[top] / sum(per_kernel.values())}
     it_bytes = algorithmic_bytes_iter(n_rows, m_cols, nnz, binarize)
