@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ 
                                                     const double *__restrict__ theta,
                                                     const uint8_t *__restrict__ labels, double cw0, double cw1,
                                                     double inv_n, double scale, unsigned long long *__restrict__ G,
-                                                    double *__restrict__ lossterm, const PgState *st) {
+                                                    double *__restrict__ lossterm, const PgState *st, int scatter) {
   if (st && st->done == 1) return;
   // 64-bit accumulators as two 32-bit words: shared memory has native 32-bit atomic adds only
   // (a 64-bit add would be a compare-and-swap loop); the carry out of the low word is added to
@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ 
       else             { w = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
       bias_acc += __double2ll_rn(w * scale);
     }
+    if (!scatter) continue;               // loss-only pass (the hook after the last iteration)
     w = __shfl_sync(0xffffffffu, w, 0);
     const double ws = w * scale;          // scale is a power of two: exact
     for (int64_t p = a + lane; p < b; p += 32) {
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) imp_pass(const ImpParams P, int64_t n, co
                                                 const double *__restrict__ theta, const uint8_t *__restrict__ labels,
                                                 double cw0, double cw1, double inv_n, double scale,
                                                 unsigned long long *__restrict__ H, unsigned long long *__restrict__ G,
-                                                double *__restrict__ lossterm, const PgState *st) {
+                                                double *__restrict__ lossterm, const PgState *st, int scatter) {
   if (st && st->done == 1) return;
   constexpr int CC = CACHE > 0 ? CACHE : 1;
   constexpr uint32_t NOIDX = 0xFFFFFFFFu;
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(256) imp_pass(const ImpParams P, int64_t n, co
       if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lossterm[row] = -cw1 * r; }
       else             { w = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
     }
+    if (!scatter) continue;               // loss-only pass (the hook after the last iteration)
     w = __shfl_sync(0xffffffffu, w, 0);
     const unsigned long long q = (unsigned long long)__double2ll_rn(w * scale);
     if (lane == 0) bias_acc += (long long)q;
@@ -517,7 +519,7 @@ bool use_implicit(const Matrix &M) {
   return env == 1 && ctx().implicit_ok && M.imp && M.vt == VAL_U32 && M.n > 0;
 }
 
-void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
+void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st, int scatter) {
   const Implicit &I = *M.imp;
   const SeqSet &S = *I.seqs;
   ImpParams P{};
@@ -525,7 +527,7 @@ void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st)
   for (int k = 0; k < 16; k++) { P.level_off[k] = I.level_off[k]; P.fo[k] = I.fo[k]; }
   const int64_t total = I.fo[I.N + 1];
   if (!wk.T.p) { wk.T.alloc((size_t)total); wk.H.alloc((size_t)total); }
-  KL_CUDA(cudaMemsetAsync(wk.H.p, 0, (size_t)total * sizeof(unsigned long long), ctx().stream));
+  if (scatter) KL_CUDA(cudaMemsetAsync(wk.H.p, 0, (size_t)total * sizeof(unsigned long long), ctx().stream));
   KL_LAUNCH(imp_build_T, (unsigned)((total + 255) / 256), 256, 0, P, I.bitmap.p, I.rank.p, wk.theta.p, wk.T.p, total, st);
   const int64_t steps = (S.max_len + I.N - 1 + 31) / 32;
   int64_t blocks = (int64_t)ctx().sm_count * 8, need = (M.n + 7) / 8;
@@ -533,22 +535,24 @@ void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st)
   const double inv_n = 1.0 / (double)M.n_global;
   if (steps <= 16)
     KL_LAUNCH((imp_pass<16>), (unsigned)blocks, 256, 0, P, M.n, S.len.p, S.blk.p, S.bits2.p, S.inv16.p, wk.T.p, wk.theta.p,
-              M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st);
+              M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st, scatter);
   else
     KL_LAUNCH((imp_pass<0>), (unsigned)blocks, 256, 0, P, M.n, S.len.p, S.blk.p, S.bits2.p, S.inv16.p, wk.T.p, wk.theta.p,
-              M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st);
+              M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st, scatter);
+  if (!scatter) return;
   for (int j = I.N - 1; j >= I.M; j--)
     KL_LAUNCH(imp_fold_level, (unsigned)(((1u << (2 * j)) + 255) / 256), 256, 0, P, j, wk.H.p, st);
   KL_LAUNCH(imp_columns, (unsigned)((M.m + 255) / 256), 256, 0, P, M.class_ids.p, M.m, wk.H.p, wk.G.p, st);
 }
 
 // the fused pass: loss terms + fixed-point gradient of the single-feature coefficients (all ranks)
+// scatter = 0: loss terms only (G is left untouched)
 template <typename VT>
-void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
-  KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
+void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, int scatter = 1) {
+  if (scatter) KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
   if (M.n > 0) {
     if (use_implicit(M)) {
-      launch_implicit(M, wk, cw, st);
+      launch_implicit(M, wk, cw, st, scatter);
     } else {
       int per_sm = 0;
       KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, 0));
@@ -556,10 +560,10 @@ void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st) {
       int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
       if (blocks > need) blocks = need;
       KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
-                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st);
+                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter);
     }
   }
-  if (M.sharded) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
+  if (M.sharded && scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
 }
 
 void alloc_work(const Matrix &M, int64_t ntheta, Work &wk) {
@@ -696,9 +700,11 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
     if (nb < 1) nb = 1;
     issued += nb;
     for (int64_t it = 0; it < nb; it++) {
+      // pass number max_iter (0-based) only evaluates the hook's loss at the final theta: no gradient
+      const int scatter = (issued - nb + it) < max_iter ? 1 : 0;
       dispatch_vt(M, [&](auto *tag) {
         using VT = typename std::remove_pointer<decltype(tag)>::type;
-        launch_fused<VT>(M, wk, cw, st.p);
+        launch_fused<VT>(M, wk, cw, st.p, scatter);
         reduce_sum(M, wk.lossterm.p, M.n, wk, wk.scalars.p, st.p);
         KL_LAUNCH(hook_kernel, 1, 256, 0, st.p, wk.scalars.p, wk.theta.p, M.m, inv_n, lambda, epsilon_loss);
         KL_LAUNCH(prox_update, PROX_BLOCKS, 256, 0, st.p, wk.theta.p, wk.G.p, wk.inv_scale, ntheta, step, lambda,
