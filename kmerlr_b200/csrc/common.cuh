@@ -187,15 +187,33 @@ struct Implicit {
   DevBuf<uint32_t> bitmap, rank;   // class set over dense ids: column = rank[id>>5] + popc(bits below)
 };                                 // (the dense class id of every column is Matrix::class_ids)
 
-// KmerDataSet in HBM: CSR rows (without the bias column) + labels + classes; a CSC view is built
-// lazily for the pair-feature (co-occurrence) gradient only
+// where row i of a matrix lives: compact CSR (rowptr) or fixed-stride rows straight from the extraction
+struct Rows {
+  const int64_t *rowptr;     // compact: row i = [rowptr[i], rowptr[i+1])
+  const uint32_t *rowcnt;    // padded:  row i = [i*stride, i*stride + rowcnt[i])
+  int64_t stride;            // 0 = compact
+#ifdef __CUDACC__
+  __device__ __forceinline__ void range(int64_t row, int64_t &a, int64_t &b) const {
+    if (stride) { a = row * stride; b = a + rowcnt[row]; }
+    else { a = rowptr[row]; b = rowptr[row + 1]; }
+  }
+#endif
+};
+
+// KmerDataSet in HBM: sparse rows (without the bias column) + labels + classes; a CSC view is built
+// lazily for the pair-feature (co-occurrence) gradient only.  Matrices that come out of the extraction
+// keep the fixed-stride row layout the kernel wrote (no second copy); matrix_compact() turns them into
+// compact CSR for the few consumers that need contiguous entries (export, CSC transpose).
 struct Matrix : Object {
   int64_t n = 0, m = 0, nnz = 0;
   ValType vt = VAL_U32;
-  DevBuf<int64_t> rowptr;    // n+1
-  DevBuf<uint32_t> col;      // nnz
-  DevBuf<uint32_t> val_u32;  // nnz (VAL_U32)
-  DevBuf<double> val_f64;    // nnz (VAL_F64)
+  int64_t row_stride = 0;    // > 0: padded rows, rowcnt valid, rowptr unused
+  DevBuf<uint32_t> rowcnt;   // n (padded layout)
+  DevBuf<int64_t> rowptr;    // n+1 (compact layout)
+  DevBuf<uint32_t> col;      // nnz, or n*row_stride
+  DevBuf<uint32_t> val_u32;  // (VAL_U32)
+  DevBuf<double> val_f64;    // (VAL_F64)
+  Rows rows() const { return Rows{rowptr.p, rowcnt.p, row_stride}; }
   // CSC view (built on first use by ensure_csc): entries of column c in ascending row order
   bool has_csc = false;
   DevBuf<int64_t> colptr;    // m+1
@@ -259,8 +277,9 @@ void matrix_class_list(Matrix &M);   // fills class_k / class_code if they are s
 // matrix.cu
 std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const int32_t *col,
                                         const double *val, int flags);
-void matrix_rows(const Matrix &M, int64_t *rowptr, int32_t *col, double *val);
+void matrix_rows(Matrix &M, int64_t *rowptr, int32_t *col, double *val);
 void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n);
+void matrix_compact(Matrix &M);      // padded rows -> compact CSR (no-op for compact matrices)
 void ensure_csc(Matrix &M);
 std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel);
 double matrix_maxsq(Matrix &M);

@@ -58,6 +58,9 @@ struct XParams {
   const uint16_t *inv16;
   const uint2 *tl;                 // x = table index of the code | table index of its image << 16, y = class id
   uint32_t *st_id, *st_cnt, *rowcnt, *bitmap, *ovf;
+  const uint2 *nbx;                // numbering set (all classes of the configuration, or the frozen list)
+  int filter;                      // drop ids outside the numbering set
+  unsigned long long *stats;       // [0] max_i sum_j v_ij^2, [1] max v_ij
 };
 
 __device__ __forceinline__ uint32_t tab_off(int k) {  // sum_{j=1}^{k-1} 4^j
@@ -162,11 +165,14 @@ struct BaseReader {
 };
 
 struct Emitter {
-  uint32_t *sid, *scnt;            // this row's staging slices
+  uint32_t *sid, *scnt;            // this row's slices of the column / count arrays
   uint32_t *obs, *bitmap;          // observed classes: per-block (shared) and global bitmap
+  const uint2 *nbx;                // numbering set, per 32 ids: x = member bits, y = column of the first member
   uint32_t obs_bits;               // ids below this are marked in obs
   uint32_t cursor;
-  int binarize, mark;
+  int binarize, mark, filter;      // filter: ids outside the numbering set are dropped (frozen class list)
+  unsigned long long sq;           // per lane: sum of squared counts / largest count emitted
+  uint32_t vm;
   // mark one class id as observed
   __device__ __forceinline__ void mark_id(uint32_t id) {
     if (!mark) return;
@@ -178,14 +184,28 @@ struct Emitter {
   __device__ __forceinline__ void mark_word(uint32_t word_index, uint32_t bits) {
     if (mark && (bits & ~obs[word_index])) atomicOr(obs + word_index, bits);
   }
-  // ballot-compacted emission (coalesced stores)
-  __device__ __forceinline__ void emit(bool flag, uint32_t id, uint32_t cnt) {
+  // column of a class id; false when the id is not in the numbering set
+  __device__ __forceinline__ bool column(uint32_t id, uint32_t &col) const {
+    const uint2 e = __ldg(nbx + (id >> 5));
+    const uint32_t bit = 1u << (id & 31);
+    col = e.y + __popc(e.x & (bit - 1u));
+    return (e.x & bit) != 0u;
+  }
+  __device__ __forceinline__ void stat(uint32_t cnt) {
+    sq += (unsigned long long)cnt * cnt;
+    vm = max(vm, cnt);
+  }
+  // ballot-compacted emission (coalesced stores); col_known >= 0: the column when no class is dropped
+  __device__ __forceinline__ void emit(bool flag, uint32_t id, uint32_t cnt, int64_t col_known = -1) {
+    uint32_t col = (uint32_t)col_known;
+    if (flag && (filter || col_known < 0)) { const bool member = column(id, col); if (filter) flag = member; }
     unsigned em = __ballot_sync(0xffffffffu, flag);
     if (flag) {
       uint32_t pos = cursor + __popc(em & lanemask_lt());
-      sid[pos] = id;
+      sid[pos] = col;
       if (!binarize) scnt[pos] = cnt;
       mark_id(id);
+      stat(binarize ? 1u : cnt);
     }
     cursor += __popc(em);
   }
@@ -230,10 +250,21 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
     }
   }
   __syncwarp();
-  for (int i = lane; i < total; i += 32) {
-    const uint32_t id = sbuf[i];
-    em.sid[em.cursor + i] = id;
-    em.mark_id(id);
+  // copy out: id -> column; with a frozen class list the ids outside the list are dropped here and the
+  // keep decisions (one bit per copy iteration) are replayed for the counts
+  unsigned long long keepbits = 0;
+  uint32_t kept = 0;
+  for (int i0 = 0, it = 0; i0 < total; i0 += 32, it++) {
+    const int i = i0 + (int)lane;
+    bool keep = false; uint32_t col = 0, id = 0;
+    if (i < total) { id = sbuf[i]; keep = em.column(id, col) || !em.filter; }
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      em.sid[em.cursor + kept + __popc(km & lanemask_lt())] = col;
+      em.mark_id(id);
+      keepbits |= 1ull << it;
+    }
+    kept += __popc(km);
   }
   __syncwarp();
   // round 2: counts = distance to the previous boundary
@@ -249,11 +280,25 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
       }
     }
     __syncwarp();
-    for (int i = lane; i < total; i += 32) em.scnt[em.cursor + i] = sbuf[i];
+    uint32_t k2 = 0;
+    for (int i0 = 0, it = 0; i0 < total; i0 += 32, it++) {
+      const int i = i0 + (int)lane;
+      const bool keep = (keepbits >> it) & 1ull;
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const uint32_t cnt = sbuf[i];
+        em.scnt[em.cursor + k2 + __popc(km & lanemask_lt())] = cnt;
+        em.stat(cnt);
+      }
+      k2 += __popc(km);
+    }
     __syncwarp();
+  } else {
+    em.sq += __popcll(keepbits); if (keepbits) em.vm = max(em.vm, 1u);
   }
-  em.cursor += (uint32_t)total;
+  em.cursor += kept;
 }
+
 
 // ---- the extraction kernel: one warp per sequence ------------------------------------------------
 // E = keys per lane of the register sort (0: no sorted levels, sequences of any length)
@@ -364,7 +409,9 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
     Emitter em;
     em.sid = P.st_id + row * P.stride; em.scnt = P.st_cnt + (P.binarize ? 0 : row * P.stride);
     em.obs = obs; em.bitmap = P.bitmap; em.obs_bits = (uint32_t)P.obs_words * 32u;
+    em.nbx = P.nbx; em.filter = P.filter;
     em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
+    em.sq = 0; em.vm = 0;
 
     // ---- table levels ---------------------------------------------------------------------------
     if (has_tab) {
@@ -391,7 +438,8 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
           if (i2 != i1) cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu;
           id = e.y;
         }
-        em.emit(cnt > 0, id, cnt);
+        // without a frozen list the numbering set is ALL classes: the j-th class of the list is column j
+        em.emit(cnt > 0, id, cnt, P.filter ? -1 : (int64_t)j);
       }
       __syncwarp();
     }
@@ -400,13 +448,22 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
     if (has_bm) {
       for (int k = P.b_lo; k <= P.b_hi; k++) {
         const int W = 1 << (2 * k - 5);
-        const uint32_t *bk = bm + P.bm_off[k];
+        uint32_t *bk = bm + P.bm_off[k];
         uint32_t *pk = pf + P.pf_off[k];
         const uint32_t idbase = P.level_off[k], gword = P.level_off[k] >> 5;
         for (int it = 0; it * 128 < W; it++) {
           const int wi = it * 128 + (int)lane * 4;
           uint4 w4 = make_uint4(0, 0, 0, 0);
           if (wi < W) w4 = *reinterpret_cast<const uint4 *>(bk + wi);
+          // numbering of the lane's 4 words: member bits and column of the first member (coalesced loads)
+          uint2 nx[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) nx[j] = wi < W ? __ldg(P.nbx + gword + wi + j) : make_uint2(0u, 0u);
+          if (P.filter && wi < W) {
+            // frozen class list: classes outside the list vanish here, before any slot is assigned
+            w4.x &= nx[0].x; w4.y &= nx[1].x; w4.z &= nx[2].x; w4.w &= nx[3].x;
+            *reinterpret_cast<uint4 *>(bk + wi) = w4;
+          }
           if (w4.x | w4.y | w4.z | w4.w) {
             em.mark_word(gword + wi, w4.x); em.mark_word(gword + wi + 1, w4.y);
             em.mark_word(gword + wi + 2, w4.z); em.mark_word(gword + wi + 3, w4.w);
@@ -419,17 +476,17 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
             if (lane >= (unsigned)o) incl += y;
           }
           const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-          if (wi < W) pk[wi >> 2] = em.cursor + incl - c;   // staging slot of this lane's first class
+          if (wi < W) pk[wi >> 2] = em.cursor + incl - c;   // slot of this lane's first class
           const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
           if (tot <= (uint32_t)P.ts_words) {
-            // ids through the warp's shared buffer: coalesced global stores
+            // ids through the warp's shared buffer: coalesced global stores of the columns
             uint32_t pos = incl - c;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
               uint32_t w = ws[j];
-              const uint32_t id0 = idbase + (uint32_t)(wi + j) * 32u;
               while (w) {
-                tab[pos++] = id0 + (uint32_t)(__ffs(w) - 1);
+                const uint32_t below = (w & (0u - w)) - 1u;            // bits under the lowest set bit
+                tab[pos++] = nx[j].y + __popc(nx[j].x & below);         // its column
                 w &= w - 1;
               }
             }
@@ -445,14 +502,15 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
             for (int j = 0; j < 4; j++) {
               uint32_t w = ws[j];
               while (w) {
-                int b = __ffs(w) - 1;
+                const uint32_t below = (w & (0u - w)) - 1u;
                 w &= w - 1;
-                em.sid[pos] = idbase + (uint32_t)(wi + j) * 32u + (uint32_t)b;
+                em.sid[pos] = nx[j].y + __popc(nx[j].x & below);
                 if (!P.binarize) em.scnt[pos] = 1;
                 pos++;
               }
             }
           }
+          em.sq += c; if (c) em.vm = max(em.vm, 1u);        // every class of the chunk enters with count 1
           em.cursor += tot;
         }
       }
@@ -465,9 +523,12 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
           const uint32_t e = i < (uint32_t)DUP_SMEM ? dups[i] : ovf[i - DUP_SMEM];
           const uint32_t k = e >> 26, c = e & 0x3FFFFFFu, wi = c >> 5;
           const uint32_t *bk = bm + P.bm_off[k];
+          if (!((bk[wi] >> (c & 31)) & 1u)) continue;       // class dropped by the frozen list
           uint32_t slot = pf[P.pf_off[k] + (wi >> 2)] + __popc(bk[wi] & ((1u << (c & 31)) - 1u));
           for (uint32_t j = wi & ~3u; j < wi; j++) slot += __popc(bk[j]);
-          atomicAdd(em.scnt + slot, 1u);
+          const uint32_t old = atomicAdd(em.scnt + slot, 1u);
+          em.sq += 2ull * old + 1ull;                       // (old+1)^2 - old^2
+          em.vm = max(em.vm, old + 1u);
         }
         __syncwarp();
         if (lane == 0) dupn[0] = 0;
@@ -491,7 +552,20 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         emit_sorted<EE>(K, lane, tab, em, P.level_off[k]);
       }
     }
-    if (lane == 0) P.rowcnt[row] = em.cursor;
+    // row statistics (exact integers): what the step size and the fixed-point scale of the gradient need
+    {
+      unsigned long long sq = em.sq; uint32_t vm = em.vm;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        vm = max(vm, __shfl_xor_sync(0xffffffffu, vm, o));
+      }
+      if (lane == 0) {
+        P.rowcnt[row] = em.cursor;
+        if (sq > P.stats[0]) atomicMax(P.stats, sq);
+        if ((unsigned long long)vm > P.stats[1]) atomicMax(P.stats + 1, (unsigned long long)vm);
+      }
+    }
   }
   // flush the block's observed classes
   __syncthreads();
@@ -534,74 +608,48 @@ __global__ void enumerate_bits(const uint32_t *__restrict__ bm, const uint32_t *
   }
 }
 
-// ---- compaction: staging -> final CSR with rank-mapped columns (warp per row) ----------------------
-__global__ void count_kept(const uint32_t *__restrict__ st_id, const uint32_t *__restrict__ rowcnt, int64_t stride,
-                           int64_t n, const uint32_t *__restrict__ bm, uint32_t *__restrict__ kept) {
-  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= n) return;
-  unsigned lane = lane_id();
-  uint32_t c = rowcnt[row], tot = 0;
-  for (uint32_t j = lane; j < c; j += 32) {
-    uint32_t id = st_id[row * stride + j];
-    tot += (bm[id >> 5] >> (id & 31)) & 1u;
+// ---- numbering set helpers --------------------------------------------------------------------------
+struct LevelInfo {
+  int M, N, op;
+  uint32_t level_off[16];
+};
+// every class the configuration can produce: the codes u <= image(u) of every level
+__global__ void all_classes_bits(const LevelInfo I, uint32_t *__restrict__ bm, int64_t nw) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  const uint32_t id0 = (uint32_t)(w * 32);
+  int k = I.M;
+  while (k < I.N && id0 >= I.level_off[k + 1]) k++;
+  const uint32_t u0 = id0 - I.level_off[k], nk = 1u << (2 * k);   // levels start on multiples of 32
+  uint32_t v = 0;
+  for (int b = 0; b < 32; b++) {
+    const uint32_t u = u0 + b;
+    if (u < nk && (I.op == 0 || u <= kmer_op(u, k, I.op))) v |= 1u << b;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if (lane == 0) kept[row] = tot;
+  bm[w] = v;
 }
-
-// stats[0] = max_i sum_j v_ij^2, stats[1] = max v_ij over the rows written (exact integers): what the
-// step size (kmerLr_estimator_proximal.go:54-69) and the fixed-point scale of the gradient need
-template <bool FILTER>
-__global__ void compact_rows(const uint32_t *__restrict__ st_id, const uint32_t *__restrict__ st_cnt,
-                             const uint32_t *__restrict__ rowcnt, int64_t stride, int64_t n,
-                             const uint32_t *__restrict__ bm, const uint32_t *__restrict__ rank,
-                             const int64_t *__restrict__ rowptr, uint32_t *__restrict__ col,
-                             uint32_t *__restrict__ val, unsigned long long *__restrict__ stats) {
+__global__ void interleave_numbering(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ rank, int64_t nw,
+                                     uint2 *__restrict__ out) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nw) out[w] = make_uint2(bits[w], rank[w]);
+}
+__global__ void bitmaps_differ(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, int64_t nw,
+                               uint32_t *__restrict__ flag) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nw && a[w] != b[w]) atomicOr(flag, 1u);
+}
+// columns numbered in the numbering set -> ranks among the observed classes, in place (warp per row)
+__global__ void renumber_rows(uint32_t *__restrict__ col, const uint32_t *__restrict__ rowcnt, int64_t stride, int64_t n,
+                              const uint32_t *__restrict__ ids, const uint32_t *__restrict__ bm,
+                              const uint32_t *__restrict__ rank) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
-  unsigned lane = lane_id();
-  uint32_t c = rowcnt[row];
-  int64_t outp = rowptr[row];
-  unsigned long long sq = 0; uint32_t vm = 0;
-  const uint32_t *rid = st_id + row * stride, *rcnt = val ? st_cnt + row * stride : nullptr;
-  // four chunks of 32 entries per iteration: all loads of the iteration are in flight together
-  for (uint32_t j0 = 0; j0 < c; j0 += 128) {
-    uint32_t id[4], v[4], w[4], rk[4];
-    bool in[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const uint32_t j = j0 + 32 * u + lane;
-      in[u] = j < c;
-      id[u] = in[u] ? rid[j] : 0u;
-      v[u] = (in[u] && rcnt) ? rcnt[j] : 1u;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      w[u] = in[u] ? __ldg(bm + (id[u] >> 5)) : 0u;
-      rk[u] = in[u] ? __ldg(rank + (id[u] >> 5)) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const bool keep = in[u] && (FILTER ? ((w[u] >> (id[u] & 31)) & 1u) : true);
-      const unsigned km = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const int64_t pos = outp + __popc(km & lanemask_lt());
-        col[pos] = rk[u] + __popc(w[u] & ((1u << (id[u] & 31)) - 1u));
-        if (val) val[pos] = v[u];
-        sq += (unsigned long long)v[u] * v[u]; vm = max(vm, v[u]);
-      }
-      outp += __popc(km);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    vm = max(vm, __shfl_xor_sync(0xffffffffu, vm, o));
-  }
-  if (lane == 0) {
-    if (sq > stats[0]) atomicMax(stats, sq);
-    if ((unsigned long long)vm > stats[1]) atomicMax(stats + 1, (unsigned long long)vm);
+  const unsigned lane = lane_id();
+  uint32_t *c = col + row * stride;
+  const uint32_t cnt = rowcnt[row];
+  for (uint32_t j = lane; j < cnt; j += 32) {
+    const uint32_t id = __ldg(ids + c[j]), w = __ldg(bm + (id >> 5));
+    c[j] = __ldg(rank + (id >> 5)) + __popc(w & ((1u << (id & 31)) - 1u));
   }
 }
 
@@ -616,14 +664,15 @@ __device__ __forceinline__ uint32_t row_lookup(const uint32_t *col, const uint32
   return 0u;
 }
 template <bool WRITE>
-__global__ void features_rows(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+__global__ void features_rows(const Rows R, const uint32_t *__restrict__ col,
                               const uint32_t *__restrict__ val, int64_t n, const int32_t *__restrict__ feat,
                               int64_t nf, uint32_t *__restrict__ cnt_out, const int64_t *__restrict__ orowptr,
                               uint32_t *__restrict__ ocol, uint32_t *__restrict__ oval) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
   unsigned lane = lane_id();
-  int64_t a = rowptr[row], b = rowptr[row + 1];
+  int64_t a, b;
+  R.range(row, a, b);
   int64_t outp = WRITE ? orowptr[row] : 0;
   uint32_t tot = 0;
   for (int64_t j0 = 0; j0 < nf; j0 += 32) {
@@ -796,7 +845,7 @@ static std::shared_ptr<Matrix> apply_features(Matrix &cls, const int32_t *featur
   unsigned grid = (unsigned)((cls.n * 32 + 127) / 128);
   out->rowptr.alloc((size_t)cls.n + 1);
   if (cls.n > 0) {
-    KL_LAUNCH((features_rows<false>), grid, 128, 0, cls.rowptr.p, cls.col.p, val, cls.n, dfeat.p, nf, cnt.p, nullptr,
+    KL_LAUNCH((features_rows<false>), grid, 128, 0, cls.rows(), cls.col.p, val, cls.n, dfeat.p, nf, cnt.p, nullptr,
               nullptr, nullptr);
     exclusive_scan_u32_to_i64(cnt.p, out->rowptr.p, cls.n);
     KL_CUDA(cudaMemcpyAsync(&out->nnz, out->rowptr.p + cls.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
@@ -807,7 +856,7 @@ static std::shared_ptr<Matrix> apply_features(Matrix &cls, const int32_t *featur
   out->col.alloc((size_t)(out->nnz ? out->nnz : 1));
   if (out->vt == VAL_U32) out->val_u32.alloc((size_t)(out->nnz ? out->nnz : 1));
   if (cls.n > 0)
-    KL_LAUNCH((features_rows<true>), grid, 128, 0, cls.rowptr.p, cls.col.p, val, cls.n, dfeat.p, nf, nullptr,
+    KL_LAUNCH((features_rows<true>), grid, 128, 0, cls.rows(), cls.col.p, val, cls.n, dfeat.p, nf, nullptr,
               out->rowptr.p, out->col.p, out->vt == VAL_U32 ? out->val_u32.p : nullptr);
   sync_stream();
   return out;
@@ -884,11 +933,22 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   // classes of the table levels
   if (P.t_lo <= P.t_hi) P.tl = table_classes(P.op, P.t_lo, P.t_hi, P.level_off, &P.tl_cnt);
   Trace tr("extract");
-  DevBuf<uint32_t> st_id((size_t)(s.n ? s.n * stride : 1));
-  DevBuf<uint32_t> st_cnt((size_t)(P.binarize ? 1 : (s.n ? s.n * stride : 1)));
-  DevBuf<uint32_t> rowcnt((size_t)(s.n ? s.n : 1));
-  DevBuf<uint32_t> bitmap((size_t)nw);
+  auto out = std::make_shared<Matrix>();
+  out->n = s.n; out->vt = P.binarize ? VAL_ONE : VAL_U32;
+  out->sharded = sharded; out->n_global = s.n;
+  // the kernel writes the rows of the matrix itself: fixed stride, final column numbers
+  out->row_stride = stride;
+  out->col.alloc((size_t)(s.n ? s.n * stride : 1));
+  if (!P.binarize) out->val_u32.alloc((size_t)(s.n ? s.n * stride : 1));
+  out->rowcnt.alloc((size_t)(s.n ? s.n : 1));
+  DevBuf<uint32_t> dummy_cnt(1);
+  // numbering set: the frozen list, or every class the configuration can produce (then the columns
+  // are final unless some class never shows up, see below)
+  DevBuf<uint32_t> nb((size_t)nw), nbrank((size_t)nw + 1), pc((size_t)nw), bitmap((size_t)nw);
   std::vector<uint32_t> frozen_bits;       // host image of the frozen class set (alive until the next sync)
+  LevelInfo LI{};
+  LI.M = cfg.M; LI.N = cfg.N; LI.op = P.op;
+  for (int k = cfg.M; k <= cfg.N + 1; k++) LI.level_off[k] = P.level_off[k];
   if (n_frozen > 0) {
     frozen_bits.assign((size_t)nw, 0u);
     uint64_t prev = 0;
@@ -900,11 +960,19 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
       prev = id;
       frozen_bits[id >> 5] |= 1u << (id & 31);
     }
-    bitmap.upload(frozen_bits.data(), (size_t)nw);
+    nb.upload(frozen_bits.data(), (size_t)nw);
   } else {
-    bitmap.zero();
+    KL_LAUNCH(all_classes_bits, (unsigned)((nw + 255) / 256), 256, 0, LI, nb.p, nw);
   }
-  P.st_id = st_id.p; P.st_cnt = st_cnt.p; P.rowcnt = rowcnt.p; P.bitmap = bitmap.p;
+  KL_LAUNCH(popc_words, (unsigned)((nw + 255) / 256), 256, 0, nb.p, nw, pc.p);
+  exclusive_scan_u32(pc.p, nbrank.p, nw);
+  bitmap.zero();
+  DevBuf<unsigned long long> stats(2);
+  stats.zero();
+  P.st_id = out->col.p; P.st_cnt = P.binarize ? dummy_cnt.p : out->val_u32.p; P.rowcnt = out->rowcnt.p;
+  DevBuf<uint2> nbx((size_t)nw);
+  KL_LAUNCH(interleave_numbering, (unsigned)((nw + 255) / 256), 256, 0, nb.p, nbrank.p, nw, nbx.p);
+  P.bitmap = bitmap.p; P.nbx = nbx.p; P.filter = n_frozen > 0; P.stats = stats.p;
   P.mark = n_frozen == 0;
   // repeats beyond the shared-memory list of a warp (low-complexity rows): one global list per warp
   DevBuf<uint32_t> ovf;
@@ -913,7 +981,7 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
     ovf.alloc((size_t)ctx().sm_count * 64 * (size_t)P.ovf_stride);
     P.ovf = ovf.p;
   }
-  tr.mark("alloc staging");
+  tr.mark("alloc");
 
   if (s.n > 0) {
     // host sequences arrive in chunks: copy of chunk c+1 overlaps pack + extraction of chunk c
@@ -935,35 +1003,21 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
     P.row0 = 0; P.n = s.n;
   }
   tr.mark("extract_kernel");
-  // class set: observed union (all ranks; the frozen list was uploaded before the kernel)
-  if (n_frozen == 0 && sharded) {
-    DevBuf<uint8_t> bytes((size_t)nbits);
-    KL_LAUNCH(bitmap_to_bytes, (unsigned)((nbits + 255) / 256), 256, 0, bitmap.p, nbits, bytes.p);
-    comm_allreduce_max_u8(bytes.p, nbits);
-    KL_LAUNCH(bytes_to_bitmap, (unsigned)((nw + 255) / 256), 256, 0, bytes.p, nbits, bitmap.p, nw);
-  }
-  DevBuf<uint32_t> pc((size_t)nw), rank((size_t)nw + 1);
-  KL_LAUNCH(popc_words, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, nw, pc.p);
-  exclusive_scan_u32(pc.p, rank.p, nw);
-  auto out = std::make_shared<Matrix>();
-  out->n = s.n; out->vt = P.binarize ? VAL_ONE : VAL_U32;
-  out->sharded = sharded; out->n_global = s.n;
-  // row pointers of the final CSR
-  out->rowptr.alloc((size_t)s.n + 1);
-  DevBuf<uint32_t> kept;
-  const uint32_t *cnt_final = rowcnt.p;
-  unsigned wgrid = (unsigned)((s.n * 32 + 127) / 128);
-  if (s.n > 0) {
-    if (n_frozen > 0) {
-      kept.alloc((size_t)s.n);
-      KL_LAUNCH(count_kept, wgrid, 128, 0, st_id.p, rowcnt.p, stride, s.n, bitmap.p, kept.p);
-      cnt_final = kept.p;
+  // observed classes of all ranks; do they cover the numbering set?
+  DevBuf<uint32_t> differ(1);
+  differ.zero();
+  if (n_frozen == 0) {
+    if (sharded) {
+      DevBuf<uint8_t> bytes((size_t)nbits);
+      KL_LAUNCH(bitmap_to_bytes, (unsigned)((nbits + 255) / 256), 256, 0, bitmap.p, nbits, bytes.p);
+      comm_allreduce_max_u8(bytes.p, nbits);
+      KL_LAUNCH(bytes_to_bitmap, (unsigned)((nw + 255) / 256), 256, 0, bytes.p, nbits, bitmap.p, nw);
     }
-    exclusive_scan_u32_to_i64(cnt_final, out->rowptr.p, s.n);
-  } else {
-    out->rowptr.zero();
+    KL_LAUNCH(bitmaps_differ, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, nb.p, nw, differ.p);
   }
-  // one round trip for the three sizes: classes, stored entries, global number of rows
+  // one round trip: classes, stored entries, "columns are final", row statistics, global number of rows
+  DevBuf<int64_t> rp((size_t)s.n + 1);
+  if (s.n > 0) exclusive_scan_u32_to_i64(out->rowcnt.p, rp.p, s.n); else rp.zero();
   DevBuf<int64_t> nglob(1);
   int64_t nn = s.n;
   if (sharded) {
@@ -971,39 +1025,40 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
     comm_allreduce_sum_i64(nglob.p, 1);
     nglob.download(&nn, 1);
   }
-  uint32_t m32 = 0;
-  KL_CUDA(cudaMemcpyAsync(&m32, rank.p + nw, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
-  KL_CUDA(cudaMemcpyAsync(&out->nnz, out->rowptr.p + s.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
+  uint32_t m32 = 0, hdiffer = 0;
+  unsigned long long hstats[2] = {0, 0};
+  KL_CUDA(cudaMemcpyAsync(&m32, nbrank.p + nw, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
+  KL_CUDA(cudaMemcpyAsync(&out->nnz, rp.p + s.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
+  differ.download(&hdiffer, 1);
+  stats.download(hstats, 2);
   sync_stream();
-  out->m = (int64_t)m32; out->n_global = nn;
-  tr.mark("ranks + rowptr");
+  out->n_global = nn;
+  out->has_local_stats = true;
+  out->local_maxsq = (double)hstats[0]; out->local_vmax = (double)hstats[1];
+  tr.mark("sizes");
+  if (hdiffer) {
+    // some class of the configuration never occurs: the columns are the ranks among the OBSERVED
+    // classes (kmerLr_data.go:316-324), renumber the stored columns in place
+    DevBuf<uint32_t> rank2((size_t)nw + 1), ids_nb((size_t)(m32 ? m32 : 1));
+    KL_LAUNCH(popc_words, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, nw, pc.p);
+    exclusive_scan_u32(pc.p, rank2.p, nw);
+    KL_LAUNCH(enumerate_bits, (unsigned)((nw + 255) / 256), 256, 0, nb.p, nbrank.p, nw, ids_nb.p);
+    if (s.n > 0)
+      KL_LAUNCH(renumber_rows, (unsigned)((s.n * 32 + 127) / 128), 128, 0, out->col.p, out->rowcnt.p, stride, s.n, ids_nb.p,
+                bitmap.p, rank2.p);
+    KL_CUDA(cudaMemcpyAsync(&m32, rank2.p + nw, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
+    sync_stream();
+    nb = std::move(bitmap); nbrank = std::move(rank2);
+    tr.mark("renumber");
+  }
+  out->m = (int64_t)m32;
   // class list: dense ids stay on the device, (k, code) pairs are decoded on demand
   out->n_classes = (int64_t)m32;
   out->class_ids.alloc((size_t)(m32 ? m32 : 1));
-  KL_LAUNCH(enumerate_bits, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, rank.p, nw, out->class_ids.p);
+  KL_LAUNCH(enumerate_bits, (unsigned)((nw + 255) / 256), 256, 0, nb.p, nbrank.p, nw, out->class_ids.p);
   out->class_M = cfg.M; out->class_N = cfg.N; out->classes_on_host = false;
   for (int k = cfg.M; k <= cfg.N + 1; k++) out->class_level_off[k] = P.level_off[k];
-  // final CSR
-  out->col.alloc((size_t)(out->nnz ? out->nnz : 1));
-  if (out->vt == VAL_U32) out->val_u32.alloc((size_t)(out->nnz ? out->nnz : 1));
-  DevBuf<unsigned long long> stats(2);
-  stats.zero();
-  if (s.n > 0) {
-    uint32_t *vp = out->vt == VAL_U32 ? out->val_u32.p : nullptr;
-    if (n_frozen > 0)
-      KL_LAUNCH((compact_rows<true>), wgrid, 128, 0, st_id.p, st_cnt.p, rowcnt.p, stride, s.n, bitmap.p, rank.p,
-                out->rowptr.p, out->col.p, vp, stats.p);
-    else
-      KL_LAUNCH((compact_rows<false>), wgrid, 128, 0, st_id.p, st_cnt.p, rowcnt.p, stride, s.n, bitmap.p, rank.p,
-                out->rowptr.p, out->col.p, vp, stats.p);
-  }
-  unsigned long long hstats[2] = {0, 0};
-  stats.download(hstats, 2);
-  sync_stream();
-  out->has_local_stats = true;
-  out->local_maxsq = (double)hstats[0]; out->local_vmax = (double)hstats[1];
-  tr.mark("compact");
-  if (n_features > 0) return apply_features(*out, features, n_features);
+  if (n_features > 0) { sync_stream(); return apply_features(*out, features, n_features); }
   // count matrices with one column per class keep what the matrix-free logistic pass needs
   if (!P.binarize && cfg.N <= IMP_MAX_N && s.n > 0 && m32 > 0) {
     auto imp = std::make_shared<Implicit>();
@@ -1014,9 +1069,10 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
       imp->fo[k] = fo;
       if (k <= cfg.N) fo += 1u << (2 * k);
     }
-    imp->bitmap = std::move(bitmap); imp->rank = std::move(rank);
+    imp->bitmap = std::move(nb); imp->rank = std::move(nbrank);
     out->imp = imp;
   }
+  sync_stream();
   return out;
 }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ double valf(const VT *val, int64_t p) { return val ? 
 
 // rows pass: MODE 0 = z only, 1 = log sigma(z), 2 = w_i and loss term
 template <typename VT, int MODE>
-__global__ void rows_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+__global__ void rows_kernel(const Rows R, const uint32_t *__restrict__ col,
                             const VT *__restrict__ val, int64_t n, int64_t m, const double *__restrict__ theta,
                             int cooc, const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n,
                             double *__restrict__ out, double *__restrict__ lossterm, const PgState *st) {
@@ -47,7 +47,8 @@ __global__ void rows_kernel(const int64_t *__restrict__ rowptr, const uint32_t *
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
   unsigned lane = lane_id();
-  int64_t a = rowptr[row], b = rowptr[row + 1];
+  int64_t a, b;
+  R.range(row, a, b);
   double s = 0.0;
   for (int64_t p = a + lane; p < b; p += 32) s += valf(val, p) * __ldg(theta + col[p] + 1);
   if (cooc) {
@@ -103,7 +104,7 @@ __global__ void reduce_stage2(const double *__restrict__ part, int np, double *_
 constexpr int HOT_COLS = 4096;   // columns < HOT_COLS accumulate in shared memory (32 KB)
 
 template <typename VT>
-__global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+__global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t *__restrict__ col,
                                                     const VT *__restrict__ val, int64_t n, int64_t m,
                                                     const double *__restrict__ theta,
                                                     const uint8_t *__restrict__ labels, double cw0, double cw1,
@@ -121,7 +122,8 @@ __global__ void __launch_bounds__(256) fused_kernel(const int64_t *__restrict__ 
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   long long bias_acc = 0;
   for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
-    const int64_t a = rowptr[row], b = rowptr[row + 1];
+    int64_t a, b;
+    R.range(row, a, b);
     double s = 0.0;
     for (int64_t p = a + lane; p < b; p += 32) s += valf(val, p) * __ldg(theta + col[p] + 1);
     s = warp_sum_down(s);
@@ -314,7 +316,7 @@ __global__ void imp_columns(const ImpParams P, const uint32_t *__restrict__ col_
 
 // pair mode: the weights come from the pair-aware rows kernel; same fixed-point accumulation
 template <typename VT>
-__global__ void scatter_w(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+__global__ void scatter_w(const Rows R, const uint32_t *__restrict__ col,
                           const VT *__restrict__ val, int64_t n, const double *__restrict__ w, double scale,
                           unsigned long long *__restrict__ G) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -322,7 +324,9 @@ __global__ void scatter_w(const int64_t *__restrict__ rowptr, const uint32_t *__
   unsigned lane = lane_id();
   const double ws = w[row] * scale;
   if (lane == 0) atomicAdd(&G[0], (unsigned long long)__double2ll_rn(ws));
-  for (int64_t p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32)
+  int64_t a, b;
+  R.range(row, a, b);
+  for (int64_t p = a + lane; p < b; p += 32)
     atomicAdd(&G[col[p] + 1], (unsigned long long)__double2ll_rn(ws * valf(val, p)));
 }
 
@@ -498,7 +502,7 @@ void launch_rows(const Matrix &M, const double *theta, int cooc, const double cw
                  const PgState *st) {
   if (M.n == 0) return;
   double inv_n = 1.0 / (double)M.n_global;
-  KL_LAUNCH((rows_kernel<VT, MODE>), warp_grid(M.n, 256), 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m,
+  KL_LAUNCH((rows_kernel<VT, MODE>), warp_grid(M.n, 256), 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m,
             theta, cooc, M.labels.p, cw ? cw[0] : 1.0, cw ? cw[1] : 1.0, inv_n, out, lossterm, st);
 }
 
@@ -559,7 +563,7 @@ void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, in
       if (per_sm < 1) per_sm = 1;
       int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
       if (blocks > need) blocks = need;
-      KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
+      KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
                 M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter);
     }
   }
@@ -628,7 +632,7 @@ void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2]
       ensure_csc(M);
       KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
       if (M.n > 0)
-        KL_LAUNCH((scatter_w<VT>), warp_grid(M.n, 256), 256, 0, M.rowptr.p, M.col.p, csr_val<VT>(M), M.n, wk.w.p,
+        KL_LAUNCH((scatter_w<VT>), warp_grid(M.n, 256), 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, wk.w.p,
                   wk.scale, wk.G.p);
       if (M.sharded) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
       if (M.m > 1) {

@@ -166,7 +166,7 @@ __device__ __forceinline__ double row_value(const uint32_t *col, const VT *val, 
 }
 
 template <typename VT, bool WRITE>
-__global__ void reduce_rows(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+__global__ void reduce_rows(const Rows R, const uint32_t *__restrict__ col,
                             const VT *__restrict__ val, int64_t n, const int64_t *__restrict__ selA,
                             const int64_t *__restrict__ selB, int64_t nsel, uint32_t *__restrict__ cnt_out,
                             const int64_t *__restrict__ orowptr, uint32_t *__restrict__ ocol,
@@ -174,7 +174,8 @@ __global__ void reduce_rows(const int64_t *__restrict__ rowptr, const uint32_t *
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
   unsigned lane = lane_id();
-  int64_t a = rowptr[row], b = rowptr[row + 1];
+  int64_t a, b;
+  R.range(row, a, b);
   int64_t outp = WRITE ? orowptr[row] : 0;
   uint32_t tot = 0;
   for (int64_t j0 = 0; j0 < nsel; j0 += 32) {
@@ -197,17 +198,19 @@ __global__ void reduce_rows(const int64_t *__restrict__ rowptr, const uint32_t *
 }
 
 template <typename VT>
-__global__ void row_sqnorm_max(const int64_t *__restrict__ rowptr, const VT *__restrict__ val, int64_t n,
+__global__ void row_sqnorm_max(const Rows R, const VT *__restrict__ val, int64_t n,
                                unsigned long long *__restrict__ out) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
   unsigned lane = lane_id();
   double s = 0.0;
+  int64_t a, b;
+  R.range(row, a, b);
   if (val) {
-    for (int64_t p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32) { double v = (double)val[p]; s += v * v; }
+    for (int64_t p = a + lane; p < b; p += 32) { double v = (double)val[p]; s += v * v; }
     s = warp_sum(s);
   } else {
-    s = (double)(rowptr[row + 1] - rowptr[row]);
+    s = (double)(b - a);
   }
   // non-negative doubles compare like their bit patterns
   if (lane == 0) atomicMax(out, (unsigned long long)__double_as_longlong(s));
@@ -263,8 +266,43 @@ std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *row
   return M;
 }
 
-void matrix_rows(const Matrix &M, int64_t *rowptr, int32_t *col, double *val) {
+// padded rows (extraction layout) -> compact CSR: one gather, the padded arrays are released
+template <typename VT>
+__global__ void gather_rows(const uint32_t *__restrict__ rowcnt, int64_t stride, int64_t n,
+                            const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col,
+                            const VT *__restrict__ val, uint32_t *__restrict__ ocol, VT *__restrict__ oval) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const unsigned lane = lane_id();
+  const int64_t a = row * stride, o = rowptr[row];
+  const uint32_t c = rowcnt[row];
+  for (uint32_t j = lane; j < c; j += 32) {
+    ocol[o + j] = col[a + j];
+    if (val) oval[o + j] = val[a + j];
+  }
+}
+
+void matrix_compact(Matrix &M) {
+  if (M.row_stride == 0) return;
   require_ready();
+  M.rowptr.alloc((size_t)M.n + 1);
+  if (M.n > 0) exclusive_scan_u32_to_i64(M.rowcnt.p, M.rowptr.p, M.n); else M.rowptr.zero();
+  DevBuf<uint32_t> ncol((size_t)(M.nnz ? M.nnz : 1)), nval;
+  if (M.vt == VAL_U32) nval.alloc((size_t)(M.nnz ? M.nnz : 1));
+  if (M.n > 0)
+    KL_LAUNCH((gather_rows<uint32_t>), (unsigned)((M.n * 32 + 127) / 128), 128, 0, M.rowcnt.p, M.row_stride, M.n,
+              M.rowptr.p, M.col.p, M.vt == VAL_U32 ? M.val_u32.p : (const uint32_t *)nullptr, ncol.p,
+              M.vt == VAL_U32 ? nval.p : (uint32_t *)nullptr);
+  sync_stream();
+  M.col = std::move(ncol);
+  if (M.vt == VAL_U32) M.val_u32 = std::move(nval);
+  M.rowcnt.release();
+  M.row_stride = 0;
+}
+
+void matrix_rows(Matrix &M, int64_t *rowptr, int32_t *col, double *val) {
+  require_ready();
+  matrix_compact(M);
   M.rowptr.download(rowptr, (size_t)M.n + 1);
   std::vector<uint32_t> c32((size_t)M.nnz);
   M.col.download(c32.data(), (size_t)M.nnz);
@@ -341,6 +379,7 @@ static void build_csc(Matrix &M, const VT *val, VT *cval) {
 
 void ensure_csc(Matrix &M) {
   if (M.has_csc) return;
+  matrix_compact(M);          // the transpose walks the stored entries as one contiguous array
   M.colptr.alloc((size_t)M.m + 1);
   M.crow.alloc((size_t)(M.nnz ? M.nnz : 1));
   if (M.m == 0 || M.n == 0 || M.nnz == 0) {
@@ -385,7 +424,7 @@ std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nse
   auto run = [&](auto *valp) {
     using VT = typename std::remove_const<typename std::remove_pointer<decltype(valp)>::type>::type;
     if (M.n > 0) {
-      KL_LAUNCH((reduce_rows<VT, false>), wgrid, 128, 0, M.rowptr.p, M.col.p, valp, M.n, dA.p, dB.p, ns, cnt.p,
+      KL_LAUNCH((reduce_rows<VT, false>), wgrid, 128, 0, M.rows(), M.col.p, valp, M.n, dA.p, dB.p, ns, cnt.p,
                 nullptr, nullptr, nullptr);
       exclusive_scan_u32_to_i64(cnt.p, R->rowptr.p, M.n);
       KL_CUDA(cudaMemcpyAsync(&R->nnz, R->rowptr.p + M.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
@@ -396,7 +435,7 @@ std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nse
     R->col.alloc((size_t)(R->nnz ? R->nnz : 1));
     R->val_f64.alloc((size_t)(R->nnz ? R->nnz : 1));
     if (M.n > 0)
-      KL_LAUNCH((reduce_rows<VT, true>), wgrid, 128, 0, M.rowptr.p, M.col.p, valp, M.n, dA.p, dB.p, ns, nullptr,
+      KL_LAUNCH((reduce_rows<VT, true>), wgrid, 128, 0, M.rows(), M.col.p, valp, M.n, dA.p, dB.p, ns, nullptr,
                 R->rowptr.p, R->col.p, R->val_f64.p);
     sync_stream();
   };
@@ -423,9 +462,9 @@ double matrix_maxsq(Matrix &M) {
     d.zero();
     if (M.n > 0) {
       unsigned wgrid = (unsigned)((M.n * 32 + 127) / 128);
-      if (M.vt == VAL_U32) KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rowptr.p, M.val_u32.p, M.n, d.p);
-      else if (M.vt == VAL_F64) KL_LAUNCH((row_sqnorm_max<double>), wgrid, 128, 0, M.rowptr.p, M.val_f64.p, M.n, d.p);
-      else KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rowptr.p, (const uint32_t *)nullptr, M.n, d.p);
+      if (M.vt == VAL_U32) KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rows(), M.val_u32.p, M.n, d.p);
+      else if (M.vt == VAL_F64) KL_LAUNCH((row_sqnorm_max<double>), wgrid, 128, 0, M.rows(), M.val_f64.p, M.n, d.p);
+      else KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rows(), (const uint32_t *)nullptr, M.n, d.p);
     }
     unsigned long long bits = 0;
     d.download(&bits, 1);
@@ -450,6 +489,7 @@ double matrix_vmax(Matrix &M) {
   if (M.has_local_stats) {
     v = M.local_vmax;
   } else {
+    matrix_compact(M);
     DevBuf<unsigned long long> d(1);
     d.zero();
     if (M.nnz > 0) {

@@ -1,0 +1,83 @@
+"""Multi-GPU parity check (not collected by pytest; needs N >= 2 B200s):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/multi_gpu_check.py
+
+Every rank extracts its contiguous shard with KMERLR_FLAG_SHARDED; the class numbering, the gradient
+(int64 fixed-point all-reduce), the loss and a few proximal-gradient iterations must equal what ONE GPU
+computes on the whole set -- the gradient bit for bit.  Rank 0 prints one line per check.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import kmerlr_b200 as K
+    from kmerlr_b200 import api, shard, synth
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K.init(local)
+    ok = True
+    for M, N, L, flags in [(1, 8, 500, dict(revcomp=True)), (1, 10, 200, dict(revcomp=True, binarize=True)), (3, 7, 120, dict())]:
+        n_fg, n_bg = 3001, 2500
+        fb, fo = synth.sequences(n_fg, L, 1, planted=True)
+        bb, bo = synth.sequences(n_bg, L, 2)
+        kc = K.NewKmerCounter(M, N, **flags)
+        binz = flags.get("binarize", False)
+        # one GPU, whole set (no communicator yet / not sharded)
+        full = K.compile_training_data(None, kc, None, None, True, binz, (fb, fo), (bb, bo))
+        rng = np.random.default_rng(17)
+        theta = rng.normal(scale=0.01, size=full.m + 1)
+        cw = (0.9, 1.2)
+        lr = K.logisticRegression(theta, cw, 0.0)
+        g_full, l_full = lr.Gradient(None, full), lr.Loss(full)
+        est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=4)
+        est.Theta = np.zeros(full.m + 1); est.ClassWeights = np.array(cw)
+        est.estimate_proximal(full, 1e-3)
+        th_full = est.Theta.copy()
+        k_full, c_full = full.Kmers()
+        full.free()
+        # sharded
+        K.comm_init_torch()
+        fpart, bpart, labels = shard.shard_training_set((fb, fo), (bb, bo), rank, world)
+        mine = K.compile_training_data(None, kc, None, None, True, binz, fpart, bpart, sharded=True)
+        k_s, c_s = mine.Kmers()
+        g_s, l_s = lr.Gradient(None, mine), lr.Loss(mine)
+        est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=4)
+        est.Theta = np.zeros(mine.m + 1); est.ClassWeights = np.array(cw)
+        est.estimate_proximal(mine, 1e-3)
+        checks = {
+            "classes": mine.m == len(k_full) and np.array_equal(k_s, k_full) and np.array_equal(c_s, c_full),
+            "gradient bit-identical": np.array_equal(g_s, g_full),
+            "loss": abs(l_s - l_full) <= 1e-14 * abs(l_full),
+            "theta after 4 iterations": np.array_equal(est.Theta, th_full),
+        }
+        rows = torch.tensor([mine.n], device="cuda")
+        dist.all_reduce(rows)
+        checks["rows"] = int(rows.item()) == n_fg + n_bg
+        mine.free()
+        K.comm_destroy()
+        flat = torch.tensor([int(all(checks.values()))], device="cuda")
+        dist.all_reduce(flat, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("k=%d..%d L=%d %s world=%d: %s" % (M, N, L, flags, world, checks), flush=True)
+        ok = ok and bool(flat.item())
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
