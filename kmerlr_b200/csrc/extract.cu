@@ -250,6 +250,38 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
     }
   }
   __syncwarp();
+  if (!em.filter) {
+    // no class is dropped: slot i of the buffer is entry i of the level
+    for (int i = lane; i < total; i += 32) {
+      const uint32_t id = sbuf[i];
+      uint32_t col;
+      em.column(id, col);
+      em.sid[em.cursor + i] = col;
+      em.mark_id(id);
+    }
+    __syncwarp();
+    if (!em.binarize) {
+#pragma unroll
+      for (int r = 0; r < E; r++) {
+        if ((cls >> r) & 1) {
+          const MaskT below = cls & (((MaskT)1 << r) - 1), bbelow = bnd & (((MaskT)1 << r) - 1);
+          const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
+          const int st = bbelow ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bbelow) : 63 - __clzll(bbelow))
+                                : start0;
+          const uint32_t cnt = (uint32_t)((int)lane * E + r - st);
+          sbuf[j] = cnt;
+          em.stat(cnt);
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < total; i += 32) em.scnt[em.cursor + i] = sbuf[i];
+      __syncwarp();
+    } else {
+      em.sq += (unsigned long long)c; if (c) em.vm = max(em.vm, 1u);
+    }
+    em.cursor += (uint32_t)total;
+    return;
+  }
   // copy out: id -> column; with a frozen class list the ids outside the list are dropped here and the
   // keep decisions (one bit per copy iteration) are replayed for the counts
   unsigned long long keepbits = 0;
@@ -337,29 +369,24 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
       for (int i = lane; i < TAB_WORDS; i += 32) tab[i] = 0;
     __syncwarp();
 
-    // ---- pass over the positions: lane handles steps u in [u0, u0+steps) of [0, L+N-1) -----------
-    // after consuming base u the window is [u-N+1, u]: FW = its forward code (the k-mers STARTING
-    // at p = u-N+1 are its prefixes), S2 = its image under revcomp / reverse (the images of those
-    // k-mers are its SUFFIXES), IV = invalid flags of the window
-    const int total_steps = L + N - 1;
-    const int steps = (total_steps + 31) / 32;
-    const int u0 = (int)lane * steps;
+    // ---- pass over the positions: lane handles the start positions p = lane, lane + 32, ... ----------
+    // The N bases starting at p are 2N consecutive bits of the packed words (first base in the low
+    // bits): one funnel shift.  Read that way the k-mer starting at p is the LOW 2k bits, its
+    // reverse complement (first base most significant, the code order) is the complement of those
+    // bits and its forward code is their digit reversal -- no rolling state, no warm-up.
+    const int steps = (L + 31) / 32;
     uint32_t FWL[EE];                 // (forward code << 4) | valid length, per position of this lane
 #pragma unroll
     for (int r = 0; r < EE; r++) FWL[r] = 0;
     {
-      BaseReader rd; rd.init(b2, iv16, L);
-      uint32_t FW = 0, S2 = 0, IV = 0xFFFFFFFFu;
-      auto consume = [&](int idx) {
-        uint32_t x, inv; rd.get(idx, x, inv);
-        FW = ((FW << 2) | x) & maskN;
-        if (op == 1) S2 = (S2 >> 2) | ((3u - x) << (2 * (N - 1)));
-        else if (op == 3) S2 = (S2 >> 2) | (x << (2 * (N - 1)));
-        IV = (IV << 1) | inv;
-      };
-      auto produce = [&]() -> uint32_t {
-        const uint32_t xw = IV & maskNb;
-        const int len_f = N - 32 + __clz(xw);           // valid bases forward from the window start
+      auto visit = [&](int p) -> uint32_t {
+        const int wi = p >> 4, sh = p & 15;
+        const uint32_t e = __funnelshift_r(__ldg(b2 + wi), __ldg(b2 + wi + 1), 2 * sh) & maskN;
+        const uint32_t ivb = (((uint32_t)__ldg(iv16 + wi) | ((uint32_t)__ldg(iv16 + wi + 1) << 16)) >> sh) |
+                             (1u << min(N, L - p));       // the sequence ends: no k-mer reaches past L
+        const int len_f = __ffs(ivb) - 1;                 // valid bases from p on (<= N)
+        const uint32_t FW = swap_pairs(__brev(e)) >> (32 - 2 * N);
+        const uint32_t S2 = op == 1 ? (~e) & maskN : e;   // image of the window under revcomp / reverse
         if (len_f >= M) {
           // table levels: one count at the deepest table level this suffix reaches
           if (has_tab) {
@@ -380,27 +407,24 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
               const uint32_t bit = 1u << (c & 31);
               const uint32_t old = atomicOr(bm + P.bm_off[k] + (c >> 5), bit);
               if ((old & bit) && !P.binarize) {
-                const uint32_t at = atomicAdd(dupn, 1u), e = ((uint32_t)k << 26) | c;
-                if (at < (uint32_t)DUP_SMEM) dups[at] = e; else ovf[at - DUP_SMEM] = e;
+                const uint32_t at = atomicAdd(dupn, 1u), ee = ((uint32_t)k << 26) | c;
+                if (at < (uint32_t)DUP_SMEM) dups[at] = ee; else ovf[at - DUP_SMEM] = ee;
               }
             }
           }
         }
         return (FW << 4) | (uint32_t)len_f;
       };
-      for (int idx = u0 - N + 1; idx < u0; idx++) consume(idx);
       if (E > 0) {
 #pragma unroll
         for (int i = 0; i < EE; i++) {
-          if (i < steps && u0 + i < total_steps) {
-            consume(u0 + i);
-            FWL[i] = produce();
-          }
+          const int p = i * 32 + (int)lane;
+          if (p < L) FWL[i] = visit(p);
         }
       } else {
-        for (int i = 0; i < steps && u0 + i < total_steps; i++) {
-          consume(u0 + i);
-          produce();
+        for (int i = 0; i < steps; i++) {
+          const int p = i * 32 + (int)lane;
+          if (p < L) visit(p);
         }
       }
     }
@@ -780,8 +804,10 @@ static std::shared_ptr<SeqSet> sequences_alloc(const int64_t *off, int64_t n, st
   s->len.upload(len.data(), (size_t)n);
   s->blk.upload(blk.data(), (size_t)n + 1);
   int64_t words = s->total_blocks * 4;
-  s->bits2.alloc((size_t)(words ? words : 1));
-  s->inv16.alloc((size_t)(words ? words : 1));
+  s->bits2.alloc((size_t)words + 1);     // + 1: the kernels read the word after the last base
+  s->inv16.alloc((size_t)words + 1);
+  KL_CUDA(cudaMemsetAsync(s->bits2.p + words, 0, sizeof(uint32_t), ctx().stream));
+  KL_CUDA(cudaMemsetAsync(s->inv16.p + words, 0, sizeof(uint16_t), ctx().stream));
   sync_stream();                  // len / blk are stack vectors of this call
   return s;
 }
@@ -881,7 +907,7 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   P.t_lo = cfg.M; P.t_hi = cfg.N < KT_MAX ? cfg.N : KT_MAX;
   // levels above the tables: per-row bitmaps up to level 7, a register sort per level above that;
   // rows too long for the register sort (more than 64 positions per lane) keep level 8 on a bitmap
-  const int64_t steps = (s.max_len + cfg.N - 1 + 31) / 32;
+  const int64_t steps = (s.max_len + 31) / 32;           // start positions per lane
   const int kb = steps > 64 ? KB_MAX : KB_DEFAULT;
   P.b_lo = cfg.M > KT_MAX + 1 ? cfg.M : KT_MAX + 1; P.b_hi = cfg.N < kb ? cfg.N : kb;
   P.s_lo = cfg.M > kb + 1 ? cfg.M : kb + 1;

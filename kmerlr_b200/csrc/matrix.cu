@@ -451,14 +451,17 @@ std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nse
   return R;
 }
 
-// max_i ||x_i||^2 without the bias (estimate_step_size, kmerLr_estimator_proximal.go:54-69)
-double matrix_maxsq(Matrix &M) {
-  if (M.has_maxsq) return M.maxsq;
-  double v = 0.0;
+// max_i ||x_i||^2 without the bias (estimate_step_size, kmerLr_estimator_proximal.go:54-69) and
+// max |x_ij| over the stored entries (fixed-point scale of the gradient accumulation): computed together,
+// one MAX all-reduce over the ranks
+static void ensure_stats(Matrix &M) {
+  if (M.has_maxsq && M.has_vmax) return;
+  double v[2] = {0.0, 0.0};
   if (M.has_local_stats) {
-    v = M.local_maxsq;
+    v[0] = M.local_maxsq; v[1] = M.local_vmax;
   } else {
-    DevBuf<unsigned long long> d(1);
+    matrix_compact(M);
+    DevBuf<unsigned long long> d(2);
     d.zero();
     if (M.n > 0) {
       unsigned wgrid = (unsigned)((M.n * 32 + 127) / 128);
@@ -466,51 +469,35 @@ double matrix_maxsq(Matrix &M) {
       else if (M.vt == VAL_F64) KL_LAUNCH((row_sqnorm_max<double>), wgrid, 128, 0, M.rows(), M.val_f64.p, M.n, d.p);
       else KL_LAUNCH((row_sqnorm_max<uint32_t>), wgrid, 128, 0, M.rows(), (const uint32_t *)nullptr, M.n, d.p);
     }
-    unsigned long long bits = 0;
-    d.download(&bits, 1);
+    if (M.nnz > 0) {
+      if (M.vt == VAL_U32) KL_LAUNCH((abs_max<uint32_t>), 1024, 256, 0, M.val_u32.p, M.nnz, d.p + 1);
+      else if (M.vt == VAL_F64) KL_LAUNCH((abs_max<double>), 1024, 256, 0, M.val_f64.p, M.nnz, d.p + 1);
+    }
+    unsigned long long bits[2] = {0, 0};
+    d.download(bits, 2);
     sync_stream();
-    memcpy(&v, &bits, sizeof(v));
+    memcpy(v, bits, sizeof(v));
+    if (M.vt == VAL_ONE) v[1] = M.nnz > 0 ? 1.0 : 0.0;
   }
   if (M.sharded) {
-    DevBuf<double> t(1);
-    t.upload(&v, 1);
-    comm_allreduce_max_f64(t.p, 1);
-    t.download(&v, 1);
+    DevBuf<double> t(2);
+    t.upload(v, 2);
+    comm_allreduce_max_f64(t.p, 2);
+    t.download(v, 2);
     sync_stream();
   }
-  M.maxsq = v; M.has_maxsq = true;
-  return v;
+  M.maxsq = v[0]; M.has_maxsq = true;
+  M.vmax = v[1]; M.has_vmax = true;
 }
 
-// max |x_ij| over the stored entries (fixed-point scale of the gradient accumulation)
+double matrix_maxsq(Matrix &M) {
+  ensure_stats(M);
+  return M.maxsq;
+}
+
 double matrix_vmax(Matrix &M) {
-  if (M.has_vmax) return M.vmax;
-  double v = 0.0;
-  if (M.has_local_stats) {
-    v = M.local_vmax;
-  } else {
-    matrix_compact(M);
-    DevBuf<unsigned long long> d(1);
-    d.zero();
-    if (M.nnz > 0) {
-      if (M.vt == VAL_U32) KL_LAUNCH((abs_max<uint32_t>), 1024, 256, 0, M.val_u32.p, M.nnz, d.p);
-      else if (M.vt == VAL_F64) KL_LAUNCH((abs_max<double>), 1024, 256, 0, M.val_f64.p, M.nnz, d.p);
-    }
-    unsigned long long bits = 0;
-    d.download(&bits, 1);
-    sync_stream();
-    memcpy(&v, &bits, sizeof(v));
-    if (M.vt == VAL_ONE) v = M.nnz > 0 ? 1.0 : 0.0;
-  }
-  if (M.sharded) {
-    DevBuf<double> t(1);
-    t.upload(&v, 1);
-    comm_allreduce_max_f64(t.p, 1);
-    t.download(&v, 1);
-    sync_stream();
-  }
-  M.vmax = v; M.has_vmax = true;
-  return v;
+  ensure_stats(M);
+  return M.vmax;
 }
 
 }  // namespace kl
