@@ -181,8 +181,8 @@ def workload_config(args, world):
                         (args.config.upper(), n_fg, n_bg, L, M, N, ", binarized" if binarize else ""),
             "sequences_per_gpu": n_fg + n_bg, "seq_len": L, "k_min": M, "k_max": N,
             "parallelism": "sample-sharded x%d" % world,
-            "l2": "inputs larger than L2: every step streams the staged rows and the CSR matrix (3 GB each at C2), "
-                  "the 126 MB L2 holds none of it across steps"}
+            "l2": "working set larger than L2: every step writes the matrix rows (3.5 GB at C2) and re-reads the packed "
+                  "sequences after them, so nothing survives in the 126 MB L2 from one step to the next"}
 
 
 def main():
