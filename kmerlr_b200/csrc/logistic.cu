@@ -466,6 +466,145 @@ __global__ void prox_finish(PgState *st, const double *__restrict__ blockmax, in
   }
 }
 
+// ---- small problems (reduced matrices of the leapfrog path: <= 1023 columns, short rows) -----------------
+// An iteration is latency / launch bound there, so it is two launches: fused_small_kernel (8 lanes per
+// row, theta and the fixed-point gradient accumulators in shared memory, loss partial per block) and
+// tail_small_kernel (one block: loss, hook, prox update, stopping rule, clears G for the next pass).
+constexpr int SMALL_MAX_THETA = 1024;
+constexpr int SMALL_LPR = 8;
+
+template <typename VT>
+__global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
+                                                          const VT *__restrict__ val, int64_t n, int64_t ntheta,
+                                                          const double *__restrict__ theta,
+                                                          const uint8_t *__restrict__ labels, double cw0, double cw1,
+                                                          double inv_n, double scale, unsigned long long *__restrict__ G,
+                                                          double *__restrict__ blockloss, const PgState *st, int scatter) {
+  if (st->done == 1) return;
+  __shared__ uint32_t acc_lo[SMALL_MAX_THETA], acc_hi[SMALL_MAX_THETA];
+  __shared__ double sth[SMALL_MAX_THETA];
+  __shared__ double red[256];
+  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) { acc_lo[i] = 0u; acc_hi[i] = 0u; sth[i] = theta[i]; }
+  __syncthreads();
+  const int sl = threadIdx.x & (SMALL_LPR - 1);
+  const int64_t gsub = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SMALL_LPR;
+  const int64_t nsub = ((int64_t)gridDim.x * blockDim.x) / SMALL_LPR;
+  auto add = [&](uint32_t c, unsigned long long q) {
+    const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
+    const uint32_t old = atomicAdd(&acc_lo[c], lo);
+    const uint32_t add_hi = hi + ((old + lo) < old ? 1u : 0u);
+    if (add_hi) atomicAdd(&acc_hi[c], add_hi);
+  };
+  double lacc = 0.0;
+  // every lane of the warp runs the same number of iterations (the shuffles are warp wide)
+  const int64_t rounds = (n + nsub - 1) / nsub;
+  for (int64_t it = 0; it < rounds; it++) {
+    const int64_t row = gsub + it * nsub;
+    const bool live = row < n;
+    int64_t a = 0, b = 0;
+    if (live) R.range(row, a, b);
+    double s = 0.0;
+    for (int64_t p = a + sl; p < b; p += SMALL_LPR) s += valf(val, p) * sth[col[p] + 1];
+#pragma unroll
+    for (int o = SMALL_LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, SMALL_LPR);
+    double w = 0.0;
+    if (live && sl == 0) {
+      // Gradient weight (:166-178) and Loss term (:257-263)
+      double z = sth[0] + s, r = -log_add0(-z);
+      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lacc += -cw1 * r; }
+      else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
+    }
+    w = __shfl_sync(0xffffffffu, w, 0, SMALL_LPR);
+    if (!scatter || !live) continue;
+    const double ws = w * scale;
+    if (sl == 0) add(0u, (unsigned long long)__double2ll_rn(ws));
+    for (int64_t p = a + sl; p < b; p += SMALL_LPR)
+      add(col[p] + 1u, (unsigned long long)__double2ll_rn(ws * valf(val, p)));
+  }
+  // loss partial of the block: fixed tree
+  red[threadIdx.x] = lacc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) blockloss[blockIdx.x] = red[0];
+  if (scatter)
+    for (int i = threadIdx.x; i < ntheta; i += blockDim.x) {
+      unsigned long long v = ((unsigned long long)acc_hi[i] << 32) | acc_lo[i];
+      if (v) atomicAdd(&G[i], v);
+    }
+}
+
+// hook (kmerLr_estimator_hook.go:46-99) + prox step + eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98)
+__global__ void __launch_bounds__(256) tail_small_kernel(PgState *st, const double *__restrict__ blockloss, int nblocks,
+                                                         double *__restrict__ theta, unsigned long long *__restrict__ G,
+                                                         double inv_scale, int64_t ntheta, double inv_n, double lambda,
+                                                         double eps_loss, double step, double eps, long long max_iter) {
+  if (st->done == 1) return;
+  __shared__ double sh[256], shx[256], shd[256], shn[256];
+  __shared__ int s_done;
+  const int t = threadIdx.x;
+  // loss = sum of the block partials (index order inside a thread, fixed tree across threads) + L1 term
+  double s = 0.0, l1 = 0.0;
+  for (int i = t; i < nblocks; i += 256) s += blockloss[i];
+  if (!isnan(lambda) && lambda != 0.0)
+    for (int64_t j = 1 + t; j < ntheta; j += 256) l1 += lambda * fabs(theta[j]);
+  sh[t] = s; shx[t] = l1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) { sh[t] += sh[t + o]; shx[t] += shx[t + o]; }
+    __syncthreads();
+  }
+  if (t == 0) {
+    const double l = sh[0] * inv_n + shx[0];
+    st->lossval = l;
+    if (st->first) st->first = 0;                 // loss at the start point: no hook call yet
+    else {
+      double tmp = st->loss_old; st->loss_old = st->loss_new; st->loss_new = tmp;
+      if (eps_loss != 0.0) {
+        st->loss_new = l;
+        if (st->done == 0 && fabs(st->loss_old - st->loss_new) < eps_loss) st->done = 1;
+      }
+      if (st->done == 2) st->done = 1;
+    }
+    s_done = st->done;
+  }
+  __syncthreads();
+  if (!s_done) {
+    double mx = 0.0, md = 0.0, nn = 0.0;
+    for (int64_t k = t; k < ntheta; k += 256) {
+      double g = (double)(long long)G[k] * inv_scale;
+      double t0 = theta[k], t1 = t0 - step * g;
+      if (k > 0) {
+        if (t1 >= 0.0) t1 = fmax(fabs(t1) - step * lambda, 0.0);
+        else           t1 = -fmax(fabs(t1) - step * lambda, 0.0);
+      }
+      theta[k] = t1;
+      if (isnan(t1)) nn = 1.0;
+      mx = fmax(mx, fabs(t1));
+      md = fmax(md, fabs(t1 - t0));
+    }
+    shx[t] = mx; shd[t] = md; shn[t] = nn;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (t < o) { shx[t] = fmax(shx[t], shx[t + o]); shd[t] = fmax(shd[t], shd[t + o]); shn[t] = fmax(shn[t], shn[t + o]); }
+      __syncthreads();
+    }
+    if (t == 0) {
+      mx = shx[0]; md = shd[0];
+      st->iter += 1;
+      if (shn[0] != 0.0) { st->delta = nan(""); st->done = 1; }
+      else {
+        st->delta = mx != 0.0 ? md / mx : md;
+        if ((mx != 0.0 && md / mx <= eps) || (mx == 0.0 && md == 0.0)) st->done = 1;
+        else if (st->iter >= max_iter) st->done = 2;
+      }
+    }
+  }
+  for (int64_t k = t; k < ntheta; k += 256) G[k] = 0ull;    // the next pass accumulates from zero
+}
+
 constexpr int PROX_BLOCKS = 64;
 
 struct Work {
@@ -695,7 +834,17 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   h.loss_old = hook ? hook[0] : NAN; h.loss_new = hook ? hook[1] : NAN; h.lossval = NAN;
   st.upload(&h, 1);
   const double inv_n = 1.0 / (double)M.n_global;
-  const int64_t BATCH = 16;
+  // reduced matrices: two launches per iteration, long batches between host round trips
+  const bool small = !M.sharded && ntheta <= SMALL_MAX_THETA && !use_implicit(M) && M.n > 0;
+  const int64_t BATCH = small ? 256 : 16;
+  int small_blocks = 0;
+  DevBuf<double> blockloss;
+  if (small) {
+    int64_t nb = (int64_t)ctx().sm_count * 8, need = (M.n * SMALL_LPR + 255) / 256;
+    small_blocks = (int)(nb < need ? nb : need);
+    blockloss.alloc((size_t)small_blocks);
+    KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)ntheta * sizeof(unsigned long long), ctx().stream));
+  }
   int64_t issued = 0;
   while (true) {
     // max_iter prox steps need max_iter + 1 row passes (the last one only evaluates the hook)
@@ -706,6 +855,16 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
     for (int64_t it = 0; it < nb; it++) {
       // pass number max_iter (0-based) only evaluates the hook's loss at the final theta: no gradient
       const int scatter = (issued - nb + it) < max_iter ? 1 : 0;
+      if (small) {
+        dispatch_vt(M, [&](auto *tag) {
+          using VT = typename std::remove_pointer<decltype(tag)>::type;
+          KL_LAUNCH((fused_small_kernel<VT>), (unsigned)small_blocks, 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, ntheta,
+                    wk.theta.p, M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.G.p, blockloss.p, st.p, scatter);
+        });
+        KL_LAUNCH(tail_small_kernel, 1, 256, 0, st.p, blockloss.p, small_blocks, wk.theta.p, wk.G.p, wk.inv_scale, ntheta,
+                  inv_n, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
+        continue;
+      }
       dispatch_vt(M, [&](auto *tag) {
         using VT = typename std::remove_pointer<decltype(tag)>::type;
         launch_fused<VT>(M, wk, cw, st.p, scatter);
