@@ -109,13 +109,14 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
                                                     const double *__restrict__ theta,
                                                     const uint8_t *__restrict__ labels, double cw0, double cw1,
                                                     double inv_n, double scale, unsigned long long *__restrict__ G,
-                                                    double *__restrict__ lossterm, const PgState *st, int scatter) {
+                                                    double *__restrict__ lossterm, const PgState *st, int scatter,
+                                                    int hot_limit) {
   if (st && st->done == 1) return;
   // 64-bit accumulators as two 32-bit words: shared memory has native 32-bit atomic adds only
   // (a 64-bit add would be a compare-and-swap loop); the carry out of the low word is added to
   // the high word by the thread whose add wrapped, so the pair is an exact 64-bit sum
   __shared__ uint32_t hot_lo[HOT_COLS], hot_hi[HOT_COLS];
-  const int64_t hot_cols = m < HOT_COLS ? m : HOT_COLS;
+  const int64_t hot_cols = m < hot_limit ? m : hot_limit;
   for (int i = threadIdx.x; i < hot_cols; i += blockDim.x) { hot_lo[i] = 0u; hot_hi[i] = 0u; }
   __syncthreads();
   const unsigned lane = lane_id();
@@ -703,7 +704,7 @@ void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, in
       int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
       if (blocks > need) blocks = need;
       KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
-                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter);
+                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter, ctx().hot_cols);
     }
   }
   if (M.sharded && scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
