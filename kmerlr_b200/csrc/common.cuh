@@ -63,7 +63,7 @@ struct Ctx {
   double last_ms = 0.0;
   bool profiling = false;
   bool implicit_ok = true;   // kmerlr_option("implicit")
-  int hot_cols = 4096;       // kmerlr_option("hot_cols"): columns of the CSR pass that accumulate in shared memory
+  int hot_cols = 6144;       // kmerlr_option("hot_cols"): columns of the CSR pass that accumulate in shared memory
   // communicator (NCCL via dlopen, see comm.cu)
   void *comm = nullptr;
   int rank = 0, world = 1;

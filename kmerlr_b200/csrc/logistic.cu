@@ -101,7 +101,7 @@ __global__ void reduce_stage2(const double *__restrict__ part, int np, double *_
 // the fused pass: persistent blocks, one warp per row
 //   G[0]    += round(w_i * S)                 (bias, Go index 0)
 //   G[c+1]  += round(w_i * v_ic * S)          for every entry of the row
-constexpr int HOT_COLS = 4096;   // columns < HOT_COLS accumulate in shared memory (32 KB)
+constexpr int HOT_COLS_MAX = 16384;   // at most this many columns accumulate in shared memory (8 B each)
 
 template <typename VT>
 __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t *__restrict__ col,
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
   // 64-bit accumulators as two 32-bit words: shared memory has native 32-bit atomic adds only
   // (a 64-bit add would be a compare-and-swap loop); the carry out of the low word is added to
   // the high word by the thread whose add wrapped, so the pair is an exact 64-bit sum
-  __shared__ uint32_t hot_lo[HOT_COLS], hot_hi[HOT_COLS];
+  extern __shared__ uint32_t hot_smem[];
+  uint32_t *hot_lo = hot_smem, *hot_hi = hot_smem + hot_limit;
   const int64_t hot_cols = m < hot_limit ? m : hot_limit;
   for (int i = threadIdx.x; i < hot_cols; i += blockDim.x) { hot_lo[i] = 0u; hot_hi[i] = 0u; }
   __syncthreads();
@@ -468,81 +469,18 @@ __global__ void prox_finish(PgState *st, const double *__restrict__ blockmax, in
 }
 
 // ---- small problems (reduced matrices of the leapfrog path: <= 1023 columns, short rows) -----------------
-// An iteration is latency / launch bound there, so it is two launches: fused_small_kernel (8 lanes per
+// An iteration is latency / launch bound there, so it is ONE launch: fused_small_kernel (8 lanes per
 // row, theta and the fixed-point gradient accumulators in shared memory, loss partial per block) and
-// tail_small_kernel (one block: loss, hook, prox update, stopping rule, clears G for the next pass).
+// the block that finishes last runs small_tail (loss, hook, prox update, stopping rule, clears G).
 constexpr int SMALL_MAX_THETA = 1024;
 constexpr int SMALL_LPR = 8;
 
-template <typename VT>
-__global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
-                                                          const VT *__restrict__ val, int64_t n, int64_t ntheta,
-                                                          const double *__restrict__ theta,
-                                                          const uint8_t *__restrict__ labels, double cw0, double cw1,
-                                                          double inv_n, double scale, unsigned long long *__restrict__ G,
-                                                          double *__restrict__ blockloss, const PgState *st, int scatter) {
-  if (st->done == 1) return;
-  __shared__ uint32_t acc_lo[SMALL_MAX_THETA], acc_hi[SMALL_MAX_THETA];
-  __shared__ double sth[SMALL_MAX_THETA];
-  __shared__ double red[256];
-  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) { acc_lo[i] = 0u; acc_hi[i] = 0u; sth[i] = theta[i]; }
-  __syncthreads();
-  const int sl = threadIdx.x & (SMALL_LPR - 1);
-  const int64_t gsub = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SMALL_LPR;
-  const int64_t nsub = ((int64_t)gridDim.x * blockDim.x) / SMALL_LPR;
-  auto add = [&](uint32_t c, unsigned long long q) {
-    const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
-    const uint32_t old = atomicAdd(&acc_lo[c], lo);
-    const uint32_t add_hi = hi + ((old + lo) < old ? 1u : 0u);
-    if (add_hi) atomicAdd(&acc_hi[c], add_hi);
-  };
-  double lacc = 0.0;
-  // every lane of the warp runs the same number of iterations (the shuffles are warp wide)
-  const int64_t rounds = (n + nsub - 1) / nsub;
-  for (int64_t it = 0; it < rounds; it++) {
-    const int64_t row = gsub + it * nsub;
-    const bool live = row < n;
-    int64_t a = 0, b = 0;
-    if (live) R.range(row, a, b);
-    double s = 0.0;
-    for (int64_t p = a + sl; p < b; p += SMALL_LPR) s += valf(val, p) * sth[col[p] + 1];
-#pragma unroll
-    for (int o = SMALL_LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, SMALL_LPR);
-    double w = 0.0;
-    if (live && sl == 0) {
-      // Gradient weight (:166-178) and Loss term (:257-263)
-      double z = sth[0] + s, r = -log_add0(-z);
-      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lacc += -cw1 * r; }
-      else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
-    }
-    w = __shfl_sync(0xffffffffu, w, 0, SMALL_LPR);
-    if (!scatter || !live) continue;
-    const double ws = w * scale;
-    if (sl == 0) add(0u, (unsigned long long)__double2ll_rn(ws));
-    for (int64_t p = a + sl; p < b; p += SMALL_LPR)
-      add(col[p] + 1u, (unsigned long long)__double2ll_rn(ws * valf(val, p)));
-  }
-  // loss partial of the block: fixed tree
-  red[threadIdx.x] = lacc;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) blockloss[blockIdx.x] = red[0];
-  if (scatter)
-    for (int i = threadIdx.x; i < ntheta; i += blockDim.x) {
-      unsigned long long v = ((unsigned long long)acc_hi[i] << 32) | acc_lo[i];
-      if (v) atomicAdd(&G[i], v);
-    }
-}
-
-// hook (kmerLr_estimator_hook.go:46-99) + prox step + eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98)
-__global__ void __launch_bounds__(256) tail_small_kernel(PgState *st, const double *__restrict__ blockloss, int nblocks,
-                                                         double *__restrict__ theta, unsigned long long *__restrict__ G,
-                                                         double inv_scale, int64_t ntheta, double inv_n, double lambda,
-                                                         double eps_loss, double step, double eps, long long max_iter) {
-  if (st->done == 1) return;
+// hook (kmerLr_estimator_hook.go:46-99) + prox step + eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98),
+// run by ONE block of 256 threads once every block's partials are in
+__device__ __forceinline__ void small_tail(PgState *st, const double *__restrict__ blockloss, int nblocks,
+                                           double *__restrict__ theta, unsigned long long *__restrict__ G,
+                                           double inv_scale, int64_t ntheta, double inv_n, double lambda,
+                                           double eps_loss, double step, double eps, long long max_iter) {
   __shared__ double sh[256], shx[256], shd[256], shn[256];
   __shared__ int s_done;
   const int t = threadIdx.x;
@@ -604,6 +542,81 @@ __global__ void __launch_bounds__(256) tail_small_kernel(PgState *st, const doub
     }
   }
   for (int64_t k = t; k < ntheta; k += 256) G[k] = 0ull;    // the next pass accumulates from zero
+}
+
+template <typename VT>
+__global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
+                                                          const VT *__restrict__ val, int64_t n, int64_t ntheta,
+                                                          double *theta, const uint8_t *__restrict__ labels,
+                                                          double cw0, double cw1, double inv_n, double scale,
+                                                          unsigned long long *G, double *blockloss, PgState *st,
+                                                          int scatter, unsigned int *counter, double inv_scale,
+                                                          double lambda, double eps_loss, double step, double eps,
+                                                          long long max_iter) {
+  if (st->done == 1) return;
+  __shared__ uint32_t acc_lo[SMALL_MAX_THETA], acc_hi[SMALL_MAX_THETA];
+  __shared__ int s_last;
+  __shared__ double sth[SMALL_MAX_THETA];
+  __shared__ double red[256];
+  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) { acc_lo[i] = 0u; acc_hi[i] = 0u; sth[i] = theta[i]; }
+  __syncthreads();
+  const int sl = threadIdx.x & (SMALL_LPR - 1);
+  const int64_t gsub = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SMALL_LPR;
+  const int64_t nsub = ((int64_t)gridDim.x * blockDim.x) / SMALL_LPR;
+  auto add = [&](uint32_t c, unsigned long long q) {
+    const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
+    const uint32_t old = atomicAdd(&acc_lo[c], lo);
+    const uint32_t add_hi = hi + ((old + lo) < old ? 1u : 0u);
+    if (add_hi) atomicAdd(&acc_hi[c], add_hi);
+  };
+  double lacc = 0.0;
+  // every lane of the warp runs the same number of iterations (the shuffles are warp wide)
+  const int64_t rounds = (n + nsub - 1) / nsub;
+  for (int64_t it = 0; it < rounds; it++) {
+    const int64_t row = gsub + it * nsub;
+    const bool live = row < n;
+    int64_t a = 0, b = 0;
+    if (live) R.range(row, a, b);
+    double s = 0.0;
+    for (int64_t p = a + sl; p < b; p += SMALL_LPR) s += valf(val, p) * sth[col[p] + 1];
+#pragma unroll
+    for (int o = SMALL_LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, SMALL_LPR);
+    double w = 0.0;
+    if (live && sl == 0) {
+      // Gradient weight (:166-178) and Loss term (:257-263)
+      double z = sth[0] + s, r = -log_add0(-z);
+      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lacc += -cw1 * r; }
+      else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
+    }
+    w = __shfl_sync(0xffffffffu, w, 0, SMALL_LPR);
+    if (!scatter || !live) continue;
+    const double ws = w * scale;
+    if (sl == 0) add(0u, (unsigned long long)__double2ll_rn(ws));
+    for (int64_t p = a + sl; p < b; p += SMALL_LPR)
+      add(col[p] + 1u, (unsigned long long)__double2ll_rn(ws * valf(val, p)));
+  }
+  // loss partial of the block: fixed tree
+  red[threadIdx.x] = lacc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) blockloss[blockIdx.x] = red[0];
+  if (scatter)
+    for (int i = threadIdx.x; i < ntheta; i += blockDim.x) {
+      unsigned long long v = ((unsigned long long)acc_hi[i] << 32) | acc_lo[i];
+      if (v) atomicAdd(&G[i], v);
+    }
+  // the block that finishes last runs the tail of the iteration (its reads see every block's results)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  small_tail(st, blockloss, (int)gridDim.x, theta, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter);
+  if (threadIdx.x == 0) *counter = 0u;
 }
 
 constexpr int PROX_BLOCKS = 64;
@@ -698,13 +711,17 @@ void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, in
     if (use_implicit(M)) {
       launch_implicit(M, wk, cw, st, scatter);
     } else {
+      int hot = ctx().hot_cols;
+      if (hot > M.m) hot = (int)M.m;
+      const size_t smem = (size_t)hot * 8;
+      KL_CUDA(cudaFuncSetAttribute(fused_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HOT_COLS_MAX * 8));
       int per_sm = 0;
-      KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, 0));
+      KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, smem));
       if (per_sm < 1) per_sm = 1;
       int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
       if (blocks > need) blocks = need;
-      KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
-                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter, ctx().hot_cols);
+      KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, smem, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
+                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter, hot);
     }
   }
   if (M.sharded && scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
@@ -840,10 +857,13 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   const int64_t BATCH = small ? 256 : 16;
   int small_blocks = 0;
   DevBuf<double> blockloss;
+  DevBuf<unsigned int> counter;
   if (small) {
     int64_t nb = (int64_t)ctx().sm_count * 8, need = (M.n * SMALL_LPR + 255) / 256;
     small_blocks = (int)(nb < need ? nb : need);
     blockloss.alloc((size_t)small_blocks);
+    counter.alloc(1);
+    counter.zero();
     KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)ntheta * sizeof(unsigned long long), ctx().stream));
   }
   int64_t issued = 0;
@@ -860,10 +880,9 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
         dispatch_vt(M, [&](auto *tag) {
           using VT = typename std::remove_pointer<decltype(tag)>::type;
           KL_LAUNCH((fused_small_kernel<VT>), (unsigned)small_blocks, 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, ntheta,
-                    wk.theta.p, M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.G.p, blockloss.p, st.p, scatter);
+                    wk.theta.p, M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.G.p, blockloss.p, st.p, scatter, counter.p,
+                    wk.inv_scale, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
         });
-        KL_LAUNCH(tail_small_kernel, 1, 256, 0, st.p, blockloss.p, small_blocks, wk.theta.p, wk.G.p, wk.inv_scale, ntheta,
-                  inv_n, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
         continue;
       }
       dispatch_vt(M, [&](auto *tag) {
