@@ -34,7 +34,7 @@ typedef struct kmerlr_config {
   int32_t M, N;
   int32_t complement, reverse, revcomp;
   int32_t binarize;
-  int32_t alphabet;       /* 0 = nucleotide (GPU path); 1 = gapped nucleotide (not on GPU yet) */
+  int32_t alphabet;       /* 0 = nucleotide; 1 = gapped nucleotide (sort-based path, N <= 11) */
   int32_t max_ambiguous;  /* -1 = nil */
 } kmerlr_config;
 

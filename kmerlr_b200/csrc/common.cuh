@@ -274,6 +274,9 @@ std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet
 std::shared_ptr<Matrix> extract_host(const kmerlr_config &cfg, const uint8_t *seq, const int64_t *off, int64_t n,
                                      const int32_t *frozen_k, const uint64_t *frozen_code, int64_t n_frozen,
                                      const int32_t *features, int64_t n_features, int flags);
+// gapped.cu
+std::shared_ptr<Matrix> extract_gapped(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs, const int32_t *frozen_k,
+                                       const uint64_t *frozen_code, int64_t n_frozen, int flags);
 void matrix_class_list(Matrix &M);   // fills class_k / class_code if they are still on the device
 // matrix.cu
 std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const int32_t *col,

@@ -893,7 +893,15 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
                                             const int32_t *features, int64_t n_features, int flags, HostFeed *feed) {
   require_ready();
   const SeqSet &s = *seqs;
-  KL_REQUIRE(cfg.alphabet == 0, "only the nucleotide alphabet is implemented on the GPU path (gapped: SURVEY 8f-3)");
+  KL_REQUIRE(cfg.alphabet == 0 || cfg.alphabet == 1, "alphabet: 0 = nucleotide, 1 = gapped nucleotide (IUPAC is not implemented)");
+  if (cfg.alphabet == 1) {
+    // gapped alphabet: the sort-based path of gapped.cu (needs the whole set packed)
+    KL_REQUIRE(n_features == 0 || n_frozen > 0, "an explicit feature list needs a frozen class list");
+    if (feed && s.n > 0) feed->feed(*seqs, 0, s.n, 0);
+    auto g = extract_gapped(cfg, seqs, frozen_k, frozen_code, n_frozen, flags);
+    if (n_features > 0) return apply_features(*g, features, n_features);
+    return g;
+  }
   KL_REQUIRE(cfg.M >= 1 && cfg.M <= cfg.N, "need 1 <= M <= N");
   KL_REQUIRE(cfg.N <= MAX_N, "k-mer length above 13 is not supported on the GPU path");
   int nops = (cfg.complement != 0) + (cfg.reverse != 0) + (cfg.revcomp != 0);

@@ -122,10 +122,57 @@ def test_frozen_counter_and_features(K, oracle, fixtures):
         assert np.array_equal(x, y)
 
 
+def test_gapped_alphabet_reference_pins(K, oracle, fixtures):
+    """TestKmers1 / TestKmers2 on the GPU (kmerLr_test.go:30-97): gapped alphabet, k = 4..8, revcomp --
+    the six (index, class, count) pins, the four pair products, frozen = unfrozen"""
+    kc, oc = cfg_pair(K, oracle, 4, 8, revcomp=True, alphabet="gapped-nucleotide")
+    buf, off, _ = cat(fixtures, "kmerLr_test", "kmerLr_test")
+    d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    ref = oracle.extract(oc, (buf, off))
+    assert d.n == 4 and d.m == 58308
+    same_matrix(d, ref)
+    names = ref.class_names()
+    rp, col, val = d.rows()
+    row0 = dict(zip(col[rp[0]:rp[1]].tolist(), val[rp[0]:rp[1]].tolist()))
+    pins = [(4671, "gntanc|gntanc", 3), (4672, "gntcaa|ttganc", 0), (5068, "aaagaaa|tttcttt", 1),
+            (5486, "aagannt|anntctt", 7), (19270, "aacgcgna|tncgcgtt", 1), (57071, "tgaatgca|tgcattca", 1)]
+    for idx, name, count in pins:                                   # kmerLr_test.go:40-43
+        assert names[idx] == name and row0.get(idx, 0) == count
+    classes = d.Kmers()
+    d2 = K.compile_test_data(None, kc, classes, None, True, False, (buf, off))       # frozen counter
+    for x, y in zip(d.rows(), d2.rows()):
+        assert np.array_equal(x, y)
+    m = d.m
+    feats = [(i, i) for i in range(0, m, 97)] + [(4671, 4672), (5068, 5486), (19270, 57071), (4671, 5486)]
+    d3 = K.compile_test_data(None, kc, classes, feats, False, False, (buf, off))
+    r3 = d3.rows()
+    last = dict(zip(r3[1][r3[0][0]:r3[0][1]].tolist(), r3[2][r3[0][0]:r3[0][1]].tolist()))
+    nf = len(feats)
+    assert [last.get(nf - 4 + i, 0) for i in range(4)] == [0, 7, 1, 21]      # kmerLr_test.go:55-66
+
+
+def test_gapped_alphabet_variants(K, oracle):
+    """gapped alphabet on ragged synthetic rows: max_ambiguous, other strand operations, binarize, invalid bases"""
+    from kmerlr_b200 import synth
+    buf, off, _ = synth.training_set(9, 8, 90)
+    buf = buf.copy()
+    buf[off[2] + 7] = ord("N")
+    seqs = (buf, off)
+    for M, N, flags in [(2, 6, dict(revcomp=True)), (3, 5, dict(max_ambiguous=1)), (4, 7, dict(reverse=True, max_ambiguous=2)),
+                        (1, 4, dict(complement=True, binarize=True)), (5, 6, dict(revcomp=True, max_ambiguous=0))]:
+        flags = dict(flags, alphabet="gapped-nucleotide")
+        ma = flags.get("max_ambiguous")
+        kc = K.NewKmerCounter(M, N, **flags)
+        oc = oracle.make_config(M, N, **{k: v for k, v in flags.items() if k != "max_ambiguous"},
+                                max_ambiguous=-1 if ma is None else ma)
+        d = K.compile_test_data(None, kc, None, None, True, flags.get("binarize", False), seqs)
+        same_matrix(d, oracle.extract(oc, seqs))
+
+
 def test_unsupported_configurations_fail_loudly(K):
     with pytest.raises(K.KmerLrError):
-        K.compile_test_data(None, K.NewKmerCounter(4, 8, revcomp=True, alphabet="gapped-nucleotide"), None, None, True,
-                            False, ["ACGTACGTACGT"])
+        K.compile_test_data(None, K.NewKmerCounter(4, 12, revcomp=True, alphabet="gapped-nucleotide"), None, None, True,
+                            False, ["ACGTACGTACGTACGT"])
     with pytest.raises(K.KmerLrError):
         K.compile_test_data(None, K.NewKmerCounter(1, 14), None, None, True, False, ["ACGTACGTACGTACGT"])
     with pytest.raises(K.KmerLrError):
