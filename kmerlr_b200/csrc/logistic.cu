@@ -477,8 +477,8 @@ constexpr int SMALL_LPR = 8;
 
 // hook (kmerLr_estimator_hook.go:46-99) + prox step + eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98),
 // run by ONE block of 256 threads once every block's partials are in
-__device__ __forceinline__ void small_tail(PgState *st, const double *__restrict__ blockloss, int nblocks,
-                                           double *__restrict__ theta, unsigned long long *__restrict__ G,
+__device__ __forceinline__ void small_tail(PgState *st, const double *blockloss, int nblocks, double *theta,
+                                           unsigned long long *G,
                                            double inv_scale, int64_t ntheta, double inv_n, double lambda,
                                            double eps_loss, double step, double eps, long long max_iter) {
   __shared__ double sh[256], shx[256], shd[256], shn[256];
@@ -486,7 +486,7 @@ __device__ __forceinline__ void small_tail(PgState *st, const double *__restrict
   const int t = threadIdx.x;
   // loss = sum of the block partials (index order inside a thread, fixed tree across threads) + L1 term
   double s = 0.0, l1 = 0.0;
-  for (int i = t; i < nblocks; i += 256) s += blockloss[i];
+  for (int i = t; i < nblocks; i += 256) s += __ldcg(blockloss + i);     // written by other blocks: read in L2
   if (!isnan(lambda) && lambda != 0.0)
     for (int64_t j = 1 + t; j < ntheta; j += 256) l1 += lambda * fabs(theta[j]);
   sh[t] = s; shx[t] = l1;
@@ -513,7 +513,7 @@ __device__ __forceinline__ void small_tail(PgState *st, const double *__restrict
   if (!s_done) {
     double mx = 0.0, md = 0.0, nn = 0.0;
     for (int64_t k = t; k < ntheta; k += 256) {
-      double g = (double)(long long)G[k] * inv_scale;
+      double g = (double)(long long)__ldcg(G + k) * inv_scale;
       double t0 = theta[k], t1 = t0 - step * g;
       if (k > 0) {
         if (t1 >= 0.0) t1 = fmax(fabs(t1) - step * lambda, 0.0);
@@ -609,6 +609,7 @@ __global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const ui
       if (v) atomicAdd(&G[i], v);
     }
   // the block that finishes last runs the tail of the iteration (its reads see every block's results)
+  if (!counter) return;                 // sharded: the collectives come first, the tail is its own launch
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
@@ -617,6 +618,30 @@ __global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const ui
   __threadfence();
   small_tail(st, blockloss, (int)gridDim.x, theta, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter);
   if (threadIdx.x == 0) *counter = 0u;
+}
+
+// sharded reduced matrices: sum of the block loss partials (fixed order) -> one double per rank ...
+__global__ void __launch_bounds__(256) small_presum_kernel(const PgState *st, const double *__restrict__ blockloss,
+                                                           int nblocks, double *__restrict__ out) {
+  if (st->done == 1) return;
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) s += blockloss[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+// ... and the tail over the gathered per-rank losses (rank order) and the all-reduced gradient
+__global__ void __launch_bounds__(256) small_tail_kernel(PgState *st, const double *partials, int nparts, double *theta,
+                                                         unsigned long long *G, double inv_scale, int64_t ntheta,
+                                                         double inv_n, double lambda, double eps_loss, double step,
+                                                         double eps, long long max_iter) {
+  if (st->done == 1) return;
+  small_tail(st, partials, nparts, theta, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter);
 }
 
 constexpr int PROX_BLOCKS = 64;
@@ -853,7 +878,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   st.upload(&h, 1);
   const double inv_n = 1.0 / (double)M.n_global;
   // reduced matrices: two launches per iteration, long batches between host round trips
-  const bool small = !M.sharded && ntheta <= SMALL_MAX_THETA && !use_implicit(M) && M.n > 0;
+  const bool small = ntheta <= SMALL_MAX_THETA && !use_implicit(M) && M.n > 0;
   const int64_t BATCH = small ? 256 : 16;
   int small_blocks = 0;
   DevBuf<double> blockloss;
@@ -880,9 +905,18 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
         dispatch_vt(M, [&](auto *tag) {
           using VT = typename std::remove_pointer<decltype(tag)>::type;
           KL_LAUNCH((fused_small_kernel<VT>), (unsigned)small_blocks, 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, ntheta,
-                    wk.theta.p, M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.G.p, blockloss.p, st.p, scatter, counter.p,
-                    wk.inv_scale, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
+                    wk.theta.p, M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.G.p, blockloss.p, st.p, scatter,
+                    M.sharded ? (unsigned int *)nullptr : counter.p, wk.inv_scale, lambda, epsilon_loss, step, epsilon,
+                    (long long)max_iter);
         });
+        if (M.sharded) {
+          // gradient: exact int64 all-reduce; loss: per-rank sums gathered and added in rank order
+          KL_LAUNCH(small_presum_kernel, 1, 256, 0, st.p, blockloss.p, small_blocks, wk.scalars.p);
+          if (scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, ntheta);
+          comm_allgather_f64(wk.scalars.p, wk.gathered.p, 1);
+          KL_LAUNCH(small_tail_kernel, 1, 256, 0, st.p, wk.gathered.p, ctx().world, wk.theta.p, wk.G.p, wk.inv_scale, ntheta,
+                    inv_n, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
+        }
         continue;
       }
       dispatch_vt(M, [&](auto *tag) {

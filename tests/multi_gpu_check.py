@@ -45,6 +45,19 @@ def main():
         est.Theta = np.zeros(full.m + 1); est.ClassWeights = np.array(cw)
         est.estimate_proximal(full, 1e-3)
         th_full = est.Theta.copy()
+        # reduced matrix (what the leapfrog path iterates on): 40 columns, 300 iterations
+        sel = np.unique(np.concatenate([[0], np.linspace(1, full.m, 40).astype(np.int64)]))
+        rfull = K.select_data(full, sel)
+        rfull.SetLabels(np.concatenate([np.ones(n_fg, dtype=np.uint8), np.zeros(n_bg, dtype=np.uint8)]))
+        est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=300)
+        est.Theta = np.zeros(len(sel)); est.ClassWeights = np.array(cw)
+        est.estimate_proximal(rfull, 1e-3)
+        thr_full = est.Theta.copy()
+        est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-9, MaxIterations=100000)
+        est.Theta = np.zeros(len(sel)); est.ClassWeights = np.array(cw)
+        it_full, _ = est.estimate_proximal(rfull, 1e-3)
+        thc_full = est.Theta.copy()
+        rfull.free()
         k_full, c_full = full.Kmers()
         full.free()
         # sharded
@@ -56,7 +69,18 @@ def main():
         est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=4)
         est.Theta = np.zeros(mine.m + 1); est.ClassWeights = np.array(cw)
         est.estimate_proximal(mine, 1e-3)
+        rmine = K.select_data(mine, sel)
+        rmine.SetLabels(labels)
+        est2 = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=300)
+        est2.Theta = np.zeros(len(sel)); est2.ClassWeights = np.array(cw)
+        est2.estimate_proximal(rmine, 1e-3)
+        est3 = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-9, MaxIterations=100000)
+        est3.Theta = np.zeros(len(sel)); est3.ClassWeights = np.array(cw)
+        it_s, _ = est3.estimate_proximal(rmine, 1e-3)
+        rmine.free()
         checks = {
+            "reduced theta after 300 iterations": np.array_equal(est2.Theta, thr_full),
+            "reduced converged (%d vs %d iterations)" % (it_s, it_full): abs(it_s - it_full) <= 2 and np.allclose(est3.Theta, thc_full, rtol=1e-6, atol=1e-12),
             "classes": mine.m == len(k_full) and np.array_equal(k_s, k_full) and np.array_equal(c_s, c_full),
             "gradient bit-identical": np.array_equal(g_s, g_full),
             "loss": abs(l_s - l_full) <= 1e-14 * abs(l_full),
