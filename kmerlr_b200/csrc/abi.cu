@@ -178,6 +178,7 @@ int kmerlr_option(const char *name, int64_t value) {
   return guarded([&] {
     KL_REQUIRE(name != nullptr, "option: null name");
     if (!strcmp(name, "implicit")) g_ctx.implicit_ok = value != 0;
+    else if (!strcmp(name, "p2p")) g_ctx.p2p_ok = value != 0;
     else if (!strcmp(name, "hot_cols")) g_ctx.hot_cols = (int)(value < 0 ? 0 : (value > 16384 ? 16384 : value));
     else fail(KMERLR_ERR_ARG, std::string("unknown option ") + name);
   }, false);

@@ -4,6 +4,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace kl {
@@ -46,6 +48,74 @@ void load_nccl() {
 
 ncclComm_t comm() { return (ncclComm_t)ctx().comm; }
 
+// ---- peer-memory mailboxes (CUDA IPC over NVLink) ---------------------------------------------------
+PeerMail *g_my_mail = nullptr;                    // this rank's mailbox (cudaMalloc)
+PeerMail *g_peer_mail[PEER_MAX_WORLD] = {nullptr};
+PeerBox *g_peer_dev = nullptr;
+
+void peer_teardown() {
+  for (int r = 0; r < PEER_MAX_WORLD; r++) {
+    if (g_peer_mail[r] && g_peer_mail[r] != g_my_mail) cudaIpcCloseMemHandle(g_peer_mail[r]);
+    g_peer_mail[r] = nullptr;
+  }
+  if (g_my_mail) { cudaFree(g_my_mail); g_my_mail = nullptr; }
+  if (g_peer_dev) { cudaFree(g_peer_dev); g_peer_dev = nullptr; }
+  ctx().peer = nullptr;
+}
+
+// every rank allocates its mailbox, the IPC handles go round with an all-gather, every rank maps the
+// others'.  Any failure leaves ctx().peer == nullptr and the NCCL collectives in charge.
+void peer_setup() {
+  const int world = ctx().world, rank = ctx().rank;
+  if (world < 2 || world > PEER_MAX_WORLD) return;
+  if (cudaMalloc((void **)&g_my_mail, sizeof(PeerMail)) != cudaSuccess) { cudaGetLastError(); g_my_mail = nullptr; return; }
+  cudaMemset(g_my_mail, 0, sizeof(PeerMail));
+  cudaIpcMemHandle_t mine;
+  int ok = cudaIpcGetMemHandle(&mine, g_my_mail) == cudaSuccess ? 1 : 0;
+  if (!ok) cudaGetLastError();
+  // handles (+ an ok byte) through NCCL
+  constexpr size_t HB = sizeof(cudaIpcMemHandle_t) + 8;
+  std::vector<unsigned char> h(HB, 0), all(HB * world, 0);
+  memcpy(h.data(), &mine, sizeof(mine));
+  h[sizeof(mine)] = (unsigned char)ok;
+  unsigned char *din = nullptr, *dout = nullptr;
+  KL_CUDA(cudaMalloc((void **)&din, HB));
+  KL_CUDA(cudaMalloc((void **)&dout, HB * world));
+  KL_CUDA(cudaMemcpy(din, h.data(), HB, cudaMemcpyHostToDevice));
+  KL_NCCL(g_nccl.AllGather(din, dout, HB, ncclUint8, comm(), ctx().stream));
+  KL_CUDA(cudaStreamSynchronize(ctx().stream));
+  KL_CUDA(cudaMemcpy(all.data(), dout, HB * world, cudaMemcpyDeviceToHost));
+  cudaFree(din); cudaFree(dout);
+  bool good = true;
+  for (int r = 0; r < world; r++) good = good && all[r * HB + sizeof(mine)] == 1;
+  if (good) {
+    for (int r = 0; r < world && good; r++) {
+      if (r == rank) { g_peer_mail[r] = g_my_mail; continue; }
+      cudaIpcMemHandle_t hr;
+      memcpy(&hr, all.data() + r * HB, sizeof(hr));
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = false; }
+      g_peer_mail[r] = (PeerMail *)p;
+    }
+  }
+  // all ranks must agree (a rank that failed to map makes everybody fall back)
+  int *dflag = nullptr;
+  KL_CUDA(cudaMalloc((void **)&dflag, sizeof(int)));
+  int hflag = good ? 1 : 0;
+  KL_CUDA(cudaMemcpy(dflag, &hflag, sizeof(int), cudaMemcpyHostToDevice));
+  KL_NCCL(g_nccl.AllReduce(dflag, dflag, 1, ncclInt32, ncclMin, comm(), ctx().stream));
+  KL_CUDA(cudaStreamSynchronize(ctx().stream));
+  KL_CUDA(cudaMemcpy(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dflag);
+  if (!hflag) { peer_teardown(); return; }
+  PeerBox hb{};
+  for (int r = 0; r < world; r++) hb.box[r] = g_peer_mail[r];
+  hb.rank = rank; hb.world = world;
+  KL_CUDA(cudaMalloc((void **)&g_peer_dev, sizeof(PeerBox)));
+  KL_CUDA(cudaMemcpy(g_peer_dev, &hb, sizeof(PeerBox), cudaMemcpyHostToDevice));
+  ctx().peer = g_peer_dev;
+}
+
 }  // namespace
 
 void comm_unique_id(void *id128) {
@@ -68,9 +138,12 @@ void comm_init(int rank, int world, const void *id128) {
   ncclComm_t c = nullptr;
   KL_NCCL(g_nccl.CommInitRank(&c, world, id, rank));
   ctx().comm = c;
+  const char *e = getenv("KMERLR_P2P");
+  if (!(e && *e == '0')) peer_setup();
 }
 
 void comm_destroy() {
+  peer_teardown();
   if (ctx().comm) {
     g_nccl.CommDestroy(comm());
     ctx().comm = nullptr;

@@ -50,6 +50,20 @@ struct Error {
 // ---------------------------------------------------------------------------------------------
 // context: one process drives one GPU
 // ---------------------------------------------------------------------------------------------
+// Mailboxes of the peer-memory exchange: rank r's mailbox holds, for both parities of the sequence
+// number, one payload slot per sender and one flag per sender (the sender's sequence number).
+constexpr int PEER_MAX_WORLD = 8;
+constexpr int PEER_PAYLOAD = 1024 + 8;          // 64-bit words per slot
+struct PeerMail {
+  unsigned long long slot[2][PEER_MAX_WORLD][PEER_PAYLOAD];
+  unsigned long long flag[2][PEER_MAX_WORLD];
+  unsigned long long seq;                        // local: sequence number of the last exchange
+};
+struct PeerBox {
+  PeerMail *box[PEER_MAX_WORLD];                 // box[r] = rank r's mailbox as mapped into this process
+  int rank, world;
+};
+
 constexpr int CTX_COPY_EVENTS = 5;   // chunks of a pipelined host feed + 1
 struct Ctx {
   bool ready = false;
@@ -67,6 +81,9 @@ struct Ctx {
   // communicator (NCCL via dlopen, see comm.cu)
   void *comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory exchange over NVLink (comm.cu): every rank owns one mailbox, mapped into all ranks
+  PeerBox *peer = nullptr;   // device copy of the mailbox table, nullptr = not available (NCCL is used)
+  bool p2p_ok = true;        // kmerlr_option("p2p")
 };
 Ctx &ctx();
 void require_ready();

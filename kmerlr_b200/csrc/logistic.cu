@@ -28,6 +28,7 @@ struct PgState {
   int done;          // 0 running, 1 stopped, 2 final loss evaluation pending
   int first;
   double delta, loss_old, loss_new, lossval;
+  int error;         // 1: a peer never answered the gradient exchange
 };
 
 __device__ __forceinline__ int64_t ind2sub(int64_t n, int64_t k1, int64_t k2) {
@@ -644,6 +645,69 @@ __global__ void __launch_bounds__(256) small_tail_kernel(PgState *st, const doub
   small_tail(st, partials, nparts, theta, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter);
 }
 
+// Sharded reduced matrices, ranks connected by NVLink: the gradient all-reduce, the loss all-gather and
+// the tail of the iteration in ONE block.  Every rank stores its payload (fixed-point gradient + loss
+// partial) straight into every rank's mailbox (peer memory, CUDA IPC), raises its flag there, waits for
+// the flags of the others in its own mailbox and sums the payloads in rank order -- integers, so every
+// rank holds the same bits -- then runs hook / prox step / stopping rule.  Two parities of slots: a
+// sender can be at most one exchange ahead of a receiver.
+__global__ void __launch_bounds__(256) small_p2p_tail_kernel(PgState *st, const PeerBox *pb, const double *__restrict__ blockloss,
+                                                             int nblocks, double *theta, unsigned long long *G,
+                                                             double *scratch, double inv_scale, int64_t ntheta, double inv_n,
+                                                             double lambda, double eps_loss, double step, double eps,
+                                                             long long max_iter) {
+  if (st->done == 1) return;
+  __shared__ double shs[256];
+  __shared__ int s_timeout;
+  const int t = threadIdx.x, me = pb->rank, world = pb->world;
+  PeerMail *mine = pb->box[me];
+  const unsigned long long seq = mine->seq + 1ull;
+  const int par = (int)(seq & 1ull);
+  if (t == 0) s_timeout = 0;
+  // loss partial of this rank: block partials in a fixed order
+  double s = 0.0;
+  for (int i = t; i < nblocks; i += 256) s += blockloss[i];
+  shs[t] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) shs[t] += shs[t + o];
+    __syncthreads();
+  }
+  // payload into every mailbox (NVLink stores), then the flag
+  for (int r = 0; r < world; r++) {
+    unsigned long long *dst = pb->box[r]->slot[par][me];
+    for (int64_t k = t; k < ntheta; k += 256) dst[k] = G[k];
+    if (t == 0) dst[ntheta] = (unsigned long long)__double_as_longlong(shs[0]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < world) {
+    volatile unsigned long long *f = &pb->box[t]->flag[par][me];
+    *f = seq;
+    // ... and wait for sender t's flag in my own mailbox
+    volatile unsigned long long *g = &mine->flag[par][t];
+    const long long t0 = clock64();
+    while (*g < seq)
+      if (clock64() - t0 > 6000000000LL) { s_timeout = 1; break; }      // ~3 s: a peer is gone
+  }
+  __syncthreads();
+  if (s_timeout) {
+    if (t == 0) { st->error = 1; st->done = 1; }
+    return;
+  }
+  __threadfence_system();
+  for (int64_t k = t; k < ntheta; k += 256) {
+    unsigned long long g = 0ull;
+    for (int r = 0; r < world; r++) g += __ldcv(&mine->slot[par][r][k]);
+    G[k] = g;
+  }
+  if (t < world) scratch[t] = __longlong_as_double((long long)__ldcv(&mine->slot[par][t][ntheta]));
+  __threadfence();
+  __syncthreads();
+  if (t == 0) mine->seq = seq;
+  small_tail(st, scratch, world, theta, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter);
+}
+
 constexpr int PROX_BLOCKS = 64;
 
 struct Work {
@@ -874,7 +938,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   DevBuf<PgState> st(1);
   PgState h{};
   h.iter = 0; h.done = max_iter > 0 ? 0 : 1; h.first = 1; h.delta = 0.0;
-  h.loss_old = hook ? hook[0] : NAN; h.loss_new = hook ? hook[1] : NAN; h.lossval = NAN;
+  h.loss_old = hook ? hook[0] : NAN; h.loss_new = hook ? hook[1] : NAN; h.lossval = NAN; h.error = 0;
   st.upload(&h, 1);
   const double inv_n = 1.0 / (double)M.n_global;
   // reduced matrices: two launches per iteration, long batches between host round trips
@@ -909,7 +973,11 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
                     M.sharded ? (unsigned int *)nullptr : counter.p, wk.inv_scale, lambda, epsilon_loss, step, epsilon,
                     (long long)max_iter);
         });
-        if (M.sharded) {
+        if (M.sharded && ctx().peer && ctx().p2p_ok) {
+          // exchange over peer memory fused with the tail of the iteration
+          KL_LAUNCH(small_p2p_tail_kernel, 1, 256, 0, st.p, ctx().peer, blockloss.p, small_blocks, wk.theta.p, wk.G.p,
+                    wk.gathered.p, wk.inv_scale, ntheta, inv_n, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
+        } else if (M.sharded) {
           // gradient: exact int64 all-reduce; loss: per-rank sums gathered and added in rank order
           KL_LAUNCH(small_presum_kernel, 1, 256, 0, st.p, blockloss.p, small_blocks, wk.scalars.p);
           if (scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, ntheta);
@@ -931,6 +999,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
     }
     st.download(&h, 1);
     sync_stream();
+    if (h.error) fail(KMERLR_ERR_CUDA, "proxgrad: a rank did not answer the gradient exchange over peer memory");
     if (h.done == 1) break;
   }
   wk.theta.download(theta, (size_t)ntheta);
