@@ -46,13 +46,13 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -71,7 +71,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, sm_load, mx, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
@@ -79,10 +79,13 @@ class ClockSampler:
                 for nm, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
+                if len(r) > 7 and float(r[7]) >= 10.0:       # the GPU was busy in this sample's window
+                    sm_load.append(float(r[0]))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        use = sm_load if sm_load else sm
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "samples_under_load": len(sm_load), "reasons": sorted(reasons)}
 
 
 def algorithmic_bytes_extract(n, L, nnz, binarize):
@@ -271,10 +274,14 @@ def main():
         data.free()
         return dt, m, checksum
 
+    # clocks / throttle reasons are sampled every 20 ms from here to the end of the e2e loop: the warm-up
+    # gives nvidia-smi time to start, every later phase is a timed region of one of the reported numbers
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.rows.clear()             # keep only what is sampled from the first timed step on
     K.api.profile(True)
     launches0 = K.launch_count()
     dev_ms, info = [], None
@@ -287,7 +294,6 @@ def main():
     launches = K.launch_count() - launches0
     prof = K.api.profile_dump()
     K.api.profile(False)
-    clocks = sampler.stop() if sampler else None
 
     # full-space prox-grad iterations back to back on a resident matrix
     data = api._extract(counter, seqs, None, None, sharded)
@@ -336,6 +342,7 @@ def main():
         if i > 1:
             e2e_s.append(dt)
     barrier()
+    clocks = sampler.stop() if sampler else None
 
     def allmax(x):
         if dist is None:

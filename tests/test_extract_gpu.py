@@ -203,3 +203,48 @@ def test_full_size_properties(K):
     d2 = K.compile_test_data(None, kc, d.Kmers(), None, True, False, (rc, off))
     for x, y in zip(d.rows(), d2.rows()):
         assert np.array_equal(x, y)
+
+
+def test_c2_full_size_invariants(K):
+    """BASELINE config C2 at full size (100 000 + 100 000 x 500 bp, k = 1..8, revcomp) through size independent
+    properties, without copying the 3 GB matrix back: every row sums to the number of k-mer instances
+    (x . 1 = 3 972), the class count is the closed form sum_k (4^k + [k even] 4^(k/2)) / 2 = 43 860, the matrix
+    does not change when every sequence is reverse complemented, and the matrix-free pass agrees with the
+    CSR pass on the full matrix"""
+    from kmerlr_b200 import synth
+    n_half, L = 100000, 500
+    buf, off, y = synth.training_set(n_half, n_half, L)
+    kc = K.NewKmerCounter(1, 8, revcomp=True)
+    d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    assert d.n == 2 * n_half
+    assert d.m == sum((4 ** k + (4 ** (k // 2) if k % 2 == 0 else 0)) // 2 for k in range(1, 9)) == 43860
+    inst = sum(L - k + 1 for k in range(1, 9))
+    ones = np.ones(d.m + 1)
+    z = K.logisticRegression(ones).LinearPdf(d)
+    assert np.all(z == 1.0 + inst)
+    assert d.nnz == int(K.logisticRegression(np.concatenate([[0.0], np.ones(d.m)])).LinearPdf(
+        K.compile_test_data(None, K.NewKmerCounter(1, 8, revcomp=True, binarize=True), d.Kmers(), None, True, True, (buf, off))).sum())
+    d.SetLabels(y)
+    rng = np.random.default_rng(5)
+    theta = rng.normal(scale=0.01, size=d.m + 1)
+    lr = K.logisticRegression(theta, (1.0, 1.0), 0.0)
+    g = lr.Gradient(None, d)
+    K.option("implicit", 0)
+    try:
+        g_csr = lr.Gradient(None, d)
+    finally:
+        K.option("implicit", 1)
+    assert np.max(np.abs(g - g_csr)) <= 1e-12 * np.max(np.abs(g))
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    rc = comp[buf.reshape(-1, L)[:, ::-1]].reshape(-1)
+    d2 = K.compile_test_data(None, kc, None, None, True, False, (rc, off))
+    d2.SetLabels(y)
+    assert (d2.n, d2.m, d2.nnz) == (d.n, d.m, d.nnz)
+    K.option("implicit", 0)
+    try:
+        assert np.array_equal(lr.Gradient(None, d2), g_csr)  # identical stored rows -> bit-identical gradient
+    finally:
+        K.option("implicit", 1)
+    assert np.max(np.abs(lr.Gradient(None, d2) - g)) <= 1e-12 * np.max(np.abs(g))
