@@ -474,7 +474,7 @@ __global__ void prox_finish(PgState *st, const double *__restrict__ blockmax, in
 // row, theta and the fixed-point gradient accumulators in shared memory, loss partial per block) and
 // the block that finishes last runs small_tail (loss, hook, prox update, stopping rule, clears G).
 constexpr int SMALL_MAX_THETA = 1024;
-constexpr int SMALL_LPR = 8;
+constexpr int SMALL_LPR = 8;           // lanes per row; the lane shuffles below assume 4 groups of 8
 
 // hook (kmerLr_estimator_hook.go:46-99) + prox step + eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98),
 // run by ONE block of 256 threads once every block's partials are in
@@ -561,9 +561,11 @@ __global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const ui
   __shared__ double red[256];
   for (int i = threadIdx.x; i < ntheta; i += blockDim.x) { acc_lo[i] = 0u; acc_hi[i] = 0u; sth[i] = theta[i]; }
   __syncthreads();
-  const int sl = threadIdx.x & (SMALL_LPR - 1);
-  const int64_t gsub = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SMALL_LPR;
-  const int64_t nsub = ((int64_t)gridDim.x * blockDim.x) / SMALL_LPR;
+  const unsigned lane = lane_id();
+  const int sl = (int)lane & (SMALL_LPR - 1), grp = (int)lane / SMALL_LPR;     // 4 groups of 8 lanes per warp
+  constexpr int GROUPS = 32 / SMALL_LPR;
+  const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   auto add = [&](uint32_t c, unsigned long long q) {
     const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
     const uint32_t old = atomicAdd(&acc_lo[c], lo);
@@ -571,30 +573,48 @@ __global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const ui
     if (add_hi) atomicAdd(&acc_hi[c], add_hi);
   };
   double lacc = 0.0;
-  // every lane of the warp runs the same number of iterations (the shuffles are warp wide)
-  const int64_t rounds = (n + nsub - 1) / nsub;
+  // A warp takes 32 consecutive rows per round.  Dot products: 8 lanes per row, 4 rows at a time; the
+  // sums are handed to lane (row - first row), so that the exp / log1p of ALL 32 rows run in one pass
+  // over full warps; then the weights go back to the 8-lane groups for the scatter.
+  const int64_t rounds = (n + nwarps * 32 - 1) / (nwarps * 32);
   for (int64_t it = 0; it < rounds; it++) {
-    const int64_t row = gsub + it * nsub;
-    const bool live = row < n;
-    int64_t a = 0, b = 0;
-    if (live) R.range(row, a, b);
-    double s = 0.0;
-    for (int64_t p = a + sl; p < b; p += SMALL_LPR) s += valf(val, p) * sth[col[p] + 1];
+    const int64_t row0 = (gwarp + it * nwarps) * 32;
+    double zmine = 0.0;
 #pragma unroll
-    for (int o = SMALL_LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, SMALL_LPR);
-    double w = 0.0;
-    if (live && sl == 0) {
-      // Gradient weight (:166-178) and Loss term (:257-263)
-      double z = sth[0] + s, r = -log_add0(-z);
-      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lacc += -cw1 * r; }
-      else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
+    for (int j = 0; j < SMALL_LPR; j++) {
+      const int64_t row = row0 + j * GROUPS + grp;
+      int64_t a = 0, b = 0;
+      if (row < n) R.range(row, a, b);
+      double s = 0.0;
+      for (int64_t p = a + sl; p < b; p += SMALL_LPR) s += valf(val, p) * sth[col[p] + 1];
+#pragma unroll
+      for (int o = SMALL_LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, SMALL_LPR);
+      const double got = __shfl_sync(0xffffffffu, s, SMALL_LPR * ((int)lane & (GROUPS - 1)));
+      if (((int)lane >> 2) == j) zmine = got;      // lane j*4+g takes the sum of group g (GROUPS = 4)
     }
-    w = __shfl_sync(0xffffffffu, w, 0, SMALL_LPR);
-    if (!scatter || !live) continue;
-    const double ws = w * scale;
-    if (sl == 0) add(0u, (unsigned long long)__double2ll_rn(ws));
-    for (int64_t p = a + sl; p < b; p += SMALL_LPR)
-      add(col[p] + 1u, (unsigned long long)__double2ll_rn(ws * valf(val, p)));
+    double wmine = 0.0;
+    {
+      const int64_t row = row0 + lane;
+      if (row < n) {
+        // Gradient weight (:166-178) and Loss term (:257-263)
+        double z = sth[0] + zmine, r = -log_add0(-z), w;
+        if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lacc += -cw1 * r; }
+        else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
+        wmine = w * scale;                          // scale is a power of two: exact
+      }
+    }
+    if (!scatter) continue;
+#pragma unroll
+    for (int j = 0; j < SMALL_LPR; j++) {
+      const int64_t row = row0 + j * GROUPS + grp;
+      const double ws = __shfl_sync(0xffffffffu, wmine, j * GROUPS + grp);
+      if (row >= n) continue;
+      int64_t a, b;
+      R.range(row, a, b);
+      if (sl == 0) add(0u, (unsigned long long)__double2ll_rn(ws));
+      for (int64_t p = a + sl; p < b; p += SMALL_LPR)
+        add(col[p] + 1u, (unsigned long long)__double2ll_rn(ws * valf(val, p)));
+    }
   }
   // loss partial of the block: fixed tree
   red[threadIdx.x] = lacc;
