@@ -21,51 +21,13 @@
 // bitmap of observed (or frozen) classes; observed classes are gathered per block in shared memory.
 // Host sequences (kmerlr_extract) arrive in chunks on a copy stream while earlier chunks are
 // packed and extracted.
-#include "common.cuh"
-
-#include <type_traits>
+#include "extract_kernel.cuh"
 
 namespace kl {
 
 namespace {
 
-constexpr uint32_t SENT = 0xFFFFFFFFu;    // sort key of a position without a valid k-mer (sorts last)
-constexpr uint32_t NOKEY = 0xFFFFFFFEu;   // "no previous key" in front of the sorted array
-constexpr int KT_MAX = 5;          // levels <= KT_MAX use direct count tables
-constexpr int KB_MAX = 8;          // highest level that can use a per-row bitmap
-constexpr int KB_DEFAULT = 7;      // ... level 8 does so only when the rows are too long for the register sort
-constexpr int MAX_N = 13;          // 2*13 code bits + 4 length bits per position
-constexpr int TAB_WORDS = 688;     // (4+16+64+256+1024)/2 = 682 packed u16 pairs, padded
-constexpr int DUP_SMEM = 108;      // repeats of the bitmap levels kept in shared memory (the rest: global list)
-constexpr int OBS_MAX_LEVEL = 8;   // marks of observed classes of levels <= 8 are gathered per block in smem
-
-struct XParams {
-  int M, N, op, binarize;
-  int t_lo, t_hi;                  // table levels (empty if t_lo > t_hi)
-  int b_lo, b_hi;                  // bitmap levels (empty if b_lo > b_hi)
-  int s_lo;                        // sorted levels [s_lo, N] (empty if s_lo > N)
-  int mark;                        // mark observed classes in the bitmap
-  uint32_t level_off[MAX_N + 2];   // dense id of (k, code 0), multiples of 32
-  uint32_t bm_off[KB_MAX + 2];     // word offset of level k's bitmap inside the per-warp bitmap area
-  uint32_t pf_off[KB_MAX + 2];     // word offset of level k's prefix array (one entry per 4 words)
-  uint32_t tl_cnt;                 // classes of the table levels (flat list tl, in (k, code) order)
-  int bm_words, pf_words, ts_words;// per-warp shared memory areas, in 32-bit words
-  int warp_words;                  // total per-warp shared memory, in 32-bit words
-  int obs_words;                   // per-block bitmap of observed classes (levels <= OBS_MAX_LEVEL)
-  int64_t stride, n, row0, ovf_stride;   // the launch covers the rows [row0, n)
-  const int64_t *len, *blk;
-  const uint32_t *bits2;
-  const uint16_t *inv16;
-  const uint2 *tl;                 // x = table index of the code | table index of its image << 16, y = class id
-  uint32_t *st_id, *st_cnt, *rowcnt, *bitmap, *ovf;
-  const uint2 *nbx;                // numbering set (all classes of the configuration, or the frozen list)
-  int filter;                      // drop ids outside the numbering set
-  unsigned long long *stats;       // [0] max_i sum_j v_ij^2, [1] max v_ij
-};
-
-__device__ __forceinline__ uint32_t tab_off(int k) {  // sum_{j=1}^{k-1} 4^j
-  return ((1u << (2 * k)) - 4u) / 3u;
-}
+using namespace xk;
 
 // ---- pack: ASCII -> 2 bit codes + invalid mask --------------------------------------------------
 __global__ void pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off,
@@ -93,511 +55,6 @@ __global__ void pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__re
   }
   bits2[w] = bits;
   inv16[w] = (uint16_t)inv;
-}
-
-// ---- bitonic sort of 32*E keys in registers, index = lane*E + r, ascending ----------------------
-__device__ __forceinline__ void ce(uint32_t &a, uint32_t &b) {
-  uint32_t lo = min(a, b), hi = max(a, b);
-  a = lo; b = hi;
-}
-
-template <int E>
-__device__ __forceinline__ void warp_sort(uint32_t (&K)[E], unsigned lane) {
-#pragma unroll
-  for (int k = 2; k <= 32 * E; k <<= 1) {
-    // first stage of the merge: partner = i ^ (k-1)
-    if (k <= E) {
-#pragma unroll
-      for (int r = 0; r < E; r++) {
-        int pr = r ^ (k - 1);
-        if (pr > r) ce(K[r], K[pr]);
-      }
-    } else {
-      const int lm = k / E - 1;                       // lane xor mask
-      const bool keepmin = (lane & ((k / E) >> 1)) == 0;
-#pragma unroll
-      for (int r = 0; r < E / 2; r++) {
-        uint32_t a = K[r], b = K[E - 1 - r];
-        uint32_t va = __shfl_xor_sync(0xffffffffu, b, lm);   // partner's K[E-1-r]
-        uint32_t vb = __shfl_xor_sync(0xffffffffu, a, lm);   // partner's K[r]
-        K[r] = keepmin ? min(a, va) : max(a, va);
-        K[E - 1 - r] = keepmin ? min(b, vb) : max(b, vb);
-      }
-    }
-    // remaining half-cleaners
-#pragma unroll
-    for (int j = k / 4; j >= 1; j >>= 1) {
-      if (j < E) {
-#pragma unroll
-        for (int r = 0; r < E; r++)
-          if ((r & j) == 0) ce(K[r], K[r | j]);
-      } else {
-        const int lm = j / E;
-        const bool keepmin = (lane & lm) == 0;
-#pragma unroll
-        for (int r = 0; r < E; r++) {
-          uint32_t v = __shfl_xor_sync(0xffffffffu, K[r], lm);
-          K[r] = keepmin ? min(K[r], v) : max(K[r], v);
-        }
-      }
-    }
-  }
-}
-
-// ---- per-lane streaming reader of the packed sequence -------------------------------------------
-struct BaseReader {
-  const uint32_t *bits2;
-  const uint16_t *inv16;
-  int L, cur_word;
-  uint32_t w, iv;
-  __device__ __forceinline__ void init(const uint32_t *b, const uint16_t *m, int len) {
-    bits2 = b; inv16 = m; L = len; cur_word = -1; w = 0; iv = 0;
-  }
-  // base idx -> (code, invalid); out of range = invalid
-  __device__ __forceinline__ void get(int idx, uint32_t &x, uint32_t &inv) {
-    if ((unsigned)idx >= (unsigned)L) { x = 0; inv = 1; return; }
-    int wi = idx >> 4;
-    if (wi != cur_word) { cur_word = wi; w = __ldg(bits2 + wi); iv = __ldg(inv16 + wi); }
-    int sh = idx & 15;
-    x = (w >> (2 * sh)) & 3u;
-    inv = (iv >> sh) & 1u;
-  }
-};
-
-struct Emitter {
-  uint32_t *sid, *scnt;            // this row's slices of the column / count arrays
-  uint32_t *obs, *bitmap;          // observed classes: per-block (shared) and global bitmap
-  const uint2 *nbx;                // numbering set, per 32 ids: x = member bits, y = column of the first member
-  uint32_t obs_bits;               // ids below this are marked in obs
-  uint32_t cursor;
-  int binarize, mark, filter;      // filter: ids outside the numbering set are dropped (frozen class list)
-  unsigned long long sq;           // per lane: sum of squared counts / largest count emitted
-  uint32_t vm;
-  // mark one class id as observed
-  __device__ __forceinline__ void mark_id(uint32_t id) {
-    if (!mark) return;
-    const uint32_t bit = 1u << (id & 31), w = id >> 5;
-    if (id < obs_bits) { if (!(obs[w] & bit)) atomicOr(obs + w, bit); }
-    else if (!(bitmap[w] & bit)) atomicOr(bitmap + w, bit);
-  }
-  // OR a word of 32 consecutive class ids (a level <= OBS_MAX_LEVEL) into the block's bitmap
-  __device__ __forceinline__ void mark_word(uint32_t word_index, uint32_t bits) {
-    if (mark && (bits & ~obs[word_index])) atomicOr(obs + word_index, bits);
-  }
-  // column of a class id; false when the id is not in the numbering set
-  __device__ __forceinline__ bool column(uint32_t id, uint32_t &col) const {
-    const uint2 e = __ldg(nbx + (id >> 5));
-    const uint32_t bit = 1u << (id & 31);
-    col = e.y + __popc(e.x & (bit - 1u));
-    return (e.x & bit) != 0u;
-  }
-  __device__ __forceinline__ void stat(uint32_t cnt) {
-    sq += (unsigned long long)cnt * cnt;
-    vm = max(vm, cnt);
-  }
-  // ballot-compacted emission (coalesced stores); col_known >= 0: the column when no class is dropped
-  __device__ __forceinline__ void emit(bool flag, uint32_t id, uint32_t cnt, int64_t col_known = -1) {
-    uint32_t col = (uint32_t)col_known;
-    if (flag && (filter || col_known < 0)) { const bool member = column(id, col); if (filter) flag = member; }
-    unsigned em = __ballot_sync(0xffffffffu, flag);
-    if (flag) {
-      uint32_t pos = cursor + __popc(em & lanemask_lt());
-      sid[pos] = col;
-      if (!binarize) scnt[pos] = cnt;
-      mark_id(id);
-      stat(binarize ? 1u : cnt);
-    }
-    cursor += __popc(em);
-  }
-};
-
-__host__ __device__ constexpr int ext_threads(int E) { return E <= 16 ? 512 : (E == 32 ? 256 : 128); }
-
-// ---- sorted level: the canonical codes of one level, sorted in registers -----------------------------
-// K[r] sits at sorted index lane*E + r.  A run (equal keys) is one class, its length the count; a run
-// is emitted by the lane holding the position right after it.  Ids and counts go through the warp's
-// shared-memory buffer so that the global stores are coalesced.
-template <int E>
-__device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lane, uint32_t *sbuf, Emitter &em,
-                                            uint32_t idbase) {
-  using MaskT = typename std::conditional<(E <= 32), uint32_t, unsigned long long>::type;
-  uint32_t prevlast = __shfl_up_sync(0xffffffffu, K[E - 1], 1);
-  if (lane == 0) prevlast = NOKEY;
-  // bit r of bnd: a run starts at this lane's key r (sorted index lane*E + r)
-  MaskT bnd = (MaskT)(K[0] != prevlast);
-#pragma unroll
-  for (int r = 1; r < E; r++) bnd |= (MaskT)(K[r] != K[r - 1]) << r;
-  // a run is emitted by the position right after it: every boundary but sorted index 0
-  const MaskT cls = lane == 0 ? (bnd & ~(MaskT)1) : bnd;
-  const int c = sizeof(MaskT) == 4 ? __popc((uint32_t)cls) : __popcll(cls);
-  const int lastb = bnd ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bnd) : 63 - __clzll(bnd)) : -1;
-  int incl = c, mx = lastb;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int y = __shfl_up_sync(0xffffffffu, incl, o), z = __shfl_up_sync(0xffffffffu, mx, o);
-    if (lane >= (unsigned)o) { incl += y; mx = max(mx, z); }
-  }
-  const int base = incl - c, total = __shfl_sync(0xffffffffu, incl, 31);
-  int start0 = __shfl_up_sync(0xffffffffu, mx, 1);   // last boundary before this lane's keys
-  if (lane == 0) start0 = 0;
-  // round 1: ids
-#pragma unroll
-  for (int r = 0; r < E; r++) {
-    if ((cls >> r) & 1) {
-      const MaskT below = cls & (((MaskT)1 << r) - 1);
-      const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
-      sbuf[j] = idbase + (r == 0 ? prevlast : K[r > 0 ? r - 1 : 0]);
-    }
-  }
-  __syncwarp();
-  if (!em.filter) {
-    // no class is dropped: slot i of the buffer is entry i of the level
-    for (int i = lane; i < total; i += 32) {
-      const uint32_t id = sbuf[i];
-      uint32_t col;
-      em.column(id, col);
-      em.sid[em.cursor + i] = col;
-      em.mark_id(id);
-    }
-    __syncwarp();
-    if (!em.binarize) {
-#pragma unroll
-      for (int r = 0; r < E; r++) {
-        if ((cls >> r) & 1) {
-          const MaskT below = cls & (((MaskT)1 << r) - 1), bbelow = bnd & (((MaskT)1 << r) - 1);
-          const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
-          const int st = bbelow ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bbelow) : 63 - __clzll(bbelow))
-                                : start0;
-          const uint32_t cnt = (uint32_t)((int)lane * E + r - st);
-          sbuf[j] = cnt;
-          em.stat(cnt);
-        }
-      }
-      __syncwarp();
-      for (int i = lane; i < total; i += 32) em.scnt[em.cursor + i] = sbuf[i];
-      __syncwarp();
-    } else {
-      em.sq += (unsigned long long)c; if (c) em.vm = max(em.vm, 1u);
-    }
-    em.cursor += (uint32_t)total;
-    return;
-  }
-  // copy out: id -> column; with a frozen class list the ids outside the list are dropped here and the
-  // keep decisions (one bit per copy iteration) are replayed for the counts
-  unsigned long long keepbits = 0;
-  uint32_t kept = 0;
-  for (int i0 = 0, it = 0; i0 < total; i0 += 32, it++) {
-    const int i = i0 + (int)lane;
-    bool keep = false; uint32_t col = 0, id = 0;
-    if (i < total) { id = sbuf[i]; keep = em.column(id, col) || !em.filter; }
-    const unsigned km = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      em.sid[em.cursor + kept + __popc(km & lanemask_lt())] = col;
-      em.mark_id(id);
-      keepbits |= 1ull << it;
-    }
-    kept += __popc(km);
-  }
-  __syncwarp();
-  // round 2: counts = distance to the previous boundary
-  if (!em.binarize) {
-#pragma unroll
-    for (int r = 0; r < E; r++) {
-      if ((cls >> r) & 1) {
-        const MaskT below = cls & (((MaskT)1 << r) - 1), bbelow = bnd & (((MaskT)1 << r) - 1);
-        const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
-        const int st = bbelow ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bbelow) : 63 - __clzll(bbelow))
-                              : start0;
-        sbuf[j] = (uint32_t)((int)lane * E + r - st);
-      }
-    }
-    __syncwarp();
-    uint32_t k2 = 0;
-    for (int i0 = 0, it = 0; i0 < total; i0 += 32, it++) {
-      const int i = i0 + (int)lane;
-      const bool keep = (keepbits >> it) & 1ull;
-      const unsigned km = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        const uint32_t cnt = sbuf[i];
-        em.scnt[em.cursor + k2 + __popc(km & lanemask_lt())] = cnt;
-        em.stat(cnt);
-      }
-      k2 += __popc(km);
-    }
-    __syncwarp();
-  } else {
-    em.sq += __popcll(keepbits); if (keepbits) em.vm = max(em.vm, 1u);
-  }
-  em.cursor += kept;
-}
-
-
-// ---- the extraction kernel: one warp per sequence ------------------------------------------------
-// E = keys per lane of the register sort (0: no sorted levels, sequences of any length)
-template <int E>
-__global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParams P) {
-  constexpr int EE = E > 0 ? E : 1;
-  extern __shared__ __align__(16) uint32_t smem[];
-  const unsigned lane = lane_id();
-  const int warp_in_block = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  // block: [observed classes]; per warp: [bitmaps][prefix][count tables | sort buffer][dup count + dups]
-  uint32_t *obs = smem;
-  uint32_t *bm = smem + P.obs_words + (size_t)warp_in_block * P.warp_words;
-  uint32_t *pf = bm + P.bm_words;
-  uint32_t *tab = pf + P.pf_words;
-  uint32_t *dupn = tab + P.ts_words;
-  uint32_t *dups = dupn + 4;
-  const int64_t gwarp = (int64_t)blockIdx.x * wpb + warp_in_block, nwarps = (int64_t)gridDim.x * wpb;
-  uint32_t *ovf = P.ovf ? P.ovf + gwarp * P.ovf_stride : nullptr;
-  const int N = P.N, M = P.M, op = P.op;
-  const bool two = op != 0;
-  const uint32_t maskN = (1u << (2 * N)) - 1u;
-  const uint32_t maskNb = (1u << N) - 1u;
-  const bool has_tab = P.t_lo <= P.t_hi, has_bm = P.b_lo <= P.b_hi, has_sort = E > 0 && P.s_lo <= N;
-
-  // shared memory starts clean; every row leaves its bitmaps clean again
-  for (int i = threadIdx.x; i < P.obs_words; i += blockDim.x) obs[i] = 0;
-  for (int i = lane; i < P.bm_words; i += 32) bm[i] = 0;
-  if (lane == 0) dupn[0] = 0;
-  __syncthreads();
-
-  for (int64_t row = P.row0 + gwarp; row < P.n; row += nwarps) {
-    const int L = (int)P.len[row];
-    const uint32_t *b2 = P.bits2 + P.blk[row] * 4;
-    const uint16_t *iv16 = P.inv16 + P.blk[row] * 4;
-    if (has_tab)
-      for (int i = lane; i < TAB_WORDS; i += 32) tab[i] = 0;
-    __syncwarp();
-
-    // ---- pass over the positions: lane handles the start positions p = lane, lane + 32, ... ----------
-    // The N bases starting at p are 2N consecutive bits of the packed words (first base in the low
-    // bits): one funnel shift.  Read that way the k-mer starting at p is the LOW 2k bits, its
-    // reverse complement (first base most significant, the code order) is the complement of those
-    // bits and its forward code is their digit reversal -- no rolling state, no warm-up.
-    const int steps = (L + 31) / 32;
-    uint32_t FWL[EE];                 // (forward code << 4) | valid length, per position of this lane
-#pragma unroll
-    for (int r = 0; r < EE; r++) FWL[r] = 0;
-    {
-      auto visit = [&](int p) -> uint32_t {
-        const int wi = p >> 4, sh = p & 15;
-        const uint32_t e = __funnelshift_r(__ldg(b2 + wi), __ldg(b2 + wi + 1), 2 * sh) & maskN;
-        const uint32_t ivb = (((uint32_t)__ldg(iv16 + wi) | ((uint32_t)__ldg(iv16 + wi + 1) << 16)) >> sh) |
-                             (1u << min(N, L - p));       // the sequence ends: no k-mer reaches past L
-        const int len_f = __ffs(ivb) - 1;                 // valid bases from p on (<= N)
-        const uint32_t FW = swap_pairs(__brev(e)) >> (32 - 2 * N);
-        const uint32_t S2 = op == 1 ? (~e) & maskN : e;   // image of the window under revcomp / reverse
-        if (len_f >= M) {
-          // table levels: one count at the deepest table level this suffix reaches
-          if (has_tab) {
-            int kk = len_f < P.t_hi ? len_f : P.t_hi;
-            if (kk >= P.t_lo) {
-              uint32_t idx = tab_off(kk) + (FW >> (2 * (N - kk)));
-              atomicAdd(tab + (idx >> 1), 1u << (16 * (idx & 1)));
-            }
-          }
-          // bitmap levels: canonical code = min(prefix, image)
-          if (has_bm) {
-            for (int k = P.b_lo; k <= P.b_hi; k++) {
-              if (len_f < k) break;
-              const uint32_t mk = (1u << (2 * k)) - 1u;
-              uint32_t c = FW >> (2 * (N - k));
-              if (op == 1 || op == 3) c = min(c, S2 & mk);
-              else if (op == 2) c = min(c, (~c) & mk);
-              const uint32_t bit = 1u << (c & 31);
-              const uint32_t old = atomicOr(bm + P.bm_off[k] + (c >> 5), bit);
-              if ((old & bit) && !P.binarize) {
-                const uint32_t at = atomicAdd(dupn, 1u), ee = ((uint32_t)k << 26) | c;
-                if (at < (uint32_t)DUP_SMEM) dups[at] = ee; else ovf[at - DUP_SMEM] = ee;
-              }
-            }
-          }
-        }
-        return (FW << 4) | (uint32_t)len_f;
-      };
-      if (E > 0) {
-#pragma unroll
-        for (int i = 0; i < EE; i++) {
-          const int p = i * 32 + (int)lane;
-          if (p < L) FWL[i] = visit(p);
-        }
-      } else {
-        for (int i = 0; i < steps; i++) {
-          const int p = i * 32 + (int)lane;
-          if (p < L) visit(p);
-        }
-      }
-    }
-    __syncwarp();
-
-    Emitter em;
-    em.sid = P.st_id + row * P.stride; em.scnt = P.st_cnt + (P.binarize ? 0 : row * P.stride);
-    em.obs = obs; em.bitmap = P.bitmap; em.obs_bits = (uint32_t)P.obs_words * 32u;
-    em.nbx = P.nbx; em.filter = P.filter;
-    em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
-    em.sq = 0; em.vm = 0;
-
-    // ---- table levels ---------------------------------------------------------------------------
-    if (has_tab) {
-      // a k-mer count is the sum of its 4 extensions plus the suffixes that end right after it
-      for (int k = P.t_hi - 1; k >= P.t_lo; k--) {
-        const uint32_t nk = 1u << (2 * k), toff = tab_off(k), coff = tab_off(k + 1);
-        for (uint32_t u = lane; u < nk; u += 32) {
-          uint32_t c0 = coff + 4 * u;                 // 4 children = two aligned words
-          uint32_t w0 = tab[c0 >> 1], w1 = tab[(c0 >> 1) + 1];
-          uint32_t sum = (w0 & 0xFFFFu) + (w0 >> 16) + (w1 & 0xFFFFu) + (w1 >> 16);
-          uint32_t idx = toff + u;
-          if (sum) atomicAdd(tab + (idx >> 1), sum << (16 * (idx & 1)));
-        }
-        __syncwarp();
-      }
-      // walk the classes of the table levels in (k, code) order: count = code + image
-      for (uint32_t base = 0; base < P.tl_cnt; base += 32) {
-        const uint32_t j = base + lane;
-        uint32_t id = 0, cnt = 0;
-        if (j < P.tl_cnt) {
-          const uint2 e = __ldg(P.tl + j);
-          const uint32_t i1 = e.x & 0xFFFFu, i2 = e.x >> 16;
-          cnt = (tab[i1 >> 1] >> (16 * (i1 & 1))) & 0xFFFFu;
-          if (i2 != i1) cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu;
-          id = e.y;
-        }
-        // without a frozen list the numbering set is ALL classes: the j-th class of the list is column j
-        em.emit(cnt > 0, id, cnt, P.filter ? -1 : (int64_t)j);
-      }
-      __syncwarp();
-    }
-
-    // ---- bitmap levels: walk the bitmap 128 words at a time (4 consecutive words per lane) ---------
-    if (has_bm) {
-      for (int k = P.b_lo; k <= P.b_hi; k++) {
-        const int W = 1 << (2 * k - 5);
-        uint32_t *bk = bm + P.bm_off[k];
-        uint32_t *pk = pf + P.pf_off[k];
-        const uint32_t idbase = P.level_off[k], gword = P.level_off[k] >> 5;
-        for (int it = 0; it * 128 < W; it++) {
-          const int wi = it * 128 + (int)lane * 4;
-          uint4 w4 = make_uint4(0, 0, 0, 0);
-          if (wi < W) w4 = *reinterpret_cast<const uint4 *>(bk + wi);
-          // numbering of the lane's 4 words: member bits and column of the first member (coalesced loads)
-          uint2 nx[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) nx[j] = wi < W ? __ldg(P.nbx + gword + wi + j) : make_uint2(0u, 0u);
-          if (P.filter && wi < W) {
-            // frozen class list: classes outside the list vanish here, before any slot is assigned
-            w4.x &= nx[0].x; w4.y &= nx[1].x; w4.z &= nx[2].x; w4.w &= nx[3].x;
-            *reinterpret_cast<uint4 *>(bk + wi) = w4;
-          }
-          if (w4.x | w4.y | w4.z | w4.w) {
-            em.mark_word(gword + wi, w4.x); em.mark_word(gword + wi + 1, w4.y);
-            em.mark_word(gword + wi + 2, w4.z); em.mark_word(gword + wi + 3, w4.w);
-          }
-          const uint32_t c = __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
-          uint32_t incl = c;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (unsigned)o) incl += y;
-          }
-          const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-          if (wi < W) pk[wi >> 2] = em.cursor + incl - c;   // slot of this lane's first class
-          const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-          if (tot <= (uint32_t)P.ts_words) {
-            // ids through the warp's shared buffer: coalesced global stores of the columns
-            uint32_t pos = incl - c;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              uint32_t w = ws[j];
-              while (w) {
-                const uint32_t below = (w & (0u - w)) - 1u;            // bits under the lowest set bit
-                tab[pos++] = nx[j].y + __popc(nx[j].x & below);         // its column
-                w &= w - 1;
-              }
-            }
-            __syncwarp();
-            for (uint32_t i = lane; i < tot; i += 32) {
-              em.sid[em.cursor + i] = tab[i];
-              if (!P.binarize) em.scnt[em.cursor + i] = 1;
-            }
-            __syncwarp();
-          } else {
-            uint32_t pos = em.cursor + incl - c;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              uint32_t w = ws[j];
-              while (w) {
-                const uint32_t below = (w & (0u - w)) - 1u;
-                w &= w - 1;
-                em.sid[pos] = nx[j].y + __popc(nx[j].x & below);
-                if (!P.binarize) em.scnt[pos] = 1;
-                pos++;
-              }
-            }
-          }
-          em.sq += c; if (c) em.vm = max(em.vm, 1u);        // every class of the chunk enters with count 1
-          em.cursor += tot;
-        }
-      }
-      __syncwarp();
-      __threadfence_block();
-      // repeats: add one to the count of the class, found by its rank in the bitmap
-      if (!P.binarize) {
-        const uint32_t nd = dupn[0];
-        for (uint32_t i = lane; i < nd; i += 32) {
-          const uint32_t e = i < (uint32_t)DUP_SMEM ? dups[i] : ovf[i - DUP_SMEM];
-          const uint32_t k = e >> 26, c = e & 0x3FFFFFFu, wi = c >> 5;
-          const uint32_t *bk = bm + P.bm_off[k];
-          if (!((bk[wi] >> (c & 31)) & 1u)) continue;       // class dropped by the frozen list
-          uint32_t slot = pf[P.pf_off[k] + (wi >> 2)] + __popc(bk[wi] & ((1u << (c & 31)) - 1u));
-          for (uint32_t j = wi & ~3u; j < wi; j++) slot += __popc(bk[j]);
-          const uint32_t old = atomicAdd(em.scnt + slot, 1u);
-          em.sq += 2ull * old + 1ull;                       // (old+1)^2 - old^2
-          em.vm = max(em.vm, old + 1u);
-        }
-        __syncwarp();
-        if (lane == 0) dupn[0] = 0;
-      }
-      for (int i = (int)lane * 4; i < P.bm_words; i += 128) *reinterpret_cast<uint4 *>(bm + i) = make_uint4(0, 0, 0, 0);
-      __syncwarp();
-    }
-
-    // ---- sorted levels: one register sort of the canonical codes per level ---------------------------
-    if (has_sort) {
-      for (int k = P.s_lo; k <= N; k++) {
-        uint32_t K[EE];
-#pragma unroll
-        for (int r = 0; r < EE; r++) {
-          const uint32_t f = FWL[r];
-          uint32_t c = (f >> 4) >> (2 * (N - k));
-          if (two) c = min(c, kmer_op(c, k, op));
-          K[r] = (int)(f & 15u) >= k ? c : SENT;
-        }
-        warp_sort<EE>(K, lane);
-        emit_sorted<EE>(K, lane, tab, em, P.level_off[k]);
-      }
-    }
-    // row statistics (exact integers): what the step size and the fixed-point scale of the gradient need
-    {
-      unsigned long long sq = em.sq; uint32_t vm = em.vm;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        vm = max(vm, __shfl_xor_sync(0xffffffffu, vm, o));
-      }
-      if (lane == 0) {
-        P.rowcnt[row] = em.cursor;
-        if (sq > P.stats[0]) atomicMax(P.stats, sq);
-        if ((unsigned long long)vm > P.stats[1]) atomicMax(P.stats + 1, (unsigned long long)vm);
-      }
-    }
-  }
-  // flush the block's observed classes
-  __syncthreads();
-  if (P.mark)
-    for (int i = threadIdx.x; i < P.obs_words; i += blockDim.x) {
-      const uint32_t w = obs[i];
-      if (w && (w & ~P.bitmap[i])) atomicOr(P.bitmap + i, w);
-    }
 }
 
 // ---- bitmap helpers -------------------------------------------------------------------------------
@@ -718,29 +175,6 @@ __global__ void features_rows(const Rows R, const uint32_t *__restrict__ col,
     tot += __popc(km);
   }
   if (!WRITE && lane == 0) cnt_out[row] = tot;
-}
-
-template <int E>
-void launch_extract(const XParams &P) {
-  // warps per block: the choice that keeps the most warps resident per SM (the block shares one
-  // bitmap of observed classes, every warp brings its own working set)
-  KL_CUDA(cudaFuncSetAttribute(extract_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  int best_wpb = 0, best_per_sm = 0;
-  for (int wpb = ext_threads(E) / 32; wpb >= 1; wpb--) {
-    size_t smem = ((size_t)P.obs_words + (size_t)wpb * P.warp_words) * sizeof(uint32_t);
-    if (smem > (size_t)227 * 1024) continue;
-    int per_sm = 0;
-    KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_kernel<E>, 32 * wpb, smem));
-    if (per_sm * wpb > best_per_sm * best_wpb) { best_wpb = wpb; best_per_sm = per_sm; }
-  }
-  KL_REQUIRE(best_wpb > 0, "sequence too long for the shared-memory working set of one warp");
-  const int wpb = best_wpb;
-  size_t smem = ((size_t)P.obs_words + (size_t)wpb * P.warp_words) * sizeof(uint32_t);
-  int64_t blocks = (int64_t)ctx().sm_count * best_per_sm;
-  int64_t need = (P.n - P.row0 + wpb - 1) / wpb;
-  if (blocks > need) blocks = need;
-  if (blocks < 1) blocks = 1;
-  KL_LAUNCH((extract_kernel<E>), (unsigned)blocks, 32 * wpb, smem, P);
 }
 
 // the classes of the table levels [t_lo, t_hi] in (k, code) order: table index of the code, table
