@@ -390,7 +390,7 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   }
   P.pf_words = (P.pf_words + 3) / 4 * 4;
   P.ts_words = 32 * E > TAB_WORDS ? 32 * E : TAB_WORDS;
-  P.warp_words = P.bm_words + P.pf_words + P.ts_words + 4 + DUP_SMEM;
+  P.warp_words = P.bm_words + P.pf_words + P.ts_words + 4;
   P.warp_words = (P.warp_words + 3) / 4 * 4;
   // the block's bitmap of observed classes covers the levels up to OBS_MAX_LEVEL
   {
@@ -442,7 +442,7 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   KL_LAUNCH(interleave_numbering, (unsigned)((nw + 255) / 256), 256, 0, nb.p, nbrank.p, nw, nbx.p);
   P.bitmap = bitmap.p; P.nbx = nbx.p; P.filter = n_frozen > 0; P.stats = stats.p;
   P.mark = n_frozen == 0;
-  // repeats beyond the shared-memory list of a warp (low-complexity rows): one global list per warp
+  // repeats of the bitmap levels: one list per warp in global memory (L2 resident)
   DevBuf<uint32_t> ovf;
   P.ovf_stride = nbl * (s.max_len > 0 ? s.max_len : 1);
   if (nbl && !P.binarize && s.n > 0) {

@@ -18,7 +18,6 @@ constexpr int KB_MAX = 8;          // highest level that can use a per-row bitma
 constexpr int KB_DEFAULT = 7;      // ... level 8 does so only when the rows are too long for the register sort
 constexpr int MAX_N = 13;          // 2*13 code bits + 4 length bits per position
 constexpr int TAB_WORDS = 688;     // (4+16+64+256+1024)/2 = 682 packed u16 pairs, padded
-constexpr int DUP_SMEM = 108;      // repeats of the bitmap levels kept in shared memory (the rest: global list)
 constexpr int OBS_MAX_LEVEL = 8;   // marks of observed classes of levels <= 8 are gathered per block in smem
 
 struct XParams {
@@ -102,26 +101,6 @@ __device__ __forceinline__ void warp_sort(uint32_t (&K)[E], unsigned lane) {
     }
   }
 }
-
-// ---- per-lane streaming reader of the packed sequence -------------------------------------------
-struct BaseReader {
-  const uint32_t *bits2;
-  const uint16_t *inv16;
-  int L, cur_word;
-  uint32_t w, iv;
-  __device__ __forceinline__ void init(const uint32_t *b, const uint16_t *m, int len) {
-    bits2 = b; inv16 = m; L = len; cur_word = -1; w = 0; iv = 0;
-  }
-  // base idx -> (code, invalid); out of range = invalid
-  __device__ __forceinline__ void get(int idx, uint32_t &x, uint32_t &inv) {
-    if ((unsigned)idx >= (unsigned)L) { x = 0; inv = 1; return; }
-    int wi = idx >> 4;
-    if (wi != cur_word) { cur_word = wi; w = __ldg(bits2 + wi); iv = __ldg(inv16 + wi); }
-    int sh = idx & 15;
-    x = (w >> (2 * sh)) & 3u;
-    inv = (iv >> sh) & 1u;
-  }
-};
 
 struct Emitter {
   uint32_t *sid, *scnt;            // this row's slices of the column / count arrays
@@ -293,7 +272,8 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
 
 // ---- the extraction kernel: one warp per sequence ------------------------------------------------
 // E = keys per lane of the register sort (0: no sorted levels, sequences of any length)
-template <int E>
+// OPT: the strand operation when it is known at compile time (1 = revcomp, the common case), -1 = P.op
+template <int E, int OPT>
 __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParams P) {
   constexpr int EE = E > 0 ? E : 1;
   extern __shared__ __align__(16) uint32_t smem[];
@@ -305,14 +285,13 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
   uint32_t *pf = bm + P.bm_words;
   uint32_t *tab = pf + P.pf_words;
   uint32_t *dupn = tab + P.ts_words;
-  uint32_t *dups = dupn + 4;
   const int64_t gwarp = (int64_t)blockIdx.x * wpb + warp_in_block, nwarps = (int64_t)gridDim.x * wpb;
   uint32_t *ovf = P.ovf ? P.ovf + gwarp * P.ovf_stride : nullptr;
-  const int N = P.N, M = P.M, op = P.op;
+  const int N = P.N, M = P.M, op = OPT >= 0 ? OPT : P.op;
   const bool two = op != 0;
   const uint32_t maskN = (1u << (2 * N)) - 1u;
-  const uint32_t maskNb = (1u << N) - 1u;
   const bool has_tab = P.t_lo <= P.t_hi, has_bm = P.b_lo <= P.b_hi, has_sort = E > 0 && P.s_lo <= N;
+  const bool single_sorted = has_sort && P.s_lo == N && op != 2;   // (complement: the image is not a window image)
 
   // shared memory starts clean; every row leaves its bitmaps clean again
   for (int i = threadIdx.x; i < P.obs_words; i += blockDim.x) obs[i] = 0;
@@ -357,8 +336,10 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
           }
           // bitmap levels: canonical code = min(prefix, image)
           if (has_bm) {
-            for (int k = P.b_lo; k <= P.b_hi; k++) {
-              if (len_f < k) break;
+#pragma unroll
+            for (int j = 0; j < KB_MAX - KT_MAX; j++) {
+              const int k = P.b_lo + j;
+              if (k > P.b_hi || len_f < k) break;
               const uint32_t mk = (1u << (2 * k)) - 1u;
               uint32_t c = FW >> (2 * (N - k));
               if (op == 1 || op == 3) c = min(c, S2 & mk);
@@ -366,13 +347,14 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
               const uint32_t bit = 1u << (c & 31);
               const uint32_t old = atomicOr(bm + P.bm_off[k] + (c >> 5), bit);
               if ((old & bit) && !P.binarize) {
-                const uint32_t at = atomicAdd(dupn, 1u), ee = ((uint32_t)k << 26) | c;
-                if (at < (uint32_t)DUP_SMEM) dups[at] = ee; else ovf[at - DUP_SMEM] = ee;
+                ovf[atomicAdd(dupn, 1u)] = ((uint32_t)k << 26) | c;     // the warp's list of repeats (L2)
               }
             }
           }
         }
-        return (FW << 4) | (uint32_t)len_f;
+        // one sorted level (s_lo == N): keep the CANONICAL code of the full window, the key of that level
+        const uint32_t keep = (single_sorted && two) ? min(FW, S2) : FW;
+        return (keep << 4) | (uint32_t)len_f;
       };
       if (E > 0) {
 #pragma unroll
@@ -503,7 +485,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
       if (!P.binarize) {
         const uint32_t nd = dupn[0];
         for (uint32_t i = lane; i < nd; i += 32) {
-          const uint32_t e = i < (uint32_t)DUP_SMEM ? dups[i] : ovf[i - DUP_SMEM];
+          const uint32_t e = ovf[i];
           const uint32_t k = e >> 26, c = e & 0x3FFFFFFu, wi = c >> 5;
           const uint32_t *bk = bm + P.bm_off[k];
           if (!((bk[wi] >> (c & 31)) & 1u)) continue;       // class dropped by the frozen list
@@ -528,7 +510,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         for (int r = 0; r < EE; r++) {
           const uint32_t f = FWL[r];
           uint32_t c = (f >> 4) >> (2 * (N - k));
-          if (two) c = min(c, kmer_op(c, k, op));
+          if (two && !single_sorted) c = min(c, kmer_op(c, k, op));
           K[r] = (int)(f & 15u) >= k ? c : SENT;
         }
         warp_sort<EE>(K, lane);
@@ -559,17 +541,17 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
     }
 }
 
-template <int E>
-void launch_extract(const XParams &P) {
+template <int E, int OPT>
+void launch_extract_op(const XParams &P) {
   // warps per block: the choice that keeps the most warps resident per SM (the block shares one
   // bitmap of observed classes, every warp brings its own working set)
-  KL_CUDA(cudaFuncSetAttribute(extract_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  KL_CUDA(cudaFuncSetAttribute((extract_kernel<E, OPT>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int best_wpb = 0, best_per_sm = 0;
   for (int wpb = ext_threads(E) / 32; wpb >= 1; wpb--) {
     size_t smem = ((size_t)P.obs_words + (size_t)wpb * P.warp_words) * sizeof(uint32_t);
     if (smem > (size_t)227 * 1024) continue;
     int per_sm = 0;
-    KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_kernel<E>, 32 * wpb, smem));
+    KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (extract_kernel<E, OPT>), 32 * wpb, smem));
     if (per_sm * wpb > best_per_sm * best_wpb) { best_wpb = wpb; best_per_sm = per_sm; }
   }
   KL_REQUIRE(best_wpb > 0, "sequence too long for the shared-memory working set of one warp");
@@ -579,7 +561,13 @@ void launch_extract(const XParams &P) {
   int64_t need = (P.n - P.row0 + wpb - 1) / wpb;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  KL_LAUNCH((extract_kernel<E>), (unsigned)blocks, 32 * wpb, smem, P);
+  KL_LAUNCH((extract_kernel<E, OPT>), (unsigned)blocks, 32 * wpb, smem, P);
+}
+
+template <int E>
+void launch_extract(const XParams &P) {
+  if (P.op == 1) launch_extract_op<E, 1>(P);
+  else launch_extract_op<E, -1>(P);
 }
 
 #endif  // KL_EXTRACT_KERNEL_IMPL

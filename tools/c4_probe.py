@@ -1,6 +1,9 @@
 """C4-shaped probe (pair features): timing of the co-occurrence gradient and one leapfrog epoch at a
-reduced sample count.  Not part of the test suite; run on a B200: python tools_c4_probe.py [n]"""
+reduced sample count.  Not part of the test suite; run on a B200: python tools/c4_probe.py [n]"""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import time
 
 import numpy as np

@@ -1,4 +1,4 @@
-"""CSR fused pass: how many columns should accumulate in shared memory?  python tools_hot_probe.py"""
+"""CSR fused pass: how many columns should accumulate in shared memory?  python tools/hot_probe.py"""
 import numpy as np
 import kmerlr_b200 as K
 from kmerlr_b200 import api, synth

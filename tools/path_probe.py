@@ -1,6 +1,9 @@
 """C2 leapfrog path probe: time to N = 10, 25, 50, 100 features on the full C2 matrix (1 GPU).
-python tools_path_probe.py [n_per_class] [max_iter]"""
+python tools/path_probe.py [n_per_class] [max_iter]"""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import time
 
 import numpy as np
