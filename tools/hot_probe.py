@@ -1,4 +1,8 @@
 """CSR fused pass: how many columns should accumulate in shared memory?  python tools/hot_probe.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import kmerlr_b200 as K
 from kmerlr_b200 import api, synth
