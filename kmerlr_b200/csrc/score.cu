@@ -144,7 +144,12 @@ __global__ void score_generic(const DevModel *__restrict__ models, int n_models,
 // so that  z(window at a) = theta_0 + sum_k Q_k[a + W - k] - Q_k[a - 1].
 struct LinearTile { int64_t region, p0; };
 
-__global__ void __launch_bounds__(256) score_linear(const DevModel *__restrict__ models, int n_models, int member,
+constexpr int SCORE_THREADS = 1024;
+__device__ __forceinline__ int level_slot(uint32_t levels, int k) {   // index of level k among the model's levels
+  return ((levels >> k) & 1u) ? __popc(levels & ((1u << k) - 1u)) : -1;
+}
+
+__global__ void __launch_bounds__(SCORE_THREADS) score_linear(const DevModel *__restrict__ models, int n_models, int member,
                                                     int accumulate, const int64_t *__restrict__ len,
                                                     const int64_t *__restrict__ blk,
                                                     const uint32_t *__restrict__ bits2,
@@ -153,64 +158,55 @@ __global__ void __launch_bounds__(256) score_linear(const DevModel *__restrict__
                                                     const int64_t *__restrict__ slot_off, int64_t W, int64_t step,
                                                     int TP, int model_index, int hs_smem, double *__restrict__ out) {
   extern __shared__ double q[];   // nlev x (TP + 1), q[.][0] = 0; then a copy of the class table
-  __shared__ double warp_tot[8];
+  __shared__ double warp_tot[SCORE_THREADS / 32];
   const DevModel md = models[model_index];
   const LinearTile tl = tiles[blockIdx.x];
   const int64_t L = len[tl.region];
   const uint32_t *b2 = bits2 + blk[tl.region] * 4;
   const uint16_t *iv = inv16 + blk[tl.region] * 4;
   const int N = md.N;
-  const uint32_t maskN = (1u << (2 * N)) - 1u, maskNb = (1u << N) - 1u;
-  // level slots
-  int lev_slot[16], nlev = 0;
-  for (int k = 0; k < 16; k++) lev_slot[k] = ((md.levels >> k) & 1u) ? nlev++ : -1;
+  const uint32_t maskN = (1u << (2 * N)) - 1u;
+  const int nlev = __popc(md.levels);
   const int stride = TP + 1;
   // small class tables are probed in shared memory (most probes miss: one LDS instead of one LDG each)
   uint32_t *skeys = reinterpret_cast<uint32_t *>(q + (size_t)nlev * stride);
   int32_t *svals = reinterpret_cast<int32_t *>(skeys + hs_smem);
   for (int i = threadIdx.x; i < hs_smem; i += blockDim.x) { skeys[i] = md.hkeys[i]; svals[i] = md.hvals[i]; }
   if (hs_smem) __syncthreads();
-  // phase 1: t_k(p) for p in [p0, p0 + TP): thread handles a contiguous run of positions
+  // phase 1: t_k(p) for p in [p0, p0 + TP).  The N bases starting at p are 2N consecutive bits of the
+  // packed words (one funnel shift, first base in the low bits): no rolling state, so the positions
+  // are simply dealt to the threads
   const int per = (TP + blockDim.x - 1) / blockDim.x;
-  {
-    int i0 = threadIdx.x * per, i1 = min(TP, i0 + per);
-    if (i0 < i1) {
-      uint32_t FW = 0, RC = 0, IV = 0xFFFFFFFFu;
-      int64_t cw = -1; uint32_t word = 0, ivw = 0;
-      auto consume = [&](int64_t idx) {
-        uint32_t x = 0, inv = 1;
-        if (idx >= 0 && idx < L) {
-          if ((idx >> 4) != cw) { cw = idx >> 4; word = __ldg(b2 + cw); ivw = __ldg(iv + cw); }
-          x = (word >> (2 * (idx & 15))) & 3u; inv = (ivw >> (idx & 15)) & 1u;
-        }
-        FW = ((FW << 2) | x) & maskN;
-        if (md.op == 1) RC = (RC >> 2) | ((3u - x) << (2 * (N - 1)));
-        else if (md.op == 3) RC = (RC >> 2) | (x << (2 * (N - 1)));
-        IV = (IV << 1) | inv;
-      };
-      int64_t p = tl.p0 + i0;
-      for (int64_t idx = p; idx < p + N - 1; idx++) consume(idx);
-      for (int i = i0; i < i1; i++, p++) {
-        consume(p + N - 1);               // window [p, p+N)
-        uint32_t xw = IV & maskNb;
-        int len_f = N - 32 + __clz(xw);
-        for (int k = md.M; k <= N; k++) {
-          int sl = lev_slot[k];
-          if (sl < 0) continue;
-          double t = 0.0;
-          if (len_f >= k) {
-            uint32_t fw = FW >> (2 * (N - k)), code = fw;
-            if (md.op == 1 || md.op == 3) code = min(fw, RC & ((1u << (2 * k)) - 1u));
-            else if (md.op == 2) code = min(fw, (~fw) & ((1u << (2 * k)) - 1u));
-            int ci = hs_smem ? table_lookup(skeys, svals, md.hmask, k, code) : model_lookup(md, k, code);
-            if (ci >= 0) t = __ldg(md.cweight + (int64_t)member * md.n_classes + ci);
-          }
-          q[sl * stride + 1 + i] = t;
-        }
-      }
+  for (int i = threadIdx.x; i < TP; i += blockDim.x) {
+    const int64_t p = tl.p0 + i;
+    int len_f = 0;
+    uint32_t FW = 0, IM = 0;
+    if (p < L) {
+      const int64_t wi = p >> 4;
+      const int sh = (int)(p & 15);
+      const uint32_t e = __funnelshift_r(__ldg(b2 + wi), __ldg(b2 + wi + 1), 2 * sh) & maskN;
+      const int64_t rest = L - p;
+      const uint32_t ivb = (((uint32_t)__ldg(iv + wi) | ((uint32_t)__ldg(iv + wi + 1) << 16)) >> sh) |
+                           (1u << (rest < N ? (int)rest : N));
+      len_f = __ffs(ivb) - 1;
+      FW = swap_pairs(__brev(e)) >> (32 - 2 * N);
+      IM = md.op == 1 ? (~e) & maskN : e;       // image of the window under revcomp / reverse
     }
-    if (threadIdx.x < nlev) q[threadIdx.x * stride] = 0.0;
+    for (int k = md.M; k <= N; k++) {
+      const int sl = level_slot(md.levels, k);
+      if (sl < 0) continue;
+      double t = 0.0;
+      if (len_f >= k) {
+        uint32_t fw = FW >> (2 * (N - k)), code = fw;
+        if (md.op == 1 || md.op == 3) code = min(fw, IM & ((1u << (2 * k)) - 1u));
+        else if (md.op == 2) code = min(fw, (~fw) & ((1u << (2 * k)) - 1u));
+        int ci = hs_smem ? table_lookup(skeys, svals, md.hmask, k, code) : model_lookup(md, k, code);
+        if (ci >= 0) t = __ldg(md.cweight + (int64_t)member * md.n_classes + ci);
+      }
+      q[sl * stride + 1 + i] = t;
+    }
   }
+  if ((int)threadIdx.x < nlev) q[threadIdx.x * stride] = 0.0;
   __syncthreads();
   // phase 2: inclusive scan per level (blocked: thread-local runs, warp scan, block carry)
   for (int sl = 0; sl < nlev; sl++) {
@@ -239,7 +235,7 @@ __global__ void __launch_bounds__(256) score_linear(const DevModel *__restrict__
     if (a + W > TP) break;
     double z = md.theta[(int64_t)member * (md.n_features + 1)];
     for (int k = md.M; k <= N; k++) {
-      int sl = lev_slot[k];
+      const int sl = level_slot(md.levels, k);
       if (sl < 0 || W < k) continue;
       const double *row = q + sl * stride;  // row[i+1] = inclusive prefix through position i
       z += row[a + W - k + 1] - row[a];
@@ -364,7 +360,7 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
         dt.upload(tiles.data(), tiles.size());
         size_t smem = (size_t)nlev * (size_t)(TP + 1) * sizeof(double) + (size_t)hs_smem * 8;
         KL_CUDA(cudaFuncSetAttribute(score_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        KL_LAUNCH(score_linear, (unsigned)tiles.size(), 256, smem, dmodels.p, n_models, 0, mi > 0 ? 1 : 0, s.len.p,
+        KL_LAUNCH(score_linear, (unsigned)tiles.size(), SCORE_THREADS, smem, dmodels.p, n_models, 0, mi > 0 ? 1 : 0, s.len.p,
                   s.blk.p, s.bits2.p, s.inv16.p, dt.p, dslot.p, W, step, (int)TP, mi, hs_smem, outbuf->val_f64.p);
         sync_stream();
       }
