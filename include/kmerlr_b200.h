@@ -64,8 +64,12 @@ int         kmerlr_profile(int enable);
 int         kmerlr_profile_read(const char *kernel_substr, double *ms_total, int64_t *launches);
 int         kmerlr_profile_dump(char *buf, int64_t buflen);
 
-/* run-time switches (tests and experiments): "implicit" = 1 (default) lets count matrices that came
- * straight from kmerlr_extract use the matrix-free logistic pass, 0 forces the CSR kernels */
+/* run-time switches (tests and experiments):
+ *   "implicit" = 1 (default) lets count matrices that came straight from kmerlr_extract use the
+ *                matrix-free logistic pass, 0 forces the pass over the stored rows;
+ *   "hot_cols" = number of columns of that stored-row pass that accumulate in shared memory (default 6144);
+ *   "p2p"      = 1 (default) lets sharded reduced-matrix iterations exchange the gradient over NVLink peer
+ *                memory, 0 forces the NCCL collectives (set it identically on every rank) */
 int         kmerlr_option(const char *name, int64_t value);
 
 /* ---- sample sharding over the GPUs of one box ------------------------------------ */
