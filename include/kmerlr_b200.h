@@ -102,6 +102,10 @@ int kmerlr_matrix_rows(kmerlr_handle h, int64_t *rowptr, int32_t *col, double *v
 int kmerlr_matrix_set_labels(kmerlr_handle h, const uint8_t *labels, int64_t n);
 int kmerlr_matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const int32_t *col,
                            const double *val, int flags, kmerlr_handle *out);
+/* per column (all ranks): sum of the values, sum of squares, largest value, number of stored entries --
+ * what TransformFull.Fit computes its offsets / scales from (kmerLr_transform.go:59-252); count and
+ * binarized matrices only.  The transform itself is a reparameterisation of theta on the host side. */
+int kmerlr_column_moments(kmerlr_handle h, double *sum_m, double *sumsq_m, double *absmax_m, int64_t *count_m);
 int kmerlr_free(kmerlr_handle h);
 
 /* ---- CoeffIndex (kmerLr_coefficients_index.go:26-54) ---------------------------------------- */

@@ -266,26 +266,117 @@ def compute_class_weights(c):
 
 
 # ---------------------------------------------------------------------------------------------------
+# data transforms (kmerLr_transform.go:33-317,584-629)
+# ---------------------------------------------------------------------------------------------------
+class Transform:
+    """Offset / Scale per coefficient, index 0 = bias (offset 0, scale 1); None = absent, as in the reference.
+
+    The reference applies (v - offset) * scale to every entry of every row, zeros included, which
+    densifies the data (kmerLr_transform.go:600-609).  Here the rows stay sparse counts in HBM: for a
+    linear model the transform is a reparameterisation,
+        theta'_j = scale_j theta_j,   theta'_0 = theta_0 - sum_j offset_j scale_j theta_j,
+        g_j = scale_j (g'_j - offset_j g'_0),
+    so every kernel runs unchanged on theta' (logisticRegression below)."""
+
+    def __init__(self, Offset=None, Scale=None):
+        self.Offset = None if Offset is None else np.ascontiguousarray(Offset, dtype=np.float64)
+        self.Scale = None if Scale is None else np.ascontiguousarray(Scale, dtype=np.float64)
+
+    def Nil(self):
+        return self.Offset is None and self.Scale is None
+
+    def Select(self, b):
+        """TransformFull.Select (kmerLr_transform.go:290-307): b = mask or ascending coefficient indices"""
+        b = np.asarray(b)
+        idx = np.nonzero(b)[0] if b.dtype == bool else b.astype(np.int64)
+        return Transform(None if self.Offset is None else self.Offset[idx], None if self.Scale is None else self.Scale[idx])
+
+
+class TransformFull(Transform):
+    def Fit(self, data, kind, cooccurrence=False):
+        """TransformFull.Fit (kmerLr_transform.go:40-252) from the column moments computed on the device"""
+        kind = (kind or "none").lower()
+        if cooccurrence:
+            raise KmerLrError(_lib.ERR_ARG, "data transforms of pair features are not implemented on the GPU path")
+        if kind in ("", "none"):
+            self.Offset = self.Scale = None
+            return self
+        m = data.m
+        s1, s2, mx = np.zeros(max(m, 1)), np.zeros(max(m, 1)), np.zeros(max(m, 1))
+        cnt = np.zeros(max(m, 1), dtype=np.int64)
+        check(lib().kmerlr_column_moments(data.h, _p(s1), _p(s2), _p(mx), _p(cnt)))
+        s1, s2, mx = s1[:m], s2[:m], mx[:m]
+        n = float(data.n_global if hasattr(data, "n_global") else data.n)
+        offset, scale = np.zeros(m + 1), np.ones(m + 1)
+        if kind in ("standardizer", "variance-scaler"):
+            mean = s1 / n
+            # sum_i (v_i - mean)^2 over ALL n samples = sum v^2 - n mean^2 (the reference adds the zero entries as
+            # (n - k) mean^2, :129-131)
+            sj = s2 - n * mean * mean
+            sj = np.where(sj < 0.0, 0.0, sj)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sc = 1.0 / np.sqrt(sj / (n - 1.0))
+            scale[1:] = np.where(sj == 0.0, 1.0, sc)
+            offset[1:] = mean
+            self.Offset, self.Scale = (offset, scale) if kind == "standardizer" else (None, scale)
+        elif kind == "max-abs-scaler":
+            with np.errstate(divide="ignore"):
+                scale[1:] = 1.0 / mx
+            self.Offset, self.Scale = None, scale
+        elif kind == "mean-scaler":
+            with np.errstate(divide="ignore"):
+                scale[1:] = n / s1
+            self.Offset, self.Scale = None, scale
+        else:
+            raise KmerLrError(_lib.ERR_ARG, "invalid data transform")
+        return self
+
+
+# ---------------------------------------------------------------------------------------------------
 # logisticRegression (kmerLr_logistic_regression.go:30-272)
 # ---------------------------------------------------------------------------------------------------
 class logisticRegression:
-    def __init__(self, Theta, ClassWeights=(1.0, 1.0), Lambda=0.0, Cooccurrence=False):
+    def __init__(self, Theta, ClassWeights=(1.0, 1.0), Lambda=0.0, Cooccurrence=False, Transform=None):
         self.Theta = np.ascontiguousarray(Theta, dtype=np.float64)
         self.ClassWeights = np.ascontiguousarray(ClassWeights, dtype=np.float64)
         self.Lambda = float(Lambda)
         self.Cooccurrence = bool(Cooccurrence)
+        self.Transform = Transform
+        if Transform is not None and not Transform.Nil() and self.Cooccurrence:
+            raise KmerLrError(_lib.ERR_ARG, "data transforms of pair features are not implemented on the GPU path")
 
     def Dim(self):
         return len(self.Theta) - 1
 
+    def _transformed(self):
+        return self.Transform is not None and not self.Transform.Nil()
+
+    def _theta_eff(self):
+        """theta' of the reparameterised model (see Transform)"""
+        if not self._transformed():
+            return self.Theta
+        t = self.Theta.copy()
+        sc = self.Transform.Scale if self.Transform.Scale is not None else np.ones(len(t))
+        if len(sc) != len(t):
+            raise KmerLrError(_lib.ERR_INTERNAL, "internal error")
+        t[1:] = t[1:] * sc[1:]
+        if self.Transform.Offset is not None:
+            t[0] = t[0] - float(np.dot(self.Transform.Offset[1:], t[1:]))
+        return np.ascontiguousarray(t)
+
+    def _penalty(self):
+        return self.Lambda == self.Lambda and self.Lambda != 0.0
+
     def LinearPdf(self, data):
+        t = self._theta_eff()
         out = np.zeros(max(data.n, 1))
-        check(lib().kmerlr_linear_pdf(data.h, _p(self.Theta), len(self.Theta), int(self.Cooccurrence), _p(out)))
+        check(lib().kmerlr_linear_pdf(data.h, _p(t), len(t), int(self.Cooccurrence), _p(out)))
         return out[:data.n]
 
     def LogPdf(self, data):
+        t = self._theta_eff()
         out = np.zeros(max(data.n, 1))
-        check(lib().kmerlr_logpdf(data.h, _p(self.Theta), len(self.Theta), int(self.Cooccurrence), _p(out)))
+        check(lib().kmerlr_logpdf(data.h, _p(t), len(t), int(self.Cooccurrence), _p(out)))
         return out[:data.n]
 
     def Gradient(self, g, data, labels=None):
@@ -295,17 +386,35 @@ class logisticRegression:
             g = np.zeros(len(self.Theta))
         elif len(g) != len(self.Theta):
             raise KmerLrError(_lib.ERR_INTERNAL, "internal error")
-        check(lib().kmerlr_gradient(data.h, _p(self.Theta), len(self.Theta), _p(self.ClassWeights), self.Lambda,
-                                    int(self.Cooccurrence), _p(g)))
+        if not self._transformed():
+            check(lib().kmerlr_gradient(data.h, _p(self.Theta), len(self.Theta), _p(self.ClassWeights), self.Lambda,
+                                        int(self.Cooccurrence), _p(g)))
+            return g
+        t = self._theta_eff()
+        check(lib().kmerlr_gradient(data.h, _p(t), len(t), _p(self.ClassWeights), 0.0, 0, _p(g)))
+        g0 = g[0]
+        if self.Transform.Offset is not None:
+            g[1:] -= self.Transform.Offset[1:] * g0
+        if self.Transform.Scale is not None:
+            g[1:] *= self.Transform.Scale[1:]
+        if self._penalty():                                  # (:237-246) on the ORIGINAL theta
+            g[1:] += self.Lambda * np.sign(self.Theta[1:])
         return g
 
     def Loss(self, data, c=None):
         if c is not None:
             data.SetLabels(c)
         out = C.c_double()
-        check(lib().kmerlr_loss(data.h, _p(self.Theta), len(self.Theta), _p(self.ClassWeights), self.Lambda,
-                                int(self.Cooccurrence), out))
-        return out.value
+        if not self._transformed():
+            check(lib().kmerlr_loss(data.h, _p(self.Theta), len(self.Theta), _p(self.ClassWeights), self.Lambda,
+                                    int(self.Cooccurrence), out))
+            return out.value
+        t = self._theta_eff()
+        check(lib().kmerlr_loss(data.h, _p(t), len(t), _p(self.ClassWeights), 0.0, 0, out))
+        r = out.value
+        if self._penalty():
+            r += self.Lambda * float(np.sum(np.abs(self.Theta[1:data.m + 1])))
+        return r
 
 
 # ---------------------------------------------------------------------------------------------------

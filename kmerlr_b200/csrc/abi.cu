@@ -294,6 +294,13 @@ int kmerlr_matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const in
   });
 }
 
+int kmerlr_column_moments(kmerlr_handle h, double *sum, double *sumsq, double *absmax, int64_t *count) {
+  return guarded([&] {
+    KL_REQUIRE(sum && sumsq && absmax && count, "null argument");
+    matrix_column_moments(*lookup<Matrix>(h, "matrix"), sum, sumsq, absmax, count);
+  });
+}
+
 int kmerlr_free(kmerlr_handle h) {
   return guarded([&] {
     KL_REQUIRE(g_objects.erase(h) == 1, "kmerlr_free: invalid handle");

@@ -300,6 +300,7 @@ std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *row
                                         const double *val, int flags);
 void matrix_rows(Matrix &M, int64_t *rowptr, int32_t *col, double *val);
 void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n);
+void matrix_column_moments(Matrix &M, double *sum, double *sumsq, double *absmax, int64_t *count);
 void matrix_compact(Matrix &M);      // padded rows -> compact CSR (no-op for compact matrices)
 void ensure_csc(Matrix &M);
 std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel);

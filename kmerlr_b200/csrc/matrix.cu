@@ -226,7 +226,62 @@ __global__ void abs_max(const VT *__restrict__ val, int64_t nnz, unsigned long l
   if (lane_id() == 0 && mx > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
 }
 
+// per column: sum of the values, sum of their squares, largest |value|, number of stored entries
+// (TransformFull.Fit, kmerLr_transform.go:59-252).  Counts are integers: exact 64-bit sums in any order.
+template <typename VT>
+__global__ void column_moments(const Rows R, const uint32_t *__restrict__ col, const VT *__restrict__ val, int64_t n,
+                               unsigned long long *__restrict__ s1, unsigned long long *__restrict__ s2,
+                               unsigned long long *__restrict__ mx, unsigned long long *__restrict__ cnt) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  int64_t a, b;
+  R.range(row, a, b);
+  for (int64_t p = a + lane_id(); p < b; p += 32) {
+    const unsigned long long v = val ? (unsigned long long)val[p] : 1ull;
+    const uint32_t c = col[p];
+    atomicAdd(s1 + c, v);
+    atomicAdd(s2 + c, v * v);
+    atomicMax(mx + c, v);
+    atomicAdd(cnt + c, 1ull);
+  }
+}
+
 }  // namespace
+
+void matrix_column_moments(Matrix &M, double *sum, double *sumsq, double *absmax, int64_t *count) {
+  require_ready();
+  KL_REQUIRE(M.vt != VAL_F64, "column_moments: only count / binarized matrices (integer values) are supported");
+  DevBuf<unsigned long long> d((size_t)(4 * (M.m ? M.m : 1)));
+  d.zero();
+  if (M.n > 0 && M.m > 0)
+    KL_LAUNCH((column_moments<uint32_t>), (unsigned)((M.n * 32 + 255) / 256), 256, 0, M.rows(), M.col.p,
+              M.vt == VAL_U32 ? M.val_u32.p : (const uint32_t *)nullptr, M.n, d.p, d.p + M.m, d.p + 2 * M.m, d.p + 3 * M.m);
+  if (M.sharded) {
+    // sums and counts add up over the ranks, the maximum is taken separately
+    DevBuf<double> mxd((size_t)(M.m ? M.m : 1));
+    std::vector<unsigned long long> tmp((size_t)M.m);
+    KL_CUDA(cudaMemcpyAsync(tmp.data(), d.p + 2 * M.m, (size_t)M.m * 8, cudaMemcpyDeviceToHost, ctx().stream));
+    sync_stream();
+    std::vector<double> hm((size_t)M.m);
+    for (int64_t j = 0; j < M.m; j++) hm[(size_t)j] = (double)tmp[(size_t)j];
+    mxd.upload(hm.data(), (size_t)M.m);
+    comm_allreduce_max_f64(mxd.p, M.m);
+    mxd.download(hm.data(), (size_t)M.m);
+    KL_CUDA(cudaMemsetAsync(d.p + 2 * M.m, 0, (size_t)M.m * 8, ctx().stream));
+    comm_allreduce_sum_i64((int64_t *)d.p, 4 * M.m);
+    sync_stream();
+    for (int64_t j = 0; j < M.m; j++) absmax[j] = hm[(size_t)j];
+  }
+  std::vector<unsigned long long> h((size_t)(4 * M.m));
+  d.download(h.data(), (size_t)(4 * M.m));
+  sync_stream();
+  for (int64_t j = 0; j < M.m; j++) {
+    sum[j] = (double)h[(size_t)j];
+    sumsq[j] = (double)h[(size_t)(M.m + j)];
+    if (!M.sharded) absmax[j] = (double)h[(size_t)(2 * M.m + j)];
+    count[j] = (int64_t)h[(size_t)(3 * M.m + j)];
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const int32_t *col,

@@ -358,3 +358,81 @@ def score_windows(models, regions, W, step, threads=0):
     out = np.zeros(max(total, 1))
     lib().ko_score_windows(arr, len(models), _p(buf), _p(off), len(off) - 1, W, step, _p(out), threads)
     return out[:total]
+
+
+# ---------------------------------------------------------------------------------------------------
+# data transforms (kmerLr_transform.go:40-252,584-629), restated with numpy on DENSIFIED rows -- the
+# reference densifies too when an offset is present (:600-609).  Small inputs only.
+# ---------------------------------------------------------------------------------------------------
+def fit_transform(mat, kind):
+    """TransformFull.Fit for single-feature matrices: returns (offset or None, scale or None), index 0 = bias"""
+    X = mat.dense()
+    n, m = X.shape
+    kind = (kind or "none").lower()
+    if kind in ("", "none"):
+        return None, None
+    if kind in ("standardizer", "variance-scaler"):
+        offset = np.zeros(m + 1)
+        scale = np.ones(m + 1)
+        offset[1:] = X.sum(axis=0) / float(n)                       # :77-104
+        for j in range(m):
+            nz = X[:, j][X[:, j] != 0]
+            sj = 0.0
+            for v in nz:                                              # :106-127, samples in order
+                sj += (v - offset[j + 1]) * (v - offset[j + 1])
+            sj += float(n - len(nz)) * offset[j + 1] * offset[j + 1]  # :129-131 zero entries
+            scale[j + 1] = 1.0 if sj == 0.0 else 1.0 / np.sqrt(sj / float(n - 1))
+        offset[0] = 0.0
+        return (offset, scale) if kind == "standardizer" else (None, scale)
+    if kind == "max-abs-scaler":
+        scale = np.ones(m + 1)
+        with np.errstate(divide="ignore"):
+            scale[1:] = 1.0 / np.abs(X).max(axis=0)                  # :161-205
+        return None, scale
+    if kind == "mean-scaler":
+        scale = np.ones(m + 1)
+        with np.errstate(divide="ignore"):
+            scale[1:] = float(n) / X.sum(axis=0)                     # :207-252
+        return None, scale
+    raise ValueError("invalid data transform")
+
+
+def _transformed_dense(mat, offset, scale):
+    X = mat.dense()
+    if offset is not None:
+        X = X - offset[None, 1:]
+    if scale is not None:
+        X = X * scale[None, 1:]
+    return X
+
+
+def _log_add0(x):
+    return np.where(x > 0, x + np.log1p(np.exp(-np.abs(x))), np.log1p(np.exp(-np.abs(x))))
+
+
+def transformed_loss(mat, labels, theta, offset, scale, cw=(1.0, 1.0), lam=0.0):
+    """Loss (kmerLr_logistic_regression.go:250-272) on Transform.Apply'd rows"""
+    theta = np.asarray(theta, dtype=np.float64)
+    z = theta[0] + _transformed_dense(mat, offset, scale) @ theta[1:]
+    lab = np.asarray(labels).astype(bool)
+    r = 0.0
+    for i in range(len(z)):                                           # serial over samples
+        r -= cw[1] * (-_log_add0(-z[i])) if lab[i] else cw[0] * (-_log_add0(z[i]))
+    r /= float(len(z))
+    if lam == lam and lam != 0.0:
+        r += lam * np.sum(np.abs(theta[1:]))
+    return float(r)
+
+
+def transformed_gradient(mat, labels, theta, offset, scale, cw=(1.0, 1.0), lam=0.0):
+    """Gradient (kmerLr_logistic_regression.go:151-248) on Transform.Apply'd rows"""
+    theta = np.asarray(theta, dtype=np.float64)
+    X = _transformed_dense(mat, offset, scale)
+    z = theta[0] + X @ theta[1:]
+    lab = np.asarray(labels).astype(bool)
+    r = -_log_add0(-z)
+    w = np.where(lab, cw[1] * (np.exp(r) - 1.0), cw[0] * np.exp(r)) / float(len(z))
+    g = np.concatenate([[w.sum()], X.T @ w])
+    if lam == lam and lam != 0.0:
+        g[1:] += lam * np.sign(theta[1:])
+    return g

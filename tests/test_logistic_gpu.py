@@ -95,6 +95,40 @@ def test_matrix_free_pass_equals_csr_pass(K, oracle, M, N, L, flags):
     assert np.allclose(est.Theta, oth, rtol=1e-9, atol=1e-13)
 
 
+def test_kmers5_standardizer_golden_and_transforms(K, oracle, fixtures):
+    """kmerLr_test.go:155-190 through the C ABI: k = 2..6 revcomp counts + standardizer, Loss at the golden theta
+    with lambda = 4.460029 is the reference's 1.107745182633717.  The rows stay sparse counts in HBM, the
+    transform is a reparameterisation of theta (api.Transform); all four transforms against the numpy
+    restatement of kmerLr_transform.go, which densifies like the reference does"""
+    d, ref, y = build(K, oracle, fixtures, 2, 6, revcomp=True)
+    t = K.TransformFull().Fit(d, "standardizer")
+    ooff, osc = oracle.fit_transform(ref, "standardizer")
+    assert np.allclose(t.Offset, ooff, rtol=1e-13, atol=0.0) and np.allclose(t.Scale, osc, rtol=1e-12, atol=0.0)
+    names = ref.class_names()
+    sel = [0, names.index("aaaatt|aatttt") + 1, names.index("caggag|ctcctg") + 1]
+    assert sel == [0, 703, 1673]
+    rd = K.select_data(d, sel)
+    rd.SetLabels(y)
+    theta = [5.552570741538388e-05, -0.00772452196477929, 0.09287154394711336]       # :166-174
+    lr = K.logisticRegression(theta, (1.0, 1.0), 4.460029e+00, Transform=t.Select(sel))
+    assert abs(lr.Loss(rd) - 1.107745182633717) <= 1e-13                               # :186
+    rng = np.random.default_rng(12)
+    cw = (0.8, 1.3)
+    for kind in ("standardizer", "variance-scaler", "max-abs-scaler", "mean-scaler"):
+        t = K.TransformFull().Fit(d, kind)
+        oo, os_ = oracle.fit_transform(ref, kind)
+        th = rng.normal(scale=0.01, size=d.m + 1)
+        th[rng.integers(1, d.m + 1, size=d.m // 2)] = 0.0
+        lr = K.logisticRegression(th, cw, 0.01, Transform=t)
+        olo = oracle.transformed_loss(ref, y, th, oo, os_, cw, 0.01)
+        assert abs(lr.Loss(d) - olo) <= 1e-11 * abs(olo)
+        close_g(lr.Gradient(None, d), oracle.transformed_gradient(ref, y, th, oo, os_, cw, 0.01))
+        z = th[0] + oracle._transformed_dense(ref, oo, os_) @ th[1:]
+        assert np.allclose(lr.LinearPdf(d), z, rtol=1e-10, atol=1e-11)
+    with pytest.raises(K.KmerLrError):
+        K.TransformFull().Fit(d, "no-such-transform")
+
+
 def test_identical_columns_get_identical_gradients(K, oracle, fixtures):
     """what leapfrog tie handling rests on: the column reduction depends on the column only"""
     d, ref, y = build(K, oracle, fixtures, 2, 6, fg="kmerLr_test_co_fg", bg="kmerLr_test_co_bg", revcomp=True, binarize=True)

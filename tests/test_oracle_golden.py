@@ -154,6 +154,22 @@ def test_kmers5_nucleotide_counts_and_first_lambda(oracle, fixtures):
     assert names.index("aaaatt|aatttt") == 702 and names.index("caggag|ctcctg") == 1672
 
 
+def test_kmers5_standardizer_loss_golden(oracle, fixtures):
+    """kmerLr_test.go:155-190: k = 2..6 revcomp counts + standardizer; Loss at the golden theta with
+    lambda = 4.460029 is 1.107745182633717 -- reproduced to the last digit (counting, transform and loss)"""
+    O = oracle
+    cfg = O.make_config(2, 6, revcomp=True)
+    buf, off, y = cat(fixtures, "kmerLr_test_fg", "kmerLr_test_bg")
+    m = O.extract(cfg, (buf, off))
+    names = m.class_names()
+    c1, c2 = names.index("aaaatt|aatttt"), names.index("caggag|ctcctg")
+    offset, scale = O.fit_transform(m, "standardizer")
+    sel = [0, c1 + 1, c2 + 1]
+    rm = O.reduce(m, sel)
+    theta = [5.552570741538388e-05, -0.00772452196477929, 0.09287154394711336]       # :166-174
+    assert O.transformed_loss(rm, y, theta, offset[sel], scale[sel], lam=4.460029e+00) == 1.107745182633717   # :186
+
+
 def test_go118_sort_matches_reference_structure(oracle):
     """small arrays go through the shell pass + insertion sort: equal keys keep a defined order"""
     O = oracle
