@@ -131,6 +131,12 @@ int kmerlr_select(kmerlr_handle h, const double class_w[2], int cooccurrence, in
                   const int64_t *active_idx, const double *active_theta, int64_t n_active, int tie,
                   double epsilon_lambda, double prev_lambda, uint8_t *mask_out, int64_t ntheta,
                   double *lambda_out, int64_t *c_out, int *ok_out, double *g_out_or_null);
+/* the same selection for a gradient the caller already holds (e.g. the gradient under a data transform,
+ * which is a reparameterisation on the host side): everything of Select after its gradient call */
+int kmerlr_select_from_gradient(const double *g, int64_t ntheta, int64_t N, const int64_t *active_idx,
+                                const double *active_theta, int64_t n_active, int tie, double epsilon_lambda,
+                                double prev_lambda, uint8_t *mask_out, double *lambda_out, int64_t *c_out,
+                                int *ok_out);
 /* featureSelection.Data (kmerLr_feature_selection.go:309-343): sel[0] = 0 (bias) */
 int kmerlr_reduce(kmerlr_handle h, const int64_t *sel, int64_t nsel, kmerlr_handle *out);
 

@@ -21,7 +21,7 @@ SYMBOLS = [
     "kmerlr_sequences_create", "kmerlr_extract_resident", "kmerlr_extract", "kmerlr_matrix_info",
     "kmerlr_matrix_classes", "kmerlr_column_moments", "kmerlr_matrix_rows", "kmerlr_matrix_set_labels", "kmerlr_matrix_from_csr",
     "kmerlr_free", "kmerlr_coeff_dim", "kmerlr_coeff_ind2sub", "kmerlr_coeff_sub2ind", "kmerlr_linear_pdf",
-    "kmerlr_logpdf", "kmerlr_gradient", "kmerlr_loss", "kmerlr_class_weights", "kmerlr_select", "kmerlr_reduce",
+    "kmerlr_logpdf", "kmerlr_gradient", "kmerlr_loss", "kmerlr_class_weights", "kmerlr_select", "kmerlr_select_from_gradient", "kmerlr_reduce",
     "kmerlr_step_size", "kmerlr_proxgrad", "kmerlr_window_slots", "kmerlr_score_windows",
     "kmerlr_score_windows_resident",
 ]
@@ -93,6 +93,7 @@ def lib():
     L.kmerlr_class_weights.argtypes = [h, vp]
     L.kmerlr_select.argtypes = [h, vp, C.c_int, i64, dbl, vp, vp, i64, C.c_int, dbl, dbl, vp, i64, pdbl, pi64,
                                 C.POINTER(C.c_int), vp]
+    L.kmerlr_select_from_gradient.argtypes = [vp, i64, i64, vp, vp, i64, C.c_int, dbl, dbl, vp, pdbl, pi64, C.POINTER(C.c_int)]
     L.kmerlr_reduce.argtypes = [h, vp, i64, ph]
     L.kmerlr_step_size.argtypes = [h, dbl, dbl, pdbl]
     L.kmerlr_proxgrad.argtypes = [h, vp, i64, vp, dbl, dbl, dbl, dbl, dbl, i64, vp, pi64, pdbl]

@@ -445,9 +445,10 @@ def select_data(data, sel):
 
 
 class featureSelector:
-    def __init__(self, ClassWeights, Cooccurrence, N, M, Epsilon=0.0, tie=TIE_GO118):
+    def __init__(self, ClassWeights, Cooccurrence, N, M, Epsilon=0.0, tie=TIE_GO118, Transform=None):
         self.ClassWeights = np.ascontiguousarray(ClassWeights, dtype=np.float64)
         self.Cooccurrence, self.N, self.M, self.Epsilon, self.tie = bool(Cooccurrence), int(N), int(M), Epsilon, tie
+        self.Transform = Transform          # TransformFull of the full space (featureSelector.Transform)
 
     def Select(self, data, theta0, active_idx, active_theta, lambda_prev, want_gradient=False):
         if self.M != data.Dim() - 1:
@@ -456,15 +457,22 @@ class featureSelector:
         ai = np.ascontiguousarray(active_idx, dtype=np.int64)
         at = np.ascontiguousarray(active_theta, dtype=np.float64)
         mask = np.zeros(nt, dtype=np.uint8)
-        g = np.zeros(nt) if want_gradient else None
         lam, c, ok = C.c_double(), C.c_int64(), C.c_int()
-        check(lib().kmerlr_select(data.h, _p(self.ClassWeights), int(self.Cooccurrence), self.N, float(theta0),
-                                  _p(ai), _p(at), len(ai), self.tie, self.Epsilon, float(lambda_prev), _p(mask), nt,
-                                  lam, c, ok, _p(g)))
         t = np.zeros(nt)
         t[0] = theta0
         nz = at != 0.0
         t[ai[nz]] = at[nz]
+        if self.Transform is not None and not self.Transform.Nil():
+            # gradient under the transform (kmerLr_feature_selection.go:221-229 with lr.Transform set):
+            # reparameterised on the host side, then the selection proper
+            g = logisticRegression(t, self.ClassWeights, 0.0, self.Cooccurrence, self.Transform).Gradient(None, data)
+            check(lib().kmerlr_select_from_gradient(_p(g), nt, self.N, _p(ai), _p(at), len(ai), self.tie, self.Epsilon,
+                                                    float(lambda_prev), _p(mask), lam, c, ok))
+        else:
+            g = np.zeros(nt) if want_gradient else None
+            check(lib().kmerlr_select(data.h, _p(self.ClassWeights), int(self.Cooccurrence), self.N, float(theta0),
+                                      _p(ai), _p(at), len(ai), self.tie, self.Epsilon, float(lambda_prev), _p(mask), nt,
+                                      lam, c, ok, _p(g)))
         s = featureSelection(self, mask.astype(bool), c.value, t)
         s.g = g
         return s, lam.value, bool(ok.value)

@@ -355,6 +355,16 @@ int kmerlr_select(kmerlr_handle h, const double class_w[2], int cooccurrence, in
   });
 }
 
+int kmerlr_select_from_gradient(const double *g, int64_t ntheta, int64_t N, const int64_t *active_idx,
+                                const double *active_theta, int64_t n_active, int tie, double epsilon_lambda,
+                                double prev_lambda, uint8_t *mask_out, double *lambda_out, int64_t *c_out, int *ok_out) {
+  return guarded([&] {
+    KL_REQUIRE(g && mask_out && lambda_out && c_out && ok_out && ntheta >= 1, "null argument");
+    select_from_gradient(g, ntheta, N, active_idx, active_theta, n_active, tie, epsilon_lambda, prev_lambda, mask_out,
+                         lambda_out, c_out, ok_out);
+  }, false);
+}
+
 int kmerlr_reduce(kmerlr_handle h, const int64_t *sel, int64_t nsel, kmerlr_handle *out) {
   return guarded([&] {
     KL_REQUIRE(out, "null output handle");

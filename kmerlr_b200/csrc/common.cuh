@@ -318,6 +318,9 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
 void select(Matrix &M, const double cw[2], int cooc, int64_t N, double theta0, const int64_t *active_idx,
             const double *active_theta, int64_t n_active, int tie, double eps_lambda, double prev_lambda,
             uint8_t *mask, int64_t ntheta, double *lambda_out, int64_t *c_out, int *ok_out, double *g_out);
+void select_from_gradient(const double *g, int64_t ntheta, int64_t N, const int64_t *active_idx, const double *active_theta,
+                          int64_t n_active, int tie, double eps_lambda, double prev_lambda, uint8_t *mask,
+                          double *lambda_out, int64_t *c_out, int *ok_out);
 // score.cu
 void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, int64_t W, int64_t step,
                    double *out_host, std::shared_ptr<Object> *out_dev);

@@ -116,26 +116,22 @@ struct LegacySorter {
 
 }  // namespace
 
-void select(Matrix &M, const double cw[2], int cooc, int64_t N, double theta0, const int64_t *active_idx,
-            const double *active_theta, int64_t n_active, int tie, double eps_lambda, double prev_lambda,
-            uint8_t *b, int64_t ntheta, double *lambda_out, int64_t *c_out, int *ok_out, double *g_out) {
-  require_ready();
-  const int64_t dim = cooc ? kmerlr_coeff_dim(M.m) : M.m + 1;
-  KL_INVARIANT(ntheta == dim);
+// featureSelector.Select after its gradient call (kmerLr_feature_selection.go:88-134,179-192): b = mask,
+// top 2N by |g| under the tie rule, lambda.  g is the full-space gradient at the embedded theta.
+void select_from_gradient(const double *gin, int64_t ntheta, int64_t N, const int64_t *active_idx,
+                          const double *active_theta, int64_t n_active, int tie, double eps_lambda, double prev_lambda,
+                          uint8_t *b, double *lambda_out, int64_t *c_out, int *ok_out) {
   KL_REQUIRE(N >= 1, "select: N must be positive");
   KL_REQUIRE(tie == KMERLR_TIE_GO118 || tie == KMERLR_TIE_INDEX, "select: unknown tie rule");
+  std::vector<double> g(gin, gin + ntheta);
   // alloc + restoreNonzero (:164-219): only coefficients with theta != 0 survive
-  std::vector<double> t((size_t)ntheta, 0.0), g((size_t)ntheta);
   std::fill(b, b + ntheta, (uint8_t)0);
-  b[0] = 1; t[0] = theta0;
+  b[0] = 1;
   int64_t c = 0;
   for (int64_t i = 0; i < n_active; i++) {
     KL_REQUIRE(active_idx[i] >= 1 && active_idx[i] < ntheta, "select: active coefficient index out of range");
-    if (active_theta[i] != 0.0) { t[active_idx[i]] = active_theta[i]; b[active_idx[i]] = 1; c++; }
+    if (active_theta[i] != 0.0) { b[active_idx[i]] = 1; c++; }
   }
-  // gradient(data, t)[1:]  (:221-229): no penalty term
-  gradient(M, t.data(), ntheta, cw, 0.0, cooc, g.data());
-  if (g_out) std::copy(g.begin(), g.end(), g_out);
   const int64_t len = ntheta - 1;
   const int64_t top = len <= 2 * N ? len : 2 * N;
   std::vector<double> gs(g.begin() + 1, g.end());
@@ -175,6 +171,27 @@ void select(Matrix &M, const double cw[2], int cooc, int64_t N, double theta0, c
   }
   *lambda_out = l; *c_out = c;
   *ok_out = ok || (eps_lambda > 0.0 && std::fabs(prev_lambda - l) >= eps_lambda);
+}
+
+void select(Matrix &M, const double cw[2], int cooc, int64_t N, double theta0, const int64_t *active_idx,
+            const double *active_theta, int64_t n_active, int tie, double eps_lambda, double prev_lambda,
+            uint8_t *b, int64_t ntheta, double *lambda_out, int64_t *c_out, int *ok_out, double *g_out) {
+  require_ready();
+  const int64_t dim = cooc ? kmerlr_coeff_dim(M.m) : M.m + 1;
+  KL_INVARIANT(ntheta == dim);
+  KL_REQUIRE(N >= 1, "select: N must be positive");
+  // theta embedded in the full space (:164-219)
+  std::vector<double> t((size_t)ntheta, 0.0), g((size_t)ntheta);
+  t[0] = theta0;
+  for (int64_t i = 0; i < n_active; i++) {
+    KL_REQUIRE(active_idx[i] >= 1 && active_idx[i] < ntheta, "select: active coefficient index out of range");
+    if (active_theta[i] != 0.0) t[active_idx[i]] = active_theta[i];
+  }
+  // gradient(data, t)[1:]  (:221-229): no penalty term
+  gradient(M, t.data(), ntheta, cw, 0.0, cooc, g.data());
+  if (g_out) std::copy(g.begin(), g.end(), g_out);
+  select_from_gradient(g.data(), ntheta, N, active_idx, active_theta, n_active, tie, eps_lambda, prev_lambda, b,
+                       lambda_out, c_out, ok_out);
 }
 
 }  // namespace kl

@@ -127,6 +127,13 @@ def test_kmers5_standardizer_golden_and_transforms(K, oracle, fixtures):
         assert np.allclose(lr.LinearPdf(d), z, rtol=1e-10, atol=1e-11)
     with pytest.raises(K.KmerLrError):
         K.TransformFull().Fit(d, "no-such-transform")
+    # first leapfrog epoch of TestKmers5 (--lambda-auto=2 with the standardizer): the two classes the reference's
+    # test finds in the model (kmerLr_test.go:175-184) and the lambda of SURVEY section 0
+    t = K.TransformFull().Fit(d, "standardizer")
+    fs = K.featureSelector((1.0, 1.0), False, 2, d.m, tie=K.TIE_GO118, Transform=t)
+    selection, lam, ok = fs.Select(d, 0.0, [], [], 0.0)
+    assert ok and selection.sel.tolist() == [0, 703, 1673]
+    assert abs(lam - 0.3345505506971979) <= 1e-12
 
 
 def test_identical_columns_get_identical_gradients(K, oracle, fixtures):
