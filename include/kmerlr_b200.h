@@ -171,6 +171,11 @@ int64_t kmerlr_window_slots(int64_t len, int64_t W, int64_t step);
 int kmerlr_score_windows(const kmerlr_model *models, int n_models, const uint8_t *seq,
                          const int64_t *region_off, int64_t n_regions, int64_t W, int64_t step,
                          double *out);
+/* predict_window of the `predict --sliding-window` command (kmerLr_predict.go:89-124): one classifier, every
+ * sequence gets len - W slots (none if len <= W) and the window starting at j = 0, step, 2 step, ... < len - W
+ * lands in slot j; the other slots stay 0.0.  The classifier's Transform is not applied there either. */
+int kmerlr_predict_windows(const kmerlr_model *model, const uint8_t *seq, const int64_t *seq_off, int64_t n_seq,
+                           int64_t W, int64_t step, double *out);
 int kmerlr_score_windows_resident(const kmerlr_model *models, int n_models, kmerlr_handle sequences,
                                   int64_t W, int64_t step, double *out_host_or_null,
                                   kmerlr_handle *out_dev_or_null);

@@ -577,6 +577,18 @@ class genomicKmerLr:
             p += s
         return res
 
+    def predict_window(self, sequences, window_size, window_step):
+        """predict_window (kmerLr_predict.go:89-124), first classifier: predictions[i][j] for the window at j"""
+        buf, off = flatten(sequences)
+        slots = [max(int(off[i + 1] - off[i]) - window_size, 0) for i in range(len(off) - 1)]
+        out = np.zeros(max(sum(slots), 1))
+        check(lib().kmerlr_predict_windows(self._arr, _p(buf), _p(off), len(off) - 1, window_size, window_step, _p(out)))
+        res, p = [], 0
+        for s in slots:
+            res.append(out[p:p + s].copy())
+            p += s
+        return res
+
     def predict_resident(self, sequences, window_size, window_step, fetch=False, total_slots=0):
         out = np.zeros(max(total_slots, 1)) if fetch else None
         check(lib().kmerlr_score_windows_resident(self._arr, len(self.classifiers), sequences.h, window_size,

@@ -403,6 +403,16 @@ int kmerlr_score_windows(const kmerlr_model *models, int n_models, const uint8_t
   });
 }
 
+// predict_window (kmerLr_predict.go:89-124): one classifier, len - W slots per sequence, slot j = window at j
+int kmerlr_predict_windows(const kmerlr_model *model, const uint8_t *seq, const int64_t *seq_off, int64_t n_seq,
+                           int64_t W, int64_t step, double *out) {
+  return guarded([&] {
+    KL_REQUIRE(model && out, "null argument");
+    auto s = sequences_create(seq, seq_off, n_seq);
+    score_windows(model, 1, *s, W, step, out, nullptr, 1);
+  });
+}
+
 int kmerlr_score_windows_resident(const kmerlr_model *models, int n_models, kmerlr_handle sequences, int64_t W,
                                   int64_t step, double *out_host_or_null, kmerlr_handle *out_dev_or_null) {
   return guarded([&] {

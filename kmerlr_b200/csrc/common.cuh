@@ -323,7 +323,7 @@ void select_from_gradient(const double *g, int64_t ntheta, int64_t N, const int6
                           double *lambda_out, int64_t *c_out, int *ok_out);
 // score.cu
 void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, int64_t W, int64_t step,
-                   double *out_host, std::shared_ptr<Object> *out_dev);
+                   double *out_host, std::shared_ptr<Object> *out_dev, int layout = 0);
 // comm.cu
 void comm_unique_id(void *id128);
 void comm_init(int rank, int world, const void *id128);

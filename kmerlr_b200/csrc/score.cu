@@ -77,7 +77,7 @@ __global__ void score_generic(const DevModel *__restrict__ models, int n_models,
                               const uint16_t *__restrict__ inv16, int64_t n_regions,
                               const int64_t *__restrict__ win_off, const int64_t *__restrict__ slot_off,
                               int64_t total_windows, int64_t W, int64_t step, int max_classes,
-                              double *__restrict__ out) {
+                              int64_t slot_stride, double *__restrict__ out) {
   extern __shared__ uint32_t smem[];
   const unsigned lane = lane_id();
   uint32_t *cnt = smem + (size_t)(threadIdx.x >> 5) * max_classes;
@@ -133,7 +133,7 @@ __global__ void score_generic(const DevModel *__restrict__ models, int n_models,
       total += summarize(md.summary, lp, md.n_members);
       __syncwarp();
     }
-    if (lane == 0) out[slot_off[r] + w] = total;
+    if (lane == 0) out[slot_off[r] + w * slot_stride] = total;
   }
 }
 
@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_linear(const DevModel *__
                                                     const uint16_t *__restrict__ inv16,
                                                     const LinearTile *__restrict__ tiles,
                                                     const int64_t *__restrict__ slot_off, int64_t W, int64_t step,
-                                                    int TP, int model_index, int hs_smem, double *__restrict__ out) {
+                                                    int TP, int model_index, int hs_smem, int64_t slot_stride,
+                                                    double *__restrict__ out) {
   extern __shared__ double q[];   // nlev x (TP + 1), q[.][0] = 0; then a copy of the class table
   __shared__ double warp_tot[SCORE_THREADS / 32];
   const DevModel md = models[model_index];
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_linear(const DevModel *__
       z += row[a + W - k + 1] - row[a];
     }
     double lp = -log_add0(-z);
-    int64_t o = slot_off[tl.region] + w;
+    int64_t o = slot_off[tl.region] + w * slot_stride;
     if (accumulate) out[o] += lp; else out[o] = lp;
   }
 }
@@ -256,8 +257,10 @@ struct HostModel {
 
 }  // namespace
 
+// layout 0: predict_window_genomic -- n/step + 1 slots per region, window j*step in slot j
+// layout 1: predict_window (kmerLr_predict.go:89-124) -- n = len - W slots, window starting at j in slot j
 void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, int64_t W, int64_t step,
-                   double *out_host, std::shared_ptr<Object> *out_dev) {
+                   double *out_host, std::shared_ptr<Object> *out_dev, int layout) {
   require_ready();
   KL_REQUIRE(n_models >= 1 && W >= 1 && step >= 1, "score_windows: bad arguments");
   std::vector<std::unique_ptr<HostModel>> hm;
@@ -325,7 +328,7 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
   sync_stream();
   std::vector<int64_t> slot_off((size_t)s.n + 1, 0), win_off((size_t)s.n + 1, 0);
   for (int64_t r = 0; r < s.n; r++) {
-    slot_off[r + 1] = slot_off[r] + kmerlr_window_slots(len[r], W, step);
+    slot_off[r + 1] = slot_off[r] + (layout == 1 ? (len[r] - W > 0 ? len[r] - W : 0) : kmerlr_window_slots(len[r], W, step));
     win_off[r + 1] = win_off[r] + (len[r] - W > 0 ? (len[r] - W + step - 1) / step : 0);
   }
   const int64_t total_slots = slot_off[s.n], total_windows = win_off[s.n];
@@ -361,7 +364,7 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
         size_t smem = (size_t)nlev * (size_t)(TP + 1) * sizeof(double) + (size_t)hs_smem * 8;
         KL_CUDA(cudaFuncSetAttribute(score_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KL_LAUNCH(score_linear, (unsigned)tiles.size(), SCORE_THREADS, smem, dmodels.p, n_models, 0, mi > 0 ? 1 : 0, s.len.p,
-                  s.blk.p, s.bits2.p, s.inv16.p, dt.p, dslot.p, W, step, (int)TP, mi, hs_smem, outbuf->val_f64.p);
+                  s.blk.p, s.bits2.p, s.inv16.p, dt.p, dslot.p, W, step, (int)TP, mi, hs_smem, layout == 1 ? step : (int64_t)1, outbuf->val_f64.p);
         sync_stream();
       }
     } else {
@@ -370,7 +373,8 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
       int64_t blocks = (total_windows + 3) / 4, cap = (int64_t)ctx().sm_count * 16;
       if (blocks > cap) blocks = cap;
       KL_LAUNCH(score_generic, (unsigned)blocks, 128, smem, dmodels.p, n_models, s.len.p, s.blk.p, s.bits2.p,
-                s.inv16.p, s.n, dwin.p, dslot.p, total_windows, W, step, max_classes, outbuf->val_f64.p);
+                s.inv16.p, s.n, dwin.p, dslot.p, total_windows, W, step, max_classes, layout == 1 ? step : (int64_t)1,
+                outbuf->val_f64.p);
     }
   }
   if (out_host) outbuf->val_f64.download(out_host, (size_t)total_slots);

@@ -76,6 +76,27 @@ def test_generic_models(K, oracle):
     check(K, oracle, [km, km2], [om, om2], seqs, 150, 25)
 
 
+def test_predict_window_layout(K, oracle):
+    """predict --sliding-window (kmerLr_predict.go:89-124): len - W slots per sequence, the window starting at j
+    in slot j, the slots in between stay 0.0; same scores as the genomic layout"""
+    seqs = regions()
+    km, om = make_model(K, oracle, seqs[:1], 1, 8, 60, seed=4, revcomp=True)
+    g = K.genomicKmerLr([km])
+    W, step = 200, 7
+    pw = g.predict_window(seqs, W, step)
+    gen = g.predict_window_genomic(seqs, W, step)
+    for s, a, b in zip(seqs, pw, gen):
+        n = len(s) - W
+        assert len(a) == max(n, 0)
+        if n <= 0:
+            continue
+        starts = np.arange(0, n, step)
+        assert np.array_equal(a[starts], b[:len(starts)])
+        rest = np.ones(n, dtype=bool)
+        rest[starts] = False
+        assert np.all(a[rest] == 0.0)
+
+
 def test_ensemble_without_summary_fails(K, oracle):
     seqs = regions()[:1]
     km, _ = make_model(K, oracle, seqs, 2, 4, 10, members=2, summary="")
