@@ -56,7 +56,10 @@ for case in range(n_cases):
             th = rng.normal(scale=0.05, size=d.m + 1)
             lr = K.logisticRegression(th, (0.7, 1.4), 0.0)
             g, og = lr.Gradient(None, d2), O.gradient(ref, y, th, (0.7, 1.4))
-            ok = np.max(np.abs(g - og)) <= 1e-9 * max(np.max(np.abs(og)), 1e-300)
+            # fixed-point accumulation: absolute precision nnz(column) * 2^-60 * max(cw) * max|v|, which
+            # only shows when every weight underflows it (one saturated row)
+            vmax = float(np.max(d.rows()[2])) if d.nnz else 1.0
+            ok = np.max(np.abs(g - og)) <= 1e-9 * np.max(np.abs(og)) + 1e-15 * d.n * 1.4 * vmax
             lo, olo = lr.Loss(d2), O.loss(ref, y, th, (0.7, 1.4))
             ok = ok and abs(lo - olo) <= 1e-11 * abs(olo)
             if ok and d.m > 3:
@@ -66,7 +69,10 @@ for case in range(n_cases):
                 ok = (ds.n, ds.m, ds.nnz) == (rs.n, rs.m, rs.nnz) and all(np.array_equal(x, y2) for x, y2 in zip(ds.rows(), rs.rows()))
         if not ok:
             bad += 1
-            print("MISMATCH", tag, flush=True)
+            print("MISMATCH", tag, (d.n, d.m, d.nnz), (ref.n, ref.m, ref.nnz), flush=True)
+            os.makedirs("gpurun_out", exist_ok=True)
+            with open("gpurun_out/fuzz_case_%d.txt" % case, "w") as f:
+                f.write(repr(dict(M=M, N=N, flags=flags, binz=binz, seqs=seqs)))
     except K.KmerLrError as e:
         # documented limits (k > 8 with rows beyond the register sort, gapped size limits) must fail loudly
         print("refused", tag, "--", str(e)[:90], flush=True)
