@@ -6,9 +6,11 @@
 
 One STEP = one pass of the hot path over one batch of synthetic input of the BASELINE.json
 configs[1] shape (C2): extract 100 000 fg + 100 000 bg sequences x 500 bp, k = 1..8, revcomp-merged,
-into the sparse count matrix, then one full-space proximal-gradient iteration on it (rows pass:
-z, loss, weights; columns pass: X^T w; prox update).  N > 1: every rank (GPU) gets its own
+into the sparse count matrix, then one full-space proximal-gradient iteration on it (one pass: z, loss,
+weights, X^T w; prox update; then the hook's loss at the new theta).  N > 1: every rank (GPU) gets its own
 200 000-sequence shard (weak scaling); the class union and the gradient are reduced over NCCL.
+Beside the headline the line carries: full-space iterations/s, reduced-matrix (100 columns) iterations/s,
+sliding-window scoring on a bounded genome, the roofline of the dominant kernel, clocks, the CPU baseline.
 
 `value` is timed on the device (CUDA events on the library's stream) with the packed sequences
 already resident in HBM; `e2e` is the same step through the host-buffer C-ABI calls

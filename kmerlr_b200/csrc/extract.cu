@@ -363,7 +363,7 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   }
   P.level_off[cfg.N + 1] = (uint32_t)dense;
   const int64_t nbits = (int64_t)dense, nw = (nbits + 31) / 32;
-  // staging stride: upper bound on distinct classes of one sequence
+  // row stride of the matrix: upper bound on the distinct classes of one sequence
   int64_t stride = 0;
   for (int k = cfg.M; k <= cfg.N; k++) {
     int64_t inst = s.max_len - k + 1; if (inst < 0) inst = 0;
