@@ -72,7 +72,7 @@ static void decode(uint64_t code, int k, int A, uint8_t *l) {
 int ko_class_name(const ko_config *cfg, int32_t k, uint64_t code, char *buf, int buflen) {
   static const char L[] = "acgtn";
   int A = alphabet_size(cfg);
-  uint8_t l[KO_MAXK], t[4][KO_MAXK];
+  uint8_t l[KO_MAXK] = {0}, t[4][KO_MAXK];
   uint64_t c[4];
   int nm = 0;
   decode(code, k, A, l);
@@ -138,10 +138,6 @@ static inline int32_t kc_get(const kc_map *m, uint64_t key) {
     if (m->e[i].key == KEY_EMPTY) return 0;
     i = (i + 1) & (m->cap - 1);
   }
-}
-static int cmp_entry(const void *a, const void *b) {
-  uint64_t x = ((const kc_entry *)a)->key, y = ((const kc_entry *)b)->key;
-  return x < y ? -1 : (x > y ? 1 : 0);
 }
 static int cmp_u64(const void *a, const void *b) {
   uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
