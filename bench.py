@@ -320,11 +320,12 @@ def main():
     try:
         est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=50)
         est.Theta = np.zeros(len(sel)); est.ClassWeights = cw
-        est.estimate_proximal(rd, lam)
+        lam_red = 1e-6                     # small enough that theta leaves 0 and the iterations keep running
+        est.estimate_proximal(rd, lam_red)
         est.MaxIterations = red_iters
         est.Theta = np.zeros(len(sel))
         barrier()
-        done_iters, _ = est.estimate_proximal(rd, lam)
+        done_iters, _ = est.estimate_proximal(rd, lam_red)
         red_ms = K.last_device_ms()
         reduced = {"columns": int(len(sel) - 1), "nnz": int(rd.nnz), "iterations": int(done_iters),
                    "ms_per_iter": red_ms / max(done_iters, 1), "iters_per_sec": 1e3 * max(done_iters, 1) / red_ms,
