@@ -9,7 +9,8 @@
  * Parity status: PINNED for k-mer indices / class names / counts (kmerLr_test.go:40-43,55-66),
  * CoeffIndex (round trip), leapfrog lambda (README.md:39 = 2.496875), the TestKmers6 tie group
  * and Go<=1.18 sort order (kmerLr_test.go:205-206), the loss/prediction known answers
- * (kmerLr_test.go:224,228,248).  The reference itself cannot be built here (no Go toolchain;
+ * (kmerLr_test.go:224,228,248), the TestKmers5 loss under the standardizer (kmerLr_test.go:186, numpy
+ * restatement of the transform in oracle.py).  The reference itself cannot be built here (no Go toolchain;
  * gonetics / autodiff are not vendored), so there is no oracle/_ref.  UNPINNED (no reference
  * test exists): non-ACGT input handling, --complement / --reverse alone, MaxAmbiguous >= 0,
  * estimate_proximal / estimate_coordinate (dead code in the reference, no test), genomic scoring.
