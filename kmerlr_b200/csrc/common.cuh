@@ -64,7 +64,7 @@ struct PeerBox {
   int rank, world;
 };
 
-constexpr int CTX_COPY_EVENTS = 5;   // chunks of a pipelined host feed + 1
+constexpr int CTX_COPY_EVENTS = 6;   // chunks of a pipelined host feed + 1
 struct Ctx {
   bool ready = false;
   int device = 0;

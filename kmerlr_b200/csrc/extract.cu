@@ -213,67 +213,87 @@ const uint2 *table_classes(int op, int t_lo, int t_hi, const uint32_t *level_off
 
 }  // namespace
 
-// ---------------------------------------------------------------------------------------------------
-// lengths and block offsets on the device, packed arrays allocated but not filled yet; the host copies
-// of the block offsets and of the offsets relative to the first base come back for the feeding loop
-static std::shared_ptr<SeqSet> sequences_alloc(const int64_t *off, int64_t n, std::vector<int64_t> &blk,
-                                               std::vector<int64_t> &rel) {
-  require_ready();
-  KL_REQUIRE(n >= 0 && off != nullptr, "sequences: bad arguments");
-  auto s = std::make_shared<SeqSet>();
-  s->n = n;
-  std::vector<int64_t> len((size_t)n);
-  blk.assign((size_t)n + 1, 0); rel.assign((size_t)n + 1, 0);
-  for (int64_t i = 0; i < n; i++) {
-    len[i] = off[i + 1] - off[i];
-    KL_REQUIRE(len[i] >= 0, "sequences: offsets must be non-decreasing");
-    if (len[i] > s->max_len) s->max_len = len[i];
-    blk[i + 1] = blk[i] + (len[i] + 63) / 64;
-    rel[i + 1] = off[i + 1] - off[0];
-  }
-  s->total_bases = n ? off[n] - off[0] : 0;
-  s->total_blocks = blk[n];
-  s->len.alloc((size_t)(n ? n : 1));
-  s->blk.alloc((size_t)n + 1);
-  s->len.upload(len.data(), (size_t)n);
-  s->blk.upload(blk.data(), (size_t)n + 1);
-  int64_t words = s->total_blocks * 4;
-  s->bits2.alloc((size_t)words + 1);     // + 1: the kernels read the word after the last base
-  s->inv16.alloc((size_t)words + 1);
-  KL_CUDA(cudaMemsetAsync(s->bits2.p + words, 0, sizeof(uint32_t), ctx().stream));
-  KL_CUDA(cudaMemsetAsync(s->inv16.p + words, 0, sizeof(uint16_t), ctx().stream));
-  sync_stream();                  // len / blk are stack vectors of this call
-  return s;
+// Per-sequence metadata on the device from ONE upload of the caller's offsets: len[i], and blk = the
+// exclusive scan of ceil(len / 64).
+static __global__ void seq_meta_kernel(const int64_t *__restrict__ off, int64_t n, int64_t *__restrict__ len,
+                                uint32_t *__restrict__ nblk) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t l = off[i + 1] - off[i];
+  len[i] = l;
+  nblk[i] = (uint32_t)((l + 63) >> 6);
 }
 
 // Host sequences feeding an extraction: the ASCII bytes go to the device in chunks on the copy stream
-// while the previous chunk is packed and extracted on the main stream.
+// while the previous chunk is packed and extracted on the main stream.  The host keeps only the chunk
+// boundaries (rows, 64-base blocks, bytes); the per-sequence arrays are derived on the device.
 struct HostFeed {
-  const uint8_t *seq = nullptr;   // first base of sequence 0
-  std::vector<int64_t> blk, rel;
-  DevBuf<uint8_t> raw;
-  DevBuf<int64_t> doff;
-  // copy the bases of the sequences [r0, r1) and pack them (main stream waits for the copy)
-  void feed(SeqSet &s, int64_t r0, int64_t r1, int slot) {
-    const int64_t b0 = rel[r0], b1 = rel[r1];
+  const uint8_t *seq = nullptr;   // base 0 of the caller's buffer (offsets are absolute)
+  int nchunks = 1;
+  int64_t row[CTX_COPY_EVENTS] = {0}, blk[CTX_COPY_EVENTS] = {0}, byte[CTX_COPY_EVENTS] = {0};
+  // chunk sizes double (1, 2, 4, ... parts): the first kernel starts after a short copy, and the copy of
+  // the next chunk, which is faster than the extraction of the current one, is always done in time
+  static int64_t cut(int64_t n, int c, int nchunks) { return n * ((1 << c) - 1) / ((1 << nchunks) - 1); }
+  DevBuf<uint8_t> raw;            // bytes [byte[0], byte[nchunks])
+  DevBuf<int64_t> doff;           // the caller's offsets
+  // copy the bases of chunk c (every chunk for c < 0) and pack them (main stream waits for the copy)
+  void feed(SeqSet &s, int c) {
+    const int c0 = c < 0 ? 0 : c, c1 = c < 0 ? nchunks : c + 1;
+    const int64_t b0 = byte[c0], b1 = byte[c1];
     if (b1 > b0) {
-      KL_CUDA(cudaMemcpyAsync(raw.p + b0, seq + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, ctx().copy_stream));
-      KL_CUDA(cudaEventRecord(ctx().copy_ev[slot], ctx().copy_stream));
-      KL_CUDA(cudaStreamWaitEvent(ctx().stream, ctx().copy_ev[slot], 0));
+      KL_CUDA(cudaMemcpyAsync(raw.p + (b0 - byte[0]), seq + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice,
+                              ctx().copy_stream));
+      KL_CUDA(cudaEventRecord(ctx().copy_ev[c0], ctx().copy_stream));
+      KL_CUDA(cudaStreamWaitEvent(ctx().stream, ctx().copy_ev[c0], 0));
     }
-    const int64_t w0 = blk[r0] * 4, w1 = blk[r1] * 4;
+    const int64_t w0 = blk[c0] * 4, w1 = blk[c1] * 4;
     if (w1 > w0)
-      KL_LAUNCH(pack_kernel, (unsigned)((w1 - w0 + 255) / 256), 256, 0, raw.p, doff.p, s.blk.p, s.n, w0, w1, s.bits2.p,
-                s.inv16.p);
+      KL_LAUNCH(pack_kernel, (unsigned)((w1 - w0 + 255) / 256), 256, 0, raw.p - byte[0], doff.p, s.blk.p, s.n, w0, w1,
+                s.bits2.p, s.inv16.p);
   }
 };
 
 static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t *off, int64_t n, HostFeed &hf) {
-  auto s = sequences_alloc(off, n, hf.blk, hf.rel);
-  hf.seq = seq + (n ? off[0] : 0);
-  hf.raw.alloc((size_t)(s->total_bases ? s->total_bases : 1));
+  require_ready();
+  KL_REQUIRE(n >= 0 && off != nullptr, "sequences: bad arguments");
+  auto s = std::make_shared<SeqSet>();
+  s->n = n;
+  hf.seq = seq;
+  hf.nchunks = n >= 4096 ? CTX_COPY_EVENTS - 1 : 1;
+  // one pass over the offsets: validation, longest sequence, block counts at the chunk boundaries
+  int64_t blocks = 0, max_len = 0, min_len = 0;
+  for (int c = 0; c < hf.nchunks; c++) {
+    const int64_t r0 = HostFeed::cut(n, c, hf.nchunks), r1 = HostFeed::cut(n, c + 1, hf.nchunks);
+    hf.row[c] = r0; hf.blk[c] = blocks; hf.byte[c] = off[r0];
+    for (int64_t i = r0; i < r1; i++) {
+      const int64_t l = off[i + 1] - off[i];
+      max_len = l > max_len ? l : max_len;
+      min_len = l < min_len ? l : min_len;
+      blocks += (l + 63) >> 6;
+    }
+  }
+  KL_REQUIRE(min_len >= 0, "sequences: offsets must be non-decreasing");
+  hf.row[hf.nchunks] = n; hf.blk[hf.nchunks] = blocks; hf.byte[hf.nchunks] = off[n];
+  s->max_len = max_len;
+  s->total_bases = off[n] - off[0];
+  s->total_blocks = blocks;
   hf.doff.alloc((size_t)n + 1);
-  hf.doff.upload(hf.rel.data(), (size_t)n + 1);
+  hf.doff.upload(off, (size_t)n + 1);
+  s->len.alloc((size_t)(n ? n : 1));
+  s->blk.alloc((size_t)n + 1);
+  if (n > 0) {
+    DevBuf<uint32_t> nblk((size_t)n);
+    KL_LAUNCH(seq_meta_kernel, (unsigned)((n + 255) / 256), 256, 0, hf.doff.p, n, s->len.p, nblk.p);
+    exclusive_scan_u32_to_i64(nblk.p, s->blk.p, n);
+  } else {
+    s->blk.zero();
+  }
+  const int64_t words = blocks * 4;
+  s->bits2.alloc((size_t)words + 1);     // + 1: the kernels read the word after the last base
+  s->inv16.alloc((size_t)words + 1);
+  KL_CUDA(cudaMemsetAsync(s->bits2.p + words, 0, sizeof(uint32_t), ctx().stream));
+  KL_CUDA(cudaMemsetAsync(s->inv16.p + words, 0, sizeof(uint16_t), ctx().stream));
+  hf.raw.alloc((size_t)(s->total_bases ? s->total_bases : 1));
   // the copy stream must not run ahead of the allocation / earlier work on the main stream
   KL_CUDA(cudaEventRecord(ctx().copy_ev[CTX_COPY_EVENTS - 1], ctx().stream));
   KL_CUDA(cudaStreamWaitEvent(ctx().copy_stream, ctx().copy_ev[CTX_COPY_EVENTS - 1], 0));
@@ -283,7 +303,7 @@ static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t
 std::shared_ptr<SeqSet> sequences_create(const uint8_t *seq, const int64_t *off, int64_t n) {
   HostFeed hf;
   auto s = sequences_begin(seq, off, n, hf);
-  if (n > 0) hf.feed(*s, 0, n, 0);
+  if (n > 0) hf.feed(*s, -1);
   sync_stream();
   return s;
 }
@@ -331,7 +351,7 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   if (cfg.alphabet == 1) {
     // gapped alphabet: the sort-based path of gapped.cu (needs the whole set packed)
     KL_REQUIRE(n_features == 0 || n_frozen > 0, "an explicit feature list needs a frozen class list");
-    if (feed && s.n > 0) feed->feed(*seqs, 0, s.n, 0);
+    if (feed && s.n > 0) feed->feed(*seqs, -1);
     auto g = extract_gapped(cfg, seqs, frozen_k, frozen_code, n_frozen, flags);
     if (n_features > 0) return apply_features(*g, features, n_features);
     return g;
@@ -453,10 +473,10 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
 
   if (s.n > 0) {
     // host sequences arrive in chunks: copy of chunk c+1 overlaps pack + extraction of chunk c
-    const int nchunks = (feed && s.n >= 4096) ? CTX_COPY_EVENTS - 1 : 1;
+    const int nchunks = feed ? feed->nchunks : 1;
     for (int c = 0; c < nchunks; c++) {
-      const int64_t r0 = s.n * c / nchunks, r1 = s.n * (c + 1) / nchunks;
-      if (feed) feed->feed(*seqs, r0, r1, c);
+      const int64_t r0 = feed ? feed->row[c] : 0, r1 = feed ? feed->row[c + 1] : s.n;
+      if (feed) feed->feed(*seqs, c);
       P.row0 = r0; P.n = r1;
       switch (E) {
         case 0: launch_extract<0>(P); break;

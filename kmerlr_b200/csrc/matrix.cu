@@ -377,8 +377,9 @@ void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n) {
   KL_REQUIRE(n == M.n, "labels: length does not match the number of rows");
   M.labels.alloc((size_t)(n ? n : 1));
   std::vector<uint8_t> l((size_t)n);
-  int64_t cnt[2] = {0, 0};
-  for (int64_t i = 0; i < n; i++) { l[i] = labels[i] ? 1 : 0; cnt[l[i]]++; }
+  int64_t ones = 0;
+  for (int64_t i = 0; i < n; i++) { const uint8_t v = labels[i] != 0; l[i] = v; ones += v; }
+  int64_t cnt[2] = {n - ones, ones};
   M.labels.upload(l.data(), (size_t)n);
   if (M.sharded) {
     DevBuf<int64_t> tmp(2);
