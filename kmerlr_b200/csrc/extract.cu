@@ -260,6 +260,7 @@ static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t
   s->n = n;
   hf.seq = seq;
   hf.nchunks = n >= 4096 ? CTX_COPY_EVENTS - 1 : 1;
+  Trace tr("feed");
   // one pass over the offsets: validation, longest sequence, block counts at the chunk boundaries
   int64_t blocks = 0, max_len = 0, min_len = 0;
   for (int c = 0; c < hf.nchunks; c++) {
@@ -277,6 +278,7 @@ static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t
   s->max_len = max_len;
   s->total_bases = off[n] - off[0];
   s->total_blocks = blocks;
+  tr.mark("host pass", false);
   hf.doff.alloc((size_t)n + 1);
   hf.doff.upload(off, (size_t)n + 1);
   s->len.alloc((size_t)(n ? n : 1));
@@ -297,6 +299,7 @@ static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t
   // the copy stream must not run ahead of the allocation / earlier work on the main stream
   KL_CUDA(cudaEventRecord(ctx().copy_ev[CTX_COPY_EVENTS - 1], ctx().stream));
   KL_CUDA(cudaStreamWaitEvent(ctx().copy_stream, ctx().copy_ev[CTX_COPY_EVENTS - 1], 0));
+  tr.mark("offsets, metadata");
   return s;
 }
 
