@@ -79,6 +79,35 @@ def test_ragged_empty_and_invalid(K, oracle):
     assert (d.n, d.m, d.nnz) == (0, 0, 0)
 
 
+def test_chunked_host_feed_ragged_nonzero_first_offset(K, oracle):
+    """n >= 4096 takes the pipelined feed (5 chunks of doubling size); the offsets need not start at 0,
+    rows are ragged and some are empty; the resident path (K.Sequences) must agree"""
+    rng = np.random.default_rng(23)
+    n = 5003
+    lens = rng.integers(0, 70, size=n)
+    lens[rng.integers(0, n, size=200)] = 0
+    lens[:3] = [0, 0, 1]
+    lens[-2:] = [0, 65]
+    lead = 37
+    off = np.concatenate([[lead], lead + np.cumsum(lens)]).astype(np.int64)
+    buf = rng.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8), size=int(off[-1]) + 11,
+                     p=[.2, .2, .2, .2, .045, .045, .045, .045, .02])
+    seqs = [bytes(buf[off[i]:off[i + 1]]) for i in range(n)]
+    for M, N, flags in [(1, 6, dict(revcomp=True)), (3, 8, dict())]:
+        kc, oc = cfg_pair(K, oracle, M, N, **flags)
+        ref = oracle.extract(oc, seqs)
+        d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+        same_matrix(d, ref)
+        d.free()
+        res = K.Sequences((buf, off))
+        d = K.compile_test_data(None, kc, None, None, True, False, res)
+        same_matrix(d, ref)
+        d.free()
+    with pytest.raises(K.KmerLrError):
+        bad = off.copy(); bad[100] = bad[101] + 5
+        K.compile_test_data(None, K.NewKmerCounter(1, 6), None, None, True, False, (buf, bad))
+
+
 def test_low_complexity_repeats(K, oracle):
     """homopolymers and short tandem repeats: almost every k-mer instance repeats an earlier one (the
     repeat lists of the bitmap levels overflow their shared-memory part), counts up to L"""
