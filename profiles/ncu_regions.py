@@ -13,7 +13,7 @@ for r in rows:
     except ValueError: continue
     tot_s+=s; tot_i+=i
     name="other:"+cur
-    if cur=="extract.cu":
+    if cur==(sys.argv[3] if len(sys.argv)>3 else "extract.cu"):
         for nm,lo,hi in bounds:
             if lo<=ln<=hi: name=nm;break
     a=agg.setdefault(name,[0,0]); a[0]+=s; a[1]+=i

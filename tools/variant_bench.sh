@@ -1,0 +1,9 @@
+#!/bin/bash
+# A/B timing of kernel variants: every variants/lib*.so replaces the in-tree library for one short bench run.
+cp kmerlr_b200/libkmerlr_b200.so /tmp/lib_orig.so
+for f in variants/lib*.so; do
+  cp "$f" kmerlr_b200/libkmerlr_b200.so
+  printf "%s " "$f"
+  timeout 300 python bench.py --no-cpu-baseline --score-mbp 0 --iters 2 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['kernels_ms_per_step']['extract_kernel'], d['e2e']['ms_per_step'])"
+done
+cp /tmp/lib_orig.so kmerlr_b200/libkmerlr_b200.so
