@@ -225,6 +225,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     K.init(local_rank)
     if world > 1:
+        from kmerlr_b200 import shard
+        cpus = shard.bind_host_to_gpu(local_rank)      # host buffers on the GPU's own socket
+        if os.environ.get("KMERLR_BENCH_VERBOSE"):
+            print("rank %d: %s host cpus local to the gpu" % (rank, len(cpus) if cpus else "no"), file=sys.stderr)
         K.comm_init_torch()
     sharded = world > 1
 

@@ -51,3 +51,31 @@ def assign_regions(lengths, world):
         owner[i] = r
         load[r] += lengths[i]
     return owner
+
+
+def bind_host_to_gpu(device):
+    """Pin this process (and the pinned host buffers it allocates afterwards, by first touch) to the CPUs
+    NVML reports as local to CUDA device `device`: with one process per GPU the host-to-device copies of
+    kmerlr_extract then stay on the GPU's own socket.  Returns the CPU list, or None when NVML, the PCI id
+    or the affinity call is not available (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device)
+        try:
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1 and c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
