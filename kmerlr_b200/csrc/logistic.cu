@@ -545,8 +545,16 @@ __device__ __forceinline__ void small_tail(PgState *st, const double *blockloss,
   for (int64_t k = t; k < ntheta; k += 256) G[k] = 0ull;    // the next pass accumulates from zero
 }
 
+#ifndef KL_SMALL_UNROLL
+#define KL_SMALL_UNROLL 2
+#endif
+constexpr int SMALL_UNROLL = KL_SMALL_UNROLL;
+#ifndef KL_SMALL_BPS
+#define KL_SMALL_BPS 6
+#endif
+constexpr int SMALL_BLOCKS_PER_SM = KL_SMALL_BPS;   // resident blocks per SM the register budget is held to
 template <typename VT>
-__global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
+__global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
                                                           const VT *__restrict__ val, int64_t n, int64_t ntheta,
                                                           double *theta, const uint8_t *__restrict__ labels,
                                                           double cw0, double cw1, double inv_n, double scale,
@@ -580,12 +588,13 @@ __global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const ui
   for (int64_t it = 0; it < rounds; it++) {
     const int64_t row0 = (gwarp + it * nwarps) * 32;
     double zmine = 0.0;
-#pragma unroll
+#pragma unroll SMALL_UNROLL
     for (int j = 0; j < SMALL_LPR; j++) {
       const int64_t row = row0 + j * GROUPS + grp;
       int64_t a = 0, b = 0;
       if (row < n) R.range(row, a, b);
       double s = 0.0;
+#pragma unroll SMALL_UNROLL
       for (int64_t p = a + sl; p < b; p += SMALL_LPR) s += valf(val, p) * sth[col[p] + 1];
 #pragma unroll
       for (int o = SMALL_LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, SMALL_LPR);
@@ -604,7 +613,7 @@ __global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const ui
       }
     }
     if (!scatter) continue;
-#pragma unroll
+#pragma unroll SMALL_UNROLL
     for (int j = 0; j < SMALL_LPR; j++) {
       const int64_t row = row0 + j * GROUPS + grp;
       const double ws = __shfl_sync(0xffffffffu, wmine, j * GROUPS + grp);
@@ -612,6 +621,7 @@ __global__ void __launch_bounds__(256) fused_small_kernel(const Rows R, const ui
       int64_t a, b;
       R.range(row, a, b);
       if (sl == 0) add(0u, (unsigned long long)__double2ll_rn(ws));
+#pragma unroll SMALL_UNROLL
       for (int64_t p = a + sl; p < b; p += SMALL_LPR)
         add(col[p] + 1u, (unsigned long long)__double2ll_rn(ws * valf(val, p)));
     }
@@ -968,7 +978,8 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   DevBuf<double> blockloss;
   DevBuf<unsigned int> counter;
   if (small) {
-    int64_t nb = (int64_t)ctx().sm_count * 8, need = (M.n * SMALL_LPR + 255) / 256;
+    // one wave: as many blocks as are resident at once (a second, partly filled wave costs a whole round)
+    int64_t nb = (int64_t)ctx().sm_count * SMALL_BLOCKS_PER_SM, need = (M.n * SMALL_LPR + 255) / 256;
     small_blocks = (int)(nb < need ? nb : need);
     blockloss.alloc((size_t)small_blocks);
     counter.alloc(1);
