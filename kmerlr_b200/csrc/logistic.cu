@@ -806,7 +806,8 @@ void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st,
   if (scatter) KL_CUDA(cudaMemsetAsync(wk.H.p, 0, (size_t)total * sizeof(unsigned long long), ctx().stream));
   KL_LAUNCH(imp_build_T, (unsigned)((total + 255) / 256), 256, 0, P, I.bitmap.p, I.rank.p, wk.theta.p, wk.T.p, total, st);
   const int64_t steps = (S.max_len + I.N - 1 + 31) / 32;
-  int64_t blocks = (int64_t)ctx().sm_count * 8, need = (M.n + 7) / 8;
+  // many small blocks: the hardware block scheduler evens out the tail (64 per SM: 1.06 ms at C2, 8 per SM: 1.23 ms)
+  int64_t blocks = (int64_t)ctx().sm_count * 64, need = (M.n + 7) / 8;
   if (blocks > need) blocks = need;
   const double inv_n = 1.0 / (double)M.n_global;
   if (steps <= 16)
