@@ -477,7 +477,10 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   if (s.n > 0) {
     // host sequences arrive in chunks: copy of chunk c+1 overlaps pack + extraction of chunk c
     const int nchunks = feed ? feed->nchunks : 1;
+    DevBuf<uint32_t> ticket((size_t)nchunks);     // next group of rows of each launch
+    ticket.zero();
     for (int c = 0; c < nchunks; c++) {
+      P.ticket = ticket.p + c;
       const int64_t r0 = feed ? feed->row[c] : 0, r1 = feed ? feed->row[c + 1] : s.n;
       if (feed) feed->feed(*seqs, c);
       P.row0 = r0; P.n = r1;

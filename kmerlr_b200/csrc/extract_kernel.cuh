@@ -42,6 +42,7 @@ struct XParams {
   const uint2 *nbx;                // numbering set (all classes of the configuration, or the frozen list)
   int filter;                      // drop ids outside the numbering set
   unsigned long long *stats;       // [0] max_i sum_j v_ij^2, [1] max v_ij
+  uint32_t *ticket;                // rows are handed out to the blocks in groups of one row per warp
 };
 
 __device__ __forceinline__ uint32_t tab_off(int k) {  // sum_{j=1}^{k-1} 4^j
@@ -304,8 +305,15 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
   // rate).  The warps of a block therefore start every row together: a fetched line then serves
   // many warps (measured 3.03 -> 2.73 ms at C2).  More barriers inside the row, 1024-thread blocks and
   // a compact re-rolled body were all measured slower.  A warp past the last row runs an empty row.
-  for (int64_t row0 = P.row0 + (int64_t)blockIdx.x * wpb; row0 < P.n; row0 += nwarps) {
+  // Groups of rows (one row per warp) are handed out through a ticket counter: the blocks that run
+  // faster take more groups.
+  uint32_t *s_ticket = smem + P.obs_words + P.bm_words + P.pf_words + P.ts_words + 1;   // warp 0's spare word
+  for (;;) {
     __syncthreads();
+    if (threadIdx.x == 0) *s_ticket = atomicAdd(P.ticket, 1u);
+    __syncthreads();
+    const int64_t row0 = P.row0 + (int64_t)*s_ticket * wpb;
+    if (row0 >= P.n) break;
     const int64_t row = row0 + warp_in_block;
     const bool active = row < P.n;
     const int L = active ? (int)P.len[row] : 0;
