@@ -102,6 +102,7 @@ __global__ void reduce_stage2(const double *__restrict__ part, int np, double *_
 // the fused pass: persistent blocks, one warp per row
 //   G[0]    += round(w_i * S)                 (bias, Go index 0)
 //   G[c+1]  += round(w_i * v_ic * S)          for every entry of the row
+constexpr int FUSED_ROWS = 8;          // rows per ticket of the fused pass
 constexpr int HOT_COLS_MAX = 16384;   // at most this many columns accumulate in shared memory (8 B each)
 
 template <typename VT>
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
                                                     const uint8_t *__restrict__ labels, double cw0, double cw1,
                                                     double inv_n, double scale, unsigned long long *__restrict__ G,
                                                     double *__restrict__ lossterm, const PgState *st, int scatter,
-                                                    int hot_limit) {
+                                                    int hot_limit, unsigned long long *__restrict__ ticket) {
   if (st && st->done == 1) return;
   // 64-bit accumulators as two 32-bit words: shared memory has native 32-bit atomic adds only
   // (a 64-bit add would be a compare-and-swap loop); the carry out of the low word is added to
@@ -122,9 +123,15 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
   for (int i = threadIdx.x; i < hot_cols; i += blockDim.x) { hot_lo[i] = 0u; hot_hi[i] = 0u; }
   __syncthreads();
   const unsigned lane = lane_id();
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   long long bias_acc = 0;
-  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
+  // rows are handed out FUSED_ROWS at a time through a ticket counter: warps on faster SMs take more
+  for (;;) {
+    unsigned long long t0 = 0;
+    if (lane == 0) t0 = atomicAdd(ticket, (unsigned long long)FUSED_ROWS);
+    const int64_t first = (int64_t)__shfl_sync(0xffffffffu, t0, 0);
+    if (first >= n) break;
+    const int64_t last = first + FUSED_ROWS < n ? first + FUSED_ROWS : n;
+   for (int64_t row = first; row < last; row++) {
     int64_t a, b;
     R.range(row, a, b);
     double s = 0.0;
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
         if (add_hi) atomicAdd(&hot_hi[c], add_hi);
       } else atomicAdd(&G[c + 1], q);
     }
+   }
   }
   if (lane == 0 && bias_acc != 0) atomicAdd(&G[0], (unsigned long long)bias_acc);
   __syncthreads();
@@ -826,7 +834,9 @@ void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st,
 // scatter = 0: loss terms only (G is left untouched)
 template <typename VT>
 void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, int scatter = 1) {
-  if (scatter) KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
+  // G[m+1] is the row ticket of fused_kernel
+  if (scatter) KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 2) * sizeof(unsigned long long), ctx().stream));
+  else KL_CUDA(cudaMemsetAsync(wk.G.p + M.m + 1, 0, sizeof(unsigned long long), ctx().stream));
   if (M.n > 0) {
     if (use_implicit(M)) {
       launch_implicit(M, wk, cw, st, scatter);
@@ -841,7 +851,8 @@ void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, in
       int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
       if (blocks > need) blocks = need;
       KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, smem, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
-                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter, hot);
+                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter, hot,
+                wk.G.p + M.m + 1);
     }
   }
   if (M.sharded && scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
@@ -852,7 +863,7 @@ void alloc_work(const Matrix &M, int64_t ntheta, Work &wk) {
   wk.w.alloc((size_t)(M.n ? M.n : 1));
   wk.lossterm.alloc((size_t)(M.n ? M.n : 1));
   wk.g.alloc((size_t)ntheta);
-  wk.G.alloc((size_t)M.m + 1);
+  wk.G.alloc((size_t)M.m + 2);      // + the row ticket of fused_kernel
   wk.red.alloc(RED_BLOCKS);
   wk.scalars.alloc(8);
   wk.blockmax.alloc(3 * PROX_BLOCKS);
