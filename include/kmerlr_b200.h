@@ -69,7 +69,9 @@ int         kmerlr_profile_dump(char *buf, int64_t buflen);
  *                matrix-free logistic pass, 0 forces the pass over the stored rows;
  *   "hot_cols" = number of columns of that stored-row pass that accumulate in shared memory (default 6144);
  *   "p2p"      = 1 (default) lets sharded reduced-matrix iterations exchange the gradient over NVLink peer
- *                memory, 0 forces the NCCL collectives (set it identically on every rank) */
+ *                memory, 0 forces the NCCL collectives (set it identically on every rank);
+ *   "persistent" = 1 (default) runs the reduced-matrix iterations of one GPU as one cooperative launch per
+ *                batch of iterations (grid barriers), 0 as one launch per iteration */
 int         kmerlr_option(const char *name, int64_t value);
 
 /* ---- sample sharding over the GPUs of one box ------------------------------------ */

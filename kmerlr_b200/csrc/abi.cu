@@ -179,6 +179,7 @@ int kmerlr_option(const char *name, int64_t value) {
     KL_REQUIRE(name != nullptr, "option: null name");
     if (!strcmp(name, "implicit")) g_ctx.implicit_ok = value != 0;
     else if (!strcmp(name, "p2p")) g_ctx.p2p_ok = value != 0;
+    else if (!strcmp(name, "persistent")) g_ctx.coop_ok = value != 0 && g_ctx.coop_supported;
     else if (!strcmp(name, "hot_cols")) g_ctx.hot_cols = (int)(value < 0 ? 0 : (value > 16384 ? 16384 : value));
     else fail(KMERLR_ERR_ARG, std::string("unknown option ") + name);
   }, false);
@@ -203,6 +204,8 @@ int kmerlr_init(int device) {
     KL_CUDA(cudaSetDevice(device));
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
+    g_ctx.coop_supported = prop.cooperativeLaunch != 0;
+    g_ctx.coop_ok = g_ctx.coop_supported;
     KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
     KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < CTX_COPY_EVENTS; i++) KL_CUDA(cudaEventCreateWithFlags(&g_ctx.copy_ev[i], cudaEventDisableTiming));

@@ -84,6 +84,8 @@ struct Ctx {
   // peer-memory exchange over NVLink (comm.cu): every rank owns one mailbox, mapped into all ranks
   PeerBox *peer = nullptr;   // device copy of the mailbox table, nullptr = not available (NCCL is used)
   bool p2p_ok = true;        // kmerlr_option("p2p")
+  bool coop_supported = true;
+  bool coop_ok = true;       // kmerlr_option("persistent"); false when the device cannot launch cooperatively
 };
 Ctx &ctx();
 void require_ready();

@@ -12,6 +12,8 @@
 // two features with identical columns get bit-identical gradients (what leapfrog tie handling
 // needs), and an int64 all-reduce over the ranks gives the same bits as one GPU.
 // The first columns (the dense low-k classes) accumulate in shared memory, the rest in L2.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 #include <cmath>
@@ -489,7 +491,8 @@ constexpr int SMALL_LPR = 8;           // lanes per row; the lane shuffles below
 __device__ __forceinline__ void small_tail(PgState *st, const double *blockloss, int nblocks, double *theta,
                                            unsigned long long *G,
                                            double inv_scale, int64_t ntheta, double inv_n, double lambda,
-                                           double eps_loss, double step, double eps, long long max_iter) {
+                                           double eps_loss, double step, double eps, long long max_iter,
+                                           bool clear_g = true) {
   __shared__ double sh[256], shx[256], shd[256], shn[256];
   __shared__ int s_done;
   const int t = threadIdx.x;
@@ -550,7 +553,8 @@ __device__ __forceinline__ void small_tail(PgState *st, const double *blockloss,
       }
     }
   }
-  for (int64_t k = t; k < ntheta; k += 256) G[k] = 0ull;    // the next pass accumulates from zero
+  if (clear_g)
+    for (int64_t k = t; k < ntheta; k += 256) G[k] = 0ull;    // the next pass accumulates from zero
 }
 
 #ifndef KL_SMALL_UNROLL
@@ -561,21 +565,17 @@ constexpr int SMALL_UNROLL = KL_SMALL_UNROLL;
 #define KL_SMALL_BPS 6
 #endif
 constexpr int SMALL_BLOCKS_PER_SM = KL_SMALL_BPS;   // resident blocks per SM the register budget is held to
-template <typename VT>
-__global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
-                                                          const VT *__restrict__ val, int64_t n, int64_t ntheta,
-                                                          double *theta, const uint8_t *__restrict__ labels,
-                                                          double cw0, double cw1, double inv_n, double scale,
-                                                          unsigned long long *G, double *blockloss, PgState *st,
-                                                          int scatter, unsigned int *counter, double inv_scale,
-                                                          double lambda, double eps_loss, double step, double eps,
-                                                          long long max_iter) {
-  if (st->done == 1) return;
-  __shared__ uint32_t acc_lo[SMALL_MAX_THETA], acc_hi[SMALL_MAX_THETA];
-  __shared__ int s_last;
-  __shared__ double sth[SMALL_MAX_THETA];
-  __shared__ double red[256];
-  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) { acc_lo[i] = 0u; acc_hi[i] = 0u; sth[i] = theta[i]; }
+// the row pass of one block: z, loss terms, weights, fixed-point gradient into G; loss partial into blockloss
+template <typename VT, bool LOAD_THETA = true>
+__device__ __forceinline__ void small_rows(const Rows &R, const uint32_t *__restrict__ col, const VT *__restrict__ val,
+                                           int64_t n, int64_t ntheta, const double *theta,
+                                           const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n,
+                                           double scale, unsigned long long *G, double *blockloss, int scatter,
+                                           uint32_t *acc_lo, uint32_t *acc_hi, double *sth, double *red) {
+  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) {
+    acc_lo[i] = 0u; acc_hi[i] = 0u;
+    if (LOAD_THETA) sth[i] = theta[i];
+  }
   __syncthreads();
   const unsigned lane = lane_id();
   const int sl = (int)lane & (SMALL_LPR - 1), grp = (int)lane / SMALL_LPR;     // 4 groups of 8 lanes per warp
@@ -647,6 +647,24 @@ __global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_kernel(c
       unsigned long long v = ((unsigned long long)acc_hi[i] << 32) | acc_lo[i];
       if (v) atomicAdd(&G[i], v);
     }
+}
+
+template <typename VT>
+__global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
+                                                          const VT *__restrict__ val, int64_t n, int64_t ntheta,
+                                                          double *theta, const uint8_t *__restrict__ labels,
+                                                          double cw0, double cw1, double inv_n, double scale,
+                                                          unsigned long long *G, double *blockloss, PgState *st,
+                                                          int scatter, unsigned int *counter, double inv_scale,
+                                                          double lambda, double eps_loss, double step, double eps,
+                                                          long long max_iter) {
+  if (st->done == 1) return;
+  __shared__ uint32_t acc_lo[SMALL_MAX_THETA], acc_hi[SMALL_MAX_THETA];
+  __shared__ int s_last;
+  __shared__ double sth[SMALL_MAX_THETA];
+  __shared__ double red[256];
+  small_rows<VT>(R, col, val, n, ntheta, theta, labels, cw0, cw1, inv_n, scale, G, blockloss, scatter, acc_lo, acc_hi, sth,
+                 red);
   // the block that finishes last runs the tail of the iteration (its reads see every block's results)
   if (!counter) return;                 // sharded: the collectives come first, the tail is its own launch
   __threadfence();
@@ -657,6 +675,50 @@ __global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_kernel(c
   __threadfence();
   small_tail(st, blockloss, (int)gridDim.x, theta, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter);
   if (threadIdx.x == 0) *counter = 0u;
+}
+
+// One GPU, reduced matrix: MANY iterations in one cooperative launch, ONE grid barrier per iteration and no
+// serial section.  Every block keeps theta and the iteration state in shared memory; a pass is the row
+// pass of all blocks (gradient into G[pass % 3], loss partials into blockloss[pass & 1]), the grid
+// barrier, and the tail of the iteration (small_tail: loss, hook, prox step, stopping rule) run by EVERY
+// block on the same inputs in the same order -- the same result everywhere, bit for bit, so nobody waits
+// for a block 0.  G is triple buffered: block 0 clears G[(pass + 1) % 3] during pass `pass`; that buffer
+// was last read in the tail of pass - 2, which every block left before it arrived at the barrier of
+// pass - 1.  The loss partials of pass + 2 overwrite those of `pass` for the same reason.  The passes of
+// one launch are pass0, pass0 + 1, ...; pass number max_iter only evaluates the hook's loss.
+template <typename VT>
+__global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_persistent(
+    const Rows R, const uint32_t *__restrict__ col, const VT *__restrict__ val, int64_t n, int64_t ntheta, double *theta,
+    const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n, double scale, unsigned long long *G3,
+    double *blockloss2, PgState *st, long long pass0, int npass, double inv_scale, double lambda, double eps_loss,
+    double step, double eps, long long max_iter) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ uint32_t acc_lo[SMALL_MAX_THETA], acc_hi[SMALL_MAX_THETA];
+  __shared__ double sth[SMALL_MAX_THETA];
+  __shared__ double red[256];
+  __shared__ PgState ls;
+  if (threadIdx.x == 0) ls = *st;
+  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) sth[i] = theta[i];
+  __syncthreads();
+  const int nblocks = (int)gridDim.x;
+  for (int it = 0; it < npass; it++) {
+    if (ls.done == 1) break;
+    const long long pass = pass0 + it;
+    const int scatter = pass < max_iter ? 1 : 0;
+    unsigned long long *G = G3 + (pass % 3) * ntheta, *Gnext = G3 + ((pass + 1) % 3) * ntheta;
+    double *blockloss = blockloss2 + (pass & 1) * nblocks;
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < ntheta; i += blockDim.x) Gnext[i] = 0ull;
+    small_rows<VT, false>(R, col, val, n, ntheta, sth, labels, cw0, cw1, inv_n, scale, G, blockloss, scatter, acc_lo, acc_hi,
+                          sth, red);
+    grid.sync();
+    small_tail(&ls, blockloss, nblocks, sth, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter, false);
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < ntheta; i += blockDim.x) theta[i] = sth[i];
+    if (threadIdx.x == 0) *st = ls;
+  }
 }
 
 // sharded reduced matrices: sum of the block loss partials (fixed order) -> one double per rank ...
@@ -985,15 +1047,28 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   const double inv_n = 1.0 / (double)M.n_global;
   // reduced matrices: two launches per iteration, long batches between host round trips
   const bool small = ntheta <= SMALL_MAX_THETA && !use_implicit(M) && M.n > 0;
-  const int64_t BATCH = small ? 256 : 16;
+  // one GPU: the passes of a batch are ONE cooperative launch (grid barriers instead of launches)
+  const bool persistent = small && !M.sharded && ctx().coop_ok;
+  const int64_t BATCH = persistent ? 4096 : (small ? 256 : 16);
   int small_blocks = 0;
   DevBuf<double> blockloss;
   DevBuf<unsigned int> counter;
+  DevBuf<unsigned long long> G3;      // persistent path: triple-buffered gradient accumulators
   if (small) {
     // one wave: as many blocks as are resident at once (a second, partly filled wave costs a whole round)
     int64_t nb = (int64_t)ctx().sm_count * SMALL_BLOCKS_PER_SM, need = (M.n * SMALL_LPR + 255) / 256;
+    if (persistent) {
+      int per_sm = 0;
+      dispatch_vt(M, [&](auto *tag) {
+        using VT = typename std::remove_pointer<decltype(tag)>::type;
+        KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_persistent<VT>, 256, 0));
+      });
+      KL_INVARIANT(per_sm >= 1);
+      nb = (int64_t)ctx().sm_count * per_sm;       // a cooperative grid must be resident as a whole
+    }
     small_blocks = (int)(nb < need ? nb : need);
-    blockloss.alloc((size_t)small_blocks);
+    blockloss.alloc((size_t)small_blocks * (persistent ? 2 : 1));
+    if (persistent) { G3.alloc((size_t)(3 * ntheta)); G3.zero(); }
     counter.alloc(1);
     counter.zero();
     KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)ntheta * sizeof(unsigned long long), ctx().stream));
@@ -1005,7 +1080,32 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
     if (nb > BATCH) nb = BATCH;
     if (nb < 1) nb = 1;
     issued += nb;
-    for (int64_t it = 0; it < nb; it++) {
+    if (persistent) {
+      dispatch_vt(M, [&](auto *tag) {
+        using VT = typename std::remove_pointer<decltype(tag)>::type;
+        Rows rows = M.rows();
+        const uint32_t *colp = M.col.p;
+        const VT *valp = csr_val<VT>(M);
+        int64_t n = M.n, nt = ntheta;
+        double *thp = wk.theta.p;
+        const uint8_t *lab = M.labels.p;
+        double cw0 = cw[0], cw1 = cw[1], invn = inv_n, scale = wk.scale, inv_scale = wk.inv_scale;
+        unsigned long long *Gp = G3.p;
+        double *bl = blockloss.p;
+        PgState *stp = st.p;
+        long long pass0 = (long long)(issued - nb), mi = (long long)max_iter;
+        int npass = (int)nb;
+        double lam = lambda, el = epsilon_loss, stp_size = step, eps = epsilon;
+        void *args[] = {&rows, &colp, &valp, &n, &nt, &thp, &lab, &cw0, &cw1, &invn, &scale, &Gp, &bl, &stp, &pass0, &npass,
+                        &inv_scale, &lam, &el, &stp_size, &eps, &mi};
+        if (ctx().profiling) profile_begin("fused_small_persistent");
+        KL_CUDA(cudaLaunchCooperativeKernel((const void *)fused_small_persistent<VT>, dim3((unsigned)small_blocks), dim3(256),
+                                            args, 0, ctx().stream));
+        if (ctx().profiling) profile_end();
+        ctx().launches++;
+      });
+    }
+    for (int64_t it = 0; it < nb && !persistent; it++) {
       // pass number max_iter (0-based) only evaluates the hook's loss at the final theta: no gradient
       const int scatter = (issued - nb + it) < max_iter ? 1 : 0;
       if (small) {

@@ -266,3 +266,34 @@ def test_proxgrad_matches_oracle_iteration_by_iteration(K, oracle):
         assert np.max(np.abs(est.Theta - oth)) <= 1e-9
         assert np.array_equal(est.Theta == 0.0, oth == 0.0)
         assert abs(delta - odelta) <= 1e-6 * max(abs(odelta), 1e-300)
+
+
+def test_persistent_reduced_iterations_equal_per_launch(K, oracle):
+    """reduced matrices on one GPU: the cooperative many-iterations launch (grid barriers) must give the
+    iterates of the one-launch-per-iteration path bit for bit, whatever stops the loop"""
+    from kmerlr_b200 import synth
+    buf, off, y = synth.training_set(700, 650, 150)
+    kc = K.NewKmerCounter(1, 6, revcomp=True)
+    d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    sel = np.unique(np.concatenate([[0], np.linspace(1, d.m, 40).astype(np.int64)]))
+    rd = K.select_data(d, sel)
+    rd.SetLabels(y)
+    cw = np.array([0.8, 1.3])
+    try:
+        for eps, eps_loss, lam, cap in [(0.0, 0.0, 1e-3, 37), (0.0, 0.0, 1e-4, 4500), (1e-6, 0.0, 1e-3, 100000),
+                                        (0.0, 1e-9, 1e-3, 100000), (0.0, 0.0, 1e-3, 0), (0.0, 0.0, 1e-3, 1)]:
+            res = []
+            for mode in (0, 1):
+                K.option("persistent", mode)
+                est = K.KmerLrEstimator(Epsilon=eps, EpsilonLoss=eps_loss, MaxIterations=cap)
+                est.Theta = np.zeros(len(sel)); est.ClassWeights = cw
+                it, delta = est.estimate_proximal(rd, lam)
+                res.append((it, delta, est.Theta.copy()))
+            assert res[0][0] == res[1][0], (cap, res[0][0], res[1][0])
+            assert res[0][1] == res[1][1] or (np.isnan(res[0][1]) and np.isnan(res[1][1]))
+            assert np.array_equal(res[0][2], res[1][2])
+            if cap in (37, 4500):
+                assert res[0][0] == cap
+    finally:
+        K.option("persistent", 1)
+        rd.free(); d.free()
