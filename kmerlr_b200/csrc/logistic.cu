@@ -484,7 +484,6 @@ __global__ void prox_finish(PgState *st, const double *__restrict__ blockmax, in
 // row, theta and the fixed-point gradient accumulators in shared memory, loss partial per block) and
 // the block that finishes last runs small_tail (loss, hook, prox update, stopping rule, clears G).
 constexpr int SMALL_MAX_THETA = 1024;
-constexpr int SMALL_LPR = 8;           // lanes per row; the lane shuffles below assume 4 groups of 8
 
 // hook (kmerLr_estimator_hook.go:46-99) + prox step + eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98),
 // run by ONE block of 256 threads once every block's partials are in
@@ -557,15 +556,15 @@ __device__ __forceinline__ void small_tail(PgState *st, const double *blockloss,
     for (int64_t k = t; k < ntheta; k += 256) G[k] = 0ull;    // the next pass accumulates from zero
 }
 
-#ifndef KL_SMALL_UNROLL
-#define KL_SMALL_UNROLL 2
-#endif
-constexpr int SMALL_UNROLL = KL_SMALL_UNROLL;
 #ifndef KL_SMALL_BPS
 #define KL_SMALL_BPS 6
 #endif
 constexpr int SMALL_BLOCKS_PER_SM = KL_SMALL_BPS;   // resident blocks per SM the register budget is held to
-// the row pass of one block: z, loss terms, weights, fixed-point gradient into G; loss partial into blockloss
+// the row pass of one block: z, loss terms, weights, fixed-point gradient into G; loss partial into blockloss.
+// ONE THREAD PER ROW: the rows are a handful of entries long, so a lane walks its row serially (the sum
+// runs in entry order, as the reference's does) and nothing is spent on lane hand-offs; the rows of a warp
+// are consecutive, their entries sit next to each other in memory.  (8 lanes per row cost 107 warp
+// instructions per row at C2 and made the iteration instruction bound.)
 template <typename VT, bool LOAD_THETA = true>
 __device__ __forceinline__ void small_rows(const Rows &R, const uint32_t *__restrict__ col, const VT *__restrict__ val,
                                            int64_t n, int64_t ntheta, const double *theta,
@@ -577,11 +576,6 @@ __device__ __forceinline__ void small_rows(const Rows &R, const uint32_t *__rest
     if (LOAD_THETA) sth[i] = theta[i];
   }
   __syncthreads();
-  const unsigned lane = lane_id();
-  const int sl = (int)lane & (SMALL_LPR - 1), grp = (int)lane / SMALL_LPR;     // 4 groups of 8 lanes per warp
-  constexpr int GROUPS = 32 / SMALL_LPR;
-  const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   auto add = [&](uint32_t c, unsigned long long q) {
     const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
     const uint32_t old = atomicAdd(&acc_lo[c], lo);
@@ -589,50 +583,20 @@ __device__ __forceinline__ void small_rows(const Rows &R, const uint32_t *__rest
     if (add_hi) atomicAdd(&acc_hi[c], add_hi);
   };
   double lacc = 0.0;
-  // A warp takes 32 consecutive rows per round.  Dot products: 8 lanes per row, 4 rows at a time; the
-  // sums are handed to lane (row - first row), so that the exp / log1p of ALL 32 rows run in one pass
-  // over full warps; then the weights go back to the 8-lane groups for the scatter.
-  const int64_t rounds = (n + nwarps * 32 - 1) / (nwarps * 32);
-  for (int64_t it = 0; it < rounds; it++) {
-    const int64_t row0 = (gwarp + it * nwarps) * 32;
-    double zmine = 0.0;
-#pragma unroll SMALL_UNROLL
-    for (int j = 0; j < SMALL_LPR; j++) {
-      const int64_t row = row0 + j * GROUPS + grp;
-      int64_t a = 0, b = 0;
-      if (row < n) R.range(row, a, b);
-      double s = 0.0;
-#pragma unroll SMALL_UNROLL
-      for (int64_t p = a + sl; p < b; p += SMALL_LPR) s += valf(val, p) * sth[col[p] + 1];
-#pragma unroll
-      for (int o = SMALL_LPR / 2; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o, SMALL_LPR);
-      const double got = __shfl_sync(0xffffffffu, s, SMALL_LPR * ((int)lane & (GROUPS - 1)));
-      if (((int)lane >> 2) == j) zmine = got;      // lane j*4+g takes the sum of group g (GROUPS = 4)
-    }
-    double wmine = 0.0;
-    {
-      const int64_t row = row0 + lane;
-      if (row < n) {
-        // Gradient weight (:166-178) and Loss term (:257-263)
-        double z = sth[0] + zmine, r = -log_add0(-z), w;
-        if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lacc += -cw1 * r; }
-        else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
-        wmine = w * scale;                          // scale is a power of two: exact
-      }
-    }
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += nthreads) {
+    int64_t a, b;
+    R.range(row, a, b);
+    double s = 0.0;
+    for (int64_t p = a; p < b; p++) s += valf(val, p) * sth[col[p] + 1];
+    // Gradient weight (:166-178) and Loss term (:257-263)
+    double z = sth[0] + s, r = -log_add0(-z), w;
+    if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lacc += -cw1 * r; }
+    else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
     if (!scatter) continue;
-#pragma unroll SMALL_UNROLL
-    for (int j = 0; j < SMALL_LPR; j++) {
-      const int64_t row = row0 + j * GROUPS + grp;
-      const double ws = __shfl_sync(0xffffffffu, wmine, j * GROUPS + grp);
-      if (row >= n) continue;
-      int64_t a, b;
-      R.range(row, a, b);
-      if (sl == 0) add(0u, (unsigned long long)__double2ll_rn(ws));
-#pragma unroll SMALL_UNROLL
-      for (int64_t p = a + sl; p < b; p += SMALL_LPR)
-        add(col[p] + 1u, (unsigned long long)__double2ll_rn(ws * valf(val, p)));
-    }
+    const double ws = w * scale;                    // scale is a power of two: exact
+    add(0u, (unsigned long long)__double2ll_rn(ws));
+    for (int64_t p = a; p < b; p++) add(col[p] + 1u, (unsigned long long)__double2ll_rn(ws * valf(val, p)));
   }
   // loss partial of the block: fixed tree
   red[threadIdx.x] = lacc;
@@ -1056,7 +1020,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   DevBuf<unsigned long long> G3;      // persistent path: triple-buffered gradient accumulators
   if (small) {
     // one wave: as many blocks as are resident at once (a second, partly filled wave costs a whole round)
-    int64_t nb = (int64_t)ctx().sm_count * SMALL_BLOCKS_PER_SM, need = (M.n * SMALL_LPR + 255) / 256;
+    int64_t nb = (int64_t)ctx().sm_count * SMALL_BLOCKS_PER_SM, need = (M.n + 255) / 256;
     if (persistent) {
       int per_sm = 0;
       dispatch_vt(M, [&](auto *tag) {
