@@ -37,7 +37,7 @@ def launch_count():
 
 
 def option(name, value):
-    """run-time switches of the library (kmerlr_option): "implicit" 0/1"""
+    """run-time switches of the library (kmerlr_option): "implicit", "hot_cols", "p2p", "persistent" (see include/kmerlr_b200.h)"""
     check(lib().kmerlr_option(name.encode(), int(value)))
 
 
