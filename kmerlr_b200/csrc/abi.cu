@@ -208,6 +208,8 @@ int kmerlr_init(int device) {
     g_ctx.coop_ok = g_ctx.coop_supported;
     KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
     KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    KL_CUDA(cudaStreamCreateWithFlags(&g_ctx.alt_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) KL_CUDA(cudaEventCreateWithFlags(&g_ctx.join_ev[i], cudaEventDisableTiming));
     for (int i = 0; i < CTX_COPY_EVENTS; i++) KL_CUDA(cudaEventCreateWithFlags(&g_ctx.copy_ev[i], cudaEventDisableTiming));
 
     KL_CUDA(cudaEventCreate(&g_ctx.ev0));
@@ -227,6 +229,9 @@ int kmerlr_shutdown(void) {
       cudaStreamSynchronize(g_ctx.copy_stream);
       for (int i = 0; i < CTX_COPY_EVENTS; i++) cudaEventDestroy(g_ctx.copy_ev[i]);
       cudaStreamDestroy(g_ctx.copy_stream);
+      cudaStreamSynchronize(g_ctx.alt_stream);
+      cudaStreamDestroy(g_ctx.alt_stream);
+      for (int i = 0; i < 2; i++) cudaEventDestroy(g_ctx.join_ev[i]);
       cudaStreamDestroy(g_ctx.stream);
       g_ctx = Ctx();
     }

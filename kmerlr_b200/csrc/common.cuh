@@ -64,13 +64,15 @@ struct PeerBox {
   int rank, world;
 };
 
-constexpr int CTX_COPY_EVENTS = 6;   // chunks of a pipelined host feed + 1
+constexpr int CTX_COPY_EVENTS = 11;   // chunks of a pipelined host feed + 1
 struct Ctx {
   bool ready = false;
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;            // host -> device feeds overlapping the kernels
+  cudaStream_t alt_stream = nullptr;             // odd chunks of a pipelined feed: their kernels overlap the tails of the even ones
+  cudaEvent_t join_ev[2] = {nullptr, nullptr};
   cudaEvent_t copy_ev[CTX_COPY_EVENTS] = {nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;

@@ -21,6 +21,8 @@
 // bitmap of observed (or frozen) classes; observed classes are gathered per block in shared memory.
 // Host sequences (kmerlr_extract) arrive in chunks on a copy stream while earlier chunks are
 // packed and extracted.
+#include <cmath>
+
 #include "extract_kernel.cuh"
 
 namespace kl {
@@ -231,9 +233,16 @@ struct HostFeed {
   const uint8_t *seq = nullptr;   // base 0 of the caller's buffer (offsets are absolute)
   int nchunks = 1;
   int64_t row[CTX_COPY_EVENTS] = {0}, blk[CTX_COPY_EVENTS] = {0}, byte[CTX_COPY_EVENTS] = {0};
-  // chunk sizes double (1, 2, 4, ... parts): the first kernel starts after a short copy, and the copy of
-  // the next chunk, which is faster than the extraction of the current one, is always done in time
-  static int64_t cut(int64_t n, int c, int nchunks) { return n * ((1 << c) - 1) / ((1 << nchunks) - 1); }
+  // Chunk sizes grow geometrically: the first kernel starts after a short copy, and the copy of chunk c+1
+  // must end before the extraction of chunk c does, or the GPU idles.  At C2 the extraction (+ pack) of a
+  // chunk takes 1.45 x its copy time (2.8 ms vs 1.9 ms for the whole set), so the growth factor has to
+  // stay below that: 1.35 (doubling sizes left the GPU waiting at every chunk: 3.9 ms vs 3.4 ms).
+  static int64_t cut(int64_t n, int c, int nchunks) {
+    if (c <= 0) return 0;
+    if (c >= nchunks) return n;
+    const double g = 1.35;
+    return (int64_t)((double)n * (pow(g, c) - 1.0) / (pow(g, nchunks) - 1.0));
+  }
   DevBuf<uint8_t> raw;            // bytes [byte[0], byte[nchunks])
   DevBuf<int64_t> doff;           // the caller's offsets
   // copy the bases of chunk c (every chunk for c < 0) and pack them (main stream waits for the copy)
@@ -259,7 +268,7 @@ static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t
   auto s = std::make_shared<SeqSet>();
   s->n = n;
   hf.seq = seq;
-  hf.nchunks = n >= 4096 ? CTX_COPY_EVENTS - 1 : 1;
+  hf.nchunks = (int)(n / 8192 < 1 ? 1 : (n / 8192 > CTX_COPY_EVENTS - 1 ? CTX_COPY_EVENTS - 1 : n / 8192));
   Trace tr("feed");
   // one pass over the offsets: validation, longest sequence, block counts at the chunk boundaries
   int64_t blocks = 0, max_len = 0, min_len = 0;
@@ -479,7 +488,25 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
     const int nchunks = feed ? feed->nchunks : 1;
     DevBuf<uint32_t> ticket((size_t)nchunks);     // next group of rows of each launch
     ticket.zero();
+    // A chunk's kernel ends with a tail of about one row time (64 us at C2) in which the SMs run dry.  Odd
+    // chunks therefore run on a second stream: their blocks move in as the blocks of the chunk before
+    // them leave.  Two kernels can then be in flight, each with its own lists of repeats.
+    const bool two_streams = feed && nchunks > 1;
+    DevBuf<uint32_t> ovf2;
+    if (two_streams && P.ovf) ovf2.alloc((size_t)ctx().sm_count * 64 * (size_t)P.ovf_stride);
+    struct StreamSwap {            // launches go to ctx().stream: point it at the chunk's stream for a while
+      cudaStream_t saved;
+      explicit StreamSwap(cudaStream_t run) : saved(ctx().stream) { ctx().stream = run; }
+      ~StreamSwap() { ctx().stream = saved; }
+    };
+    if (two_streams) {
+      KL_CUDA(cudaEventRecord(ctx().join_ev[0], ctx().stream));
+      KL_CUDA(cudaStreamWaitEvent(ctx().alt_stream, ctx().join_ev[0], 0));
+    }
+    uint32_t *const ovf_even = P.ovf;
     for (int c = 0; c < nchunks; c++) {
+      StreamSwap on((two_streams && (c & 1)) ? ctx().alt_stream : ctx().stream);
+      P.ovf = (two_streams && (c & 1) && ovf_even) ? ovf2.p : ovf_even;
       P.ticket = ticket.p + c;
       const int64_t r0 = feed ? feed->row[c] : 0, r1 = feed ? feed->row[c + 1] : s.n;
       if (feed) feed->feed(*seqs, c);
@@ -493,6 +520,11 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
         case 32: launch_extract<32>(P); break;
         default: launch_extract<64>(P); break;
       }
+    }
+    P.ovf = ovf_even;
+    if (two_streams) {
+      KL_CUDA(cudaEventRecord(ctx().join_ev[1], ctx().alt_stream));
+      KL_CUDA(cudaStreamWaitEvent(ctx().stream, ctx().join_ev[1], 0));
     }
     P.row0 = 0; P.n = s.n;
   }

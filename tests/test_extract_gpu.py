@@ -80,10 +80,10 @@ def test_ragged_empty_and_invalid(K, oracle):
 
 
 def test_chunked_host_feed_ragged_nonzero_first_offset(K, oracle):
-    """n >= 4096 takes the pipelined feed (5 chunks of doubling size); the offsets need not start at 0,
+    """n >= 16384 takes the pipelined feed (n / 8192 chunks of growing size, 4 here); the offsets need not start at 0,
     rows are ragged and some are empty; the resident path (K.Sequences) must agree"""
     rng = np.random.default_rng(23)
-    n = 5003
+    n = 33003
     lens = rng.integers(0, 70, size=n)
     lens[rng.integers(0, n, size=200)] = 0
     lens[:3] = [0, 0, 1]
