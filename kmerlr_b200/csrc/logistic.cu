@@ -1038,7 +1038,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   // reduced matrices: two launches per iteration, long batches between host round trips
   const bool small = ntheta <= SMALL_MAX_THETA && !use_implicit(M) && M.n > 0;
   // one GPU: the passes of a batch are ONE cooperative launch (grid barriers instead of launches)
-  const bool persistent = small && !M.sharded && ctx().coop_ok;
+  bool persistent = small && !M.sharded && ctx().coop_ok;
   const int64_t BATCH = persistent ? 4096 : (small ? 256 : 16);
   int small_blocks = 0;
   DevBuf<double> blockloss;
@@ -1089,11 +1089,19 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
         void *args[] = {&rows, &colp, &valp, &n, &nt, &thp, &lab, &cw0, &cw1, &invn, &scale, &Gp, &bl, &stp, &pass0, &npass,
                         &inv_scale, &lam, &el, &stp_size, &eps, &mi};
         if (ctx().profiling) profile_begin("fused_small_persistent");
-        KL_CUDA(cudaLaunchCooperativeKernel((const void *)fused_small_persistent<VT>, dim3((unsigned)small_blocks),
-                                            dim3(PERSIST_THREADS),
-                                            args, 0, ctx().stream));
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void *)fused_small_persistent<VT>,
+                                                          dim3((unsigned)small_blocks), dim3(PERSIST_THREADS), args, 0,
+                                                          ctx().stream);
         if (ctx().profiling) profile_end();
-        ctx().launches++;
+        if (e == cudaErrorCooperativeLaunchTooLarge) {
+          // the GPU is shared (MPS, another context): the grid cannot be resident as a whole right now.
+          // Nothing was launched; this call goes on with one launch per iteration.
+          (void)cudaGetLastError();
+          persistent = false;
+        } else {
+          KL_CUDA(e);
+          ctx().launches++;
+        }
       });
     }
     for (int64_t it = 0; it < nb && !persistent; it++) {

@@ -162,3 +162,14 @@ def test_world2_gloo_matches_single_rank(tmp_path):
         got = parts[int(owner[i])]["score%d" % i]
         assert "score%d" % i not in parts[1 - int(owner[i])].files
         assert np.array_equal(got, ref)
+
+
+def test_bind_host_to_gpu_is_harmless_without_a_gpu():
+    """no GPU / no NVML here: the helper must change nothing and say so"""
+    import os
+    from kmerlr_b200 import shard
+    before = os.sched_getaffinity(0)
+    cpus = shard.bind_host_to_gpu(0)
+    assert cpus is None or set(cpus) <= before
+    if cpus is None:
+        assert os.sched_getaffinity(0) == before
