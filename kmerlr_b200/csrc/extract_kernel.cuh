@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
   uint32_t *pf = bm + P.bm_words;
   uint32_t *tab = pf + P.pf_words;
   uint32_t *dupn = tab + P.ts_words;
-  const int64_t gwarp = (int64_t)blockIdx.x * wpb + warp_in_block, nwarps = (int64_t)gridDim.x * wpb;
+  const int64_t gwarp = (int64_t)blockIdx.x * wpb + warp_in_block;
   uint32_t *ovf = P.ovf ? P.ovf + gwarp * P.ovf_stride : nullptr;
   const int N = P.N, M = P.M, op = OPT >= 0 ? OPT : P.op;
   const bool two = op != 0;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         const int W = 1 << (2 * k - 5);
         uint32_t *bk = bm + P.bm_off[k];
         uint32_t *pk = pf + P.pf_off[k];
-        const uint32_t idbase = P.level_off[k], gword = P.level_off[k] >> 5;
+        const uint32_t gword = P.level_off[k] >> 5;
         for (int it = 0; it * 128 < W; it++) {
           const int wi = it * 128 + (int)lane * 4;
           uint4 w4 = make_uint4(0, 0, 0, 0);

@@ -22,7 +22,6 @@ namespace kl {
 
 namespace {
 
-constexpr int TASK_CHUNK = 1024;
 constexpr int RED_BLOCKS = 256;
 
 struct PgState {
@@ -480,9 +479,11 @@ __global__ void prox_finish(PgState *st, const double *__restrict__ blockmax, in
 }
 
 // ---- small problems (reduced matrices of the leapfrog path: <= 1023 columns, short rows) -----------------
-// An iteration is latency / launch bound there, so it is ONE launch: fused_small_kernel (8 lanes per
-// row, theta and the fixed-point gradient accumulators in shared memory, loss partial per block) and
-// the block that finishes last runs small_tail (loss, hook, prox update, stopping rule, clears G).
+// An iteration is latency / launch bound there.  Sharded matrices: ONE launch of fused_small_kernel per
+// iteration (one thread per row, theta and the fixed-point gradient accumulators in shared memory, loss
+// partial per block; without a communicator the block that finishes last runs small_tail: loss, hook,
+// prox update, stopping rule, clears G).  One GPU: fused_small_persistent, thousands of iterations per
+// cooperative launch.
 constexpr int SMALL_MAX_THETA = 1024;
 
 // hook (kmerLr_estimator_hook.go:46-99) + prox step + eval_stopping (kmerLr_estimator_proximal.go:30-52,88-98),

@@ -351,8 +351,8 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
         int64_t TP = (200 * 1024 - hs_smem * 8) / (8 * nlev) - 1;
         if (TP > 16384) TP = 16384;
         KL_REQUIRE(TP >= W + step, "score_windows: window too large for the shared-memory tile");
-        // windows per tile: starts a with a + W <= TP  ->  advance = number of such starts * step
-        int64_t starts = (TP - W) / step + 1, adv = starts * step;
+        // windows per tile: starts a with a + W <= TP (a tile advances by that many steps)
+        int64_t starts = (TP - W) / step + 1;
         std::vector<LinearTile> tiles;
         for (int64_t r = 0; r < s.n; r++) {
           int64_t nw = win_off[r + 1] - win_off[r];
