@@ -358,7 +358,6 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
           int64_t nw = win_off[r + 1] - win_off[r];
           for (int64_t w0 = 0; w0 < nw; w0 += starts) tiles.push_back(LinearTile{r, w0 * step});
         }
-        (void)adv;
         DevBuf<LinearTile> dt(tiles.size() ? tiles.size() : 1);
         dt.upload(tiles.data(), tiles.size());
         size_t smem = (size_t)nlev * (size_t)(TP + 1) * sizeof(double) + (size_t)hs_smem * 8;
