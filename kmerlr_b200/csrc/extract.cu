@@ -33,15 +33,27 @@ using namespace xk;
 
 // ---- pack: ASCII -> 2 bit codes + invalid mask --------------------------------------------------
 __global__ void pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off,
-                            const int64_t *__restrict__ blk, int64_t n, int64_t w0, int64_t w1,
+                            const int64_t *__restrict__ blk, int64_t n, int64_t total_blocks, int64_t w0, int64_t w1,
                             uint32_t *__restrict__ bits2, uint16_t *__restrict__ inv16) {
   int64_t w = w0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= w1) return;
-  // sequence owning word w: last i with blk[i]*4 <= w
-  int64_t lo = 0, hi = n;
+  // sequence owning word w: the last i with blk[i] <= b, b = the 64-base block of w.  Start from the row a
+  // set of equal-length sequences would give, gallop to a bracket, bisect inside it: a few probes (all in
+  // L1) instead of log2(n) for every word.
+  const int64_t b = w >> 2;
+  int64_t g = (int64_t)((double)b * (double)n / (double)total_blocks);
+  g = g < 0 ? 0 : (g > n - 1 ? n - 1 : g);
+  int64_t lo, hi, stepw = 1;
+  if (blk[g] <= b) {
+    lo = g; hi = g + 1;
+    while (hi < n && blk[hi] <= b) { lo = hi; stepw <<= 1; hi = hi + stepw < n ? hi + stepw : n; }
+  } else {
+    hi = g; lo = g - 1;
+    while (lo > 0 && blk[lo] > b) { hi = lo; stepw <<= 1; lo = lo - stepw > 0 ? lo - stepw : 0; }
+  }
   while (hi - lo > 1) {
     int64_t mid = (lo + hi) >> 1;
-    if (blk[mid] * 4 <= w) lo = mid; else hi = mid;
+    if (blk[mid] <= b) lo = mid; else hi = mid;
   }
   int64_t i = lo, j0 = (w - blk[i] * 4) * 16, L = off[i + 1] - off[i];
   const uint8_t *s = seq + off[i];
@@ -257,7 +269,8 @@ struct HostFeed {
     }
     const int64_t w0 = blk[c0] * 4, w1 = blk[c1] * 4;
     if (w1 > w0)
-      KL_LAUNCH(pack_kernel, (unsigned)((w1 - w0 + 255) / 256), 256, 0, raw.p - byte[0], doff.p, s.blk.p, s.n, w0, w1,
+      KL_LAUNCH(pack_kernel, (unsigned)((w1 - w0 + 255) / 256), 256, 0, raw.p - byte[0], doff.p, s.blk.p, s.n,
+                s.total_blocks, w0, w1,
                 s.bits2.p, s.inv16.p);
   }
 };
