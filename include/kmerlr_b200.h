@@ -150,6 +150,15 @@ int kmerlr_proxgrad(kmerlr_handle h, double *theta_inout, int64_t ntheta, const 
                     double lambda, double l2, double step_factor, double epsilon, double epsilon_loss,
                     int64_t max_iter, double hook_state[2], int64_t *iters_out, double *delta_out);
 
+/* ---- IRLS + coordinate-descent estimator (kmerLr_estimator_coordinate.go:31-139), reduced matrices only
+ * (ntheta <= 1024: it keeps the dense Gram matrix, as the reference does), one GPU.  The reference never
+ * calls it and its theta slices alias (:89-91); built with the slices de-aliased, like kmerlr_proxgrad.
+ * The IRLS weights use compute_class_weights(labels) (:88), the hook's loss class_w_hook (the estimator's
+ * ClassWeights, kmerLr_estimator_hook.go:36-42) and lambda = l1reg / n.  sweeps_out = coordinate sweeps done. */
+int kmerlr_coordinate(kmerlr_handle h, double *theta_inout, int64_t ntheta, const double class_w_hook[2],
+                      double l1reg, double l2reg, double epsilon, double epsilon_loss, int64_t max_iter,
+                      double hook_state[2], int64_t *sweeps_out, double *delta_out);
+
 /* ---- stage 3: genomicKmerLr.Predict / predict_window_genomic (kmerLr_predict_genomic.go:134-171)
  * One model = one KmerLrEnsemble; the per-window result is the sum over models of the ensemble
  * summary of log sigma(x . theta) (kmerLr_classifier_ensemble.go:64-139). */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "kmerlr_matrix_classes", "kmerlr_column_moments", "kmerlr_matrix_rows", "kmerlr_matrix_set_labels", "kmerlr_matrix_from_csr",
     "kmerlr_free", "kmerlr_coeff_dim", "kmerlr_coeff_ind2sub", "kmerlr_coeff_sub2ind", "kmerlr_linear_pdf",
     "kmerlr_logpdf", "kmerlr_gradient", "kmerlr_loss", "kmerlr_class_weights", "kmerlr_select", "kmerlr_select_from_gradient", "kmerlr_reduce",
-    "kmerlr_step_size", "kmerlr_proxgrad", "kmerlr_window_slots", "kmerlr_score_windows", "kmerlr_predict_windows",
+    "kmerlr_step_size", "kmerlr_proxgrad", "kmerlr_coordinate", "kmerlr_window_slots", "kmerlr_score_windows", "kmerlr_predict_windows",
     "kmerlr_score_windows_resident",
 ]
 
@@ -97,6 +97,7 @@ def lib():
     L.kmerlr_reduce.argtypes = [h, vp, i64, ph]
     L.kmerlr_step_size.argtypes = [h, dbl, dbl, pdbl]
     L.kmerlr_proxgrad.argtypes = [h, vp, i64, vp, dbl, dbl, dbl, dbl, dbl, i64, vp, pi64, pdbl]
+    L.kmerlr_coordinate.argtypes = [h, vp, i64, vp, dbl, dbl, dbl, dbl, i64, vp, pi64, pdbl]
     L.kmerlr_window_slots.restype = i64
     L.kmerlr_window_slots.argtypes = [i64, i64, i64]
     L.kmerlr_score_windows.argtypes = [C.POINTER(Model), C.c_int, vp, vp, i64, i64, i64, vp]

@@ -507,6 +507,18 @@ class KmerLrEstimator:
         self.Theta = theta
         return iters.value, delta.value
 
+    def estimate_coordinate(self, data_train):
+        """estimate_coordinate (kmerLr_estimator_coordinate.go:86-139) on a reduced data set: IRLS outer
+        iterations, cyclic coordinate descent on the dense Gram matrix inside (theta slices de-aliased).
+        L1Reg / L2Reg are the estimator's (sum scale, as the reference applies them).  Returns (sweeps, delta)."""
+        theta = np.ascontiguousarray(self.Theta, dtype=np.float64).copy()
+        sweeps, delta = C.c_int64(), C.c_double()
+        check(lib().kmerlr_coordinate(data_train.h, _p(theta), len(theta), _p(self.ClassWeights), float(self.L1Reg),
+                                      self.L2Reg, self.Epsilon, self.EpsilonLoss, self.MaxIterations,
+                                      _p(self.hook_state), sweeps, delta))
+        self.Theta = theta
+        return sweeps.value, delta.value
+
     def estimate_loop(self, data, lambdaAuto, balance=False):
         """estimate_loop (kmerLr_estimator.go:209-255): leapfrog epochs until Select returns !ok."""
         n = data.n

@@ -398,6 +398,16 @@ int kmerlr_proxgrad(kmerlr_handle h, double *theta_inout, int64_t ntheta, const 
   });
 }
 
+int kmerlr_coordinate(kmerlr_handle h, double *theta_inout, int64_t ntheta, const double class_w_hook[2], double l1reg,
+                      double l2reg, double epsilon, double epsilon_loss, int64_t max_iter, double hook_state[2],
+                      int64_t *sweeps_out, double *delta_out) {
+  return guarded([&] {
+    KL_REQUIRE(theta_inout && class_w_hook, "coordinate: null argument");
+    coordinate(*lookup<Matrix>(h, "matrix"), theta_inout, ntheta, class_w_hook, l1reg, l2reg, epsilon, epsilon_loss,
+               max_iter, hook_state, sweeps_out, delta_out);
+  });
+}
+
 int64_t kmerlr_window_slots(int64_t len, int64_t W, int64_t step) {
   int64_t n = len - W;
   return n > 0 ? n / step + 1 : 0;

@@ -315,6 +315,9 @@ void linear_pdf(Matrix &M, const double *theta, int64_t ntheta, int cooc, double
 void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc,
               double *g_host);
 double loss(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc);
+void coordinate(Matrix &M, double *theta, int64_t ntheta, const double cw_hook[2], double l1reg, double l2reg,
+                double epsilon, double epsilon_loss, int64_t max_iter, double hook[2], int64_t *sweeps_out,
+                double *delta_out);
 void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], double lambda, double l2,
               double step_factor, double epsilon, double epsilon_loss, int64_t max_iter, double hook[2],
               int64_t *iters, double *delta);

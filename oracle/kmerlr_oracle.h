@@ -13,7 +13,8 @@
  * restatement of the transform in oracle.py).  The reference itself cannot be built here (no Go toolchain;
  * gonetics / autodiff are not vendored), so there is no oracle/_ref.  UNPINNED (no reference
  * test exists): non-ACGT input handling, --complement / --reverse alone, MaxAmbiguous >= 0,
- * estimate_proximal / estimate_coordinate (dead code in the reference, no test), genomic scoring.
+ * estimate_proximal / estimate_coordinate (dead code in the reference, no test; estimate_coordinate is
+ * restated in numpy, oracle.py:coordinate, and pinned by optimality properties only), genomic scoring.
  *
  * Every function cites the reference file:line it follows.
  */

@@ -436,3 +436,69 @@ def transformed_gradient(mat, labels, theta, offset, scale, cw=(1.0, 1.0), lam=0
     if lam == lam and lam != 0.0:
         g[1:] += lam * np.sign(theta[1:])
     return g
+
+
+# ---------------------------------------------------------------------------------------------------
+# estimate_coordinate (kmerLr_estimator_coordinate.go:31-139): numpy restatement, loops as in the Go code
+# (the three theta slices de-aliased: theta0 = start of the outer iteration, theta0_ = before the sweep).
+# The reference never calls this function and no test of it exists: PARITY UNPINNED -- the CUDA path is
+# checked against this restatement only.
+# ---------------------------------------------------------------------------------------------------
+def _eval_stopping(xs, x1, eps):
+    """eval_stopping (kmerLr_estimator_proximal.go:30-52) -> (stop, delta)"""
+    if np.any(np.isnan(x1)):
+        return True, float("nan")
+    max_x = float(np.max(np.abs(x1))) if len(x1) else 0.0
+    max_d = float(np.max(np.abs(x1 - xs))) if len(x1) else 0.0
+    delta = max_d / max_x if max_x != 0.0 else max_d
+    return ((max_x != 0.0 and max_d / max_x <= eps) or (max_x == 0.0 and max_d == 0.0)), delta
+
+
+def coordinate(rmat, labels, theta, cw_hook=(1.0, 1.0), l1reg=0.0, l2reg=0.0, epsilon=0.0, epsilon_loss=0.0,
+               max_iter=100, hook=None):
+    """-> (theta, coordinate sweeps done, delta of the last eval_stopping).  hook = [loss_old, loss_new] list."""
+    y = np.asarray(labels, dtype=bool)
+    X = np.hstack([np.ones((rmat.n, 1)), rmat.dense()])          # convert_counts: column 0 = bias (:204)
+    n, d = X.shape
+    cw = class_weights(labels)                                   # compute_class_weights (:88)
+    theta1 = np.array(theta, dtype=np.float64)
+    hk = hook if hook is not None else [float("nan"), float("nan")]
+
+    def run_hook(th):                                            # kmerLr_estimator_hook.go:46-99
+        hk[0], hk[1] = hk[1], hk[0]
+        if epsilon_loss != 0.0:
+            hk[1] = loss(rmat, labels, th, cw_hook, l1reg / n)
+            return abs(hk[0] - hk[1]) < epsilon_loss
+        return False
+
+    sweeps, delta, it = 0, 0.0, 0
+    with np.errstate(all="ignore"):
+        while it < max_iter:                                     # :96
+            r = X @ theta1                                       # LinearPdf
+            p = np.exp(-_log_add0(-r))
+            w = p * (1.0 - p)
+            z = np.where(y, r + (1.0 - p) / w, r + (0.0 - p) / w)
+            w = w * np.where(y, cw[1], cw[0])
+            theta0 = theta1.copy()                               # :112-115
+            xy = X.T @ (w * z)                                   # :40-50
+            xx = X.T @ (w[:, None] * X)
+            norm = np.diag(xx).copy()
+            while it < max_iter:                                 # :55
+                theta0_ = theta1.copy()
+                for j in range(d):                               # :57-72
+                    t = xy[j] + norm[j] * theta1[j] - xx[j] @ theta1
+                    if j > 0:
+                        t = max(abs(t) - l1reg, 0.0) if t >= 0.0 else -max(abs(t) - l1reg, 0.0)
+                    theta1[j] = t / (norm[j] + l2reg)
+                sweeps += 1
+                stop, delta = _eval_stopping(theta0_, theta1, epsilon)
+                if stop or run_hook(theta1):
+                    break
+                it += 1
+            stop, delta = _eval_stopping(theta0, theta1, epsilon)  # :117
+            if stop or run_hook(theta1):
+                break
+            it += 1
+    if np.any(np.isnan(theta1)):
+        theta1[:] = np.nan
+    return theta1, sweeps, delta

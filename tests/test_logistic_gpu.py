@@ -297,3 +297,47 @@ def test_persistent_reduced_iterations_equal_per_launch(K, oracle):
     finally:
         K.option("persistent", 1)
         rd.free(); d.free()
+
+
+def test_coordinate_estimator_matches_restatement(K, oracle):
+    """estimate_coordinate (kmerLr_estimator_coordinate.go:31-139, slices de-aliased) on reduced matrices: the
+    CUDA path (fixed-point Gram matrix, one-block sweeps) against the numpy restatement -- same number of
+    sweeps, same theta.  The reference holds no golden for this function (it is never called)."""
+    from kmerlr_b200 import synth
+    O = oracle
+    buf, off, y = synth.training_set(900, 700, 150)
+    kc, oc = K.NewKmerCounter(1, 6, revcomp=True), O.make_config(1, 6, revcomp=True)
+    d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    ref = O.extract(oc, (buf, off))
+    sel = np.unique(np.concatenate([[0], np.linspace(1, d.m, 25).astype(np.int64)]))
+    rd = K.select_data(d, sel); rd.SetLabels(y)
+    rr = O.reduce(ref, sel)
+    cwh = np.array([0.9, 1.2])
+    try:
+        for eps, eps_loss, l1, l2, cap in [(0.0, 0.0, 0.0, 0.0, 25), (1e-4, 0.0, 2.0, 0.0, 5000), (1e-3, 0.0, 20.0, 0.5, 5000),
+                                           (0.0, 1e-6, 1.0, 0.0, 5000), (0.0, 0.0, 1.0, 0.0, 0)]:
+            est = K.KmerLrEstimator(Epsilon=eps, EpsilonLoss=eps_loss, L2Reg=l2, MaxIterations=cap)
+            est.Theta = np.zeros(len(sel)); est.ClassWeights = cwh; est.L1Reg = l1
+            sweeps, delta = est.estimate_coordinate(rd)
+            oth, osw, odelta = O.coordinate(rr, y, np.zeros(len(sel)), cwh, l1, l2, eps, eps_loss, cap)
+            assert sweeps == osw, (eps, eps_loss, l1, cap, sweeps, osw)
+            assert np.allclose(est.Theta, oth, rtol=1e-8, atol=1e-10)
+            assert np.array_equal(est.Theta == 0.0, oth == 0.0)
+            assert abs(delta - odelta) <= 1e-6 * max(abs(odelta), 1e-12)
+        # warm start from a fitted theta; binarized (VAL_ONE) matrix
+        kb = K.NewKmerCounter(1, 6, revcomp=True, binarize=True)
+        db = K.compile_test_data(None, kb, None, None, True, True, (buf, off))
+        rb = K.select_data(db, sel); rb.SetLabels(y)
+        rrb = O.reduce(O.extract(O.make_config(1, 6, revcomp=True, binarize=True), (buf, off)), sel)
+        est = K.KmerLrEstimator(Epsilon=1e-5, EpsilonLoss=0.0, MaxIterations=300)
+        est.Theta = oth.copy(); est.L1Reg = 0.5
+        sweeps, _ = est.estimate_coordinate(rb)
+        oth2, osw2, _ = O.coordinate(rrb, y, oth.copy(), (1.0, 1.0), 0.5, 0.0, 1e-5, 0.0, 300)
+        assert sweeps == osw2 and np.allclose(est.Theta, oth2, rtol=1e-8, atol=1e-10)
+        rb.free(); db.free()
+        # not a reduced matrix: refused loudly
+        with pytest.raises(K.KmerLrError):
+            est = K.KmerLrEstimator(MaxIterations=3); est.Theta = np.zeros(d.m + 1)
+            d.SetLabels(y); est.estimate_coordinate(d)
+    finally:
+        rd.free(); d.free()

@@ -202,3 +202,35 @@ def test_window_scoring_quirks(oracle):
     # equals KmerLrEnsemble.Predict on each window
     w3 = O.extract(cfg, [seq[30:230]], frozen=(k, code))
     assert abs(O.log_pdf(w3, theta)[0] - out[3]) < 1e-15
+
+
+def test_coordinate_estimator_restatement_properties(oracle):
+    """estimate_coordinate has no golden in the reference (dead code, never called): the numpy restatement is
+    pinned by what the algorithm must do.  (1) With L1Reg = 0 and a tolerance the sweeps stop at, repeated IRLS
+    steps reach the maximum-likelihood point: the gradient under the computed class weights vanishes.
+    (2) A fixed point of the sweeps satisfies the KKT conditions of the weighted lasso problem of that IRLS
+    step.  (3) The Go loop structure: sweeps and outer steps share ONE iteration counter."""
+    O = oracle
+    rng = np.random.default_rng(3)
+    n, m = 500, 10
+    D = ((rng.random((n, m)) < 0.3) * rng.integers(1, 4, size=(n, m))).astype(float)
+    y = (D[:, 0] * 0.8 - D[:, 1] * 0.6 + 0.4 * rng.normal(size=n)) > 0
+    mat = O.from_dense(D)
+    cw = O.class_weights(y)
+    th, sweeps, delta = O.coordinate(mat, y, np.zeros(m + 1), l1reg=0.0, epsilon=1e-7, max_iter=5000)
+    g = O.gradient(mat, y, th, cw)
+    assert np.max(np.abs(g)) < 1e-6 and delta <= 1e-7 and sweeps < 5000
+    # (2) one IRLS step, many sweeps: KKT of  1/2 sum w (z - x theta)^2 + l1 |theta_{1:}|
+    l1 = 3.0
+    th0 = np.zeros(m + 1)
+    th1, sweeps1, _ = O.coordinate(mat, y, th0, l1reg=l1, epsilon=0.0, max_iter=400)
+    assert sweeps1 == 400                # the inner loop uses up the shared counter: ONE IRLS step, 400 sweeps
+    X = np.hstack([np.ones((n, 1)), D])
+    r = X @ th0; p = 1 / (1 + np.exp(-r)); w = p * (1 - p); z = r + (y - p) / w; w = w * np.where(y, cw[1], cw[0])
+    corr = X.T @ (w * (z - X @ th1))
+    assert abs(corr[0]) < 1e-6
+    for j in range(1, m + 1):
+        if th1[j] != 0.0:
+            assert abs(corr[j] - l1 * np.sign(th1[j])) < 1e-6
+        else:
+            assert abs(corr[j]) <= l1 + 1e-9
