@@ -341,3 +341,46 @@ def test_coordinate_estimator_matches_restatement(K, oracle):
             d.SetLabels(y); est.estimate_coordinate(d)
     finally:
         rd.free(); d.free()
+
+
+def test_proxgrad_is_resumable_in_slices(K, oracle):
+    """the Go hook (trace / verbose / adaptive step, kmerLr_estimator_hook.go:46-99) wants to see theta every k
+    iterations: kmerlr_proxgrad run in slices of k iterations (theta and hook_state carried over) must give the
+    iterates of one long call bit for bit, full-space path and reduced path, and stop at the same place"""
+    from kmerlr_b200 import synth
+    buf, off, y = synth.training_set(400, 400, 150)
+    kc = K.NewKmerCounter(1, 6, revcomp=True)
+    d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    d.SetLabels(y)
+    sel = np.unique(np.concatenate([[0], np.linspace(1, d.m, 30).astype(np.int64)]))
+    rd = K.select_data(d, sel); rd.SetLabels(y)
+    try:
+        for data, ntheta, lam in [(d, d.m + 1, 2e-3), (rd, len(sel), 1e-3)]:
+            one = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-300, MaxIterations=30)
+            one.Theta = np.zeros(ntheta)
+            it1, _ = one.estimate_proximal(data, lam)
+            sl = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-300, MaxIterations=10)
+            sl.Theta = np.zeros(ntheta)
+            total = 0
+            for _ in range(3):
+                it, _ = sl.estimate_proximal(data, lam)
+                total += it
+            assert (it1, total) == (30, 30)
+            assert np.array_equal(one.Theta, sl.Theta)
+            assert np.array_equal(one.hook_state, sl.hook_state)
+            # a loss-based stop inside a slice stops the sliced run at the same iteration
+            one = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-5, MaxIterations=5000)
+            one.Theta = np.zeros(ntheta)
+            it1, _ = one.estimate_proximal(data, lam)
+            sl = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-5, MaxIterations=7)
+            sl.Theta = np.zeros(ntheta)
+            total = 0
+            while True:
+                it, _ = sl.estimate_proximal(data, lam)
+                total += it
+                if it < 7 or total > 6000:
+                    break
+            assert 0 < it1 < 5000 and total == it1
+            assert np.array_equal(one.Theta, sl.Theta)
+    finally:
+        rd.free(); d.free()
