@@ -4,7 +4,7 @@ the leapfrog selection, and sliding-window genomic scoring.  See DESIGN.md / INT
 from ._lib import KmerLrError, SO_PATH, TIE_GO118, TIE_INDEX  # noqa: F401
 from .api import (  # noqa: F401
     CoeffIndex, KmerDataSet, KmerLrEstimator, NewKmerCounter, Sequences, Transform, TransformFull, comm_destroy, comm_init,
-    comm_init_torch, comm_unique_id, compile_test_data, compile_training_data, compute_class_weights,
+    comm_init_torch, comm_unique_id, compile_test_data, compile_data, compile_training_data, compute_class_weights,
     featureSelector, flatten, from_csr, from_dense, genomicKmerLr, init, last_device_ms, launch_count,
     logisticRegression, option, select_data, shutdown,
 )

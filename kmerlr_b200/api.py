@@ -258,6 +258,27 @@ def compile_test_data(config, kmersCounter, kmers, features, generate_features, 
     return _extract(cfg, sequences, kmers, features, False)
 
 
+def compile_data(config, kmersCounter, kmers, features, generate_features, binarize, sequence_sets):
+    """compile_data (kmerLr_data.go:339-358): several sequence sets, ONE class numbering (the union of the
+    classes observed in all of them, or the supplied list), one KmerDataSet per set.  The union comes from one
+    extraction over the concatenation; every set is then extracted against that frozen list, which gives the
+    rows `counts_list.Slice(k[i], k[i+1])` would."""
+    del config, generate_features
+    cfg = Config.from_buffer_copy(kmersCounter)
+    cfg.binarize = int(binarize)
+    sets = [flatten(s) for s in sequence_sets]
+    if kmers is None or len(kmers[0]) == 0:
+        buf = np.concatenate([b[:o[-1]] for b, o in sets] + [np.zeros(1, dtype=np.uint8)])
+        offs, base = [np.zeros(1, dtype=np.int64)], 0
+        for b, o in sets:
+            offs.append(o[1:] - o[0] + base)
+            base += int(o[-1] - o[0])
+        joint = _extract(cfg, (buf, np.concatenate(offs)), None, None, False)
+        kmers = joint.Kmers()
+        joint.free()
+    return [_extract(cfg, s, kmers, features, False) for s in sets]
+
+
 def compute_class_weights(c):
     """compute_class_weights (kmerLr_data.go:178-193); pure arithmetic on the label counts"""
     c = np.asarray(c, dtype=bool)

@@ -277,3 +277,28 @@ def test_c2_full_size_invariants(K):
     finally:
         K.option("implicit", 1)
     assert np.max(np.abs(lr.Gradient(None, d2) - g)) <= 1e-12 * np.max(np.abs(g))
+
+
+def test_compile_data_shares_one_numbering(K, oracle):
+    """compile_data (kmerLr_data.go:339-358): the sets get the column numbering of their union"""
+    from kmerlr_b200 import synth
+    a = synth.sequences(40, 90, 1)
+    b = synth.sequences(25, 60, 2)
+    c = synth.sequences(1, 30, 3)
+    kc, oc = cfg_pair(K, oracle, 2, 7, revcomp=True)
+    parts = K.compile_data(None, kc, None, None, True, False, [a, b, c])
+    buf = np.concatenate([a[0][:a[1][-1]], b[0][:b[1][-1]], c[0][:c[1][-1]]])
+    off = np.concatenate([a[1], b[1][1:] + a[1][-1], c[1][1:] + a[1][-1] + b[1][-1]])
+    ref = oracle.extract(oc, (buf, off))
+    rp, rc, rv = ref.rows()
+    lo = 0
+    for part in parts:
+        assert part.m == ref.m
+        k, code = part.Kmers(); ok, ocode = ref.classes()
+        assert np.array_equal(k, ok) and np.array_equal(code, ocode)
+        p, cc, v = part.rows()
+        assert np.array_equal(p, rp[lo:lo + part.n + 1] - rp[lo])
+        assert np.array_equal(cc, rc[rp[lo]:rp[lo + part.n]]) and np.array_equal(v, rv[rp[lo]:rp[lo + part.n]])
+        lo += part.n
+        part.free()
+    assert lo == ref.n
