@@ -168,6 +168,8 @@ class KmerDataSet:
 
     def Kmers(self):
         """class list as (k, code) arrays; the Go side rebuilds KmerClass names from them"""
+        if getattr(self, "_kmers", None) is not None:
+            return self._kmers
         k = np.zeros(max(self.n_classes, 1), dtype=np.int32)
         code = np.zeros(max(self.n_classes, 1), dtype=np.uint64)
         check(lib().kmerlr_matrix_classes(self.h, _p(k), _p(code)))
@@ -233,11 +235,25 @@ def _extract(config, seqs, kmers, features, sharded):
     return KmerDataSet(h.value)
 
 
+def _convert(cfg, seqs, kmers, features, generate_features, sharded):
+    """scan_sequences + convert_counts_list.  convert_counts (kmerLr_data.go:197-235) builds one column per class
+    only when the feature list is empty AND generate_features is set; with an empty list and generate_features
+    off (`n = len(features) + 1`, :212) the rows hold the bias alone, while Kmers stays the class list."""
+    if generate_features or (features is not None and len(features)):
+        return _extract(cfg, seqs, kmers, features, sharded)
+    full = _extract(cfg, seqs, kmers, None, sharded)
+    ks, n = full.Kmers(), full.n
+    full.free()
+    data = from_csr(n, 0, np.zeros(n + 1, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0), sharded)
+    data._kmers = ks
+    return data
+
+
 def compile_training_data(config, kmersCounter, kmers, features, generate_features, binarize, fg, bg,
                           sharded=False):
     """compile_training_data (kmerLr_data.go:306-325).  fg / bg are the sequences import_fasta returned
     (lists of str/bytes, or (buffer, offsets)); labels = true for fg."""
-    del config, generate_features
+    del config
     cfg = Config.from_buffer_copy(kmersCounter)
     cfg.binarize = int(binarize)
     fb, fo = flatten(fg)
@@ -245,17 +261,17 @@ def compile_training_data(config, kmersCounter, kmers, features, generate_featur
     nfg, nbg = len(fo) - 1, len(bo) - 1
     buf = np.concatenate([fb[:fo[-1]], bb[:bo[-1]]]) if (fo[-1] + bo[-1]) else np.zeros(1, dtype=np.uint8)
     off = np.concatenate([fo, bo[1:] + fo[-1]])
-    data = _extract(cfg, (buf, off), kmers, features, sharded)
+    data = _convert(cfg, (buf, off), kmers, features, generate_features, sharded)
     data.SetLabels(np.concatenate([np.ones(nfg, dtype=np.uint8), np.zeros(nbg, dtype=np.uint8)]))
     return data
 
 
 def compile_test_data(config, kmersCounter, kmers, features, generate_features, binarize, sequences):
     """compile_test_data (kmerLr_data.go:327-335): counter frozen to the classifier's k-mers."""
-    del config, generate_features
+    del config
     cfg = Config.from_buffer_copy(kmersCounter)
     cfg.binarize = int(binarize)
-    return _extract(cfg, sequences, kmers, features, False)
+    return _convert(cfg, sequences, kmers, features, generate_features, False)
 
 
 def compile_data(config, kmersCounter, kmers, features, generate_features, binarize, sequence_sets):
@@ -263,7 +279,7 @@ def compile_data(config, kmersCounter, kmers, features, generate_features, binar
     classes observed in all of them, or the supplied list), one KmerDataSet per set.  The union comes from one
     extraction over the concatenation; every set is then extracted against that frozen list, which gives the
     rows `counts_list.Slice(k[i], k[i+1])` would."""
-    del config, generate_features
+    del config
     cfg = Config.from_buffer_copy(kmersCounter)
     cfg.binarize = int(binarize)
     sets = [flatten(s) for s in sequence_sets]
@@ -276,7 +292,7 @@ def compile_data(config, kmersCounter, kmers, features, generate_features, binar
         joint = _extract(cfg, (buf, np.concatenate(offs)), None, None, False)
         kmers = joint.Kmers()
         joint.free()
-    return [_extract(cfg, s, kmers, features, False) for s in sets]
+    return [_convert(cfg, s, kmers, features, generate_features, False) for s in sets]
 
 
 def compute_class_weights(c):

@@ -302,3 +302,19 @@ def test_compile_data_shares_one_numbering(K, oracle):
         lo += part.n
         part.free()
     assert lo == ref.n
+
+
+def test_generate_features_off_with_empty_feature_list_gives_bias_only_rows(K):
+    """convert_counts (kmerLr_data.go:197-235): `len(features) == 0 && generate_features` is the only way to one
+    column per class; an empty list with generate_features off leaves the bias alone, Kmers stays the class list"""
+    from kmerlr_b200 import synth
+    seqs = synth.sequences(30, 80, 5)
+    kc = K.NewKmerCounter(1, 4, revcomp=True)
+    full = K.compile_test_data(None, kc, None, None, True, False, seqs)
+    d = K.compile_test_data(None, kc, None, None, False, False, seqs)
+    assert (d.n, d.m, d.nnz) == (30, 0, 0) and d.Dim() == 1
+    k, code = d.Kmers(); fk, fcode = full.Kmers()
+    assert np.array_equal(k, fk) and np.array_equal(code, fcode)
+    lr = K.logisticRegression(np.array([0.37]), (1.0, 1.0), 0.0)
+    assert np.array_equal(lr.LinearPdf(d), np.full(30, 0.37))
+    d.free(); full.free()
