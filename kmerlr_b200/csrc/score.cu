@@ -145,6 +145,11 @@ __global__ void score_generic(const DevModel *__restrict__ models, int n_models,
 struct LinearTile { int64_t region, p0; };
 
 constexpr int SCORE_THREADS = 1024;
+// levels k <= SCORE_KD of a small model: the class weight of every code in a direct table in shared
+// memory (one LDS per position and level instead of a hash probe sequence + a gather of the weight)
+constexpr int SCORE_KD = 5;
+constexpr int SCORE_WT = (4 + 16 + 64 + 256 + 1024);     // sum_{k=1..5} 4^k entries
+__device__ __forceinline__ uint32_t score_doff(int k) { return ((1u << (2 * k)) - 4u) / 3u; }   // sum_{j<k} 4^j
 __device__ __forceinline__ int level_slot(uint32_t levels, int k) {   // index of level k among the model's levels
   return ((levels >> k) & 1u) ? __popc(levels & ((1u << k) - 1u)) : -1;
 }
@@ -172,8 +177,19 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_linear(const DevModel *__
   // small class tables are probed in shared memory (most probes miss: one LDS instead of one LDG each)
   uint32_t *skeys = reinterpret_cast<uint32_t *>(q + (size_t)nlev * stride);
   int32_t *svals = reinterpret_cast<int32_t *>(skeys + hs_smem);
+  double *wtab = reinterpret_cast<double *>(svals + hs_smem);
   for (int i = threadIdx.x; i < hs_smem; i += blockDim.x) { skeys[i] = md.hkeys[i]; svals[i] = md.hvals[i]; }
-  if (hs_smem) __syncthreads();
+  if (hs_smem) {
+    for (int i = threadIdx.x; i < SCORE_WT; i += blockDim.x) wtab[i] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < hs_smem; i += blockDim.x) {
+      const uint32_t key = skeys[i];
+      if (key != HEMPTY && (int)(key >> 26) <= SCORE_KD)
+        wtab[score_doff((int)(key >> 26)) + (key & 0x3FFFFFFu)] =
+            __ldg(md.cweight + (int64_t)member * md.n_classes + svals[i]);
+    }
+    __syncthreads();
+  }
   // phase 1: t_k(p) for p in [p0, p0 + TP).  The N bases starting at p are 2N consecutive bits of the
   // packed words (one funnel shift, first base in the low bits): no rolling state, so the positions
   // are simply dealt to the threads
@@ -201,8 +217,12 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_linear(const DevModel *__
         uint32_t fw = FW >> (2 * (N - k)), code = fw;
         if (md.op == 1 || md.op == 3) code = min(fw, IM & ((1u << (2 * k)) - 1u));
         else if (md.op == 2) code = min(fw, (~fw) & ((1u << (2 * k)) - 1u));
-        int ci = hs_smem ? table_lookup(skeys, svals, md.hmask, k, code) : model_lookup(md, k, code);
-        if (ci >= 0) t = __ldg(md.cweight + (int64_t)member * md.n_classes + ci);
+        if (hs_smem && k <= SCORE_KD) {
+          t = wtab[score_doff(k) + code];
+        } else {
+          int ci = hs_smem ? table_lookup(skeys, svals, md.hmask, k, code) : model_lookup(md, k, code);
+          if (ci >= 0) t = __ldg(md.cweight + (int64_t)member * md.n_classes + ci);
+        }
       }
       q[sl * stride + 1 + i] = t;
     }
@@ -348,7 +368,8 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
         // tile: as many positions as 200 KB of prefix sums allow, at least W + step
         const int64_t hs = (int64_t)d.hmask + 1;
         const int hs_smem = hs * 8 <= 16 * 1024 ? (int)hs : 0;
-        int64_t TP = (200 * 1024 - hs_smem * 8) / (8 * nlev) - 1;
+        const int wt_bytes = hs_smem ? SCORE_WT * 8 : 0;      // direct weight tables of the levels <= SCORE_KD
+        int64_t TP = (200 * 1024 - hs_smem * 8 - wt_bytes) / (8 * nlev) - 1;
         if (TP > 16384) TP = 16384;
         KL_REQUIRE(TP >= W + step, "score_windows: window too large for the shared-memory tile");
         // windows per tile: starts a with a + W <= TP (a tile advances by that many steps)
@@ -360,7 +381,7 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
         }
         DevBuf<LinearTile> dt(tiles.size() ? tiles.size() : 1);
         dt.upload(tiles.data(), tiles.size());
-        size_t smem = (size_t)nlev * (size_t)(TP + 1) * sizeof(double) + (size_t)hs_smem * 8;
+        size_t smem = (size_t)nlev * (size_t)(TP + 1) * sizeof(double) + (size_t)hs_smem * 8 + (size_t)wt_bytes;
         KL_CUDA(cudaFuncSetAttribute(score_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KL_LAUNCH(score_linear, (unsigned)tiles.size(), SCORE_THREADS, smem, dmodels.p, n_models, 0, mi > 0 ? 1 : 0, s.len.p,
                   s.blk.p, s.bits2.p, s.inv16.p, dt.p, dslot.p, W, step, (int)TP, mi, hs_smem, layout == 1 ? step : (int64_t)1, outbuf->val_f64.p);
