@@ -144,6 +144,176 @@ def bench_scoring(K, mbp, rank, reps=3):
             "achieved_gbs": windows * (step / 4 + 8) / t / 1e9, "model": model, "sample": (buf, off)}
 
 
+
+def leg_c3(K, api, synth, shard, rank, world, dist, allmax, allsum, peak, iters=10, reps=3):
+    """BASELINE configs[2]: ONE set of 2 M sequences x 200 bp, k = 1..10 binarized, revcomp-merged, sample-sharded over
+    the ranks (strong scaling): extraction of the rank's shard (class union OR-ed over NCCL), then full-space
+    proximal-gradient iterations with the int64 all-reduce of the (m+1)-word fixed-point gradient"""
+    import numpy as np
+    n_fg, n_bg, L, M, N, binarize = CONFIGS["c3"]
+    lo, hi = shard.sample_range(n_fg + n_bg, rank, world)
+    f_lo, f_hi, b_lo, b_hi = min(lo, n_fg), min(hi, n_fg), max(lo - n_fg, 0), max(hi - n_fg, 0)
+    fb, fo = synth.sequences(f_hi - f_lo, L, 1, planted=True, first=f_lo)
+    bb, bo = synth.sequences(b_hi - b_lo, L, 2, planted=False, first=b_lo)
+    buf = np.concatenate([fb, bb])
+    off = np.concatenate([fo, bo[1:] + fo[-1]])
+    labels = np.concatenate([np.ones(f_hi - f_lo, dtype=np.uint8), np.zeros(b_hi - b_lo, dtype=np.uint8)])
+    counter = K.NewKmerCounter(M, N, revcomp=True, binarize=binarize)
+    seqs = K.Sequences((buf, off))
+    sharded = world > 1
+    ext = []
+    data = None
+    for i in range(reps + 1):
+        if data is not None:
+            data.free()
+        data = api._extract(counter, seqs, None, None, sharded)
+        if i > 0:
+            ext.append(K.last_device_ms())
+    data.SetLabels(labels)
+    est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-300, MaxIterations=2)
+    est.Theta = np.zeros(data.m + 1)
+    est.estimate_proximal(data, 1e-3)
+    est.MaxIterations = iters
+    est.Theta = np.zeros(data.m + 1)
+    K.api.profile(True)
+    if dist is not None:
+        dist.barrier()
+    est.estimate_proximal(data, 1e-3)
+    it_ms = K.last_device_ms() / iters
+    prof = K.api.profile_dump()
+    K.api.profile(False)
+    ar_ms = sum(v[0] for k, v in prof.items() if k.startswith("nccl_")) / iters
+    pass_ms = sum(v[0] for k, v in prof.items() if "imp_pass" in k or "fused_kernel" in k or "low_accumulate" in k) / iters
+    n_loc, m, nnz_loc = data.n, data.m, data.nnz
+    data.free(); seqs.free()
+    ext_ms, it_ms, ar_ms, pass_ms = allmax(float(np.mean(ext))), allmax(it_ms), allmax(ar_ms), allmax(pass_ms)
+    nnz = int(allsum(float(nnz_loc)))
+    n = n_fg + n_bg
+    it_bytes = algorithmic_bytes_iter(n, m, nnz, binarize)
+    ex_bytes = algorithmic_bytes_extract(n, L, nnz, binarize)
+    return {"workload": "C3: 2 000 000 sequences x 200 bp in total, k=1..10 binarized, revcomp-merged, contiguous sample "
+                        "shards over %d GPU(s) (strong scaling)" % world,
+            "n_total": n, "n_per_gpu": int(n_loc), "m": int(m), "nnz_total": nnz,
+            "extract_ms": ext_ms, "extract_sequences_per_sec": n / (ext_ms * 1e-3),
+            "extract_frac_of_hbm_peak": ex_bytes / world / (ext_ms * 1e-3) / 1e9 / peak,
+            "ms_per_iter": it_ms, "iters_per_sec": 1e3 / it_ms, "logistic_pass_ms": pass_ms,
+            "allreduce_ms_per_iter": ar_ms, "allreduce_share_of_iter": ar_ms / it_ms if it_ms > 0 else None,
+            "allreduce_bytes": 8 * (m + 1), "algorithmic_bytes_per_iter": it_bytes,
+            "iter_achieved_gbs_per_gpu": it_bytes / world / (it_ms * 1e-3) / 1e9,
+            "iter_frac_of_hbm_peak": it_bytes / world / (it_ms * 1e-3) / 1e9 / peak}
+
+
+def leg_path(K, synth, targets=(10, 25, 50, 100)):
+    """BASELINE configs[1] as it is worded: the proximal-gradient leapfrog path to 100 features on the C2 set
+    (1 GPU; EpsilonLoss = 1e-8 as the CLI default, `|g| desc, index asc` tie rule)"""
+    n_fg, n_bg, L, M, N, _ = CONFIGS["c2"]
+    buf, off, y = synth.training_set(n_fg, n_bg, L)
+    t0 = time.perf_counter()
+    d = K.compile_test_data(None, K.NewKmerCounter(M, N, revcomp=True), None, None, True, False, (buf, off))
+    d.SetLabels(y)
+    t_extract = time.perf_counter() - t0
+    est = K.KmerLrEstimator(EpsilonLoss=1e-8, MaxIterations=10 ** 9, tie=K.TIE_INDEX)
+    out, t_all = [], time.perf_counter()
+    for n_feat in targets:
+        t0 = time.perf_counter()
+        epochs = est.estimate_loop(d, n_feat)
+        out.append({"features": n_feat, "epochs": int(epochs), "iterations": int(sum(p[1] for p in est.path[-epochs:])),
+                    "lambda": float(est.path[-1][0]), "active": int(len(est.active_idx)), "s": time.perf_counter() - t0})
+    total = time.perf_counter() - t_all
+    d.free()
+    return {"path_to_100_features_s": total, "extract_s": t_extract, "iterations": int(sum(o["iterations"] for o in out)),
+            "epochs": int(sum(o["epochs"] for o in out)), "targets": out,
+            "note": "wall clock through the C ABI, estimate_loop per target warm-started as Estimate does "
+                    "(kmerLr_estimator.go:257-270); iteration counts are those of the reference's fixed-step ISTA"}
+
+
+def leg_c4(K, synth, n=20000, folds=5, n_feat=20, max_epochs=12):
+    """BASELINE configs[3]: pair features over k = 1..6 (CoeffIndex.Dim = 3.84 M coefficients), leapfrog path to N = 20,
+    5-fold cross-validation with fold = i mod 5 over fg||bg (no shuffle).  Per fold: extraction of the training rows,
+    the pair gradient / Select of every epoch, the reduced solves, loss on the held-out fold."""
+    import numpy as np
+    buf, off, y = synth.training_set(n // 2, n // 2, 500)
+    kc = K.NewKmerCounter(1, 6, revcomp=True)
+    fold = np.arange(n) % folds
+    out = []
+    lens = np.diff(off)
+    for f in range(folds):
+        t_fold = time.perf_counter()
+        tr, te = np.nonzero(fold != f)[0], np.nonzero(fold == f)[0]
+
+        def take(rows):
+            o = np.concatenate([[0], np.cumsum(lens[rows])]).astype(np.int64)
+            b = np.concatenate([buf[off[i]:off[i + 1]] for i in rows]) if len(rows) else np.zeros(1, dtype=np.uint8)
+            return b, o
+        t0 = time.perf_counter()
+        dtr = K.compile_test_data(None, kc, None, None, True, False, take(tr))
+        dtr.SetLabels(y[tr])
+        t_extract = time.perf_counter() - t0
+        nt = K.CoeffIndex(dtr.m).Dim()
+        lr = K.logisticRegression(np.zeros(nt), (1.0, 1.0), 0.0, Cooccurrence=True)
+        lr.Gradient(None, dtr)                       # builds the transposed view once
+        t0 = time.perf_counter()
+        lr.Gradient(None, dtr)
+        grad_wall, grad_dev = time.perf_counter() - t0, K.last_device_ms()
+        sel = K.featureSelector((1.0, 1.0), True, n_feat, dtr.m, tie=K.TIE_INDEX)
+        t0 = time.perf_counter()
+        sel.Select(dtr, 0.0, [], [], 0.0)
+        select_wall = time.perf_counter() - t0
+        est = K.KmerLrEstimator(Cooccurrence=True, EpsilonLoss=1e-8, MaxIterations=10 ** 7, MaxEpochs=max_epochs, tie=K.TIE_INDEX)
+        t0 = time.perf_counter()
+        epochs = est.estimate_loop(dtr, n_feat)
+        t_path = time.perf_counter() - t0
+        # held-out loss with the fold's model (kmerLr_classifier.go:107-147 SelectData + Loss)
+        feats = [K.CoeffIndex(dtr.m).Sub2Ind(int(i) - 1) for i in est.active_idx]
+        dte = K.compile_test_data(None, kc, dtr.Kmers(), feats, False, False, take(te))
+        dte.SetLabels(y[te])
+        loss = K.logisticRegression(est.Theta, (1.0, 1.0), 0.0).Loss(dte)
+        dtr.free(); dte.free()
+        out.append({"fold": f, "n_train": int(len(tr)), "extract_s": t_extract, "pair_gradient_ms": grad_dev,
+                    "pair_gradient_wall_ms": 1e3 * grad_wall, "select_wall_ms": 1e3 * select_wall, "epochs": int(epochs),
+                    "iterations": int(sum(p[1] for p in est.path)), "path_s": t_path, "lambda": float(est.path[-1][0]),
+                    "active": int(len(est.active_idx)), "test_loss": float(loss), "wall_s": time.perf_counter() - t_fold})
+    return {"workload": "C4: %d sequences x 500 bp, k=1..6 revcomp, pair features (%d coefficients), N=%d, %d folds (fold = i mod %d)"
+                        % (n, K.CoeffIndex(2772).Dim(), n_feat, folds, folds),
+            "pair_gradient_ms": float(np.mean([o["pair_gradient_ms"] for o in out])),
+            "select_wall_ms": float(np.mean([o["select_wall_ms"] for o in out])),
+            "fold_wall_s": float(np.mean([o["wall_s"] for o in out])), "folds": out}
+
+
+def leg_c5(K, lib, torch, rank, world, mbp=384.0):
+    """BASELINE configs[4] at a bounded size per GPU: sliding-window scoring (W = 200, step = 10) through the
+    host-buffer C-ABI call -- H2D of the ASCII contigs, packing, scoring, D2H of every window score inside the timer"""
+    import ctypes as C
+    import numpy as np
+    from kmerlr_b200 import synth, _lib
+    W, step, ncontig = 200, 10, 24
+    clen = int(mbp * 1e6) // ncontig
+    total = clen * ncontig
+    pin = torch.empty(total, dtype=torch.uint8).pin_memory()
+    pin.numpy()[:] = synth.random_bases(total, 3, offset=rank * total)
+    off = np.arange(ncontig + 1, dtype=np.int64) * clen
+    ck, cc = canonical_classes(100, 1, 8)
+    theta = np.random.default_rng(9).normal(scale=0.05, size=(1, len(ck) + 1))
+    model = dict(counter=K.NewKmerCounter(1, 8, revcomp=True), class_k=ck, class_code=cc,
+                 features=[(i, i) for i in range(len(ck))], theta=theta, summary="")
+    g = K.genomicKmerLr([model])
+    slots = ncontig * int(lib.kmerlr_window_slots(clen, W, step))
+    windows = ncontig * ((clen - W + step - 1) // step)
+    out = torch.empty(slots, dtype=torch.float64).pin_memory()
+    times = []
+    for i in range(4):
+        t0 = time.perf_counter()
+        _lib.check(lib.kmerlr_score_windows(g._arr, 1, C.c_void_p(pin.data_ptr()), off.ctypes.data_as(C.c_void_p), ncontig,
+                                            W, step, C.c_void_p(out.data_ptr())))
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    return {"workload": "C5 slice: %.0f Mbp per GPU in %d contigs, W=%d, step=%d, 100-feature k=1..8 model" % (mbp, ncontig, W, step),
+            "e2e_windows_per_sec": windows / t, "e2e_bases_per_sec": total / t, "e2e_ms": 1e3 * t, "windows": int(windows),
+            "h2d_bytes": int(total + off.nbytes), "d2h_bytes": int(8 * slots), "device_ms_last_call": K.last_device_ms(),
+            "checksum": float(out.numpy()[:1000].sum())}
+
+
 def run_reference(args, rank, world):
     """the reference's own CPU algorithm (oracle port: per-sequence hash-map counting, union + sort,
     O(n m) convert_counts walk, serial-over-samples gradient / loss) on the box's host cores"""
@@ -202,6 +372,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--score-mbp", type=float, default=96.0, help="genome size of the window-scoring leg (0 = skip)")
     ap.add_argument("--short", action="store_true", help="profiling runs only: allow fewer than 3 warm-up steps")
+    ap.add_argument("--legs", default="auto", help="extra legs on the same JSON line: comma list of c3,path,c4,c5; "
+                    "auto = all four on one GPU, c3,c5 on several; none = headline only")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.short:
         args.warmup = 3
@@ -358,6 +530,36 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    legs = args.legs
+    if legs == "auto":
+        legs = ("c3,path,c4,c5" if world == 1 else "c3,c5") if args.config == "c2" else "none"
+    legs = [x for x in legs.split(",") if x and x != "none"]
+    seqs.free()
+    extra = {}
+    peak0, _ = peaks()
+    from kmerlr_b200 import shard as shard_mod
+    if "c3" in legs:
+        extra["c3"] = leg_c3(K, api, synth, shard_mod, rank, world, dist, allmax, allsum, peak0)
+    if "c5" in legs:
+        c5 = leg_c5(K, K.api.lib(), torch, rank, world)
+        ms5 = allmax(c5["e2e_ms"])
+        c5["e2e_windows_per_sec"] = world * c5["windows"] / (ms5 * 1e-3)     # every rank its own contigs, no collective
+        c5["e2e_bases_per_sec"] *= world * c5["e2e_ms"] / ms5
+        c5["e2e_ms"] = ms5
+        extra["c5"] = c5
+    if rank == 0 and "path" in legs:
+        extra["c2_path"] = leg_path(K, synth)
+    if rank == 0 and "c4" in legs:
+        extra["c4"] = leg_c4(K, synth)
+    barrier()
+
     ms_step = allmax(float(np.mean(dev_ms)))
     ms_e2e = allmax(1e3 * float(np.mean(e2e_s)))
     ms_iter = allmax(iter_ms / args.iters)
@@ -425,6 +627,7 @@ def main():
         "roofline": roof,
         "clocks": clocks,
     }
+    line.update(extra)
     if genomic is not None:
         gmodel, gsample = genomic.pop("model"), genomic.pop("sample")
         if world > 1:

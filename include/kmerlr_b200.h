@@ -65,8 +65,10 @@ int         kmerlr_profile_read(const char *kernel_substr, double *ms_total, int
 int         kmerlr_profile_dump(char *buf, int64_t buflen);
 
 /* run-time switches (tests and experiments):
- *   "implicit" = 1 (default) lets count matrices that came straight from kmerlr_extract use the
- *                matrix-free logistic pass, 0 forces the pass over the stored rows;
+ *   "implicit" = 1 (default) lets matrices that came straight from kmerlr_extract (count or binarized, one
+ *                column per class) use the matrix-free logistic pass, 0 forces the pass over the stored rows;
+ *   "super_len" = length S of the super k-mer tables of that pass (S - N + 1 positions share one table
+ *                entry; -1 = automatic: 10 for N <= 8, else 11; 0 = off);
  *   "hot_cols" = number of columns of that stored-row pass that accumulate in shared memory (default 6144);
  *   "p2p"      = 1 (default) lets sharded reduced-matrix iterations exchange the gradient over NVLink peer
  *                memory, 0 forces the NCCL collectives (set it identically on every rank);

@@ -37,7 +37,8 @@ def launch_count():
 
 
 def option(name, value):
-    """run-time switches of the library (kmerlr_option): "implicit", "hot_cols", "p2p", "persistent" (see include/kmerlr_b200.h)"""
+    """run-time switches of the library (kmerlr_option): "implicit", "super_len", "hot_cols", "p2p", "persistent"
+    (see include/kmerlr_b200.h)"""
     check(lib().kmerlr_option(name.encode(), int(value)))
 
 

@@ -111,6 +111,9 @@ template <typename F>
 int guarded(F &&f, bool timed = true) {
   std::lock_guard<std::mutex> lock(g_mutex);
   try {
+    // the current device is per host THREAD: cgo moves goroutines between OS threads, and kmerlr_init
+    // bound only the thread that ran it
+    if (g_ctx.ready) KL_CUDA(cudaSetDevice(g_ctx.device));
     if (timed && g_ctx.ready) KL_CUDA(cudaEventRecord(g_ctx.ev0, g_ctx.stream));
     f();
     if (timed && g_ctx.ready) {
@@ -178,6 +181,7 @@ int kmerlr_option(const char *name, int64_t value) {
   return guarded([&] {
     KL_REQUIRE(name != nullptr, "option: null name");
     if (!strcmp(name, "implicit")) g_ctx.implicit_ok = value != 0;
+    else if (!strcmp(name, "super_len")) g_ctx.super_len = (int)(value < 0 ? -1 : (value > IMP_SUPER_MAX ? IMP_SUPER_MAX : value));
     else if (!strcmp(name, "p2p")) g_ctx.p2p_ok = value != 0;
     else if (!strcmp(name, "persistent")) g_ctx.coop_ok = value != 0 && g_ctx.coop_supported;
     else if (!strcmp(name, "hot_cols")) g_ctx.hot_cols = (int)(value < 0 ? 0 : (value > 16384 ? 16384 : value));

@@ -158,22 +158,30 @@ static void need_comm() {
 void comm_allreduce_sum_f64(double *dev, int64_t count) {
   if (ctx().world == 1) return;
   need_comm();
+  if (ctx().profiling) profile_begin("nccl_allreduce_sum_f64");
   KL_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, comm(), ctx().stream));
+  if (ctx().profiling) profile_end();
 }
 void comm_allreduce_sum_i64(int64_t *dev, int64_t count) {
   if (ctx().world == 1) return;
   need_comm();
+  if (ctx().profiling) profile_begin("nccl_allreduce_sum_i64");
   KL_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclInt64, ncclSum, comm(), ctx().stream));
+  if (ctx().profiling) profile_end();
 }
 void comm_allreduce_max_f64(double *dev, int64_t count) {
   if (ctx().world == 1) return;
   need_comm();
+  if (ctx().profiling) profile_begin("nccl_allreduce_max_f64");
   KL_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclMax, comm(), ctx().stream));
+  if (ctx().profiling) profile_end();
 }
 void comm_allreduce_max_u8(uint8_t *dev, int64_t count) {
   if (ctx().world == 1) return;
   need_comm();
+  if (ctx().profiling) profile_begin("nccl_allreduce_max_u8");
   KL_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclUint8, ncclMax, comm(), ctx().stream));
+  if (ctx().profiling) profile_end();
 }
 void comm_allgather_f64(const double *dev_in, double *dev_out, int64_t count_per_rank) {
   if (ctx().world == 1) {
@@ -182,7 +190,9 @@ void comm_allgather_f64(const double *dev_in, double *dev_out, int64_t count_per
     return;
   }
   need_comm();
+  if (ctx().profiling) profile_begin("nccl_allgather_f64");
   KL_NCCL(g_nccl.AllGather(dev_in, dev_out, (size_t)count_per_rank, ncclFloat64, comm(), ctx().stream));
+  if (ctx().profiling) profile_end();
 }
 
 }  // namespace kl

@@ -79,6 +79,7 @@ struct Ctx {
   double last_ms = 0.0;
   bool profiling = false;
   bool implicit_ok = true;   // kmerlr_option("implicit")
+  int super_len = -1;        // kmerlr_option("super_len"): length of the super k-mer tables (-1 = automatic, 0 = off)
   int hot_cols = 6144;       // kmerlr_option("hot_cols"): columns of the CSR pass that accumulate in shared memory
   // communicator (NCCL via dlopen, see comm.cu)
   void *comm = nullptr;
@@ -197,16 +198,30 @@ struct SeqSet : Object {
 
 enum ValType : int { VAL_ONE = 0, VAL_U32 = 1, VAL_F64 = 2 };
 
-// What the matrix-free logistic pass needs (logistic.cu): a count matrix that came straight out of the
-// extraction (one column per observed / frozen class, counts not binarized) is a linear function of
-// the k-mer occurrences, so X theta and X^T w can be evaluated from the packed sequences.
+// What the matrix-free logistic pass needs (logistic.cu).  A matrix that came straight out of the
+// extraction (one column per observed / frozen class) is a function of the k-mer occurrences, so X theta
+// and X^T w can be evaluated from the packed sequences instead of the stored rows:
+//   * count matrices: linear in the occurrences, every level M..N is matrix-free (Mlo = M);
+//   * binarized matrices: the table levels (k <= 5, where nearly every class repeats) are a per-row bitmap
+//     over the classes of those levels (lowbits), the levels k >= 6 are matrix-free with one correction per
+//     REPEAT of a class inside a row (the events the extraction leaves at the tail of the row's slots).
 constexpr int IMP_MAX_N = 10;      // forward-code tables of 4^1 + ... + 4^N entries
+constexpr int IMP_SUPER_MAX = 11;  // longest "super k-mer" table (4^11 entries of 8 bytes = 32 MB)
+constexpr uint32_t NOCOL = 0xFFFFFFFFu;
 struct Implicit {
   std::shared_ptr<SeqSet> seqs;
   int M = 0, N = 0, op = 0;
+  int Mlo = 0;                     // first matrix-free level (>= M)
   uint32_t level_off[16] = {0};    // dense class id of (k, code 0)
-  uint32_t fo[16] = {0};           // offset of level j in the forward-code tables, fo[N+1] = total
+  uint32_t fo[16] = {0};           // offset of level j (Mlo..N) in the forward-code tables, fo[N+1] = total
   DevBuf<uint32_t> bitmap, rank;   // class set over dense ids: column = rank[id>>5] + popc(bits below)
+  // binarized matrices only
+  bool binarized = false;
+  int low_words = 0;               // 32-bit words of a row's bitmap over the table-level classes
+  DevBuf<uint32_t> lowbits;        // n * low_words
+  DevBuf<uint32_t> lowcol;         // low_words * 32: column of the j-th table-level class (NOCOL: not a column)
+  DevBuf<int64_t> evptr;           // n + 1: the repeat events of row i are events[evptr[i] .. evptr[i+1])
+  DevBuf<uint32_t> events;         // the column of the repeated class, once per repeat
 };                                 // (the dense class id of every column is Matrix::class_ids)
 
 // where row i of a matrix lives: compact CSR (rowptr) or fixed-stride rows straight from the extraction

@@ -136,7 +136,7 @@ __global__ void bitmaps_differ(const uint32_t *__restrict__ a, const uint32_t *_
 // columns numbered in the numbering set -> ranks among the observed classes, in place (warp per row)
 __global__ void renumber_rows(uint32_t *__restrict__ col, const uint32_t *__restrict__ rowcnt, int64_t stride, int64_t n,
                               const uint32_t *__restrict__ ids, const uint32_t *__restrict__ bm,
-                              const uint32_t *__restrict__ rank) {
+                              const uint32_t *__restrict__ rank, const uint32_t *__restrict__ rowdup) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
   const unsigned lane = lane_id();
@@ -146,6 +146,36 @@ __global__ void renumber_rows(uint32_t *__restrict__ col, const uint32_t *__rest
     const uint32_t id = __ldg(ids + c[j]), w = __ldg(bm + (id >> 5));
     c[j] = __ldg(rank + (id >> 5)) + __popc(w & ((1u << (id & 31)) - 1u));
   }
+  // repeat events of binarized rows (columns too), stored downwards from the row's last slot
+  const uint32_t nd = rowdup ? rowdup[row] : 0u;
+  uint32_t *t = c + stride - 1;
+  for (uint32_t j = lane; j < nd; j += 32) {
+    const uint32_t id = __ldg(ids + t[-(int64_t)j]), w = __ldg(bm + (id >> 5));
+    t[-(int64_t)j] = __ldg(rank + (id >> 5)) + __popc(w & ((1u << (id & 31)) - 1u));
+  }
+}
+// repeat events of binarized rows: from the tail of each row's slots into one compact array (the row layout
+// may be compacted away later, the matrix-free logistic pass keeps its own copy)
+__global__ void gather_events(const uint32_t *__restrict__ col, int64_t stride, int64_t n,
+                              const int64_t *__restrict__ evptr, uint32_t *__restrict__ events) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const unsigned lane = lane_id();
+  const int64_t a = evptr[row], cnt = evptr[row + 1] - a;
+  const uint32_t *t = col + (row + 1) * stride - 1;
+  for (int64_t j = lane; j < cnt; j += 32) events[a + j] = t[-j];
+}
+// column of every class of the table levels (flat list tl), NOCOL when the class is not numbered
+__global__ void low_columns(const uint2 *__restrict__ tl, uint32_t tl_cnt, int slots, const uint32_t *__restrict__ bm,
+                            const uint32_t *__restrict__ rank, uint32_t *__restrict__ lowcol) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= slots) return;
+  uint32_t col = NOCOL;
+  if ((uint32_t)j < tl_cnt) {
+    const uint32_t id = tl[j].y, w = bm[id >> 5], bit = 1u << (id & 31);
+    if (w & bit) col = rank[id >> 5] + __popc(w & (bit - 1u));
+  }
+  lowcol[j] = col;
 }
 
 // ---- explicit feature lists: singles and pair products (convert_counts, kmerLr_data.go:210-229) ----
@@ -313,10 +343,10 @@ static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t
     s->blk.zero();
   }
   const int64_t words = blocks * 4;
-  s->bits2.alloc((size_t)words + 1);     // + 1: the kernels read the word after the last base
-  s->inv16.alloc((size_t)words + 1);
-  KL_CUDA(cudaMemsetAsync(s->bits2.p + words, 0, sizeof(uint32_t), ctx().stream));
-  KL_CUDA(cudaMemsetAsync(s->inv16.p + words, 0, sizeof(uint16_t), ctx().stream));
+  s->bits2.alloc((size_t)words + 4);     // + 4: the kernels read up to two words past the last base
+  s->inv16.alloc((size_t)words + 4);
+  KL_CUDA(cudaMemsetAsync(s->bits2.p + words, 0, 4 * sizeof(uint32_t), ctx().stream));
+  KL_CUDA(cudaMemsetAsync(s->inv16.p + words, 0, 4 * sizeof(uint16_t), ctx().stream));
   hf.raw.alloc((size_t)(s->total_bases ? s->total_bases : 1));
   // the copy stream must not run ahead of the allocation / earlier work on the main stream
   KL_CUDA(cudaEventRecord(ctx().copy_ev[CTX_COPY_EVENTS - 1], ctx().stream));
@@ -417,6 +447,12 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   }
   if (stride < 1) stride = 1;
   P.stride = stride;
+  // Binarized rows keep what the matrix-free logistic pass needs (Implicit): the class bitmap of the table
+  // levels and one event per repeat of a class of the levels above them.  The events sit in the unused tail
+  // of the row's slots: for a level whose stride term is its number of instances, entries + events = instances.
+  bool hybrid = P.binarize && cfg.N <= IMP_MAX_N && n_features == 0 && s.n > 0;
+  for (int k = cfg.M > KT_MAX + 1 ? cfg.M : KT_MAX + 1; k <= cfg.N && hybrid; k++)
+    if (s.max_len - k + 1 > ((int64_t)1 << (2 * k))) hybrid = false;
   KL_REQUIRE(s.max_len < 65536 || P.t_lo > P.t_hi, "sequences of 65536 bp or more need M > 5 on the GPU path");
   KL_REQUIRE(s.max_len < ((int64_t)1 << 30), "sequence too long");
   // keys per lane of the register sort
@@ -487,10 +523,18 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   KL_LAUNCH(interleave_numbering, (unsigned)((nw + 255) / 256), 256, 0, nb.p, nbrank.p, nw, nbx.p);
   P.bitmap = bitmap.p; P.nbx = nbx.p; P.filter = n_frozen > 0; P.stats = stats.p;
   P.mark = n_frozen == 0;
+  DevBuf<uint32_t> lowbits, rowdup;
+  if (hybrid) {
+    P.events = 1;
+    P.low_words = P.t_lo <= P.t_hi ? (int)((P.tl_cnt + 31) / 32) : 0;
+    if (P.low_words) { lowbits.alloc((size_t)s.n * P.low_words); P.lowbits = lowbits.p; }
+    rowdup.alloc((size_t)s.n);
+    P.rowdup = rowdup.p;
+  }
   // repeats of the bitmap levels: one list per warp in global memory (L2 resident)
   DevBuf<uint32_t> ovf;
   P.ovf_stride = nbl * (s.max_len > 0 ? s.max_len : 1);
-  if (nbl && !P.binarize && s.n > 0) {
+  if (nbl && (!P.binarize || hybrid) && s.n > 0) {
     ovf.alloc((size_t)ctx().sm_count * 64 * (size_t)P.ovf_stride);
     P.ovf = ovf.p;
   }
@@ -566,6 +610,13 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   }
   uint32_t m32 = 0, hdiffer = 0;
   unsigned long long hstats[2] = {0, 0};
+  DevBuf<int64_t> evptr;
+  int64_t n_events = 0;
+  if (hybrid) {
+    evptr.alloc((size_t)s.n + 1);
+    exclusive_scan_u32_to_i64(rowdup.p, evptr.p, s.n);
+    KL_CUDA(cudaMemcpyAsync(&n_events, evptr.p + s.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
+  }
   KL_CUDA(cudaMemcpyAsync(&m32, nbrank.p + nw, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
   KL_CUDA(cudaMemcpyAsync(&out->nnz, rp.p + s.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
   differ.download(&hdiffer, 1);
@@ -584,7 +635,7 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
     KL_LAUNCH(enumerate_bits, (unsigned)((nw + 255) / 256), 256, 0, nb.p, nbrank.p, nw, ids_nb.p);
     if (s.n > 0)
       KL_LAUNCH(renumber_rows, (unsigned)((s.n * 32 + 127) / 128), 128, 0, out->col.p, out->rowcnt.p, stride, s.n, ids_nb.p,
-                bitmap.p, rank2.p);
+                bitmap.p, rank2.p, hybrid ? rowdup.p : (const uint32_t *)nullptr);
     KL_CUDA(cudaMemcpyAsync(&m32, rank2.p + nw, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
     sync_stream();
     nb = std::move(bitmap); nbrank = std::move(rank2);
@@ -598,15 +649,28 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   out->class_M = cfg.M; out->class_N = cfg.N; out->classes_on_host = false;
   for (int k = cfg.M; k <= cfg.N + 1; k++) out->class_level_off[k] = P.level_off[k];
   if (n_features > 0) { sync_stream(); return apply_features(*out, features, n_features); }
-  // count matrices with one column per class keep what the matrix-free logistic pass needs
-  if (!P.binarize && cfg.N <= IMP_MAX_N && s.n > 0 && m32 > 0) {
+  // matrices with one column per class keep what the matrix-free logistic pass needs
+  if ((!P.binarize || hybrid) && cfg.N <= IMP_MAX_N && s.n > 0 && m32 > 0) {
     auto imp = std::make_shared<Implicit>();
     imp->seqs = seqs; imp->M = cfg.M; imp->N = cfg.N; imp->op = P.op;
+    imp->Mlo = P.binarize ? (cfg.M > KT_MAX + 1 ? cfg.M : KT_MAX + 1) : cfg.M;
     uint32_t fo = 0;
     for (int k = cfg.M; k <= cfg.N + 1; k++) {
       imp->level_off[k] = P.level_off[k];
       imp->fo[k] = fo;
-      if (k <= cfg.N) fo += 1u << (2 * k);
+      if (k <= cfg.N && k >= imp->Mlo) fo += 1u << (2 * k);
+    }
+    if (P.binarize) {
+      imp->binarized = true;
+      imp->low_words = P.low_words;
+      imp->lowcol.alloc((size_t)(P.low_words ? P.low_words * 32 : 1));
+      if (P.low_words)
+        KL_LAUNCH(low_columns, (unsigned)((P.low_words * 32 + 127) / 128), 128, 0, P.tl, P.tl_cnt, P.low_words * 32, nb.p,
+                  nbrank.p, imp->lowcol.p);
+      imp->lowbits = std::move(lowbits);
+      imp->events.alloc((size_t)(n_events ? n_events : 1));
+      KL_LAUNCH(gather_events, (unsigned)((s.n * 32 + 127) / 128), 128, 0, out->col.p, stride, s.n, evptr.p, imp->events.p);
+      imp->evptr = std::move(evptr);
     }
     imp->bitmap = std::move(nb); imp->rank = std::move(nbrank);
     out->imp = imp;

@@ -43,6 +43,11 @@ struct XParams {
   int filter;                      // drop ids outside the numbering set
   unsigned long long *stats;       // [0] max_i sum_j v_ij^2, [1] max v_ij
   uint32_t *ticket;                // rows are handed out to the blocks in groups of one row per warp
+  // binarized rows, for the matrix-free logistic pass (see Implicit in common.cuh)
+  uint32_t *lowbits;               // per row: bitmap over the classes of the table levels (nullptr: not wanted)
+  int low_words;
+  uint32_t *rowdup;                // per row: number of repeat events written at the tail of the row's slots
+  int events;                      // record one event (the column) per repeat of a class of a level > KT_MAX
 };
 
 __device__ __forceinline__ uint32_t tab_off(int k) {  // sum_{j=1}^{k-1} 4^j
@@ -112,6 +117,7 @@ struct Emitter {
   int binarize, mark, filter;      // filter: ids outside the numbering set are dropped (frozen class list)
   unsigned long long sq;           // per lane: sum of squared counts / largest count emitted
   uint32_t vm;
+  uint32_t ev;                     // repeat events written so far (binarized rows, downwards from the row's last slot)
   // mark one class id as observed
   __device__ __forceinline__ void mark_id(uint32_t id) {
     if (!mark) return;
@@ -135,7 +141,7 @@ struct Emitter {
     vm = max(vm, cnt);
   }
   // ballot-compacted emission (coalesced stores); col_known >= 0: the column when no class is dropped
-  __device__ __forceinline__ void emit(bool flag, uint32_t id, uint32_t cnt, int64_t col_known = -1) {
+  __device__ __forceinline__ unsigned emit(bool flag, uint32_t id, uint32_t cnt, int64_t col_known = -1) {
     uint32_t col = (uint32_t)col_known;
     if (flag && (filter || col_known < 0)) { const bool member = column(id, col); if (filter) flag = member; }
     unsigned em = __ballot_sync(0xffffffffu, flag);
@@ -147,6 +153,7 @@ struct Emitter {
       stat(binarize ? 1u : cnt);
     }
     cursor += __popc(em);
+    return em;
   }
 };
 
@@ -158,7 +165,7 @@ __host__ __device__ constexpr int ext_threads(int E) { return E <= 16 ? 512 : (E
 // shared-memory buffer so that the global stores are coalesced.
 template <int E>
 __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lane, uint32_t *sbuf, Emitter &em,
-                                            uint32_t idbase) {
+                                            uint32_t idbase, int events, int64_t stride) {
   using MaskT = typename std::conditional<(E <= 32), uint32_t, unsigned long long>::type;
   uint32_t prevlast = __shfl_up_sync(0xffffffffu, K[E - 1], 1);
   if (lane == 0) prevlast = NOKEY;
@@ -189,6 +196,53 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
     }
   }
   __syncwarp();
+  // binarized rows feeding the matrix-free logistic pass: a run of r > 1 equal keys leaves r - 1 repeat
+  // events (the column of its class) at the tail of the row's slots, in sorted order (while sbuf holds the ids)
+  auto repeat_events = [&]() {
+    uint32_t extra = 0;
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      if ((cls >> r) & 1) {
+        const MaskT bbelow = bnd & (((MaskT)1 << r) - 1);
+        const int st = bbelow ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bbelow) : 63 - __clzll(bbelow))
+                              : start0;
+        const uint32_t cnt = (uint32_t)((int)lane * E + r - st);
+        if (cnt > 1) {
+          const MaskT below = cls & (((MaskT)1 << r) - 1);
+          const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
+          uint32_t col;
+          if (em.column(sbuf[j], col) || !em.filter) extra += cnt - 1;
+        }
+      }
+    }
+    uint32_t incl = extra;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (unsigned)o) incl += y;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (tot == 0) return;
+    uint32_t *tail = em.sid + stride - 1;
+    uint32_t pos = em.ev + incl - extra;
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+      if ((cls >> r) & 1) {
+        const MaskT bbelow = bnd & (((MaskT)1 << r) - 1);
+        const int st = bbelow ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bbelow) : 63 - __clzll(bbelow))
+                              : start0;
+        const uint32_t cnt = (uint32_t)((int)lane * E + r - st);
+        if (cnt > 1) {
+          const MaskT below = cls & (((MaskT)1 << r) - 1);
+          const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
+          uint32_t col;
+          if (em.column(sbuf[j], col) || !em.filter)
+            for (uint32_t x = 1; x < cnt; x++) tail[-(int64_t)(pos++)] = col;
+        }
+      }
+    }
+    em.ev += tot;
+  };
   if (!em.filter) {
     // no class is dropped: slot i of the buffer is entry i of the level
     for (int i = lane; i < total; i += 32) {
@@ -217,6 +271,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
       __syncwarp();
     } else {
       em.sq += (unsigned long long)c; if (c) em.vm = max(em.vm, 1u);
+      if (events) { repeat_events(); __syncwarp(); }
     }
     em.cursor += (uint32_t)total;
     return;
@@ -266,6 +321,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
     __syncwarp();
   } else {
     em.sq += __popcll(keepbits); if (keepbits) em.vm = max(em.vm, 1u);
+    if (events) { repeat_events(); __syncwarp(); }
   }
   em.cursor += kept;
 }
@@ -274,7 +330,8 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
 // ---- the extraction kernel: one warp per sequence ------------------------------------------------
 // E = keys per lane of the register sort (0: no sorted levels, sequences of any length)
 // OPT: the strand operation when it is known at compile time (1 = revcomp, the common case), -1 = P.op
-template <int E, int OPT>
+// EV: binarized rows that also leave their table-level class bitmap and repeat events (XParams::events)
+template <int E, int OPT, bool EV>
 __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParams P) {
   constexpr int EE = E > 0 ? E : 1;
   extern __shared__ __align__(16) uint32_t smem[];
@@ -363,7 +420,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
               else if (op == 2) c = min(c, (~c) & mk);
               const uint32_t bit = 1u << (c & 31);
               const uint32_t old = atomicOr(bm + P.bm_off[k] + (c >> 5), bit);
-              if ((old & bit) && !P.binarize) {
+              if ((old & bit) && (!P.binarize || EV)) {
                 ovf[atomicAdd(dupn, 1u)] = ((uint32_t)k << 26) | c;     // the warp's list of repeats (L2)
               }
             }
@@ -394,6 +451,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
     em.nbx = P.nbx; em.filter = P.filter;
     em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
     em.sq = 0; em.vm = 0;
+    em.ev = 0;
 
     // ---- table levels ---------------------------------------------------------------------------
     if (has_tab) {
@@ -421,7 +479,8 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
           id = e.y;
         }
         // without a frozen list the numbering set is ALL classes: the j-th class of the list is column j
-        em.emit(cnt > 0, id, cnt, P.filter ? -1 : (int64_t)j);
+        const unsigned kept = em.emit(cnt > 0, id, cnt, P.filter ? -1 : (int64_t)j);
+        if (EV && P.lowbits && lane == 0 && active) P.lowbits[row * P.low_words + (base >> 5)] = kept;
       }
       __syncwarp();
     }
@@ -514,6 +573,35 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         }
         __syncwarp();
         if (lane == 0) dupn[0] = 0;
+      } else if (EV) {
+        // binarized rows: every repeat becomes one event = the column of its class, in a deterministic
+        // order (the list order depends on which lane lost the atomicOr): rank by (column, list index)
+        const uint32_t nd = dupn[0];
+        for (uint32_t i = lane; i < nd; i += 32) {
+          const uint32_t e = ovf[i];
+          const uint32_t k = e >> 26, c = e & 0x3FFFFFFu;
+          uint32_t col = NOCOL;
+          if ((bm[P.bm_off[k] + (c >> 5)] >> (c & 31)) & 1u) em.column(P.level_off[k] + c, col);   // else: dropped by the frozen list
+          ovf[i] = col;
+        }
+        __syncwarp();
+        uint32_t mine = 0;
+        for (uint32_t i = lane; i < nd; i += 32) {
+          const uint32_t key = ovf[i];
+          if (key == NOCOL) continue;
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < nd; j++) {
+            const uint32_t kj = ovf[j];
+            rank += (kj < key || (kj == key && j < i)) ? 1u : 0u;
+          }
+          em.sid[P.stride - 1 - (int64_t)rank] = key;
+          mine++;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        em.ev = mine;
+        __syncwarp();
+        if (lane == 0) dupn[0] = 0;
       }
       for (int i = (int)lane * 4; i < P.bm_words; i += 128) *reinterpret_cast<uint4 *>(bm + i) = make_uint4(0, 0, 0, 0);
       __syncwarp();
@@ -531,7 +619,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
           K[r] = (int)(f & 15u) >= k ? c : SENT;
         }
         warp_sort<EE>(K, lane);
-        emit_sorted<EE>(K, lane, tab, em, P.level_off[k]);
+        emit_sorted<EE>(K, lane, tab, em, P.level_off[k], EV ? 1 : 0, P.stride);
       }
     }
     // row statistics (exact integers): what the step size and the fixed-point scale of the gradient need
@@ -544,6 +632,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
       }
       if (lane == 0 && active) {
         P.rowcnt[row] = em.cursor;
+        if (EV) P.rowdup[row] = em.ev;
         if (sq > P.stats[0]) atomicMax(P.stats, sq);
         if ((unsigned long long)vm > P.stats[1]) atomicMax(P.stats + 1, (unsigned long long)vm);
       }
@@ -558,17 +647,17 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
     }
 }
 
-template <int E, int OPT>
+template <int E, int OPT, bool EV>
 void launch_extract_op(const XParams &P) {
   // warps per block: the choice that keeps the most warps resident per SM (the block shares one
   // bitmap of observed classes, every warp brings its own working set)
-  KL_CUDA(cudaFuncSetAttribute((extract_kernel<E, OPT>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  KL_CUDA(cudaFuncSetAttribute((extract_kernel<E, OPT, EV>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   int best_wpb = 0, best_per_sm = 0;
   for (int wpb = ext_threads(E) / 32; wpb >= 1; wpb--) {
     size_t smem = ((size_t)P.obs_words + (size_t)wpb * P.warp_words) * sizeof(uint32_t);
     if (smem > (size_t)227 * 1024) continue;
     int per_sm = 0;
-    KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (extract_kernel<E, OPT>), 32 * wpb, smem));
+    KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (extract_kernel<E, OPT, EV>), 32 * wpb, smem));
     if (per_sm * wpb > best_per_sm * best_wpb) { best_wpb = wpb; best_per_sm = per_sm; }
   }
   KL_REQUIRE(best_wpb > 0, "sequence too long for the shared-memory working set of one warp");
@@ -578,13 +667,18 @@ void launch_extract_op(const XParams &P) {
   int64_t need = (P.n - P.row0 + wpb - 1) / wpb;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
-  KL_LAUNCH((extract_kernel<E, OPT>), (unsigned)blocks, 32 * wpb, smem, P);
+  KL_LAUNCH((extract_kernel<E, OPT, EV>), (unsigned)blocks, 32 * wpb, smem, P);
 }
 
 template <int E>
 void launch_extract(const XParams &P) {
-  if (P.op == 1) launch_extract_op<E, 1>(P);
-  else launch_extract_op<E, -1>(P);
+  if (P.events) {
+    if (P.op == 1) launch_extract_op<E, 1, true>(P);
+    else launch_extract_op<E, -1, true>(P);
+  } else {
+    if (P.op == 1) launch_extract_op<E, 1, false>(P);
+    else launch_extract_op<E, -1, false>(P);
+  }
 }
 
 #endif  // KL_EXTRACT_KERNEL_IMPL

@@ -169,16 +169,30 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
   }
 }
 
-// ---- matrix-free pass (count matrices straight from the extraction, Matrix::imp) --------------------
+// ---- matrix-free pass (matrices straight from the extraction, Matrix::imp) ----------------------------
 // The count of class c in row i is the number of positions p of sequence i whose k-mer belongs to c, so
-//   z_i = theta_0 + sum_p T[len_p][code_p],   T[j][u] = sum_{k=M..j} theta[class of the k-prefix of u]
+//   z_i = theta_0 + sum_p T[len_p][code_p],   T[j][u] = sum_{k=Mlo..j} theta[class of the k-prefix of u]
 //   g_c = sum over the codes u of c and the levels j >= k of F_k, F_k[u] = H_k[u] + sum_x F_{k+1}[4u+x]
 // where (len_p, code_p) = the longest valid k-mer (<= N bases) starting at p and H[len_p][code_p]
-// collects round(w_i S) of every position.  One gather and one RED.64 per POSITION instead of one per
-// stored entry per level, no CSR traffic at all; the integer sums are exact, so the result equals
-// sum_i round(w_i S) count_ic bit for bit in any order.
+// collects round(w_i S) of every position.  No CSR traffic at all; the integer sums are exact, so the
+// result equals sum_i round(w_i S) count_ic bit for bit in any order.
+//
+// SUPER K-MERS: c = S - N + 1 consecutive positions whose S bases are all valid share ONE table entry,
+//   TS[U] = sum_{t<c} T[N][N-mer at offset t of U],   HS[U] += round(w_i S)
+// (U = the S-mer starting at the first of them; HS is scattered back into H[N] before the level fold), so a
+// row costs one gather and one RED.64 per GROUP of c positions instead of one per position; the positions of
+// a group that reaches past the end of the row or over an invalid base fall back to their own entries.
+//
+// BINARIZED rows (x_ic = [count_ic > 0]): the levels k >= Mlo = 6 are the count formulation minus one
+// correction per REPEAT of a class inside a row (the extraction leaves the columns of those repeats in
+// Implicit::events: theta is subtracted once per event, round(w_i S) likewise); the table levels
+// (k <= 5, where nearly every class of a row repeats) are a per-row bitmap over their classes: X theta through
+// sums precomputed per 4-bit group of the bitmap (lowtab), X^T w by low_accumulate from the stored q_i.
 struct ImpParams {
   int M, N, op;
+  int Mlo;                 // first matrix-free level
+  int S, c;                // super k-mer length, positions per group (c = S - N + 1; c = 1: S = N)
+  uint32_t sup0;           // table offset of the super level (c = 1: the offset of level N itself)
   uint32_t level_off[16], fo[16];
 };
 
@@ -188,11 +202,11 @@ __global__ void imp_build_T(const ImpParams P, const uint32_t *__restrict__ bitm
   if (st && st->done == 1) return;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
-  int j = P.M;
+  int j = P.Mlo;
   while (j < P.N && t >= (int64_t)P.fo[j + 1]) j++;
   const uint32_t u = (uint32_t)(t - P.fo[j]);
   double s = 0.0;
-  for (int k = P.M; k <= j; k++) {
+  for (int k = P.Mlo; k <= j; k++) {
     uint32_t c = u >> (2 * (j - k));
     if (P.op) c = min(c, kmer_op(c, k, P.op));
     const uint32_t id = P.level_off[k] + c, w = bitmap[id >> 5], bit = 1u << (id & 31);
@@ -201,107 +215,317 @@ __global__ void imp_build_T(const ImpParams P, const uint32_t *__restrict__ bitm
   T[t] = s;
 }
 
-// rolling window over the packed bases of one sequence (forward code + invalid mask)
-struct ImpRoller {
-  const uint32_t *b2;
-  const uint16_t *iv;
-  int L, N, M, cw;
-  uint32_t FW, IV, word, ivw, maskN, maskNb;
-  __device__ __forceinline__ void init(const uint32_t *b, const uint16_t *v, int len, int n, int m) {
-    b2 = b; iv = v; L = len; N = n; M = m; cw = -1; FW = 0; IV = 0xFFFFFFFFu; word = 0; ivw = 0;
-    maskN = (1u << (2 * n)) - 1u; maskNb = (1u << n) - 1u;
+// TS[U] = sum of the level-N entries of the c N-mers inside the S-mer U
+__global__ void imp_build_TS(const ImpParams P, double *__restrict__ T, const PgState *st) {
+  if (st && st->done == 1) return;
+  const uint32_t U = blockIdx.x * blockDim.x + threadIdx.x;
+  if (U >= (1u << (2 * P.S))) return;
+  const uint32_t maskN = (1u << (2 * P.N)) - 1u;
+  const double *TN = T + P.fo[P.N];
+  double s = 0.0;
+  for (int t = 0; t < P.c; t++) s += TN[(U >> (2 * (P.S - P.N - t))) & maskN];
+  T[P.sup0 + U] = s;
+}
+
+// H[N][N-mer at offset t of U] += HS[U]
+__global__ void imp_fold_super(const ImpParams P, unsigned long long *__restrict__ H, const PgState *st) {
+  if (st && st->done == 1) return;
+  const uint32_t U = blockIdx.x * blockDim.x + threadIdx.x;
+  if (U >= (1u << (2 * P.S))) return;
+  const unsigned long long h = H[P.sup0 + U];
+  if (!h) return;
+  const uint32_t maskN = (1u << (2 * P.N)) - 1u;
+  for (int t = 0; t < P.c; t++) atomicAdd(H + P.fo[P.N] + ((U >> (2 * (P.S - P.N - t))) & maskN), h);
+}
+
+// binarized rows: lowtab[(i * 16 + v) * lwp + l] = sum of theta over the classes (l * 32 + 4 i + b) with bit b
+// of v set -- X theta of the table levels is 8 shared-memory reads per bitmap word
+__global__ void imp_build_low(const uint32_t *__restrict__ lowcol, int low_words, int lwp,
+                              const double *__restrict__ theta, double *__restrict__ lowtab, const PgState *st) {
+  if (st && st->done == 1) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 128 * lwp) return;
+  const int l = e % lwp, v = (e / lwp) & 15, i = e / (16 * lwp);
+  double s = 0.0;
+  if (l < low_words)
+    for (int b = 0; b < 4; b++)
+      if ((v >> b) & 1) {
+        const uint32_t col = lowcol[l * 32 + 4 * i + b];
+        if (col != NOCOL) s += theta[col + 1];
+      }
+  lowtab[e] = s;
+}
+
+constexpr uint32_t IMP_NOIDX = 0xFFFFFFFFu, IMP_SINGLES = 0xFFFFFFFEu;
+
+// A lane's view of a row: up to 32 consecutive bases starting at p0, digit-reversed so that the first base
+// sits in the two top bits (a k-mer starting at base x of the window is a shift and a mask: code order,
+// first base most significant), and one "not usable" bit per base (invalid letter, or past the end of the row).
+struct ImpWindow {
+  unsigned long long rev;
+  uint32_t inv;
+  __device__ __forceinline__ void load(const uint32_t *__restrict__ b2, const uint16_t *__restrict__ iv, int L, int p0) {
+    if (p0 >= L) { rev = 0ull; inv = 0xFFFFFFFFu; return; }     // (and no load past the row)
+    const int wi = p0 >> 4, sh = p0 & 15;
+    const uint32_t w0 = __ldg(b2 + wi), w1 = __ldg(b2 + wi + 1), w2 = __ldg(b2 + wi + 2);
+    const uint32_t lo = __funnelshift_r(w0, w1, 2 * sh), hi = __funnelshift_r(w1, w2, 2 * sh);
+    rev = ((unsigned long long)swap_pairs(__brev(lo)) << 32) | swap_pairs(__brev(hi));
+    const unsigned long long iw = (unsigned long long)__ldg(iv + wi) | ((unsigned long long)__ldg(iv + wi + 1) << 16) |
+                                  ((unsigned long long)__ldg(iv + wi + 2) << 32);
+    inv = (uint32_t)(iw >> sh);
+    const int left = L - p0;                    // bases of the row from p0 on
+    if (left < 32) inv |= 0xFFFFFFFFu << left;
   }
-  __device__ __forceinline__ void consume(int idx) {
-    uint32_t x = 0, inv = 1;
-    if ((unsigned)idx < (unsigned)L) {
-      if ((idx >> 4) != cw) { cw = idx >> 4; word = __ldg(b2 + cw); ivw = __ldg(iv + cw); }
-      x = (word >> (2 * (idx & 15))) & 3u; inv = (ivw >> (idx & 15)) & 1u;
-    }
-    FW = ((FW << 2) | x) & maskN;
-    IV = (IV << 1) | inv;
-  }
-  // table index of the longest valid k-mer starting at the first base of the window, or NOIDX
-  __device__ __forceinline__ uint32_t index(const uint32_t *fo) const {
-    const int lf = N - 32 + __clz(IV & maskNb);
-    return lf >= M ? fo[lf] + (FW >> (2 * (N - lf))) : 0xFFFFFFFFu;
+  // the k bases starting at base x of the window (x + k <= 32)
+  __device__ __forceinline__ uint32_t code(int x, int k) const {
+    return (uint32_t)(rev >> (64 - 2 * (x + k))) & ((1u << (2 * k)) - 1u);
   }
 };
 
-// one warp per sequence; lane = a contiguous stretch of positions.  CACHE > 0: the table index of every
-// position stays in registers between the gather and the scatter (rows of up to 32*CACHE-N+1 bases);
-// CACHE = 0: the window is rolled twice (rows of any length)
-template <int CACHE>
-__global__ void __launch_bounds__(256) imp_pass(const ImpParams P, int64_t n, const int64_t *__restrict__ len,
-                                                const int64_t *__restrict__ blk, const uint32_t *__restrict__ bits2,
-                                                const uint16_t *__restrict__ inv16, const double *__restrict__ T,
-                                                const double *__restrict__ theta, const uint8_t *__restrict__ labels,
-                                                double cw0, double cw1, double inv_n, double scale,
-                                                unsigned long long *__restrict__ H, unsigned long long *__restrict__ G,
-                                                double *__restrict__ lossterm, const PgState *st, int scatter) {
-  if (st && st->done == 1) return;
+// group at base x of the window = c positions.  Table index of its super k-mer, IMP_SINGLES when the S bases
+// are not all usable, IMP_NOIDX when the group starts past the end of the row
+__device__ __forceinline__ uint32_t imp_group(const ImpParams &P, const ImpWindow &W, int x) {
+  const uint32_t bits = (W.inv >> x) & ((1u << P.S) - 1u);
+  return bits == 0u ? P.sup0 + W.code(x, P.S) : IMP_SINGLES;
+}
+// position at base x of the window: table index of the longest valid k-mer starting there (x + N <= 32)
+__device__ __forceinline__ uint32_t imp_single(const ImpParams &P, const ImpWindow &W, int x) {
+  const uint32_t bits = W.inv >> x;
+  int lf = bits ? __ffs(bits) - 1 : P.N;
+  if (lf > P.N) lf = P.N;
+  if (lf < P.Mlo) return IMP_NOIDX;
+  return P.fo[lf] + W.code(x, lf);
+}
+
+struct ImpArgs {
+  int64_t n;
+  const int64_t *len, *blk;
+  const uint32_t *bits2;
+  const uint16_t *inv16;
+  const double *T, *theta;
+  const uint8_t *labels;
+  double cw0, cw1, inv_n, scale;
+  unsigned long long *H, *G;
+  double *lossterm;
+  const PgState *st;
+  int scatter;
+  int rpb;                     // rows per block
+  int gw;                      // groups per window: (gw - 1) c + S <= 32
+  // binarized rows
+  const uint32_t *lowbits;
+  int low_words, lwp;
+  const double *lowtab;
+  const int64_t *evptr;
+  const uint32_t *events;
+  unsigned long long *q_out;
+};
+
+constexpr int IMP_R = 2;           // rows per warp and round
+
+// One warp per sequence, 8 warps per block; block b owns the rows [b rpb, (b+1) rpb) and works through them in
+// rounds of 8 IMP_R rows: (A) every warp decodes its rows and gathers, (B) the weights of all rows of the round
+// are computed together -- the fp64 exp / log1p of a row are ~300 instructions for ONE lane, a third of the
+// whole row when every warp did them for itself -- (C) every warp scatters.  A fine grid of short blocks: the
+// hardware block scheduler balances the SMs.  A lane owns CONSECUTIVE groups of its row, so one 64-bit window of
+// packed bases (digit-reversed once) serves all of them.
+// CACHE > 0: the lane's groups fit one window and their table indices stay in registers between gather and
+// scatter (rows of up to 32 CACHE groups); CACHE = 0: window after window, decoded twice (rows of any length).
+template <int CACHE, bool BIN>
+__global__ void __launch_bounds__(256) imp_pass(const ImpParams P, const ImpArgs A) {
+  if (A.st && A.st->done == 1) return;
   constexpr int CC = CACHE > 0 ? CACHE : 1;
-  constexpr uint32_t NOIDX = 0xFFFFFFFFu;
+  constexpr int RR = 8 * IMP_R;
+  extern __shared__ double s_low[];
+  __shared__ double s_z[RR];
+  __shared__ unsigned long long s_q[RR];
+  __shared__ unsigned long long s_bias;
+  if (BIN)
+    for (int i = threadIdx.x; i < 128 * A.lwp; i += blockDim.x) s_low[i] = A.lowtab[i];
+  if (threadIdx.x == 0) s_bias = 0ull;
+  __syncthreads();
   const unsigned lane = lane_id();
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int N = P.N;
+  const int wib = threadIdx.x >> 5;
+  const int c = P.c;
   long long bias_acc = 0;
-  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
-    const int L = (int)len[row];
-    const uint32_t *b2 = bits2 + blk[row] * 4;
-    const uint16_t *iv = inv16 + blk[row] * 4;
-    // the window after base u is [u-N+1, u]; the k-mers starting at its first base are its prefixes
-    const int total_steps = L + N - 1, steps = (total_steps + 31) / 32, u0 = (int)lane * steps;
-    uint32_t IDX[CC];
-    double s = 0.0;
-    {
-      ImpRoller R; R.init(b2, iv, L, N, P.M);
-      for (int idx = u0 - N + 1; idx < u0; idx++) R.consume(idx);
+  const int64_t first = (int64_t)blockIdx.x * A.rpb, last = first + A.rpb < A.n ? first + A.rpb : A.n;
+  for (int64_t base = first; base < last; base += RR) {
+    ImpWindow W[IMP_R];
+    uint32_t IDX[IMP_R][CC];
+    int gpl[IMP_R];                         // groups per lane of the row
+    // ---- (A) decode + gather ----
+#pragma unroll
+    for (int r = 0; r < IMP_R; r++) {
+      const int64_t row = base + wib * IMP_R + r;
+      gpl[r] = 0;
+      if (row >= last) continue;
+      const int L = (int)A.len[row];
+      const uint32_t *b2 = A.bits2 + A.blk[row] * 4;
+      const uint16_t *iv = A.inv16 + A.blk[row] * 4;
+      const int ngroups = P.Mlo <= P.N ? (L + c - 1) / c : 0;
+      const int G = (ngroups + 31) >> 5;
+      gpl[r] = G;
+      const int p0 = (int)lane * G * c;
+      double s = 0.0;
+      if (CACHE > 0) {
+        W[r].load(b2, iv, L, p0);
+#pragma unroll
+        for (int i = 0; i < CC; i++) {
+          uint32_t ix = IMP_NOIDX;
+          if (i < G) {
+            ix = imp_group(P, W[r], i * c);
+            if (ix == IMP_SINGLES)
+              for (int t = 0; t < c; t++) {
+                const uint32_t i1 = imp_single(P, W[r], i * c + t);
+                if (i1 != IMP_NOIDX) s += __ldg(A.T + i1);
+              }
+          }
+          IDX[r][i] = ix;
+        }
+#pragma unroll
+        for (int i = 0; i < CC; i++)
+          if (IDX[r][i] < IMP_SINGLES) s += __ldg(A.T + IDX[r][i]);
+      } else {
+        for (int g0 = 0; g0 < G; g0 += A.gw) {
+          ImpWindow V;
+          V.load(b2, iv, L, p0 + g0 * c);
+          const int ge = G - g0 < A.gw ? G - g0 : A.gw;
+          for (int i = 0; i < ge; i++) {
+            const uint32_t ix = imp_group(P, V, i * c);
+            if (ix == IMP_SINGLES) {
+              for (int t = 0; t < c; t++) {
+                const uint32_t i1 = imp_single(P, V, i * c + t);
+                if (i1 != IMP_NOIDX) s += __ldg(A.T + i1);
+              }
+            } else if (ix != IMP_NOIDX) s += __ldg(A.T + ix);
+          }
+        }
+      }
+      if (BIN) {
+        // table levels: 8 precomputed sums per word of the row's class bitmap
+        for (int l = (int)lane; l < A.low_words; l += 32) {
+          const uint32_t w = __ldcs(A.lowbits + row * A.low_words + l);
+#pragma unroll
+          for (int i = 0; i < 8; i++) s += s_low[(i * 16 + ((w >> (4 * i)) & 15u)) * A.lwp + l];
+        }
+        // repeats of a class inside the row: the count formulation counted them, a binarized row does not
+        const int64_t e0 = A.evptr[row];
+        const uint32_t nd = (uint32_t)(A.evptr[row + 1] - e0);
+        for (uint32_t e = lane; e < nd; e += 32) s -= __ldg(A.theta + A.events[e0 + e] + 1);
+      }
+      s = warp_sum_down(s);
+      if (lane == 0) s_z[wib * IMP_R + r] = s;
+    }
+    __syncthreads();
+    // ---- (B) Gradient weight (:166-178) and Loss term (:257-263) of the round's rows, one lane per row ----
+    if (threadIdx.x < RR && base + threadIdx.x < last) {
+      const int64_t row = base + threadIdx.x;
+      const double z = A.theta[0] + s_z[threadIdx.x], r = -log_add0(-z);
+      double w;
+      if (A.labels[row]) { w = A.inv_n * A.cw1 * (exp(r) - 1.0); A.lossterm[row] = -A.cw1 * r; }
+      else               { w = A.inv_n * A.cw0 * exp(r);         A.lossterm[row] = A.cw0 * log_add0(z); }
+      const unsigned long long q = (unsigned long long)__double2ll_rn(w * A.scale);
+      s_q[threadIdx.x] = q;
+      if (A.scatter) { bias_acc += (long long)q; if (BIN) A.q_out[row] = q; }
+    }
+    __syncthreads();
+    if (!A.scatter) continue;               // loss-only pass (the hook after the last iteration)
+    // ---- (C) scatter ----
+#pragma unroll
+    for (int r = 0; r < IMP_R; r++) {
+      const int64_t row = base + wib * IMP_R + r;
+      if (row >= last) continue;
+      const unsigned long long q = s_q[wib * IMP_R + r];
+      const int G = gpl[r];
       if (CACHE > 0) {
 #pragma unroll
         for (int i = 0; i < CC; i++) {
-          uint32_t ix = NOIDX;
-          if (i < steps && u0 + i < total_steps) { R.consume(u0 + i); ix = R.index(P.fo); }
-          IDX[i] = ix;
-          if (ix != NOIDX) s += __ldg(T + ix);
+          if (IDX[r][i] < IMP_SINGLES) atomicAdd(A.H + IDX[r][i], q);
+          else if (IDX[r][i] == IMP_SINGLES)
+            for (int t = 0; t < c; t++) {
+              const uint32_t i1 = imp_single(P, W[r], i * c + t);
+              if (i1 != IMP_NOIDX) atomicAdd(A.H + i1, q);
+            }
         }
       } else {
-        for (int i = 0; i < steps && u0 + i < total_steps; i++) {
-          R.consume(u0 + i);
-          const uint32_t ix = R.index(P.fo);
-          if (ix != NOIDX) s += __ldg(T + ix);
+        const int L = (int)A.len[row];
+        const uint32_t *b2 = A.bits2 + A.blk[row] * 4;
+        const uint16_t *iv = A.inv16 + A.blk[row] * 4;
+        const int p0 = (int)lane * G * c;
+        for (int g0 = 0; g0 < G; g0 += A.gw) {
+          ImpWindow V;
+          V.load(b2, iv, L, p0 + g0 * c);
+          const int ge = G - g0 < A.gw ? G - g0 : A.gw;
+          for (int i = 0; i < ge; i++) {
+            const uint32_t ix = imp_group(P, V, i * c);
+            if (ix == IMP_SINGLES) {
+              for (int t = 0; t < c; t++) {
+                const uint32_t i1 = imp_single(P, V, i * c + t);
+                if (i1 != IMP_NOIDX) atomicAdd(A.H + i1, q);
+              }
+            } else if (ix != IMP_NOIDX) atomicAdd(A.H + ix, q);
+          }
         }
       }
-    }
-    s = warp_sum_down(s);
-    double w = 0.0;
-    if (lane == 0) {
-      // Gradient weight (:166-178) and Loss term (:257-263)
-      double z = theta[0] + s, r = -log_add0(-z);
-      if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lossterm[row] = -cw1 * r; }
-      else             { w = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
-    }
-    if (!scatter) continue;               // loss-only pass (the hook after the last iteration)
-    w = __shfl_sync(0xffffffffu, w, 0);
-    const unsigned long long q = (unsigned long long)__double2ll_rn(w * scale);
-    if (lane == 0) bias_acc += (long long)q;
-    if (CACHE > 0) {
-#pragma unroll
-      for (int i = 0; i < CC; i++)
-        if (IDX[i] != NOIDX) atomicAdd(H + IDX[i], q);
-    } else {
-      ImpRoller R; R.init(b2, iv, L, N, P.M);
-      for (int idx = u0 - N + 1; idx < u0; idx++) R.consume(idx);
-      for (int i = 0; i < steps && u0 + i < total_steps; i++) {
-        R.consume(u0 + i);
-        const uint32_t ix = R.index(P.fo);
-        if (ix != NOIDX) atomicAdd(H + ix, q);
+      if (BIN) {
+        const unsigned long long nq = 0ull - q;
+        const int64_t e0 = A.evptr[row];
+        const uint32_t nd = (uint32_t)(A.evptr[row + 1] - e0);
+        for (uint32_t e = lane; e < nd; e += 32) atomicAdd(A.G + A.events[e0 + e] + 1, nq);
       }
     }
   }
-  if (lane == 0 && bias_acc != 0) atomicAdd(&G[0], (unsigned long long)bias_acc);
+  // bias column: one atomic per block
+  if (bias_acc != 0) atomicAdd(&s_bias, (unsigned long long)bias_acc);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_bias != 0ull) atomicAdd(&A.G[0], s_bias);
 }
 
-// F_j[u] = H_j[u] + F_{j+1}[4u .. 4u+3], in place, one launch per level from N-1 down to M
+// binarized rows, table levels: G[column of class j] += sum_i q_i [bit j of row i].  A warp walks rows; lane l
+// owns word w0 + l of the row's bitmap and keeps one 64-bit accumulator per bit in registers (no atomics in
+// the loop); the warps of a block are summed in shared memory, one atomic per class and block at the end.
+// (Folding this into imp_pass -- register accumulators per thread, flushed per block -- made the pass slower
+// than the two kernels together: 4.86 vs 3.8 + 0.65 ms at C3; imp_pass is bound by its scattered accesses and
+// lost a resident block per SM to the extra registers.)
+__global__ void __launch_bounds__(256) low_accumulate(const uint32_t *__restrict__ lowbits, int low_words, int w0, int64_t n,
+                                                      const unsigned long long *__restrict__ q,
+                                                      const uint32_t *__restrict__ lowcol, unsigned long long *__restrict__ G,
+                                                      const PgState *st) {
+  if (st && st->done == 1) return;
+  __shared__ unsigned long long sacc[32 * 32];
+  const unsigned lane = lane_id();
+  const int word = w0 + (int)lane, wib = threadIdx.x >> 5;
+  const bool on = word < low_words;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long acc[32];
+#pragma unroll
+  for (int b = 0; b < 32; b++) acc[b] = 0ull;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
+    const unsigned long long qq = q[row];
+    const uint32_t w = on ? __ldcs(lowbits + row * low_words + word) : 0u;
+#pragma unroll
+    for (int b = 0; b < 32; b++)
+      if ((w >> b) & 1u) acc[b] += qq;
+  }
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sacc[i] = 0ull;
+  __syncthreads();
+  for (int v = 0; v < (int)(blockDim.x >> 5); v++) {
+    if (wib == v) {
+#pragma unroll
+      for (int b = 0; b < 32; b++) sacc[b * 32 + lane] += acc[b];
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const int b = i >> 5, l = i & 31;
+    const unsigned long long v = sacc[i];
+    if (v && w0 + l < low_words) {
+      const uint32_t col = lowcol[(w0 + l) * 32 + b];
+      if (col != NOCOL) atomicAdd(G + col + 1, v);
+    }
+  }
+}
+
+// F_j[u] = H_j[u] + F_{j+1}[4u .. 4u+3], in place, one launch per level from N-1 down to Mlo
 __global__ void imp_fold_level(const ImpParams P, int j, unsigned long long *__restrict__ H, const PgState *st) {
   if (st && st->done == 1) return;
   const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,7 +534,8 @@ __global__ void imp_fold_level(const ImpParams P, int j, unsigned long long *__r
   H[P.fo[j] + u] += c[0] + c[1] + c[2] + c[3];
 }
 
-// G[col + 1] = F_k[code] + F_k[image(code)]
+// G[col + 1] += F_k[code] + F_k[image(code)] for the columns of the matrix-free levels (G holds the repeat
+// corrections of binarized rows by now, zero otherwise)
 __global__ void imp_columns(const ImpParams P, const uint32_t *__restrict__ col_id, int64_t m,
                             const unsigned long long *__restrict__ F, unsigned long long *__restrict__ G,
                             const PgState *st) {
@@ -320,10 +545,11 @@ __global__ void imp_columns(const ImpParams P, const uint32_t *__restrict__ col_
   const uint32_t id = col_id[j];
   int k = P.M;
   while (k < P.N && id >= P.level_off[k + 1]) k++;
+  if (k < P.Mlo) return;
   const uint32_t c = id - P.level_off[k];
   unsigned long long g = F[P.fo[k] + c];
   if (P.op) { const uint32_t r = kmer_op(c, k, P.op); if (r != c) g += F[P.fo[k] + r]; }
-  G[j + 1] = g;
+  G[j + 1] += g;
 }
 
 // pair mode: the weights come from the pair-aware rows kernel; same fixed-point accumulation
@@ -399,21 +625,30 @@ __global__ void sum_ranks(const double *__restrict__ gathered, int world, int64_
 }
 
 // hook (kmerLr_estimator_hook.go:46-99): loss = mean + lambda * sum_{j=1..m} |theta_j|
-__global__ void hook_kernel(PgState *st, const double *__restrict__ losssum, const double *__restrict__ theta,
-                            int64_t m, double inv_n, double lambda, double eps_loss) {
-  if (st->done == 1) return;
+// l1part[b] = sum over block b's stride of lambda |theta_j|, j >= 1 (fixed order: deterministic)
+__global__ void l1_partials(const PgState *st, const double *__restrict__ theta, int64_t ntheta, double lambda,
+                            double *__restrict__ l1part) {
+  if (st && st->done == 1) return;
   __shared__ double sh[256];
   double s = 0.0;
   if (!isnan(lambda) && lambda != 0.0)
-    for (int64_t j = 1 + threadIdx.x; j < m + 1; j += blockDim.x) s += lambda * fabs(theta[j]);
+    for (int64_t j = 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < ntheta; j += (int64_t)gridDim.x * blockDim.x)
+      s += lambda * fabs(theta[j]);
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
+  if (threadIdx.x == 0) l1part[blockIdx.x] = sh[0];
+}
+__global__ void hook_kernel(PgState *st, const double *__restrict__ losssum, const double *__restrict__ l1part, int nparts,
+                            double inv_n, double eps_loss) {
+  if (st->done == 1) return;
   if (threadIdx.x == 0) {
-    double l = losssum[0] * inv_n + sh[0];
+    double l1 = 0.0;
+    for (int b = 0; b < nparts; b++) l1 += l1part[b];
+    double l = losssum[0] * inv_n + l1;
     st->lossval = l;
     if (st->first) { st->first = 0; return; }   // loss at the start point: no hook call yet
     double t = st->loss_old; st->loss_old = st->loss_new; st->loss_new = t;
@@ -804,7 +1039,8 @@ constexpr int PROX_BLOCKS = 64;
 struct Work {
   DevBuf<double> theta, w, lossterm, g, red, scalars, gathered, blockmax;
   DevBuf<unsigned long long> G, H;     // H: forward-code tables of the matrix-free pass
-  DevBuf<double> T;
+  DevBuf<double> T, lowtab;
+  DevBuf<unsigned long long> q;        // binarized rows: round(w_i S) of every row, for low_accumulate
   double scale = 1.0, inv_scale = 1.0;
 };
 
@@ -849,36 +1085,87 @@ void set_scale(Matrix &M, Work &wk, const double cw[2]) {
   wk.inv_scale = std::ldexp(1.0, -e);
 }
 
-// kmerlr_option("implicit", 0) or KMERLR_IMPLICIT=0 forces the CSR kernel (tests compare the two)
+// kmerlr_option("implicit", 0) or KMERLR_IMPLICIT=0 forces the pass over the stored rows (tests compare the two)
 bool use_implicit(const Matrix &M) {
   static int env = -1;
   if (env < 0) { const char *e = getenv("KMERLR_IMPLICIT"); env = (e && *e == '0') ? 0 : 1; }
-  return env == 1 && ctx().implicit_ok && M.imp && M.vt == VAL_U32 && M.n > 0;
+  if (!(env == 1 && ctx().implicit_ok && M.imp && M.n > 0)) return false;
+  return M.imp->binarized ? M.vt == VAL_ONE : M.vt == VAL_U32;
+}
+
+// length of the super k-mer tables for k-mers of up to N bases: 4^S entries of 8 bytes for T and for H must
+// stay L2 resident (S = 10: 8 MB each, S = 11: 32 MB each)
+int super_length(int N) {
+  int S = ctx().super_len;
+  if (S < 0) S = N <= 8 ? 10 : IMP_SUPER_MAX;
+  if (S > IMP_SUPER_MAX) S = IMP_SUPER_MAX;
+  return S < N ? N : S;
+}
+
+template <int CACHE, bool BIN>
+void launch_imp_pass(const ImpParams &P, const ImpArgs &A, size_t smem) {
+  if (smem > 48 * 1024)
+    KL_CUDA(cudaFuncSetAttribute((imp_pass<CACHE, BIN>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = (A.n + A.rpb - 1) / A.rpb;
+  KL_LAUNCH((imp_pass<CACHE, BIN>), (unsigned)blocks, 256, smem, P, A);
 }
 
 void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st, int scatter) {
   const Implicit &I = *M.imp;
   const SeqSet &S = *I.seqs;
   ImpParams P{};
-  P.M = I.M; P.N = I.N; P.op = I.op;
+  P.M = I.M; P.N = I.N; P.op = I.op; P.Mlo = I.Mlo;
   for (int k = 0; k < 16; k++) { P.level_off[k] = I.level_off[k]; P.fo[k] = I.fo[k]; }
-  const int64_t total = I.fo[I.N + 1];
-  if (!wk.T.p) { wk.T.alloc((size_t)total); wk.H.alloc((size_t)total); }
-  if (scatter) KL_CUDA(cudaMemsetAsync(wk.H.p, 0, (size_t)total * sizeof(unsigned long long), ctx().stream));
-  KL_LAUNCH(imp_build_T, (unsigned)((total + 255) / 256), 256, 0, P, I.bitmap.p, I.rank.p, wk.theta.p, wk.T.p, total, st);
-  const int64_t steps = (S.max_len + I.N - 1 + 31) / 32;
-  // many small blocks: the hardware block scheduler evens out the tail (64 per SM: 1.06 ms at C2, 8 per SM: 1.23 ms)
-  int64_t blocks = (int64_t)ctx().sm_count * 64, need = (M.n + 7) / 8;
-  if (blocks > need) blocks = need;
-  const double inv_n = 1.0 / (double)M.n_global;
-  if (steps <= 16)
-    KL_LAUNCH((imp_pass<16>), (unsigned)blocks, 256, 0, P, M.n, S.len.p, S.blk.p, S.bits2.p, S.inv16.p, wk.T.p, wk.theta.p,
-              M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st, scatter);
-  else
-    KL_LAUNCH((imp_pass<0>), (unsigned)blocks, 256, 0, P, M.n, S.len.p, S.blk.p, S.bits2.p, S.inv16.p, wk.T.p, wk.theta.p,
-              M.labels.p, cw[0], cw[1], inv_n, wk.scale, wk.H.p, wk.G.p, wk.lossterm.p, st, scatter);
+  const bool levels = I.Mlo <= I.N;            // (a binarized matrix with N <= 5 has table levels only)
+  P.S = levels ? super_length(I.N) : I.N;
+  P.c = P.S - I.N + 1;
+  const int64_t tlev = levels ? I.fo[I.N + 1] : 0, tsup = P.c > 1 ? (int64_t)1 << (2 * P.S) : 0, total = tlev + tsup;
+  P.sup0 = P.c > 1 ? (uint32_t)tlev : I.fo[I.N];
+  if (wk.T.n < (size_t)(total ? total : 1)) { wk.T.alloc((size_t)(total ? total : 1)); wk.H.alloc((size_t)(total ? total : 1)); }
+  if (scatter && total) KL_CUDA(cudaMemsetAsync(wk.H.p, 0, (size_t)total * sizeof(unsigned long long), ctx().stream));
+  if (levels) {
+    KL_LAUNCH(imp_build_T, (unsigned)((tlev + 255) / 256), 256, 0, P, I.bitmap.p, I.rank.p, wk.theta.p, wk.T.p, tlev, st);
+    if (P.c > 1) KL_LAUNCH(imp_build_TS, (unsigned)((tsup + 255) / 256), 256, 0, P, wk.T.p, st);
+  }
+  ImpArgs A{};
+  A.n = M.n; A.len = S.len.p; A.blk = S.blk.p; A.bits2 = S.bits2.p; A.inv16 = S.inv16.p;
+  A.T = wk.T.p; A.theta = wk.theta.p; A.labels = M.labels.p;
+  A.cw0 = cw[0]; A.cw1 = cw[1]; A.inv_n = 1.0 / (double)M.n_global; A.scale = wk.scale;
+  A.H = wk.H.p; A.G = wk.G.p; A.lossterm = wk.lossterm.p; A.st = st; A.scatter = scatter;
+  // rows per block: 8 warps x 4 rows; binarized rows amortise the block's copy of lowtab (32 KB) over 16 per warp
+  A.rpb = I.binarized ? 128 : 32;
+  while ((M.n + A.rpb - 1) / A.rpb > 0x7fffffffLL) A.rpb *= 2;
+  size_t smem = 0;
+  if (I.binarized) {
+    A.lowbits = I.lowbits.p; A.low_words = I.low_words; A.lwp = I.low_words <= 32 ? 32 : 64;
+    if (!wk.lowtab.p) { wk.lowtab.alloc((size_t)128 * 64); wk.q.alloc((size_t)M.n); }
+    A.lowtab = wk.lowtab.p; A.evptr = I.evptr.p; A.events = I.events.p; A.q_out = wk.q.p;
+    smem = (size_t)128 * A.lwp * sizeof(double);
+    KL_LAUNCH(imp_build_low, (unsigned)((128 * A.lwp + 255) / 256), 256, 0, I.lowcol.p, I.low_words, A.lwp, wk.theta.p,
+              wk.lowtab.p, st);
+  }
+  // a lane's groups share one 64-bit window of bases when (groups - 1) c + S <= 32
+  A.gw = (32 - P.S) / P.c + 1;
+  const int64_t groups_per_lane = ((S.max_len + P.c - 1) / P.c + 31) / 32;
+  const int64_t cached = groups_per_lane <= A.gw ? groups_per_lane : 1000;
+  if (I.binarized) {
+    if (cached <= 4) launch_imp_pass<4, true>(P, A, smem);
+    else if (cached <= 8) launch_imp_pass<8, true>(P, A, smem);
+    else launch_imp_pass<0, true>(P, A, smem);
+  } else {
+    if (cached <= 4) launch_imp_pass<4, false>(P, A, smem);
+    else if (cached <= 8) launch_imp_pass<8, false>(P, A, smem);
+    else launch_imp_pass<0, false>(P, A, smem);
+  }
   if (!scatter) return;
-  for (int j = I.N - 1; j >= I.M; j--)
+  if (I.binarized)
+    for (int w0 = 0; w0 < I.low_words; w0 += 32)
+      KL_LAUNCH(low_accumulate, (unsigned)(ctx().sm_count * 2), 256, 0, I.lowbits.p, I.low_words, w0, M.n, wk.q.p, I.lowcol.p,
+                wk.G.p, st);
+  if (!scatter) return;
+  if (!levels) return;
+  if (P.c > 1) KL_LAUNCH(imp_fold_super, (unsigned)((tsup + 255) / 256), 256, 0, P, wk.H.p, st);
+  for (int j = I.N - 1; j >= I.Mlo; j--)
     KL_LAUNCH(imp_fold_level, (unsigned)(((1u << (2 * j)) + 255) / 256), 256, 0, P, j, wk.H.p, st);
   KL_LAUNCH(imp_columns, (unsigned)((M.m + 255) / 256), 256, 0, P, M.class_ids.p, M.m, wk.H.p, wk.G.p, st);
 }
@@ -919,7 +1206,7 @@ void alloc_work(const Matrix &M, int64_t ntheta, Work &wk) {
   wk.G.alloc((size_t)M.m + 2);      // + the row ticket of fused_kernel
   wk.red.alloc(RED_BLOCKS);
   wk.scalars.alloc(8);
-  wk.blockmax.alloc(3 * PROX_BLOCKS);
+  wk.blockmax.alloc(4 * PROX_BLOCKS);    // max |theta|, max |delta|, NaN flag per block + the L1 partials of the hook
   wk.gathered.alloc((size_t)(M.sharded ? ntheta * ctx().world : 1));
 }
 
@@ -1134,7 +1421,8 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
         using VT = typename std::remove_pointer<decltype(tag)>::type;
         launch_fused<VT>(M, wk, cw, st.p, scatter);
         reduce_sum(M, wk.lossterm.p, M.n, wk, wk.scalars.p, st.p);
-        KL_LAUNCH(hook_kernel, 1, 256, 0, st.p, wk.scalars.p, wk.theta.p, M.m, inv_n, lambda, epsilon_loss);
+        KL_LAUNCH(l1_partials, PROX_BLOCKS, 256, 0, st.p, wk.theta.p, M.m + 1, lambda, wk.blockmax.p + 3 * PROX_BLOCKS);
+        KL_LAUNCH(hook_kernel, 1, 32, 0, st.p, wk.scalars.p, wk.blockmax.p + 3 * PROX_BLOCKS, PROX_BLOCKS, inv_n, epsilon_loss);
         KL_LAUNCH(prox_update, PROX_BLOCKS, 256, 0, st.p, wk.theta.p, wk.G.p, wk.inv_scale, ntheta, step, lambda,
                   wk.blockmax.p);
         KL_LAUNCH(prox_finish, 1, 32, 0, st.p, wk.blockmax.p, PROX_BLOCKS, epsilon, (long long)max_iter);

@@ -95,6 +95,100 @@ def test_matrix_free_pass_equals_csr_pass(K, oracle, M, N, L, flags):
     assert np.allclose(est.Theta, oth, rtol=1e-9, atol=1e-13)
 
 
+@pytest.mark.parametrize("M,N,L,flags", [
+    (1, 10, 200, dict(revcomp=True)), (1, 8, 500, dict(revcomp=True)), (4, 9, 150, dict()), (6, 10, 90, dict(reverse=True)),
+    (1, 5, 300, dict(revcomp=True)), (2, 7, 260, dict(complement=True)), (7, 9, 333, dict(revcomp=True)),
+])
+def test_binarized_matrix_free_pass_equals_stored_pass(K, oracle, M, N, L, flags):
+    """binarized matrices straight from the extraction: the table levels as per-row class bitmaps, the levels
+    k >= 6 matrix-free with one correction per repeat of a class inside a row (events left by the extraction).
+    Against the pass over the stored rows and the oracle -- ragged rows, invalid bases, low-complexity rows
+    (nearly every instance a repeat), frozen subsets, unobserved classes (renumbered columns)"""
+    from kmerlr_b200 import synth
+    buf, off, y = synth.training_set(70, 58, L)
+    buf = buf.copy()
+    buf[off[3] + 10] = ord("N")
+    buf[off[5]:off[5] + min(L, 40)] = ord("n")
+    buf[off[7]:off[8]] = ord("A")                      # a homopolymer row
+    buf[off[9]:off[10]] = np.frombuffer(b"AC" * L, dtype=np.uint8)[:L]
+    buf[off[11]:off[12]] = np.frombuffer(b"ACGTTGCA" * L, dtype=np.uint8)[:L]
+    buf[off[13]:off[13] + L // 2] = buf[off[13] + L // 2:off[13] + 2 * (L // 2)]     # two equal halves: every k-mer twice
+    kc, oc = K.NewKmerCounter(M, N, **flags), oracle.make_config(M, N, binarize=True, **flags)
+    d = K.compile_test_data(None, kc, None, None, True, True, (buf, off))
+    ref = oracle.extract(oc, (buf, off))
+    rp, col, val = d.rows()
+    orp, ocol, _ = ref.rows()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.all(val == 1.0)
+    d.SetLabels(y)
+    rng = np.random.default_rng(M * 100 + N)
+    cw = (0.8, 1.3)
+    for super_len in (-1, 0, 11):
+        K.option("super_len", super_len)
+        try:
+            theta = rng.normal(scale=0.02, size=d.m + 1)
+            theta[rng.integers(1, d.m + 1, size=d.m // 3)] = 0.0
+            lr = K.logisticRegression(theta, cw, 0.0)
+            K.option("implicit", 1)
+            g1, l1 = lr.Gradient(None, d), lr.Loss(d)
+            K.option("implicit", 0)
+            try:
+                g0, l0 = lr.Gradient(None, d), lr.Loss(d)
+            finally:
+                K.option("implicit", 1)
+            og = oracle.gradient(ref, y, theta, cw)
+            close_g(g1, og)
+            close_g(g0, og)
+            assert np.max(np.abs(g1 - g0)) <= 1e-13 * np.max(np.abs(og))
+            assert abs(l1 - l0) <= 1e-13 * abs(l0)
+            assert abs(l1 - oracle.loss(ref, y, theta, cw)) <= RTOL_LOSS * abs(l0)
+        finally:
+            K.option("super_len", -1)
+    # identical columns get identical bits on the matrix-free path too (integer sums)
+    g = K.logisticRegression(np.zeros(d.m + 1)).Gradient(None, d)[1:]
+    X = ref.dense()
+    groups = {}
+    for j in range(d.m):
+        groups.setdefault(X[:, j].tobytes(), []).append(j)
+    for cols in groups.values():
+        assert len({g[j] for j in cols}) == 1
+    # frozen subset of the classes: absent classes contribute nothing, their repeats leave no events
+    k, code = d.Kmers()
+    sub = (k[::2], code[::2])
+    ds = K.compile_test_data(None, kc, sub, None, True, True, (buf, off))
+    ds.SetLabels(y)
+    refs = oracle.extract(oc, (buf, off), frozen=sub)
+    ths = rng.normal(scale=0.02, size=ds.m + 1)
+    close_g(K.logisticRegression(ths, cw).Gradient(None, ds), oracle.gradient(refs, y, ths, cw))
+    # proximal-gradient iterations on the full space follow the oracle's
+    est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=5)
+    est.Theta = np.zeros(d.m + 1)
+    est.ClassWeights = np.array(cw)
+    est.estimate_proximal(d, 1e-3)
+    oth, _, _ = oracle.proxgrad(ref, y, np.zeros(ref.m + 1), cw, lam=1e-3, epsilon=0.0, epsilon_loss=0.0, max_iter=5)
+    assert np.allclose(est.Theta, oth, rtol=1e-9, atol=1e-13)
+
+
+def test_matrix_free_pass_long_rows_and_super_lengths(K, oracle):
+    """rows too long for the register-cached variants (groups decoded twice), every super k-mer length"""
+    from kmerlr_b200 import synth
+    buf, off, y = synth.training_set(20, 20, 5000)
+    buf = buf.copy()
+    buf[off[2] + 2500] = ord("N")
+    for binarize, M, N in ((False, 1, 8), (True, 1, 8), (False, 3, 6)):
+        kc, oc = K.NewKmerCounter(M, N, revcomp=True), oracle.make_config(M, N, revcomp=True, binarize=binarize)
+        d = K.compile_test_data(None, kc, None, None, True, binarize, (buf, off))
+        ref = oracle.extract(oc, (buf, off))
+        d.SetLabels(y)
+        theta = np.random.default_rng(3).normal(scale=0.005, size=d.m + 1)
+        og = oracle.gradient(ref, y, theta)
+        for super_len in (0, 8, 9, 10, 11, -1):
+            K.option("super_len", super_len)
+            try:
+                close_g(K.logisticRegression(theta).Gradient(None, d), og)
+            finally:
+                K.option("super_len", -1)
+
+
 def test_kmers5_standardizer_golden_and_transforms(K, oracle, fixtures):
     """kmerLr_test.go:155-190 through the C ABI: k = 2..6 revcomp counts + standardizer, Loss at the golden theta
     with lambda = 4.460029 is the reference's 1.107745182633717.  The rows stay sparse counts in HBM, the
