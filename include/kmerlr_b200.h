@@ -101,6 +101,9 @@ int kmerlr_extract(const kmerlr_config *cfg, const uint8_t *seq, const int64_t *
 
 /* KmerDataSet accessors (Data / Labels / Kmers, kmerLr_data.go:34-38) */
 int kmerlr_matrix_info(kmerlr_handle h, int64_t *n, int64_t *m, int64_t *nnz, int64_t *n_classes);
+/* len(data.Data) of the WHOLE data set: the rows of all ranks for a sharded matrix (what the reference's
+ * n = len(data.Data) is, kmerLr_estimator.go:239), the same as *n otherwise */
+int kmerlr_matrix_rows_global(kmerlr_handle h, int64_t *n_global);
 int kmerlr_matrix_classes(kmerlr_handle h, int32_t *k_out, uint64_t *code_out);
 int kmerlr_matrix_rows(kmerlr_handle h, int64_t *rowptr, int32_t *col, double *val);
 int kmerlr_matrix_set_labels(kmerlr_handle h, const uint8_t *labels, int64_t n);

@@ -152,6 +152,8 @@ class KmerDataSet:
         n, m, nnz, nc = (C.c_int64() for _ in range(4))
         check(lib().kmerlr_matrix_info(handle, n, m, nnz, nc))
         self.n, self.m, self.nnz, self.n_classes = n.value, m.value, nnz.value, nc.value
+        check(lib().kmerlr_matrix_rows_global(handle, n))
+        self.n_global = n.value          # rows of all ranks (= n unless the matrix is a shard)
         self.Labels = None
 
     def free(self):
@@ -344,7 +346,7 @@ class TransformFull(Transform):
         cnt = np.zeros(max(m, 1), dtype=np.int64)
         check(lib().kmerlr_column_moments(data.h, _p(s1), _p(s2), _p(mx), _p(cnt)))
         s1, s2, mx = s1[:m], s2[:m], mx[:m]
-        n = float(data.n_global if hasattr(data, "n_global") else data.n)
+        n = float(data.n_global)
         offset, scale = np.zeros(m + 1), np.ones(m + 1)
         if kind in ("standardizer", "variance-scaler"):
             mean = s1 / n
@@ -559,7 +561,7 @@ class KmerLrEstimator:
 
     def estimate_loop(self, data, lambdaAuto, balance=False):
         """estimate_loop (kmerLr_estimator.go:209-255): leapfrog epochs until Select returns !ok."""
-        n = data.n
+        n = data.n_global                # len(data.Data) of the whole set: the same L1Reg on every rank
         self.ClassWeights = data.class_weights() if balance else np.ones(2)
         s = featureSelector(self.ClassWeights, self.Cooccurrence, lambdaAuto, data.m, self.EpsilonLambda, self.tie)
         r = False
@@ -574,8 +576,9 @@ class KmerLrEstimator:
             reduced = selection.Data(data)
             reduced.SetLabels(data.Labels)
             iters, _ = self.estimate_proximal(reduced, lam)
+            reduced_nnz = reduced.nnz
             reduced.free()
-            self.path.append((lam, iters, len(self.active_idx)))
+            self.path.append((lam, iters, len(self.active_idx), reduced_nnz))
             r = True
             epoch += 1
         return epoch

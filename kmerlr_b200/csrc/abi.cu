@@ -282,6 +282,13 @@ int kmerlr_matrix_info(kmerlr_handle h, int64_t *n, int64_t *m, int64_t *nnz, in
   }, false);
 }
 
+int kmerlr_matrix_rows_global(kmerlr_handle h, int64_t *n_global) {
+  return guarded([&] {
+    KL_REQUIRE(n_global, "null argument");
+    *n_global = lookup<Matrix>(h, "matrix")->n_global;
+  }, false);
+}
+
 int kmerlr_matrix_classes(kmerlr_handle h, int32_t *k_out, uint64_t *code_out) {
   return guarded([&] {
     auto M = lookup<Matrix>(h, "matrix");
@@ -350,6 +357,7 @@ int kmerlr_class_weights(kmerlr_handle h, double class_w_out[2]) {
   return guarded([&] {
     auto M = lookup<Matrix>(h, "matrix");
     KL_REQUIRE(M->has_labels, "class_weights: the matrix has no labels");
+    matrix_label_counts(*M);
     double n0 = (double)M->n_neg, n1 = (double)M->n_pos;
     class_w_out[0] = (n0 + n1) / (2.0 * n0);
     class_w_out[1] = (n0 + n1) / (2.0 * n1);

@@ -64,30 +64,48 @@ void peer_teardown() {
 }
 
 // every rank allocates its mailbox, the IPC handles go round with an all-gather, every rank maps the
-// others'.  Any failure leaves ctx().peer == nullptr and the NCCL collectives in charge.
+// others'.  Any failure on any rank leaves ctx().peer == nullptr everywhere and the NCCL collectives in
+// charge: a rank that failed locally still takes part in both agreement collectives (ok = 0), so nobody is
+// left waiting inside comm_init.  The exchange is also refused when two ranks of the communicator sit on
+// the same device: their kernels would spin on each other's flags without being guaranteed to run at the
+// same time (B200_PROFILING.md: Xid 109).
 void peer_setup() {
   const int world = ctx().world, rank = ctx().rank;
   if (world < 2 || world > PEER_MAX_WORLD) return;
-  if (cudaMalloc((void **)&g_my_mail, sizeof(PeerMail)) != cudaSuccess) { cudaGetLastError(); g_my_mail = nullptr; return; }
-  cudaMemset(g_my_mail, 0, sizeof(PeerMail));
+  constexpr size_t IDB = 32;                                   // PCI bus id of the rank's device
+  constexpr size_t HB = sizeof(cudaIpcMemHandle_t) + 8 + IDB;
+  unsigned char *din = nullptr, *dout = nullptr;
+  int *dflag = nullptr;
+  int ok = 1;
+  if (cudaMalloc((void **)&din, HB) != cudaSuccess || cudaMalloc((void **)&dout, HB * world) != cudaSuccess ||
+      cudaMalloc((void **)&dflag, sizeof(int)) != cudaSuccess) {
+    // without these three buffers the collectives below cannot run on this rank either: nothing was entered yet,
+    // and the other ranks would wait -- this is the one failure that has to be fatal
+    cudaGetLastError();
+    fail(KMERLR_ERR_CUDA, "comm_init: out of device memory for the peer-memory handshake");
+  }
+  if (cudaMalloc((void **)&g_my_mail, sizeof(PeerMail)) != cudaSuccess) { cudaGetLastError(); g_my_mail = nullptr; ok = 0; }
   cudaIpcMemHandle_t mine;
-  int ok = cudaIpcGetMemHandle(&mine, g_my_mail) == cudaSuccess ? 1 : 0;
-  if (!ok) cudaGetLastError();
-  // handles (+ an ok byte) through NCCL
-  constexpr size_t HB = sizeof(cudaIpcMemHandle_t) + 8;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    cudaMemset(g_my_mail, 0, sizeof(PeerMail));
+    if (cudaIpcGetMemHandle(&mine, g_my_mail) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  }
   std::vector<unsigned char> h(HB, 0), all(HB * world, 0);
   memcpy(h.data(), &mine, sizeof(mine));
   h[sizeof(mine)] = (unsigned char)ok;
-  unsigned char *din = nullptr, *dout = nullptr;
-  KL_CUDA(cudaMalloc((void **)&din, HB));
-  KL_CUDA(cudaMalloc((void **)&dout, HB * world));
-  KL_CUDA(cudaMemcpy(din, h.data(), HB, cudaMemcpyHostToDevice));
+  char busid[IDB] = {0};
+  if (cudaDeviceGetPCIBusId(busid, (int)IDB, ctx().device) != cudaSuccess) { cudaGetLastError(); snprintf(busid, IDB, "dev%d", ctx().device); }
+  memcpy(h.data() + sizeof(mine) + 8, busid, IDB);
+  bool good = cudaMemcpy(din, h.data(), HB, cudaMemcpyHostToDevice) == cudaSuccess;
+  // agreement step 1 (always entered): handles, ok bytes and device ids of all ranks
   KL_NCCL(g_nccl.AllGather(din, dout, HB, ncclUint8, comm(), ctx().stream));
   KL_CUDA(cudaStreamSynchronize(ctx().stream));
-  KL_CUDA(cudaMemcpy(all.data(), dout, HB * world, cudaMemcpyDeviceToHost));
-  cudaFree(din); cudaFree(dout);
-  bool good = true;
+  good = good && cudaMemcpy(all.data(), dout, HB * world, cudaMemcpyDeviceToHost) == cudaSuccess;
   for (int r = 0; r < world; r++) good = good && all[r * HB + sizeof(mine)] == 1;
+  for (int r = 0; r < world && good; r++)
+    for (int q = r + 1; q < world; q++)
+      if (!memcmp(all.data() + r * HB + sizeof(mine) + 8, all.data() + q * HB + sizeof(mine) + 8, IDB)) good = false;
   if (good) {
     for (int r = 0; r < world && good; r++) {
       if (r == rank) { g_peer_mail[r] = g_my_mail; continue; }
@@ -98,21 +116,23 @@ void peer_setup() {
       g_peer_mail[r] = (PeerMail *)p;
     }
   }
-  // all ranks must agree (a rank that failed to map makes everybody fall back)
-  int *dflag = nullptr;
-  KL_CUDA(cudaMalloc((void **)&dflag, sizeof(int)));
+  // agreement step 2 (always entered): a rank that failed to map makes everybody fall back
   int hflag = good ? 1 : 0;
-  KL_CUDA(cudaMemcpy(dflag, &hflag, sizeof(int), cudaMemcpyHostToDevice));
+  if (cudaMemcpy(dflag, &hflag, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaMemset(dflag, 0, sizeof(int)); }
   KL_NCCL(g_nccl.AllReduce(dflag, dflag, 1, ncclInt32, ncclMin, comm(), ctx().stream));
   KL_CUDA(cudaStreamSynchronize(ctx().stream));
-  KL_CUDA(cudaMemcpy(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost));
-  cudaFree(dflag);
+  if (cudaMemcpy(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); hflag = 0; }
+  cudaFree(din); cudaFree(dout); cudaFree(dflag);
   if (!hflag) { peer_teardown(); return; }
   PeerBox hb{};
   for (int r = 0; r < world; r++) hb.box[r] = g_peer_mail[r];
   hb.rank = rank; hb.world = world;
-  KL_CUDA(cudaMalloc((void **)&g_peer_dev, sizeof(PeerBox)));
-  KL_CUDA(cudaMemcpy(g_peer_dev, &hb, sizeof(PeerBox), cudaMemcpyHostToDevice));
+  if (cudaMalloc((void **)&g_peer_dev, sizeof(PeerBox)) != cudaSuccess ||
+      cudaMemcpy(g_peer_dev, &hb, sizeof(PeerBox), cudaMemcpyHostToDevice) != cudaSuccess) {
+    // (after the agreement: this rank alone would fall back, so this late failure has to be fatal as well)
+    cudaGetLastError();
+    fail(KMERLR_ERR_CUDA, "comm_init: out of device memory for the mailbox table");
+  }
   ctx().peer = g_peer_dev;
 }
 
@@ -181,6 +201,16 @@ void comm_allreduce_max_u8(uint8_t *dev, int64_t count) {
   need_comm();
   if (ctx().profiling) profile_begin("nccl_allreduce_max_u8");
   KL_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclUint8, ncclMax, comm(), ctx().stream));
+  if (ctx().profiling) profile_end();
+}
+void comm_allgather_bytes(const void *dev_in, void *dev_out, int64_t bytes_per_rank) {
+  if (ctx().world == 1) {
+    KL_CUDA(cudaMemcpyAsync(dev_out, dev_in, (size_t)bytes_per_rank, cudaMemcpyDeviceToDevice, ctx().stream));
+    return;
+  }
+  need_comm();
+  if (ctx().profiling) profile_begin("nccl_allgather_bytes");
+  KL_NCCL(g_nccl.AllGather(dev_in, dev_out, (size_t)bytes_per_rank, ncclUint8, comm(), ctx().stream));
   if (ctx().profiling) profile_end();
 }
 void comm_allgather_f64(const double *dev_in, double *dev_out, int64_t count_per_rank) {

@@ -58,6 +58,7 @@ struct PeerMail {
   unsigned long long slot[2][PEER_MAX_WORLD][PEER_PAYLOAD];
   unsigned long long flag[2][PEER_MAX_WORLD];
   unsigned long long seq;                        // local: sequence number of the last exchange
+  unsigned int senders_done;                     // local: sender blocks of the running exchange that are through
 };
 struct PeerBox {
   PeerMail *box[PEER_MAX_WORLD];                 // box[r] = rank r's mailbox as mapped into this process
@@ -260,7 +261,8 @@ struct Matrix : Object {
   // labels
   bool has_labels = false;
   DevBuf<uint8_t> labels;    // n
-  int64_t n_pos = 0, n_neg = 0;   // global counts (all ranks)
+  int64_t n_pos = 0, n_neg = 0;   // label counts: this rank's until matrix_label_counts() has summed them over the ranks
+  bool counts_global = true;
   // class list: dense class ids on the device (extraction), decoded to (k, code) on the host the first
   // time somebody asks (matrix_class_list)
   int64_t n_classes = 0;
@@ -319,6 +321,7 @@ std::shared_ptr<Matrix> matrix_from_csr(int64_t n, int64_t m, const int64_t *row
                                         const double *val, int flags);
 void matrix_rows(Matrix &M, int64_t *rowptr, int32_t *col, double *val);
 void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n);
+void matrix_label_counts(Matrix &M);   // n_pos / n_neg over all ranks (collective on a sharded matrix, first call only)
 void matrix_column_moments(Matrix &M, double *sum, double *sumsq, double *absmax, int64_t *count);
 void matrix_compact(Matrix &M);      // padded rows -> compact CSR (no-op for compact matrices)
 void ensure_csc(Matrix &M);
@@ -355,6 +358,7 @@ void comm_allreduce_sum_i64(int64_t *dev, int64_t count);
 void comm_allreduce_max_f64(double *dev, int64_t count);
 void comm_allreduce_max_u8(uint8_t *dev, int64_t count);
 void comm_allgather_f64(const double *dev_in, double *dev_out, int64_t count_per_rank);
+void comm_allgather_bytes(const void *dev_in, void *dev_out, int64_t bytes_per_rank);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -153,6 +153,7 @@ void coordinate(Matrix &M, double *theta, int64_t ntheta, const double cw_hook[2
   KL_REQUIRE(!M.sharded, "coordinate: single GPU only");
   KL_REQUIRE(M.n > 0, "coordinate: empty data set");
   // compute_class_weights(data_train.Labels) (:88; kmerLr_data.go:178-193)
+  matrix_label_counts(M);
   KL_REQUIRE(M.n_pos > 0 && M.n_neg > 0, "coordinate: both classes must be present");
   const double ntot = (double)(M.n_pos + M.n_neg);
   const double cw[2] = {ntot / (2.0 * (double)M.n_neg), ntot / (2.0 * (double)M.n_pos)};

@@ -76,19 +76,37 @@ __global__ void popc_words(const uint32_t *__restrict__ bm, int64_t nw, uint32_t
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nw) out[i] = __popc(bm[i]);
 }
-__global__ void bitmap_to_bytes(const uint32_t *__restrict__ bm, int64_t nbits, uint8_t *__restrict__ out) {
+// sharded extraction: ONE exchange.  Every rank contributes [bitmap words | rows | max row norm | max value];
+// the merge ORs the bitmaps, adds the row counts and takes the maxima of the statistics.
+__global__ void pack_exchange(const uint32_t *__restrict__ bm, int64_t nw, unsigned long long n_local,
+                              const unsigned long long *__restrict__ stats, uint32_t *__restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nbits) out[i] = (bm[i >> 5] >> (i & 31)) & 1u;
-}
-__global__ void bytes_to_bitmap(const uint8_t *__restrict__ in, int64_t nbits, uint32_t *__restrict__ bm, int64_t nw) {
-  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nw) return;
-  uint32_t v = 0;
-  for (int b = 0; b < 32; b++) {
-    int64_t i = w * 32 + b;
-    if (i < nbits && in[i]) v |= 1u << b;
+  if (i < nw) out[i] = bm[i];
+  if (i == 0) {
+    unsigned long long v[3] = {n_local, stats[0], stats[1]};
+    for (int k = 0; k < 3; k++) { out[nw + 2 * k] = (uint32_t)v[k]; out[nw + 2 * k + 1] = (uint32_t)(v[k] >> 32); }
   }
-  bm[w] = v;
+}
+__global__ void merge_exchange(const uint32_t *__restrict__ all, int world, int64_t nw, uint32_t *__restrict__ bm,
+                               unsigned long long *__restrict__ res) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = nw + 6;
+  if (i < nw) {
+    uint32_t v = 0;
+    for (int r = 0; r < world; r++) v |= all[(int64_t)r * per + i];
+    bm[i] = v;
+  }
+  if (i == 0) {
+    unsigned long long n = 0, a = 0, b = 0;
+    for (int r = 0; r < world; r++) {
+      const uint32_t *t = all + (int64_t)r * per + nw;
+      n += (unsigned long long)t[0] | ((unsigned long long)t[1] << 32);
+      const unsigned long long x = (unsigned long long)t[2] | ((unsigned long long)t[3] << 32);
+      const unsigned long long y = (unsigned long long)t[4] | ((unsigned long long)t[5] << 32);
+      a = x > a ? x : a; b = y > b ? y : b;
+    }
+    res[0] = n; res[1] = a; res[2] = b;
+  }
 }
 // ids of the set bits at their rank positions
 __global__ void enumerate_bits(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ rank, int64_t nw,
@@ -242,7 +260,9 @@ const uint2 *table_classes(int op, int t_lo, int t_hi, const uint32_t *level_off
           else r |= d << (2 * (k - 1 - i));
         }
       }
-      if (u <= r) list.push_back(make_uint2((toff + u) | ((toff + r) << 16), level_off[k] + u));
+      // table positions in u16 units with the word index swizzled as the kernel does (xk::sw)
+      auto pos = [](uint32_t i) { return (sw(i >> 1) << 1) | (i & 1u); };
+      if (u <= r) list.push_back(make_uint2(pos(toff + u) | (pos(toff + r) << 16), level_off[k] + u));
     }
   }
   auto e = std::make_unique<Entry>();
@@ -471,7 +491,7 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   }
   P.pf_words = (P.pf_words + 3) / 4 * 4;
   P.ts_words = 32 * E > TAB_WORDS ? 32 * E : TAB_WORDS;
-  P.warp_words = P.bm_words + P.pf_words + P.ts_words + 4;
+  P.warp_words = P.bm_words + P.pf_words + P.ts_words + 8;     // + repeat count, ticket, row slots of the bitmap levels
   P.warp_words = (P.warp_words + 3) / 4 * 4;
   // the block's bitmap of observed classes covers the levels up to OBS_MAX_LEVEL
   {
@@ -586,28 +606,26 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
     P.row0 = 0; P.n = s.n;
   }
   tr.mark("extract_kernel");
-  // observed classes of all ranks; do they cover the numbering set?
+  // observed classes, row count and row statistics of all ranks in ONE exchange; do the classes cover the
+  // numbering set?
   DevBuf<uint32_t> differ(1);
   differ.zero();
-  if (n_frozen == 0) {
-    if (sharded) {
-      DevBuf<uint8_t> bytes((size_t)nbits);
-      KL_LAUNCH(bitmap_to_bytes, (unsigned)((nbits + 255) / 256), 256, 0, bitmap.p, nbits, bytes.p);
-      comm_allreduce_max_u8(bytes.p, nbits);
-      KL_LAUNCH(bytes_to_bitmap, (unsigned)((nw + 255) / 256), 256, 0, bytes.p, nbits, bitmap.p, nw);
-    }
-    KL_LAUNCH(bitmaps_differ, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, nb.p, nw, differ.p);
+  DevBuf<unsigned long long> gres(3);
+  if (sharded) {
+    const int64_t xw = n_frozen == 0 ? nw : 0, per = xw + 6;
+    DevBuf<uint32_t> mine((size_t)per), all((size_t)(per * ctx().world));
+    KL_LAUNCH(pack_exchange, (unsigned)((xw + 256) / 256), 256, 0, bitmap.p, xw, (unsigned long long)s.n, stats.p, mine.p);
+    comm_allgather_bytes(mine.p, all.p, per * 4);
+    KL_LAUNCH(merge_exchange, (unsigned)((xw + 256) / 256), 256, 0, all.p, ctx().world, xw, bitmap.p, gres.p);
   }
+  if (n_frozen == 0)
+    KL_LAUNCH(bitmaps_differ, (unsigned)((nw + 255) / 256), 256, 0, bitmap.p, nb.p, nw, differ.p);
   // one round trip: classes, stored entries, "columns are final", row statistics, global number of rows
   DevBuf<int64_t> rp((size_t)s.n + 1);
   if (s.n > 0) exclusive_scan_u32_to_i64(out->rowcnt.p, rp.p, s.n); else rp.zero();
-  DevBuf<int64_t> nglob(1);
   int64_t nn = s.n;
-  if (sharded) {
-    nglob.upload(&nn, 1);
-    comm_allreduce_sum_i64(nglob.p, 1);
-    nglob.download(&nn, 1);
-  }
+  unsigned long long hres[3] = {0, 0, 0};
+  if (sharded) gres.download(hres, 3);
   uint32_t m32 = 0, hdiffer = 0;
   unsigned long long hstats[2] = {0, 0};
   DevBuf<int64_t> evptr;
@@ -622,6 +640,12 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   differ.download(&hdiffer, 1);
   stats.download(hstats, 2);
   sync_stream();
+  if (sharded) {
+    // the statistics are global already: no collective later (step size, fixed-point scale)
+    nn = (int64_t)hres[0];
+    out->maxsq = (double)hres[1]; out->vmax = (double)hres[2];
+    out->has_maxsq = out->has_vmax = true;
+  }
   out->n_global = nn;
   out->has_local_stats = true;
   out->local_maxsq = (double)hstats[0]; out->local_vmax = (double)hstats[1];

@@ -11,13 +11,21 @@
 namespace kl {
 namespace xk {
 
+#ifndef KL_X_OLDPOS
+#define KL_X_OLDPOS 0     // 1: position pass with one funnel-shift load per position (lane = positions lane, lane + 32, ...)
+#endif
+#ifndef KL_X_WALK
+#define KL_X_WALK 1       // 1: bitmap levels emitted by a walk over the set bits; 0: a slot per position computed from
+                          // prefix popcounts (measured slower: 2.90 vs 2.55 ms at C2 -- a numbering gather, three
+                          // shared-memory reads and a scattered store per position cost more than the bit loops)
+#endif
 constexpr uint32_t SENT = 0xFFFFFFFFu;    // sort key of a position without a valid k-mer (sorts last)
 constexpr uint32_t NOKEY = 0xFFFFFFFEu;   // "no previous key" in front of the sorted array
 constexpr int KT_MAX = 5;          // levels <= KT_MAX use direct count tables
 constexpr int KB_MAX = 8;          // highest level that can use a per-row bitmap
 constexpr int KB_DEFAULT = 7;      // ... level 8 does so only when the rows are too long for the register sort
 constexpr int MAX_N = 13;          // 2*13 code bits + 4 length bits per position
-constexpr int TAB_WORDS = 688;     // (4+16+64+256+1024)/2 = 682 packed u16 pairs, padded
+constexpr int TAB_WORDS = 704;     // (4+16+64+256+1024)/2 = 682 packed u16 pairs, padded to whole rows of 32 (swizzle)
 constexpr int OBS_MAX_LEVEL = 8;   // marks of observed classes of levels <= 8 are gathered per block in smem
 
 struct XParams {
@@ -37,7 +45,7 @@ struct XParams {
   const int64_t *len, *blk;
   const uint32_t *bits2;
   const uint16_t *inv16;
-  const uint2 *tl;                 // x = table index of the code | table index of its image << 16, y = class id
+  const uint2 *tl;                 // x = (swizzled) table index of the code | table index of its image << 16, y = class id
   uint32_t *st_id, *st_cnt, *rowcnt, *bitmap, *ovf;
   const uint2 *nbx;                // numbering set (all classes of the configuration, or the frozen list)
   int filter;                      // drop ids outside the numbering set
@@ -54,6 +62,15 @@ __device__ __forceinline__ uint32_t tab_off(int k) {  // sum_{j=1}^{k-1} 4^j
   return ((1u << (2 * k)) - 4u) / 3u;
 }
 
+
+// Index swizzle of the per-warp staging buffers: lanes that write runs of consecutive slots at a stride of
+// ~16 (the sorted level: E keys per lane) would all hit two banks; XOR-ing the row number into the bank bits
+// spreads them, and a read of 32 consecutive slots stays a permutation of one row (conflict free).
+#ifndef KL_X_NOSWZ
+#define KL_X_NOSWZ 0
+#endif
+__host__ __device__ __forceinline__ uint32_t sw(uint32_t j) { return KL_X_NOSWZ ? j : j ^ ((j >> 5) & 31u); }
+__host__ __device__ __forceinline__ int sw(int j) { return (int)sw((uint32_t)j); }
 
 template <int E>
 void launch_extract(const XParams &P);
@@ -192,7 +209,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
     if ((cls >> r) & 1) {
       const MaskT below = cls & (((MaskT)1 << r) - 1);
       const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
-      sbuf[j] = idbase + (r == 0 ? prevlast : K[r > 0 ? r - 1 : 0]);
+      sbuf[sw(j)] = idbase + (r == 0 ? prevlast : K[r > 0 ? r - 1 : 0]);
     }
   }
   __syncwarp();
@@ -211,7 +228,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
           const MaskT below = cls & (((MaskT)1 << r) - 1);
           const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
           uint32_t col;
-          if (em.column(sbuf[j], col) || !em.filter) extra += cnt - 1;
+          if (em.column(sbuf[sw(j)], col) || !em.filter) extra += cnt - 1;
         }
       }
     }
@@ -236,7 +253,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
           const MaskT below = cls & (((MaskT)1 << r) - 1);
           const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
           uint32_t col;
-          if (em.column(sbuf[j], col) || !em.filter)
+          if (em.column(sbuf[sw(j)], col) || !em.filter)
             for (uint32_t x = 1; x < cnt; x++) tail[-(int64_t)(pos++)] = col;
         }
       }
@@ -246,7 +263,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
   if (!em.filter) {
     // no class is dropped: slot i of the buffer is entry i of the level
     for (int i = lane; i < total; i += 32) {
-      const uint32_t id = sbuf[i];
+      const uint32_t id = sbuf[sw(i)];
       uint32_t col;
       em.column(id, col);
       em.sid[em.cursor + i] = col;
@@ -262,12 +279,12 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
           const int st = bbelow ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bbelow) : 63 - __clzll(bbelow))
                                 : start0;
           const uint32_t cnt = (uint32_t)((int)lane * E + r - st);
-          sbuf[j] = cnt;
+          sbuf[sw(j)] = cnt;
           em.stat(cnt);
         }
       }
       __syncwarp();
-      for (int i = lane; i < total; i += 32) em.scnt[em.cursor + i] = sbuf[i];
+      for (int i = lane; i < total; i += 32) em.scnt[em.cursor + i] = sbuf[sw(i)];
       __syncwarp();
     } else {
       em.sq += (unsigned long long)c; if (c) em.vm = max(em.vm, 1u);
@@ -283,7 +300,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
   for (int i0 = 0, it = 0; i0 < total; i0 += 32, it++) {
     const int i = i0 + (int)lane;
     bool keep = false; uint32_t col = 0, id = 0;
-    if (i < total) { id = sbuf[i]; keep = em.column(id, col) || !em.filter; }
+    if (i < total) { id = sbuf[sw(i)]; keep = em.column(id, col) || !em.filter; }
     const unsigned km = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       em.sid[em.cursor + kept + __popc(km & lanemask_lt())] = col;
@@ -302,7 +319,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
         const int j = base + (sizeof(MaskT) == 4 ? __popc((uint32_t)below) : __popcll(below));
         const int st = bbelow ? (int)lane * E + (sizeof(MaskT) == 4 ? 31 - __clz((uint32_t)bbelow) : 63 - __clzll(bbelow))
                               : start0;
-        sbuf[j] = (uint32_t)((int)lane * E + r - st);
+        sbuf[sw(j)] = (uint32_t)((int)lane * E + r - st);
       }
     }
     __syncwarp();
@@ -312,7 +329,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
       const bool keep = (keepbits >> it) & 1ull;
       const unsigned km = __ballot_sync(0xffffffffu, keep);
       if (keep) {
-        const uint32_t cnt = sbuf[i];
+        const uint32_t cnt = sbuf[sw(i)];
         em.scnt[em.cursor + k2 + __popc(km & lanemask_lt())] = cnt;
         em.stat(cnt);
       }
@@ -326,6 +343,29 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
   em.cursor += kept;
 }
 
+
+// A lane's view of its stretch of a row: 32 consecutive bases starting at p0, once with the first base in the
+// low bits (fwd: the k-mer starting at base x is the low 2k bits of fwd >> 2x, and the complement of those
+// bits is its reverse complement in code order) and once digit-reversed, first base in the two top bits (rev:
+// a shift and a mask give the forward code, first base most significant), + one "not usable" bit per base
+// (not ACGT, or past the end of the row).
+struct XWindow {
+  unsigned long long fwd, rev;
+  uint32_t inv;
+  __device__ __forceinline__ void load(const uint32_t *__restrict__ b2, const uint16_t *__restrict__ iv, int L, int p0) {
+    if (p0 >= L) { fwd = rev = 0ull; inv = 0xFFFFFFFFu; return; }
+    const int wi = p0 >> 4, sh = p0 & 15;
+    const uint32_t w0 = __ldg(b2 + wi), w1 = __ldg(b2 + wi + 1), w2 = __ldg(b2 + wi + 2);
+    const uint32_t lo = __funnelshift_r(w0, w1, 2 * sh), hi = __funnelshift_r(w1, w2, 2 * sh);
+    fwd = ((unsigned long long)hi << 32) | lo;
+    rev = ((unsigned long long)swap_pairs(__brev(lo)) << 32) | swap_pairs(__brev(hi));
+    const unsigned long long iw = (unsigned long long)__ldg(iv + wi) | ((unsigned long long)__ldg(iv + wi + 1) << 16) |
+                                  ((unsigned long long)__ldg(iv + wi + 2) << 32);
+    inv = (uint32_t)(iw >> sh);
+    const int left = L - p0;
+    if (left < 32) inv |= 0xFFFFFFFFu << left;
+  }
+};
 
 // ---- the extraction kernel: one warp per sequence ------------------------------------------------
 // E = keys per lane of the register sort (0: no sorted levels, sequences of any length)
@@ -381,6 +421,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
       for (int i = lane; i < TAB_WORDS; i += 32) tab[i] = 0;
     __syncwarp();
 
+#if KL_X_OLDPOS
     // ---- pass over the positions: lane handles the start positions p = lane, lane + 32, ... ----------
     // The N bases starting at p are 2N consecutive bits of the packed words (first base in the low
     // bits): one funnel shift.  Read that way the k-mer starting at p is the LOW 2k bits, its
@@ -405,7 +446,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
             int kk = len_f < P.t_hi ? len_f : P.t_hi;
             if (kk >= P.t_lo) {
               uint32_t idx = tab_off(kk) + (FW >> (2 * (N - kk)));
-              atomicAdd(tab + (idx >> 1), 1u << (16 * (idx & 1)));
+              atomicAdd(tab + sw(idx >> 1), 1u << (16 * (idx & 1)));
             }
           }
           // bitmap levels: canonical code = min(prefix, image)
@@ -445,6 +486,71 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
     }
     __syncwarp();
 
+    const int spl = (L + 31) >> 5, p0 = (int)lane * spl;
+#else
+    // ---- pass over the positions: lane owns the start positions [lane spl, (lane + 1) spl) ----------------
+    // Its stretch is read once per 16 positions as a 64-bit window of packed bases (XWindow): the k-mer
+    // starting at base x of the window is a shift and a mask -- no rolling state, no warm-up, no load or
+    // bit reversal per position.
+    const int spl = (L + 31) >> 5;    // start positions per lane
+    const int p0 = (int)lane * spl;
+    uint32_t FWL[EE];                 // (forward code << 4) | valid length, per position of this lane
+#pragma unroll
+    for (int r = 0; r < EE; r++) FWL[r] = 0;
+    {
+      const uint32_t tab_top = has_tab ? tab_off(P.t_hi) : 0u;
+      auto visit = [&](const XWindow &W, int x) -> uint32_t {
+        const int len_f = __ffs((W.inv >> x) | (1u << N)) - 1;                 // valid bases from here on (<= N)
+        const uint32_t e = (uint32_t)(W.fwd >> (2 * x)) & maskN;
+        const uint32_t FW = (uint32_t)(W.rev >> (64 - 2 * (x + N))) & maskN;
+        const uint32_t S2 = op == 1 ? (~e) & maskN : e;   // image of the window under revcomp / reverse
+        if (len_f >= M) {
+          // table levels: one count at the deepest table level this suffix reaches
+          if (has_tab) {
+            uint32_t idx;
+            if (len_f >= P.t_hi) idx = tab_top + (FW >> (2 * (N - P.t_hi)));
+            else idx = len_f >= P.t_lo ? tab_off(len_f) + (FW >> (2 * (N - len_f))) : 0xFFFFFFFFu;
+            if (idx != 0xFFFFFFFFu) atomicAdd(tab + sw(idx >> 1), 1u << (16 * (idx & 1)));
+          }
+          // bitmap levels: canonical code = min(prefix, image)
+          if (has_bm) {
+#pragma unroll
+            for (int j = 0; j < KB_MAX - KT_MAX; j++) {
+              const int k = P.b_lo + j;
+              if (k > P.b_hi || len_f < k) break;
+              const uint32_t mk = (1u << (2 * k)) - 1u;
+              uint32_t c = FW >> (2 * (N - k));
+              if (op == 1 || op == 3) c = min(c, S2 & mk);
+              else if (op == 2) c = min(c, (~c) & mk);
+              const uint32_t bit = 1u << (c & 31);
+              const uint32_t old = atomicOr(bm + P.bm_off[k] + (c >> 5), bit);
+              if ((old & bit) && (!P.binarize || EV)) {
+                ovf[atomicAdd(dupn, 1u)] = ((uint32_t)k << 26) | c;     // the warp's list of repeats (L2)
+              }
+            }
+          }
+        }
+        // one sorted level (s_lo == N): keep the CANONICAL code of the full window, the key of that level
+        const uint32_t keep = (single_sorted && two) ? min(FW, S2) : FW;
+        return (keep << 4) | (uint32_t)len_f;
+      };
+      XWindow W;
+      if (E > 0) {
+#pragma unroll
+        for (int i = 0; i < EE; i++) {
+          if ((i & 15) == 0 && i < spl) W.load(b2, iv16, L, p0 + i);
+          if (i < spl && p0 + i < L) FWL[i] = visit(W, i & 15);
+        }
+      } else {
+        for (int i = 0; i < spl && p0 + i < L; i++) {
+          if ((i & 15) == 0) W.load(b2, iv16, L, p0 + i);
+          visit(W, i & 15);
+        }
+      }
+    }
+    __syncwarp();
+
+#endif
     Emitter em;
     em.sid = P.st_id + row * P.stride; em.scnt = P.st_cnt + (P.binarize ? 0 : row * P.stride);
     em.obs = obs; em.bitmap = P.bitmap; em.obs_bits = (uint32_t)P.obs_words * 32u;
@@ -460,10 +566,10 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         const uint32_t nk = 1u << (2 * k), toff = tab_off(k), coff = tab_off(k + 1);
         for (uint32_t u = lane; u < nk; u += 32) {
           uint32_t c0 = coff + 4 * u;                 // 4 children = two aligned words
-          uint32_t w0 = tab[c0 >> 1], w1 = tab[(c0 >> 1) + 1];
+          uint32_t w0 = tab[sw(c0 >> 1)], w1 = tab[sw(c0 >> 1) ^ 1u];   // (the swizzle keeps an even / odd pair together)
           uint32_t sum = (w0 & 0xFFFFu) + (w0 >> 16) + (w1 & 0xFFFFu) + (w1 >> 16);
           uint32_t idx = toff + u;
-          if (sum) atomicAdd(tab + (idx >> 1), sum << (16 * (idx & 1)));
+          if (sum) atomicAdd(tab + sw(idx >> 1), sum << (16 * (idx & 1)));
         }
         __syncwarp();
       }
@@ -485,6 +591,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
       __syncwarp();
     }
 
+#if KL_X_WALK
     // ---- bitmap levels: walk the bitmap 128 words at a time (4 consecutive words per lane) ---------
     if (has_bm) {
       for (int k = P.b_lo; k <= P.b_hi; k++) {
@@ -527,13 +634,13 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
               uint32_t w = ws[j];
               while (w) {
                 const uint32_t below = (w & (0u - w)) - 1u;            // bits under the lowest set bit
-                tab[pos++] = nx[j].y + __popc(nx[j].x & below);         // its column
+                tab[sw(pos++)] = nx[j].y + __popc(nx[j].x & below);     // its column
                 w &= w - 1;
               }
             }
             __syncwarp();
             for (uint32_t i = lane; i < tot; i += 32) {
-              em.sid[em.cursor + i] = tab[i];
+              em.sid[em.cursor + i] = tab[sw(i)];
               if (!P.binarize) em.scnt[em.cursor + i] = 1;
             }
             __syncwarp();
@@ -555,6 +662,94 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
           em.cursor += tot;
         }
       }
+#else
+    // ---- bitmap levels ---------------------------------------------------------------------------------
+    // (1) one pass over the words of the level's bitmap (4 consecutive words per lane): frozen-list filter,
+    // marks of the observed classes, popcounts -> the slot of the first class of every PAIR of words (u16);
+    // (2) every position computes the slot of its class from that prefix and two popcounts, and puts the
+    // column there (repeats of a class write the same value to the same slot) -- no loop over set bits;
+    // (3) the staged columns leave in coalesced stores.
+    if (has_bm) {
+      for (int k = P.b_lo; k <= P.b_hi; k++) {
+        const int W = 1 << (2 * k - 5);
+        uint32_t *bk = bm + P.bm_off[k];
+        unsigned short *pk = reinterpret_cast<unsigned short *>(pf + P.pf_off[k]);
+        const uint32_t gword = P.level_off[k] >> 5;
+        uint32_t run = 0;                                     // classes of the words before this chunk
+        for (int it = 0; it * 128 < W; it++) {
+          const int wi = it * 128 + (int)lane * 4;
+          uint4 w4 = make_uint4(0, 0, 0, 0);
+          if (wi < W) w4 = *reinterpret_cast<const uint4 *>(bk + wi);
+          if (P.filter && wi < W) {
+            // frozen class list: classes outside the list vanish here, before any slot is assigned
+            w4.x &= __ldg(P.nbx + gword + wi).x; w4.y &= __ldg(P.nbx + gword + wi + 1).x;
+            w4.z &= __ldg(P.nbx + gword + wi + 2).x; w4.w &= __ldg(P.nbx + gword + wi + 3).x;
+            *reinterpret_cast<uint4 *>(bk + wi) = w4;
+          }
+          if (w4.x | w4.y | w4.z | w4.w) {
+            em.mark_word(gword + wi, w4.x); em.mark_word(gword + wi + 1, w4.y);
+            em.mark_word(gword + wi + 2, w4.z); em.mark_word(gword + wi + 3, w4.w);
+          }
+          const uint32_t c01 = __popc(w4.x) + __popc(w4.y), c = c01 + __popc(w4.z) + __popc(w4.w);
+          uint32_t incl = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += y;
+          }
+          if (wi < W) {
+            const uint32_t first = run + incl - c;
+            *reinterpret_cast<uint32_t *>(pk + (wi >> 1)) = first | ((first + c01) << 16);   // pairs (wi, wi+1), (wi+2, wi+3)
+          }
+          run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        const uint32_t tot = run;
+        const bool staged = tot <= (uint32_t)P.ts_words;
+        const uint32_t mk = (1u << (2 * k)) - 1u;
+        auto place = [&](const XWindow &V, int x) {
+          if (__ffs((V.inv >> x) | (1u << N)) - 1 < k) return;          // no valid k-mer starts here
+          uint32_t c = (uint32_t)(V.rev >> (64 - 2 * (x + k))) & mk;
+          if (op == 1) c = min(c, ~(uint32_t)(V.fwd >> (2 * x)) & mk);
+          else if (op == 3) c = min(c, (uint32_t)(V.fwd >> (2 * x)) & mk);
+          else if (op == 2) c = min(c, (~c) & mk);
+          const uint32_t wd = c >> 5, bit = 1u << (c & 31), wv = bk[wd];
+          if (!(wv & bit)) return;                                      // class dropped by the frozen list
+          uint32_t slot = pk[wd >> 1] + __popc(wv & (bit - 1u));
+          if (wd & 1u) slot += __popc(bk[wd - 1]);
+          uint32_t col;
+          em.column(P.level_off[k] + c, col);
+          if (staged) tab[sw(slot)] = col; else em.sid[em.cursor + slot] = col;
+        };
+        {
+          XWindow V;
+          if (E > 0) {
+#pragma unroll
+            for (int i = 0; i < EE; i++) {
+              if ((i & 15) == 0 && i < spl) V.load(b2, iv16, L, p0 + i);
+              if (i < spl && p0 + i < L) place(V, i & 15);
+            }
+          } else {
+            for (int i = 0; i < spl && p0 + i < L; i++) {
+              if ((i & 15) == 0) V.load(b2, iv16, L, p0 + i);
+              place(V, i & 15);
+            }
+          }
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < tot; i += 32) {
+          if (staged) em.sid[em.cursor + i] = tab[sw(i)];
+          if (!P.binarize) em.scnt[em.cursor + i] = 1;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          dupn[4 + k - P.b_lo] = em.cursor;                             // row slot of the level's first class (repeats below)
+          em.sq += tot;                                                 // every class of the level enters with count 1
+        }
+        if (tot) em.vm = max(em.vm, 1u);
+        em.cursor += tot;
+      }
+#endif
       __syncwarp();
       __threadfence_block();
       // repeats: add one to the count of the class, found by its rank in the bitmap
@@ -565,8 +760,14 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
           const uint32_t k = e >> 26, c = e & 0x3FFFFFFu, wi = c >> 5;
           const uint32_t *bk = bm + P.bm_off[k];
           if (!((bk[wi] >> (c & 31)) & 1u)) continue;       // class dropped by the frozen list
+#if KL_X_WALK
           uint32_t slot = pf[P.pf_off[k] + (wi >> 2)] + __popc(bk[wi] & ((1u << (c & 31)) - 1u));
           for (uint32_t j = wi & ~3u; j < wi; j++) slot += __popc(bk[j]);
+#else
+          uint32_t slot = dupn[4 + k - P.b_lo] + reinterpret_cast<const unsigned short *>(pf + P.pf_off[k])[wi >> 1] +
+                          __popc(bk[wi] & ((1u << (c & 31)) - 1u));
+          if (wi & 1u) slot += __popc(bk[wi - 1]);
+#endif
           const uint32_t old = atomicAdd(em.scnt + slot, 1u);
           em.sq += 2ull * old + 1ull;                       // (old+1)^2 - old^2
           em.vm = max(em.vm, old + 1u);

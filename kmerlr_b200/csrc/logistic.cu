@@ -624,6 +624,25 @@ __global__ void sum_ranks(const double *__restrict__ gathered, int world, int64_
   out[j] = s;
 }
 
+// Sharded loss: the per-rank loss sums ride in the gradient all-reduce.  Rank r puts the bits of its sum into
+// slot r and zeros into the other slots: the int64 sum over the ranks then returns every rank's bits
+// unchanged, and every rank adds the sums in rank order (the same bits everywhere).
+__global__ void pack_loss_slots(const PgState *st, const double *__restrict__ local, unsigned long long *__restrict__ slots,
+                                int rank, int world) {
+  if (st && st->done == 1) return;
+  const int r = threadIdx.x;
+  if (r < world) slots[r] = r == rank ? (unsigned long long)__double_as_longlong(local[0]) : 0ull;
+}
+__global__ void unpack_loss_slots(const PgState *st, const unsigned long long *__restrict__ slots, int world,
+                                  double *__restrict__ out) {
+  if (st && st->done == 1) return;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int r = 0; r < world; r++) s += __longlong_as_double((long long)slots[r]);
+    out[0] = s;
+  }
+}
+
 // hook (kmerLr_estimator_hook.go:46-99): loss = mean + lambda * sum_{j=1..m} |theta_j|
 // l1part[b] = sum over block b's stride of lambda |theta_j|, j >= 1 (fixed order: deterministic)
 __global__ void l1_partials(const PgState *st, const double *__restrict__ theta, int64_t ntheta, double lambda,
@@ -972,11 +991,13 @@ __global__ void __launch_bounds__(256) small_tail_kernel(PgState *st, const doub
 }
 
 // Sharded reduced matrices, ranks connected by NVLink: the gradient all-reduce, the loss all-gather and
-// the tail of the iteration in ONE block.  Every rank stores its payload (fixed-point gradient + loss
-// partial) straight into every rank's mailbox (peer memory, CUDA IPC), raises its flag there, waits for
-// the flags of the others in its own mailbox and sums the payloads in rank order -- integers, so every
-// rank holds the same bits -- then runs hook / prox step / stopping rule.  Two parities of slots: a
-// sender can be at most one exchange ahead of a receiver.
+// the tail of the iteration in ONE launch of world + 1 blocks.  Block b < world stores this rank's payload
+// (fixed-point gradient + loss partial) straight into rank b's mailbox (peer memory, CUDA IPC) and raises
+// this rank's flag there -- the world stores travel in parallel; block `world` waits for the flags of all
+// senders in its own mailbox, sums the payloads in rank order -- integers, so every rank holds the same
+// bits -- and runs hook / prox step / stopping rule.  Two parities of slots: a sender can be at most one
+// exchange ahead of a receiver.  (One block doing the world stores one after the other: 36 us per
+// iteration at 8 ranks against 20 us on one GPU.)
 __global__ void __launch_bounds__(256) small_p2p_tail_kernel(PgState *st, const PeerBox *pb, const double *__restrict__ blockloss,
                                                              int nblocks, double *theta, unsigned long long *G,
                                                              double *scratch, double inv_scale, int64_t ntheta, double inv_n,
@@ -987,38 +1008,51 @@ __global__ void __launch_bounds__(256) small_p2p_tail_kernel(PgState *st, const 
   __shared__ int s_timeout;
   const int t = threadIdx.x, me = pb->rank, world = pb->world;
   PeerMail *mine = pb->box[me];
+  // (the sequence number is bumped by the last block only after every sender block of this launch is through)
   const unsigned long long seq = mine->seq + 1ull;
   const int par = (int)(seq & 1ull);
-  if (t == 0) s_timeout = 0;
-  // loss partial of this rank: block partials in a fixed order
-  double s = 0.0;
-  for (int i = t; i < nblocks; i += 256) s += blockloss[i];
-  shs[t] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (t < o) shs[t] += shs[t + o];
+  if ((int)blockIdx.x < world) {
+    // ---- sender: payload into mailbox blockIdx.x (NVLink stores), then the flag ----
+    const int dst_rank = (int)blockIdx.x;
+    double s = 0.0;
+    for (int i = t; i < nblocks; i += 256) s += blockloss[i];      // loss partial of this rank, fixed order
+    shs[t] = s;
     __syncthreads();
-  }
-  // payload into every mailbox (NVLink stores), then the flag
-  for (int r = 0; r < world; r++) {
-    unsigned long long *dst = pb->box[r]->slot[par][me];
+    for (int o = 128; o > 0; o >>= 1) {
+      if (t < o) shs[t] += shs[t + o];
+      __syncthreads();
+    }
+    unsigned long long *dst = pb->box[dst_rank]->slot[par][me];
     for (int64_t k = t; k < ntheta; k += 256) dst[k] = G[k];
     if (t == 0) dst[ntheta] = (unsigned long long)__double_as_longlong(shs[0]);
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) {
+      *(volatile unsigned long long *)&pb->box[dst_rank]->flag[par][me] = seq;
+      __threadfence();
+      atomicAdd(&mine->senders_done, 1u);
+    }
+    return;
   }
-  __threadfence_system();
+  // ---- receiver: wait for every sender's flag in my own mailbox ----
+  if (t == 0) s_timeout = 0;
   __syncthreads();
   if (t < world) {
-    volatile unsigned long long *f = &pb->box[t]->flag[par][me];
-    *f = seq;
-    // ... and wait for sender t's flag in my own mailbox
     volatile unsigned long long *g = &mine->flag[par][t];
     const long long t0 = clock64();
     while (*g < seq)
       if (clock64() - t0 > 6000000000LL) { s_timeout = 1; break; }      // ~3 s: a peer is gone
   }
+  // ... and for my own sender blocks: they read G and the sequence number, both change below
+  if (t == 32) {
+    volatile unsigned int *d = &mine->senders_done;
+    const long long t0 = clock64();
+    while (*d < (unsigned)world)
+      if (clock64() - t0 > 6000000000LL) { s_timeout = 1; break; }
+  }
   __syncthreads();
   if (s_timeout) {
-    if (t == 0) { st->error = 1; st->done = 1; }
+    if (t == 0) { st->error = 1; st->done = 1; mine->senders_done = 0u; }
     return;
   }
   __threadfence_system();
@@ -1030,7 +1064,7 @@ __global__ void __launch_bounds__(256) small_p2p_tail_kernel(PgState *st, const 
   if (t < world) scratch[t] = __longlong_as_double((long long)__ldcv(&mine->slot[par][t][ntheta]));
   __threadfence();
   __syncthreads();
-  if (t == 0) mine->seq = seq;
+  if (t == 0) { mine->senders_done = 0u; mine->seq = seq; }
   small_tail(st, scratch, world, theta, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter);
 }
 
@@ -1170,13 +1204,13 @@ void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st,
   KL_LAUNCH(imp_columns, (unsigned)((M.m + 255) / 256), 256, 0, P, M.class_ids.p, M.m, wk.H.p, wk.G.p, st);
 }
 
-// the fused pass: loss terms + fixed-point gradient of the single-feature coefficients (all ranks)
-// scatter = 0: loss terms only (G is left untouched)
+// the fused pass: loss terms + fixed-point gradient of the single-feature coefficients of THIS rank's rows
+// (the caller reduces over the ranks); scatter = 0: loss terms only (G is left untouched)
 template <typename VT>
 void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, int scatter = 1) {
-  // G[m+1] is the row ticket of fused_kernel
-  if (scatter) KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 2) * sizeof(unsigned long long), ctx().stream));
-  else KL_CUDA(cudaMemsetAsync(wk.G.p + M.m + 1, 0, sizeof(unsigned long long), ctx().stream));
+  // G: [0, m] gradient | [m+1, m+1+world) loss slots of the ranks | [m+1+PEER_MAX_WORLD] row ticket of fused_kernel
+  if (scatter) KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 2 + PEER_MAX_WORLD) * sizeof(unsigned long long), ctx().stream));
+  else KL_CUDA(cudaMemsetAsync(wk.G.p + M.m + 1 + PEER_MAX_WORLD, 0, sizeof(unsigned long long), ctx().stream));
   if (M.n > 0) {
     if (use_implicit(M)) {
       launch_implicit(M, wk, cw, st, scatter);
@@ -1192,10 +1226,9 @@ void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, in
       if (blocks > need) blocks = need;
       KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, smem, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
                 M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter, hot,
-                wk.G.p + M.m + 1);
+                wk.G.p + M.m + 1 + PEER_MAX_WORLD);
     }
   }
-  if (M.sharded && scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
 }
 
 void alloc_work(const Matrix &M, int64_t ntheta, Work &wk) {
@@ -1203,7 +1236,7 @@ void alloc_work(const Matrix &M, int64_t ntheta, Work &wk) {
   wk.w.alloc((size_t)(M.n ? M.n : 1));
   wk.lossterm.alloc((size_t)(M.n ? M.n : 1));
   wk.g.alloc((size_t)ntheta);
-  wk.G.alloc((size_t)M.m + 2);      // + the row ticket of fused_kernel
+  wk.G.alloc((size_t)M.m + 2 + PEER_MAX_WORLD);      // + loss slots of the ranks + the row ticket of fused_kernel
   wk.red.alloc(RED_BLOCKS);
   wk.scalars.alloc(8);
   wk.blockmax.alloc(4 * PROX_BLOCKS);    // max |theta|, max |delta|, NaN flag per block + the L1 partials of the hook
@@ -1251,6 +1284,7 @@ void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2]
     using VT = typename std::remove_pointer<decltype(tag)>::type;
     if (!cooc) {
       launch_fused<VT>(M, wk, cw, nullptr);
+      if (M.sharded) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
     } else {
       // pair mode: z needs the pair terms, so the weights come from the general rows kernel; the
       // single-feature part still goes through the fixed-point pass with theta restricted to it
@@ -1405,22 +1439,32 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
         });
         if (M.sharded && ctx().peer && ctx().p2p_ok) {
           // exchange over peer memory fused with the tail of the iteration
-          KL_LAUNCH(small_p2p_tail_kernel, 1, 256, 0, st.p, ctx().peer, blockloss.p, small_blocks, wk.theta.p, wk.G.p,
+          KL_LAUNCH(small_p2p_tail_kernel, (unsigned)(ctx().world + 1), 256, 0, st.p, ctx().peer, blockloss.p, small_blocks, wk.theta.p, wk.G.p,
                     wk.gathered.p, wk.inv_scale, ntheta, inv_n, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
         } else if (M.sharded) {
           // gradient: exact int64 all-reduce; loss: per-rank sums gathered and added in rank order
+          unsigned long long *slots = wk.G.p + ntheta;
           KL_LAUNCH(small_presum_kernel, 1, 256, 0, st.p, blockloss.p, small_blocks, wk.scalars.p);
-          if (scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, ntheta);
-          comm_allgather_f64(wk.scalars.p, wk.gathered.p, 1);
-          KL_LAUNCH(small_tail_kernel, 1, 256, 0, st.p, wk.gathered.p, ctx().world, wk.theta.p, wk.G.p, wk.inv_scale, ntheta,
-                    inv_n, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
+          KL_LAUNCH(pack_loss_slots, 1, 32, 0, st.p, wk.scalars.p, slots, ctx().rank, ctx().world);
+          if (scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, ntheta + ctx().world);
+          else comm_allreduce_sum_i64((int64_t *)slots, ctx().world);
+          KL_LAUNCH(small_tail_kernel, 1, 256, 0, st.p, reinterpret_cast<const double *>(slots), ctx().world, wk.theta.p,
+                    wk.G.p, wk.inv_scale, ntheta, inv_n, lambda, epsilon_loss, step, epsilon, (long long)max_iter);
         }
         continue;
       }
       dispatch_vt(M, [&](auto *tag) {
         using VT = typename std::remove_pointer<decltype(tag)>::type;
         launch_fused<VT>(M, wk, cw, st.p, scatter);
-        reduce_sum(M, wk.lossterm.p, M.n, wk, wk.scalars.p, st.p);
+        reduce_sum(M, wk.lossterm.p, M.n, wk, wk.scalars.p, st.p, false);
+        if (M.sharded) {
+          // ONE collective per iteration: gradient words + the loss sums of the ranks
+          unsigned long long *slots = wk.G.p + M.m + 1;
+          KL_LAUNCH(pack_loss_slots, 1, 32, 0, st.p, wk.scalars.p, slots, ctx().rank, ctx().world);
+          if (scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1 + ctx().world);
+          else comm_allreduce_sum_i64((int64_t *)slots, ctx().world);
+          KL_LAUNCH(unpack_loss_slots, 1, 32, 0, st.p, slots, ctx().world, wk.scalars.p);
+        }
         KL_LAUNCH(l1_partials, PROX_BLOCKS, 256, 0, st.p, wk.theta.p, M.m + 1, lambda, wk.blockmax.p + 3 * PROX_BLOCKS);
         KL_LAUNCH(hook_kernel, 1, 32, 0, st.p, wk.scalars.p, wk.blockmax.p + 3 * PROX_BLOCKS, PROX_BLOCKS, inv_n, epsilon_loss);
         KL_LAUNCH(prox_update, PROX_BLOCKS, 256, 0, st.p, wk.theta.p, wk.G.p, wk.inv_scale, ntheta, step, lambda,

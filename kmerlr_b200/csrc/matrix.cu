@@ -379,17 +379,24 @@ void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n) {
   std::vector<uint8_t> l((size_t)n);
   int64_t ones = 0;
   for (int64_t i = 0; i < n; i++) { const uint8_t v = labels[i] != 0; l[i] = v; ones += v; }
-  int64_t cnt[2] = {n - ones, ones};
   M.labels.upload(l.data(), (size_t)n);
-  if (M.sharded) {
-    DevBuf<int64_t> tmp(2);
-    tmp.upload(cnt, 2);
-    comm_allreduce_sum_i64(tmp.p, 2);
-    tmp.download(cnt, 2);
-  }
+  sync_stream();
+  // the global counts (class weights) are summed over the ranks when somebody asks: no collective here
+  M.n_neg = n - ones; M.n_pos = ones;
+  M.counts_global = !M.sharded;
+  M.has_labels = true;
+}
+
+void matrix_label_counts(Matrix &M) {
+  if (M.counts_global) return;
+  int64_t cnt[2] = {M.n_neg, M.n_pos};
+  DevBuf<int64_t> tmp(2);
+  tmp.upload(cnt, 2);
+  comm_allreduce_sum_i64(tmp.p, 2);
+  tmp.download(cnt, 2);
   sync_stream();
   M.n_neg = cnt[0]; M.n_pos = cnt[1];
-  M.has_labels = true;
+  M.counts_global = true;
 }
 
 template <typename VT>
@@ -501,7 +508,7 @@ std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nse
   if (M.has_labels) {
     R->labels.alloc((size_t)(M.n ? M.n : 1));
     KL_CUDA(cudaMemcpyAsync(R->labels.p, M.labels.p, (size_t)M.n, cudaMemcpyDeviceToDevice, ctx().stream));
-    R->n_pos = M.n_pos; R->n_neg = M.n_neg; R->has_labels = true;
+    R->n_pos = M.n_pos; R->n_neg = M.n_neg; R->counts_global = M.counts_global; R->has_labels = true;
     sync_stream();
   }
   return R;
