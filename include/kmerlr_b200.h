@@ -113,6 +113,15 @@ int kmerlr_matrix_from_csr(int64_t n, int64_t m, const int64_t *rowptr, const in
  * what TransformFull.Fit computes its offsets / scales from (kmerLr_transform.go:59-252); count and
  * binarized matrices only.  The transform itself is a reparameterisation of theta on the host side. */
 int kmerlr_column_moments(kmerlr_handle h, double *sum_m, double *sumsq_m, double *absmax_m, int64_t *count_m);
+/* the same four moments of the pair features v_a v_b, a < b, in CoeffIndex order (position = Ind2Sub(a, b) - (m + 1)):
+ * TransformFull.Fit with cooccurrence (kmerLr_transform.go:90-99,118-127); m (m - 1) / 2 entries each */
+int kmerlr_pair_moments(kmerlr_handle h, double *sum_p, double *sumsq_p, double *absmax_p, int64_t *count_p);
+/* Transform.Apply (kmerLr_transform.go:584-629) on the rows of a (reduced) matrix, as estimate() does before it
+ * hands the data to the solver (kmerLr_estimator.go:148): offset / scale per coefficient (index 0 = bias), either
+ * may be NULL.  With an offset every entry, zeros included, becomes (v - offset_j) scale_j -- dense rows, meant for
+ * the reduced matrix of the selected features; scale only keeps the sparsity.  Returns a new matrix (labels copied). */
+int kmerlr_matrix_transform(kmerlr_handle h, const double *offset_or_null, const double *scale_or_null, int64_t len,
+                            kmerlr_handle *out);
 int kmerlr_free(kmerlr_handle h);
 
 /* ---- CoeffIndex (kmerLr_coefficients_index.go:26-54) ---------------------------------------- */

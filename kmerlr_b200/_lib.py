@@ -19,7 +19,7 @@ SYMBOLS = [
     "kmerlr_init", "kmerlr_shutdown", "kmerlr_last_error", "kmerlr_version", "kmerlr_last_device_ms",
     "kmerlr_launch_count", "kmerlr_option", "kmerlr_profile", "kmerlr_profile_read", "kmerlr_profile_dump", "kmerlr_comm_unique_id", "kmerlr_comm_init", "kmerlr_comm_destroy",
     "kmerlr_sequences_create", "kmerlr_extract_resident", "kmerlr_extract", "kmerlr_matrix_info", "kmerlr_matrix_rows_global",
-    "kmerlr_matrix_classes", "kmerlr_column_moments", "kmerlr_matrix_rows", "kmerlr_matrix_set_labels", "kmerlr_matrix_from_csr",
+    "kmerlr_matrix_classes", "kmerlr_column_moments", "kmerlr_pair_moments", "kmerlr_matrix_transform", "kmerlr_matrix_rows", "kmerlr_matrix_set_labels", "kmerlr_matrix_from_csr",
     "kmerlr_free", "kmerlr_coeff_dim", "kmerlr_coeff_ind2sub", "kmerlr_coeff_sub2ind", "kmerlr_linear_pdf",
     "kmerlr_logpdf", "kmerlr_gradient", "kmerlr_loss", "kmerlr_class_weights", "kmerlr_select", "kmerlr_select_from_gradient", "kmerlr_reduce",
     "kmerlr_step_size", "kmerlr_proxgrad", "kmerlr_coordinate", "kmerlr_window_slots", "kmerlr_score_windows", "kmerlr_predict_windows",
@@ -78,6 +78,8 @@ def lib():
     L.kmerlr_matrix_classes.argtypes = [h, vp, vp]
     L.kmerlr_matrix_rows.argtypes = [h, vp, vp, vp]
     L.kmerlr_column_moments.argtypes = [h, vp, vp, vp, vp]
+    L.kmerlr_pair_moments.argtypes = [h, vp, vp, vp, vp]
+    L.kmerlr_matrix_transform.argtypes = [h, vp, vp, i64, ph]
     L.kmerlr_matrix_set_labels.argtypes = [h, vp, i64]
     L.kmerlr_matrix_from_csr.argtypes = [i64, i64, vp, vp, vp, C.c_int, ph]
     L.kmerlr_free.argtypes = [h]

@@ -331,13 +331,24 @@ class Transform:
         idx = np.nonzero(b)[0] if b.dtype == bool else b.astype(np.int64)
         return Transform(None if self.Offset is None else self.Offset[idx], None if self.Scale is None else self.Scale[idx])
 
+    def Apply(self, data):
+        """Transform.Apply (kmerLr_transform.go:584-629) on the rows of a reduced data set, as estimate() does before
+        the solver runs (kmerLr_estimator.go:148): returns the transformed data set (a new matrix in HBM; with an
+        offset its rows are dense).  A nil transform returns `data` itself."""
+        if self.Nil():
+            return data
+        h = C.c_uint64()
+        n = len(self.Offset if self.Offset is not None else self.Scale)
+        check(lib().kmerlr_matrix_transform(data.h, _p(self.Offset), _p(self.Scale), n, h))
+        r = KmerDataSet(h.value)
+        r.Labels = data.Labels
+        return r
+
 
 class TransformFull(Transform):
     def Fit(self, data, kind, cooccurrence=False):
         """TransformFull.Fit (kmerLr_transform.go:40-252) from the column moments computed on the device"""
         kind = (kind or "none").lower()
-        if cooccurrence:
-            raise KmerLrError(_lib.ERR_ARG, "data transforms of pair features are not implemented on the GPU path")
         if kind in ("", "none"):
             self.Offset = self.Scale = None
             return self
@@ -346,6 +357,14 @@ class TransformFull(Transform):
         cnt = np.zeros(max(m, 1), dtype=np.int64)
         check(lib().kmerlr_column_moments(data.h, _p(s1), _p(s2), _p(mx), _p(cnt)))
         s1, s2, mx = s1[:m], s2[:m], mx[:m]
+        if cooccurrence:
+            # pair features v_a v_b in CoeffIndex order after the single features (kmerLr_transform.go:90-99,118-127)
+            npairs = m * (m - 1) // 2
+            p1, p2, pm = np.zeros(max(npairs, 1)), np.zeros(max(npairs, 1)), np.zeros(max(npairs, 1))
+            pc = np.zeros(max(npairs, 1), dtype=np.int64)
+            check(lib().kmerlr_pair_moments(data.h, _p(p1), _p(p2), _p(pm), _p(pc)))
+            s1, s2, mx = (np.concatenate([a, b[:npairs]]) for a, b in ((s1, p1), (s2, p2), (mx, pm)))
+            m = m + npairs
         n = float(data.n_global)
         offset, scale = np.zeros(m + 1), np.ones(m + 1)
         if kind in ("standardizer", "variance-scaler"):
@@ -382,8 +401,6 @@ class logisticRegression:
         self.Lambda = float(Lambda)
         self.Cooccurrence = bool(Cooccurrence)
         self.Transform = Transform
-        if Transform is not None and not Transform.Nil() and self.Cooccurrence:
-            raise KmerLrError(_lib.ERR_ARG, "data transforms of pair features are not implemented on the GPU path")
 
     def Dim(self):
         return len(self.Theta) - 1
@@ -431,7 +448,7 @@ class logisticRegression:
                                         int(self.Cooccurrence), _p(g)))
             return g
         t = self._theta_eff()
-        check(lib().kmerlr_gradient(data.h, _p(t), len(t), _p(self.ClassWeights), 0.0, 0, _p(g)))
+        check(lib().kmerlr_gradient(data.h, _p(t), len(t), _p(self.ClassWeights), 0.0, int(self.Cooccurrence), _p(g)))
         g0 = g[0]
         if self.Transform.Offset is not None:
             g[1:] -= self.Transform.Offset[1:] * g0
@@ -450,7 +467,7 @@ class logisticRegression:
                                     int(self.Cooccurrence), out))
             return out.value
         t = self._theta_eff()
-        check(lib().kmerlr_loss(data.h, _p(t), len(t), _p(self.ClassWeights), 0.0, 0, out))
+        check(lib().kmerlr_loss(data.h, _p(t), len(t), _p(self.ClassWeights), 0.0, int(self.Cooccurrence), out))
         r = out.value
         if self._penalty():
             r += self.Lambda * float(np.sum(np.abs(self.Theta[1:data.m + 1])))
@@ -536,6 +553,7 @@ class KmerLrEstimator:
         self.ClassWeights = np.ones(2)
         self.hook_state = np.array([np.nan, np.nan])
         self.path = []
+        self.Transform = None            # the selected transform of the last estimate (r.Transform of the reference's KmerLr)
 
     def estimate_proximal(self, data_train, lam):
         """estimate_proximal (kmerLr_estimator_proximal.go:78-120) on the (reduced) data set."""
@@ -559,11 +577,15 @@ class KmerLrEstimator:
         self.Theta = theta
         return sweeps.value, delta.value
 
-    def estimate_loop(self, data, lambdaAuto, balance=False):
-        """estimate_loop (kmerLr_estimator.go:209-255): leapfrog epochs until Select returns !ok."""
+    def estimate_loop(self, data, lambdaAuto, balance=False, transform=None):
+        """estimate_loop (kmerLr_estimator.go:209-255): leapfrog epochs until Select returns !ok.  transform: the
+        TransformFull fitted on `data` (or None): the selection gradient is taken under it, and every reduced data
+        set goes through Transform.Apply before the solver sees it, as estimate() does (kmerLr_estimator.go:148);
+        self.Theta is then the coefficient vector of the TRANSFORMED features, as in the reference's model."""
         n = data.n_global                # len(data.Data) of the whole set: the same L1Reg on every rank
         self.ClassWeights = data.class_weights() if balance else np.ones(2)
-        s = featureSelector(self.ClassWeights, self.Cooccurrence, lambdaAuto, data.m, self.EpsilonLambda, self.tie)
+        s = featureSelector(self.ClassWeights, self.Cooccurrence, lambdaAuto, data.m, self.EpsilonLambda, self.tie,
+                            Transform=transform)
         r = False
         epoch = 0
         while self.MaxEpochs == 0 or epoch < self.MaxEpochs:
@@ -575,6 +597,11 @@ class KmerLrEstimator:
             self.Theta = selection.Theta()
             reduced = selection.Data(data)
             reduced.SetLabels(data.Labels)
+            if transform is not None and not transform.Nil():
+                self.Transform = transform.Select(selection.sel)        # selection.Transform()
+                tdata = self.Transform.Apply(reduced)
+                reduced.free()
+                reduced = tdata
             iters, _ = self.estimate_proximal(reduced, lam)
             reduced_nnz = reduced.nnz
             reduced.free()
@@ -583,11 +610,11 @@ class KmerLrEstimator:
             epoch += 1
         return epoch
 
-    def Estimate(self, data, LambdaAuto, balance=False):
+    def Estimate(self, data, LambdaAuto, balance=False, transform=None):
         """Estimate (kmerLr_estimator.go:257-270): one warm-started loop per target."""
         out = []
         for n in LambdaAuto:
-            self.estimate_loop(data, n, balance)
+            self.estimate_loop(data, n, balance, transform)
             out.append((self.active_idx.copy(), self.Theta.copy()))
         return out
 

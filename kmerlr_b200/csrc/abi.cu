@@ -320,6 +320,21 @@ int kmerlr_column_moments(kmerlr_handle h, double *sum, double *sumsq, double *a
   });
 }
 
+int kmerlr_pair_moments(kmerlr_handle h, double *sum, double *sumsq, double *absmax, int64_t *count) {
+  return guarded([&] {
+    KL_REQUIRE(sum && sumsq && absmax && count, "null argument");
+    matrix_pair_moments(*lookup<Matrix>(h, "matrix"), sum, sumsq, absmax, count);
+  });
+}
+
+int kmerlr_matrix_transform(kmerlr_handle h, const double *offset_or_null, const double *scale_or_null, int64_t len,
+                            kmerlr_handle *out) {
+  return guarded([&] {
+    KL_REQUIRE(out, "null output handle");
+    *out = register_object(matrix_transform(*lookup<Matrix>(h, "matrix"), offset_or_null, scale_or_null, len));
+  });
+}
+
 int kmerlr_free(kmerlr_handle h) {
   return guarded([&] {
     KL_REQUIRE(g_objects.erase(h) == 1, "kmerlr_free: invalid handle");

@@ -323,6 +323,8 @@ void matrix_rows(Matrix &M, int64_t *rowptr, int32_t *col, double *val);
 void matrix_set_labels(Matrix &M, const uint8_t *labels, int64_t n);
 void matrix_label_counts(Matrix &M);   // n_pos / n_neg over all ranks (collective on a sharded matrix, first call only)
 void matrix_column_moments(Matrix &M, double *sum, double *sumsq, double *absmax, int64_t *count);
+void matrix_pair_moments(Matrix &M, double *sum, double *sumsq, double *absmax, int64_t *count);   // m (m - 1) / 2 pairs
+std::shared_ptr<Matrix> matrix_transform(Matrix &M, const double *offset, const double *scale, int64_t len);
 void matrix_compact(Matrix &M);      // padded rows -> compact CSR (no-op for compact matrices)
 void ensure_csc(Matrix &M);
 std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel);
@@ -331,7 +333,7 @@ double matrix_vmax(Matrix &M);
 // logistic.cu
 void linear_pdf(Matrix &M, const double *theta, int64_t ntheta, int cooc, double *out_host, bool logpdf);
 void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc,
-              double *g_host);
+              double *g_host, DevBuf<double> *g_dev = nullptr);   // g_dev: the gradient stays on the device
 double loss(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc);
 void coordinate(Matrix &M, double *theta, int64_t ntheta, const double cw_hook[2], double l1reg, double l2reg,
                 double epsilon, double epsilon_loss, int64_t max_iter, double hook[2], int64_t *sweeps_out,

@@ -1272,7 +1272,7 @@ void linear_pdf(Matrix &M, const double *theta, int64_t ntheta, int cooc, double
 }
 
 void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc,
-              double *g_host) {
+              double *g_host, DevBuf<double> *g_dev) {
   require_ready();
   check_theta(M, ntheta, cooc);
   KL_REQUIRE(M.has_labels, "gradient: the matrix has no labels (kmerlr_matrix_set_labels)");
@@ -1311,8 +1311,9 @@ void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2]
   KL_LAUNCH(finalize_g, (unsigned)((M.m + 1 + 255) / 256), 256, 0, wk.G.p, M.m + 1, wk.inv_scale, wk.g.p);
   if (!std::isnan(lambda) && lambda != 0.0)
     KL_LAUNCH(add_l1_sign, (unsigned)((ntheta + 255) / 256), 256, 0, wk.theta.p, wk.g.p, ntheta, lambda);
-  wk.g.download(g_host, (size_t)ntheta);
+  if (g_host) wk.g.download(g_host, (size_t)ntheta);
   sync_stream();
+  if (g_dev) *g_dev = std::move(wk.g);
 }
 
 double loss(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], double lambda, int cooc) {

@@ -246,7 +246,153 @@ __global__ void column_moments(const Rows R, const uint32_t *__restrict__ col, c
   }
 }
 
+// the same four moments for the pair features v_a v_b, a < b (TransformFull.Fit with cooccurrence,
+// kmerLr_transform.go:90-99,118-127): one warp per pair intersects the two CSC columns; integer values, exact
+// sums.  Output position = CoeffIndex(m).Ind2Sub(a, b) - (m + 1).
+template <typename VT>
+__global__ void pair_moments(const int64_t *__restrict__ colptr, const uint32_t *__restrict__ crow,
+                             const VT *__restrict__ cval, int64_t m, unsigned long long *__restrict__ s1,
+                             unsigned long long *__restrict__ s2, unsigned long long *__restrict__ mx,
+                             unsigned long long *__restrict__ cnt) {
+  const int64_t npairs = m * (m - 1) / 2, warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = lane_id();
+  for (int64_t pi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pi < npairs; pi += warps) {
+    // pair index -> (a, b), a < b, row-major over the strict upper triangle (= CoeffIndex order)
+    int64_t a = (int64_t)floor(((double)(2 * m - 1) - sqrt((double)(2 * m - 1) * (double)(2 * m - 1) - 8.0 * (double)pi)) / 2.0);
+    while (a > 0 && a * (2 * m - a - 1) / 2 > pi) a--;
+    while ((a + 1) * (2 * m - a - 2) / 2 <= pi) a++;
+    const int64_t b = pi - a * (2 * m - a - 1) / 2 + a + 1;
+    const int64_t a0 = colptr[a], a1 = colptr[a + 1], b0 = colptr[b], b1 = colptr[b + 1];
+    const bool swap = (a1 - a0) > (b1 - b0);
+    const int64_t q0 = swap ? b0 : a0, q1 = swap ? b1 : a1, l0 = swap ? a0 : b0, l1 = swap ? a1 : b1;
+    unsigned long long t1 = 0, t2 = 0, tm = 0, tc = 0;
+    for (int64_t p = q0 + lane; p < q1; p += 32) {
+      const uint32_t r = crow[p];
+      int64_t lo = l0, hi = l1;
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (crow[mid] < r) lo = mid + 1; else hi = mid; }
+      if (lo < l1 && crow[lo] == r) {
+        const unsigned long long v = (cval ? (unsigned long long)cval[p] : 1ull) * (cval ? (unsigned long long)cval[lo] : 1ull);
+        t1 += v; t2 += v * v; tm = v > tm ? v : tm; tc += 1;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t1 += __shfl_xor_sync(0xffffffffu, t1, o); t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+      tc += __shfl_xor_sync(0xffffffffu, tc, o);
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, tm, o);
+      tm = y > tm ? y : tm;
+    }
+    if (lane == 0) { s1[pi] = t1; s2[pi] = t2; mx[pi] = tm; cnt[pi] = tc; }
+  }
+}
+
+// Transform.Apply (kmerLr_transform.go:584-629) on the rows of a (reduced) matrix.  With an offset every entry of
+// every row, zeros included, becomes (v - offset_j) scale_j: the rows turn dense.  Scale only: v scale_j, the
+// sparsity stays.  offset / scale are indexed by coefficient (index 0 = bias, untouched).
+template <typename VT>
+__global__ void transform_dense(const Rows R, const uint32_t *__restrict__ col, const VT *__restrict__ val, int64_t n,
+                                int64_t m, const double *__restrict__ offset, const double *__restrict__ scale,
+                                uint32_t *__restrict__ ocol, double *__restrict__ oval) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  int64_t a, b;
+  R.range(row, a, b);
+  for (int64_t j = lane_id(); j < m; j += 32) {
+    int64_t lo = a, hi = b;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (col[mid] < (uint32_t)j) lo = mid + 1; else hi = mid; }
+    const double v = (lo < b && col[lo] == (uint32_t)j) ? (val ? (double)val[lo] : 1.0) : 0.0;
+    double t = v - offset[j + 1];
+    if (scale) t *= scale[j + 1];
+    ocol[row * m + j] = (uint32_t)j;
+    oval[row * m + j] = t;
+  }
+}
+template <typename VT>
+__global__ void transform_scale(const uint32_t *__restrict__ col, const VT *__restrict__ val, int64_t nnz,
+                                const double *__restrict__ scale, double *__restrict__ oval) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) oval[p] = (val ? (double)val[p] : 1.0) * scale[col[p] + 1];
+}
+
 }  // namespace
+
+std::shared_ptr<Matrix> matrix_transform(Matrix &M, const double *offset, const double *scale, int64_t len) {
+  require_ready();
+  KL_REQUIRE(len == M.m + 1, "transform: offset / scale must have one entry per coefficient (m + 1)");
+  KL_REQUIRE(offset || scale, "transform: neither offset nor scale given");
+  auto R = std::make_shared<Matrix>();
+  R->n = M.n; R->m = M.m; R->vt = VAL_F64;
+  R->sharded = M.sharded; R->n_global = M.n_global;
+  R->n_classes = M.n_classes; R->class_k = M.class_k; R->class_code = M.class_code;
+  DevBuf<double> doff, dsc;
+  if (offset) { doff.alloc((size_t)len); doff.upload(offset, (size_t)len); }
+  if (scale) { dsc.alloc((size_t)len); dsc.upload(scale, (size_t)len); }
+  R->rowptr.alloc((size_t)M.n + 1);
+  if (offset) {
+    KL_REQUIRE(M.n * M.m < ((int64_t)1 << 31), "transform: a data transform with an offset makes the rows dense; "
+               "this matrix would not fit (apply it to the reduced matrix of the selected features)");
+    R->nnz = M.n * M.m;
+    R->col.alloc((size_t)(R->nnz ? R->nnz : 1));
+    R->val_f64.alloc((size_t)(R->nnz ? R->nnz : 1));
+    std::vector<int64_t> rp((size_t)M.n + 1);
+    for (int64_t i = 0; i <= M.n; i++) rp[(size_t)i] = i * M.m;
+    R->rowptr.upload(rp.data(), (size_t)M.n + 1);
+    if (M.n > 0 && M.m > 0) {
+      const unsigned grid = (unsigned)((M.n * 32 + 127) / 128);
+      if (M.vt == VAL_U32)
+        KL_LAUNCH((transform_dense<uint32_t>), grid, 128, 0, M.rows(), M.col.p, M.val_u32.p, M.n, M.m, doff.p, dsc.p, R->col.p, R->val_f64.p);
+      else if (M.vt == VAL_F64)
+        KL_LAUNCH((transform_dense<double>), grid, 128, 0, M.rows(), M.col.p, M.val_f64.p, M.n, M.m, doff.p, dsc.p, R->col.p, R->val_f64.p);
+      else
+        KL_LAUNCH((transform_dense<uint32_t>), grid, 128, 0, M.rows(), M.col.p, (const uint32_t *)nullptr, M.n, M.m, doff.p, dsc.p, R->col.p, R->val_f64.p);
+    }
+    sync_stream();
+  } else {
+    matrix_compact(M);
+    R->nnz = M.nnz;
+    R->col.alloc((size_t)(R->nnz ? R->nnz : 1));
+    R->val_f64.alloc((size_t)(R->nnz ? R->nnz : 1));
+    KL_CUDA(cudaMemcpyAsync(R->rowptr.p, M.rowptr.p, (size_t)(M.n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx().stream));
+    if (M.nnz > 0) {
+      KL_CUDA(cudaMemcpyAsync(R->col.p, M.col.p, (size_t)M.nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx().stream));
+      const unsigned grid = (unsigned)((M.nnz + 255) / 256);
+      if (M.vt == VAL_U32) KL_LAUNCH((transform_scale<uint32_t>), grid, 256, 0, M.col.p, M.val_u32.p, M.nnz, dsc.p, R->val_f64.p);
+      else if (M.vt == VAL_F64) KL_LAUNCH((transform_scale<double>), grid, 256, 0, M.col.p, M.val_f64.p, M.nnz, dsc.p, R->val_f64.p);
+      else KL_LAUNCH((transform_scale<uint32_t>), grid, 256, 0, M.col.p, (const uint32_t *)nullptr, M.nnz, dsc.p, R->val_f64.p);
+    }
+    sync_stream();
+  }
+  if (M.has_labels) {
+    R->labels.alloc((size_t)(M.n ? M.n : 1));
+    KL_CUDA(cudaMemcpyAsync(R->labels.p, M.labels.p, (size_t)M.n, cudaMemcpyDeviceToDevice, ctx().stream));
+    R->n_pos = M.n_pos; R->n_neg = M.n_neg; R->counts_global = M.counts_global; R->has_labels = true;
+    sync_stream();
+  }
+  return R;
+}
+
+void matrix_pair_moments(Matrix &M, double *sum, double *sumsq, double *absmax, int64_t *count) {
+  require_ready();
+  KL_REQUIRE(M.vt != VAL_F64, "pair_moments: only count / binarized matrices (integer values) are supported");
+  KL_REQUIRE(!M.sharded, "pair_moments: not available on a sharded matrix");
+  const int64_t np = M.m * (M.m - 1) / 2;
+  if (np <= 0) return;
+  ensure_csc(M);
+  DevBuf<unsigned long long> d((size_t)(4 * np));
+  if (M.vt == VAL_U32)
+    KL_LAUNCH((pair_moments<uint32_t>), (unsigned)(ctx().sm_count * 8), 256, 0, M.colptr.p, M.crow.p, M.cval_u32.p, M.m, d.p,
+              d.p + np, d.p + 2 * np, d.p + 3 * np);
+  else
+    KL_LAUNCH((pair_moments<uint32_t>), (unsigned)(ctx().sm_count * 8), 256, 0, M.colptr.p, M.crow.p, (const uint32_t *)nullptr,
+              M.m, d.p, d.p + np, d.p + 2 * np, d.p + 3 * np);
+  std::vector<unsigned long long> h((size_t)(4 * np));
+  d.download(h.data(), (size_t)(4 * np));
+  sync_stream();
+  for (int64_t j = 0; j < np; j++) {
+    sum[j] = (double)h[(size_t)j]; sumsq[j] = (double)h[(size_t)(np + j)];
+    absmax[j] = (double)h[(size_t)(2 * np + j)]; count[j] = (int64_t)h[(size_t)(3 * np + j)];
+  }
+}
 
 void matrix_column_moments(Matrix &M, double *sum, double *sumsq, double *absmax, int64_t *count) {
   require_ready();

@@ -364,9 +364,20 @@ def score_windows(models, regions, W, step, threads=0):
 # data transforms (kmerLr_transform.go:40-252,584-629), restated with numpy on DENSIFIED rows -- the
 # reference densifies too when an offset is present (:600-609).  Small inputs only.
 # ---------------------------------------------------------------------------------------------------
-def fit_transform(mat, kind):
-    """TransformFull.Fit for single-feature matrices: returns (offset or None, scale or None), index 0 = bias"""
+def pair_dense(mat):
+    """the pair features v_a v_b, a < b, as dense columns in CoeffIndex order (kmerLr_coefficients_index.go:26-54)"""
     X = mat.dense()
+    n, m = X.shape
+    cols = [X[:, a] * X[:, b] for a in range(m) for b in range(a + 1, m)]
+    return np.stack(cols, axis=1) if cols else np.zeros((n, 0))
+
+
+def fit_transform(mat, kind, cooccurrence=False):
+    """TransformFull.Fit: returns (offset or None, scale or None), index 0 = bias; with cooccurrence the pair features
+    follow the single features in CoeffIndex order (kmerLr_transform.go:59-252)"""
+    X = mat.dense()
+    if cooccurrence:
+        X = np.concatenate([X, pair_dense(mat)], axis=1)
     n, m = X.shape
     kind = (kind or "none").lower()
     if kind in ("", "none"):
@@ -397,8 +408,10 @@ def fit_transform(mat, kind):
     raise ValueError("invalid data transform")
 
 
-def _transformed_dense(mat, offset, scale):
+def _transformed_dense(mat, offset, scale, cooccurrence=False):
     X = mat.dense()
+    if cooccurrence:
+        X = np.concatenate([X, pair_dense(mat)], axis=1)
     if offset is not None:
         X = X - offset[None, 1:]
     if scale is not None:
@@ -410,24 +423,24 @@ def _log_add0(x):
     return np.where(x > 0, x + np.log1p(np.exp(-np.abs(x))), np.log1p(np.exp(-np.abs(x))))
 
 
-def transformed_loss(mat, labels, theta, offset, scale, cw=(1.0, 1.0), lam=0.0):
+def transformed_loss(mat, labels, theta, offset, scale, cw=(1.0, 1.0), lam=0.0, cooccurrence=False):
     """Loss (kmerLr_logistic_regression.go:250-272) on Transform.Apply'd rows"""
     theta = np.asarray(theta, dtype=np.float64)
-    z = theta[0] + _transformed_dense(mat, offset, scale) @ theta[1:]
+    z = theta[0] + _transformed_dense(mat, offset, scale, cooccurrence) @ theta[1:]
     lab = np.asarray(labels).astype(bool)
     r = 0.0
     for i in range(len(z)):                                           # serial over samples
         r -= cw[1] * (-_log_add0(-z[i])) if lab[i] else cw[0] * (-_log_add0(z[i]))
     r /= float(len(z))
     if lam == lam and lam != 0.0:
-        r += lam * np.sum(np.abs(theta[1:]))
+        r += lam * np.sum(np.abs(theta[1:mat.m + 1]))                  # the L1 loop bound is data[0].Dim() (:255,267)
     return float(r)
 
 
-def transformed_gradient(mat, labels, theta, offset, scale, cw=(1.0, 1.0), lam=0.0):
+def transformed_gradient(mat, labels, theta, offset, scale, cw=(1.0, 1.0), lam=0.0, cooccurrence=False):
     """Gradient (kmerLr_logistic_regression.go:151-248) on Transform.Apply'd rows"""
     theta = np.asarray(theta, dtype=np.float64)
-    X = _transformed_dense(mat, offset, scale)
+    X = _transformed_dense(mat, offset, scale, cooccurrence)
     z = theta[0] + X @ theta[1:]
     lab = np.asarray(labels).astype(bool)
     r = -_log_add0(-z)
@@ -436,6 +449,89 @@ def transformed_gradient(mat, labels, theta, offset, scale, cw=(1.0, 1.0), lam=0
     if lam == lam and lam != 0.0:
         g[1:] += lam * np.sign(theta[1:])
     return g
+
+
+def select_from_gradient(g, N, active_idx, active_theta, tie=TIE_GO118, epsilon_lambda=0.0, prev_lambda=0.0):
+    """featureSelector.Select after its gradient call (kmerLr_feature_selection.go:88-134) + computeLambda (:179-192),
+    for a gradient computed elsewhere (e.g. under a data transform)"""
+    g = np.asarray(g, dtype=np.float64)
+    nt = len(g)
+    b = np.zeros(nt, dtype=bool)
+    b[0] = True
+    c = 0
+    for i, th in zip(active_idx, active_theta):
+        if th != 0.0:
+            b[int(i)] = True
+            c += 1
+    vals, idx = nlargest_abs(g[1:], tie)
+    top = min(nt - 1, 2 * N)
+    ok = False
+    for k in range(top):
+        if c >= N:
+            break
+        if not b[idx[k] + 1] and vals[k] != 0.0:
+            ok = True
+            b[idx[k] + 1] = True
+            c += 1
+    for k in range(top):
+        if c >= N:
+            break
+        if not b[idx[k] + 1]:
+            b[idx[k] + 1] = True
+            c += 1
+    if c > N:
+        ok = True
+    lam = 0.0
+    if N <= top:
+        v = abs(vals[N - 1])
+        a = np.abs(g[1:])
+        below = a[a < v]
+        lam = (v + (below.max() if len(below) else 0.0)) / 2.0
+    ok = ok or (epsilon_lambda > 0.0 and abs(prev_lambda - lam) >= epsilon_lambda)
+    return dict(ok=bool(ok), lam=float(lam), c=c, mask=b)
+
+
+def apply_transform(rmat, offset, scale):
+    """Transform.Apply (kmerLr_transform.go:584-629) on a (reduced) matrix: with an offset the rows turn dense"""
+    X = rmat.dense()
+    if offset is not None:
+        X = X - offset[None, 1:]
+    if scale is not None:
+        X = X * scale[None, 1:]
+    return from_dense(X)
+
+
+def estimate_loop_transformed(mat, labels, cw, N, offset, scale, tie=TIE_GO118, epsilon=0.0, epsilon_loss=1e-8,
+                              max_iter=100000, max_epochs=0):
+    """estimate_loop (kmerLr_estimator.go:209-255) under a data transform: the selection gradient is taken under
+    the transform (kmerLr_feature_selection.go:221-229), every reduced data set goes through Transform.Apply before
+    the solver (kmerLr_estimator.go:148).  Returns dict(active_idx, theta, lambdas, iters)."""
+    nt = mat.m + 1
+    active_idx, active_theta, th0, l1reg = np.zeros(0, dtype=np.int64), np.zeros(0), 0.0, 0.0
+    hk = HookState(float("nan"), float("nan"))
+    lambdas, iters, theta, have = [], [], np.zeros(1), False
+    epoch = 0
+    while max_epochs == 0 or epoch < max_epochs:
+        t = np.zeros(nt)
+        t[0] = th0
+        nz = active_theta != 0.0
+        t[active_idx[nz]] = active_theta[nz]
+        g = transformed_gradient(mat, labels, t, offset, scale, cw)
+        r = select_from_gradient(g, N, active_idx, active_theta, tie, prev_lambda=l1reg)
+        if not r["ok"] and have:
+            break
+        lam = r["lam"]
+        l1reg = lam * mat.n
+        sel = np.nonzero(r["mask"])[0].astype(np.int64)
+        red = apply_transform(reduce(mat, sel), None if offset is None else offset[sel], None if scale is None else scale[sel])
+        theta, it, _ = proxgrad(red, labels, t[sel], cw, lam=lam, epsilon=epsilon, epsilon_loss=epsilon_loss,
+                                max_iter=max_iter, hook=hk)
+        active_idx, active_theta, th0 = sel[1:], theta[1:], theta[0]
+        lambdas.append(lam)
+        iters.append(it)
+        have = True
+        epoch += 1
+    return dict(active_idx=active_idx, theta=theta, lambdas=lambdas, iters=iters)
 
 
 # ---------------------------------------------------------------------------------------------------

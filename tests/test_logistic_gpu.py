@@ -230,6 +230,82 @@ def test_kmers5_standardizer_golden_and_transforms(K, oracle, fixtures):
     assert abs(lam - 0.3345505506971979) <= 1e-12
 
 
+def test_kmers5_leapfrog_under_standardizer_end_to_end(K, oracle, fixtures):
+    """TestKmers5 (kmerLr_test.go:155-190) end to end through the C ABI: `learn --lambda-auto=2 --epsilon=0
+    --epsilon-loss=1e-10 --revcomp --data-transform=standardizer 2 6`.  The selection gradient is taken under the
+    transform, every reduced data set goes through Transform.Apply before the proximal-gradient solver
+    (kmerLr_estimator.go:148).  Against the oracle path: same epochs, lambda sequence, iteration counts, theta;
+    against the reference's goldens: Features [[0,0],[1,1]] = the two classes, theta within 1e-4 (two different
+    early-stopped solvers), loss_ with lambda = 4.460029 within 1e-4."""
+    d, ref, y = build(K, oracle, fixtures, 2, 6, revcomp=True)
+    t = K.TransformFull().Fit(d, "standardizer")
+    est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-10, MaxIterations=10 ** 7, tie=K.TIE_GO118)
+    epochs = est.estimate_loop(d, 2, transform=t)
+    oo, os_ = oracle.fit_transform(ref, "standardizer")
+    o = oracle.estimate_loop_transformed(ref, y, (1.0, 1.0), 2, oo, os_, tie=oracle.TIE_GO118, epsilon=0.0,
+                                         epsilon_loss=1e-10, max_iter=10 ** 7)
+    names = ref.class_names()
+    assert est.active_idx.tolist() == o["active_idx"].tolist() == [names.index("aaaatt|aatttt") + 1, names.index("caggag|ctcctg") + 1]
+    assert epochs == len(o["lambdas"]) and [p[1] for p in est.path] == list(o["iters"])
+    assert abs(est.path[0][0] - 0.3345505506971979) <= 1e-12                    # SURVEY section 0
+    assert np.allclose([p[0] for p in est.path], o["lambdas"], rtol=1e-9, atol=0.0)
+    assert np.allclose(est.Theta, o["theta"], rtol=1e-7, atol=1e-12)            # north_star: <= 1e-5
+    golden = np.array([5.552570741538388e-05, -0.00772452196477929, 0.09287154394711336])   # :166-174
+    # (the golden is an early-stopped SAGA iterate, ours an ISTA iterate stopped by the same loss rule: 8e-5 apart;
+    # the tight optimum of the objective is 2.1e-5 from the golden, SURVEY section 0)
+    assert np.max(np.abs(est.Theta - golden)) <= 1e-4
+    # loss_ of the resulting model (kmerLr_loss.go:53-60): frozen counter + Features + Transform.Select + Loss
+    sel = np.concatenate([[0], est.active_idx])
+    rd = K.select_data(d, sel)
+    rd.SetLabels(y)
+    lo = K.logisticRegression(est.Theta, (1.0, 1.0), 4.460029e+00, Transform=est.Transform).Loss(rd)
+    assert abs(lo - 1.107745182633717) <= 1e-4                                   # :186
+    # Transform.Apply itself: dense rows (v - offset) scale, against the numpy restatement
+    td = est.Transform.Apply(rd)
+    rp, col, val = td.rows()
+    X = oracle._transformed_dense(oracle.reduce(ref, sel), oo[sel], os_[sel])
+    assert td.nnz == X.size and np.array_equal(np.diff(rp), np.full(d.n, 2))
+    assert np.allclose(val.reshape(d.n, 2), X, rtol=1e-13, atol=1e-15)
+    # a scale-only transform keeps the sparsity
+    t2 = K.TransformFull().Fit(d, "max-abs-scaler")
+    ts = t2.Select(sel).Apply(rd)
+    rp2, col2, val2 = ts.rows()
+    rp0, col0, val0 = rd.rows()
+    assert np.array_equal(rp2, rp0) and np.array_equal(col2, col0)
+    assert np.allclose(val2, val0 * t2.Scale[sel][col0 + 1], rtol=1e-15, atol=0.0)
+
+
+def test_pair_features_under_a_transform(K, oracle, fixtures):
+    """kmerLr_logistic_regression.go:91-107,200-216 + kmerLr_transform.go:90-99,118-127: the transform covers the
+    pair features v_a v_b as well (offsets / scales in CoeffIndex order); on the device it stays a
+    reparameterisation of theta.  Against a dense numpy restatement on the TestKmers6 fixture."""
+    O = oracle
+    d, ref, y = build(K, O, fixtures, 2, 6, fg="kmerLr_test_co_fg", bg="kmerLr_test_co_bg", revcomp=True)
+    nt = K.CoeffIndex(d.m).Dim()
+    rng = np.random.default_rng(8)
+    cw = (0.8, 1.3)
+    for kind in ("standardizer", "variance-scaler", "max-abs-scaler", "mean-scaler"):
+        t = K.TransformFull().Fit(d, kind, cooccurrence=True)
+        oo, os_ = O.fit_transform(ref, kind, cooccurrence=True)
+        if oo is not None:
+            assert len(t.Offset) == nt and np.allclose(t.Offset, oo, rtol=1e-13, atol=0.0)
+        fin = np.isfinite(os_)
+        assert len(t.Scale) == nt and np.array_equal(np.isfinite(t.Scale), fin)
+        assert np.allclose(t.Scale[fin], os_[fin], rtol=1e-11, atol=0.0)
+        # pairs that never occur together have an infinite max-abs / mean scale in the reference too: keep theta off them
+        theta = np.zeros(nt)
+        pick = rng.choice(np.nonzero(fin)[0][1:], size=60, replace=False)
+        theta[pick] = rng.normal(scale=0.02, size=60)
+        theta[0] = 0.1
+        sc = np.where(fin, os_, 0.0)
+        lr = K.logisticRegression(theta, cw, 0.01, Cooccurrence=True, Transform=K.Transform(t.Offset, np.where(fin, t.Scale, 0.0)))
+        z = theta[0] + O._transformed_dense(ref, oo, sc, True) @ theta[1:]
+        assert np.allclose(lr.LinearPdf(d), z, rtol=1e-10, atol=1e-11)
+        olo = O.transformed_loss(ref, y, theta, oo, sc, cw, 0.01, cooccurrence=True)
+        assert abs(lr.Loss(d) - olo) <= 1e-11 * abs(olo)
+        close_g(lr.Gradient(None, d), O.transformed_gradient(ref, y, theta, oo, sc, cw, 0.01, cooccurrence=True))
+
+
 def test_identical_columns_get_identical_gradients(K, oracle, fixtures):
     """what leapfrog tie handling rests on: the column reduction depends on the column only"""
     d, ref, y = build(K, oracle, fixtures, 2, 6, fg="kmerLr_test_co_fg", bg="kmerLr_test_co_bg", revcomp=True, binarize=True)
