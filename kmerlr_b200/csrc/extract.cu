@@ -432,10 +432,20 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
     return g;
   }
   KL_REQUIRE(cfg.M >= 1 && cfg.M <= cfg.N, "need 1 <= M <= N");
-  KL_REQUIRE(cfg.N <= MAX_N, "k-mer length above 13 is not supported on the GPU path");
-  int nops = (cfg.complement != 0) + (cfg.reverse != 0) + (cfg.revcomp != 0);
-  KL_REQUIRE(nops <= 1, "at most one of complement / reverse / revcomp is supported on the GPU path");
   KL_REQUIRE(n_features == 0 || n_frozen > 0, "an explicit feature list needs a frozen class list");
+  {
+    // What the warp-per-row kernel does not take goes through the sort-based path of gapped.cu (not tuned):
+    // several strand flags at once, k-mers of 14 bases, k > 8 on rows too long for the register sort.
+    const int nops = (cfg.complement != 0) + (cfg.reverse != 0) + (cfg.revcomp != 0);
+    const bool long_sorted = cfg.N > KB_MAX && (s.max_len + 31) / 32 > 64;
+    const bool long_tables = s.max_len >= 65536 && cfg.M <= KT_MAX;      // (16-bit count tables)
+    if (nops > 1 || cfg.N > MAX_N || long_sorted || long_tables) {
+      if (feed && s.n > 0) feed->feed(*seqs, -1);
+      auto g = extract_gapped(cfg, seqs, frozen_k, frozen_code, n_frozen, flags);
+      if (n_features > 0) return apply_features(*g, features, n_features);
+      return g;
+    }
+  }
   const bool sharded = (flags & KMERLR_FLAG_SHARDED) != 0 && ctx().world > 1;
 
   XParams P{};
@@ -473,13 +483,13 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   bool hybrid = P.binarize && cfg.N <= IMP_MAX_N && n_features == 0 && s.n > 0;
   for (int k = cfg.M > KT_MAX + 1 ? cfg.M : KT_MAX + 1; k <= cfg.N && hybrid; k++)
     if (s.max_len - k + 1 > ((int64_t)1 << (2 * k))) hybrid = false;
-  KL_REQUIRE(s.max_len < 65536 || P.t_lo > P.t_hi, "sequences of 65536 bp or more need M > 5 on the GPU path");
+  KL_INVARIANT(s.max_len < 65536 || P.t_lo > P.t_hi);
   KL_REQUIRE(s.max_len < ((int64_t)1 << 30), "sequence too long");
   // keys per lane of the register sort
   int E = 0;
   if (P.s_lo <= cfg.N) {
     E = 2; while (E < steps && E < 128) E <<= 1;
-    KL_REQUIRE(E <= 64, "sequence too long for the register sort path (k > 8 needs L <= ~2000 bp)");
+    KL_INVARIANT(E <= 64);        // (longer rows went to the sort-based path above)
   }
   // per-warp shared memory
   P.bm_words = 0; P.pf_words = 0;

@@ -1,11 +1,14 @@
-// gapped.cu -- k-mer extraction over the gapped nucleotide alphabet {a, c, g, t, n} (SURVEY 8c items 3-6,
-// 8f-3): every k-mer instance contributes all its variants in which a subset of the INTERIOR positions
-// is replaced by the wildcard n (2^(k-2) variants, or those with at most max_ambiguous wildcards).
-// Codes are base-5 numbers (first letter most significant), class = min over the k-mer and its image.
-//
-// This is the configuration the reference's own exact pins use (kmerLr_test.go:30-68).  It is a
-// correctness path, not a tuned one: all (row, class) instances are materialised as 64-bit keys,
-// sorted (CUB radix sort) and run-length encoded; the runs are the stored entries in CSR order.
+// gapped.cu -- the sort-based extraction path: every (row, class) instance becomes a 64-bit key, the keys are
+// sorted (CUB radix sort) and run-length encoded; the runs are the stored entries in CSR order.  A correctness
+// path, not a tuned one, for everything the warp-per-row kernel of extract.cu does not take:
+//   * the gapped nucleotide alphabet {a, c, g, t, n}: every k-mer instance
+//     contributes all its variants in which a subset of the INTERIOR positions is replaced by the wildcard n
+//     (2^(k-2) variants, or those with at most max_ambiguous wildcards); codes are base-5 numbers.  This is the
+//     configuration the reference's own exact pins use (kmerLr_test.go:30-68);
+//   * the nucleotide alphabet with SEVERAL strand flags at once (kmerLr_learn.go:94 passes complement, reverse and
+//     revcomp independently: class = min over the k-mer and every enabled image), with k-mers of 14 bases, or
+//     with k > 8 on rows too long for the register sort of the main kernel.
+// Codes are base-|alphabet| numbers (first letter most significant), class = min over the k-mer and its images.
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -15,11 +18,14 @@ namespace kl {
 
 namespace {
 
-constexpr int GAP_MAX_N = 11;                       // 5^1 + ... + 5^11 < 2^26 dense ids
+constexpr int GAP_MAX_N = 11;                       // gapped alphabet: 5^1 + ... + 5^11 < 2^26 dense ids
+constexpr int SORT_MAX_N = 14;                      // nucleotide alphabet: 4^1 + ... + 4^14 < 2^29 dense ids
 constexpr unsigned long long GAP_NONE = ~0ull;
 
 struct GapParams {
-  int M, N, op, max_amb;
+  int M, N, max_amb;
+  int A;                        // alphabet size: 5 = gapped (wildcard variants), 4 = nucleotide
+  int revcomp, complement, reverse;
   uint32_t level_off[16];       // dense id of (k, code 0), multiples of 32
   uint32_t slots_per_pos;       // sum over k of 2^max(k-2, 0)
   uint32_t slot_off[16];        // offset of level k inside the slots of one position
@@ -41,7 +47,7 @@ __global__ void gapped_fill(const GapParams P, int64_t n, const int64_t *__restr
   const uint32_t *b2 = bits2 + blk[row] * 4;
   const uint16_t *iv = inv16 + blk[row] * 4;
   unsigned long long *out = keys + t * P.slots_per_pos;
-  uint32_t l[GAP_MAX_N + 1];
+  uint32_t l[SORT_MAX_N + 1];
   int valid = 0;                                    // valid bases from p on
   for (int j = 0; j < P.N && p + j < L; j++) {
     const int64_t idx = p + j;
@@ -49,27 +55,25 @@ __global__ void gapped_fill(const GapParams P, int64_t n, const int64_t *__restr
     l[j] = (b2[idx >> 4] >> (2 * (idx & 15))) & 3u;
     valid = j + 1;
   }
+  const unsigned long long A = (unsigned long long)P.A;
   for (int k = P.M; k <= P.N; k++) {
-    const int nin = k >= 2 ? k - 2 : 0;
+    const int nin = (P.A == 5 && k >= 2) ? k - 2 : 0;
     unsigned long long *o = out + P.slot_off[k];
     for (uint32_t mask = 0; mask < (1u << nin); mask++) {
       unsigned long long key = GAP_NONE;
       if (valid >= k && (P.max_amb < 0 || __popc(mask) <= P.max_amb)) {
         // variant digits v[j]: wildcard where the mask says so (interior positions 1 .. k-2)
-        unsigned long long c0 = 0, c1 = 0;
+        auto digit = [&](int j) -> uint32_t { return (j >= 1 && j <= nin && ((mask >> (j - 1)) & 1u)) ? 4u : l[j]; };
+        unsigned long long c0 = 0, cc = 0, cr = 0, crc = 0;
         for (int j = 0; j < k; j++) {
-          const uint32_t v = (j >= 1 && j <= nin && ((mask >> (j - 1)) & 1u)) ? 4u : l[j];
-          c0 = c0 * 5ull + v;
+          c0 = c0 * A + digit(j);
+          cc = cc * A + gap_comp(digit(j));                 // complement keeps the order
+          cr = cr * A + digit(k - 1 - j);                   // reverse keeps the letters
+          crc = crc * A + gap_comp(digit(k - 1 - j));
         }
-        if (P.op) {
-          for (int i = 0; i < k; i++) {
-            const int j = (P.op == 2) ? i : k - 1 - i;                       // complement keeps the order
-            uint32_t v = (j >= 1 && j <= nin && ((mask >> (j - 1)) & 1u)) ? 4u : l[j];
-            if (P.op != 3) v = gap_comp(v);                                  // reverse keeps the letters
-            c1 = c1 * 5ull + v;
-          }
-          if (c1 < c0) c0 = c1;
-        }
+        if (P.complement && cc < c0) c0 = cc;
+        if (P.reverse && cr < c0) c0 = cr;
+        if (P.revcomp && crc < c0) c0 = crc;
         key = ((unsigned long long)row << 40) | (unsigned long long)(P.level_off[k] + (uint32_t)c0);
       }
       o[mask] = key;
@@ -124,18 +128,11 @@ __global__ void gap_enumerate_bits(const uint32_t *__restrict__ bm, const uint32
     v &= v - 1;
   }
 }
-__global__ void gap_bitmap_to_bytes(const uint32_t *__restrict__ bm, int64_t nbits, uint8_t *__restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nbits) out[i] = (bm[i >> 5] >> (i & 31)) & 1u;
-}
-__global__ void gap_bytes_to_bitmap(const uint8_t *__restrict__ in, int64_t nbits, uint32_t *__restrict__ bm, int64_t nw) {
-  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void gap_or_ranks(const uint32_t *__restrict__ all, int world, int64_t nw, uint32_t *__restrict__ bm) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nw) return;
   uint32_t v = 0;
-  for (int b = 0; b < 32; b++) {
-    int64_t i = w * 32 + b;
-    if (i < nbits && in[i]) v |= 1u << b;
-  }
+  for (int r = 0; r < world; r++) v |= all[(int64_t)r * nw + w];
   bm[w] = v;
 }
 
@@ -145,18 +142,19 @@ std::shared_ptr<Matrix> extract_gapped(const kmerlr_config &cfg, std::shared_ptr
                                        const uint64_t *frozen_code, int64_t n_frozen, int flags) {
   require_ready();
   const SeqSet &s = *seqs;
+  const bool gapped = cfg.alphabet == 1;
   KL_REQUIRE(cfg.M >= 1 && cfg.M <= cfg.N, "need 1 <= M <= N");
-  KL_REQUIRE(cfg.N <= GAP_MAX_N, "gapped alphabet: k-mer length above 11 is not supported on the GPU path");
-  int nops = (cfg.complement != 0) + (cfg.reverse != 0) + (cfg.revcomp != 0);
-  KL_REQUIRE(nops <= 1, "at most one of complement / reverse / revcomp is supported on the GPU path");
-  KL_REQUIRE(s.n < ((int64_t)1 << 24), "gapped alphabet: at most 2^24 sequences per call");
+  if (gapped) KL_REQUIRE(cfg.N <= GAP_MAX_N, "gapped alphabet: k-mer length above 11 is not supported on the GPU path");
+  else KL_REQUIRE(cfg.N <= SORT_MAX_N, "k-mer length above 14 is not supported on the GPU path");
+  KL_REQUIRE(s.n < ((int64_t)1 << 24), "sort-based extraction path: at most 2^24 sequences per call");
   const bool sharded = (flags & KMERLR_FLAG_SHARDED) != 0 && ctx().world > 1;
   GapParams P{};
-  P.M = cfg.M; P.N = cfg.N; P.max_amb = cfg.max_ambiguous;
-  P.op = cfg.revcomp ? 1 : (cfg.complement ? 2 : (cfg.reverse ? 3 : 0));
+  P.M = cfg.M; P.N = cfg.N; P.max_amb = gapped ? cfg.max_ambiguous : -1;
+  P.A = gapped ? 5 : 4;
+  P.revcomp = cfg.revcomp != 0; P.complement = cfg.complement != 0; P.reverse = cfg.reverse != 0;
   uint64_t dense = 0, p5 = 1;
   for (int k = 1; k <= cfg.N; k++) {
-    p5 *= 5;
+    p5 *= (uint64_t)P.A;
     if (k < cfg.M) continue;
     P.level_off[k] = (uint32_t)dense;
     dense += (p5 + 31) / 32 * 32;
@@ -164,14 +162,14 @@ std::shared_ptr<Matrix> extract_gapped(const kmerlr_config &cfg, std::shared_ptr
   P.level_off[cfg.N + 1] = (uint32_t)dense;
   const int64_t nbits = (int64_t)dense, nw = nbits / 32;
   P.slots_per_pos = 0;
-  for (int k = cfg.M; k <= cfg.N; k++) { P.slot_off[k] = P.slots_per_pos; P.slots_per_pos += 1u << (k >= 2 ? k - 2 : 0); }
+  for (int k = cfg.M; k <= cfg.N; k++) { P.slot_off[k] = P.slots_per_pos; P.slots_per_pos += gapped ? 1u << (k >= 2 ? k - 2 : 0) : 1u; }
   // positions of every row (host: the lengths are needed for the offsets)
   std::vector<int64_t> len((size_t)s.n), posoff((size_t)s.n + 1, 0);
   s.len.download(len.data(), (size_t)s.n);
   sync_stream();
   for (int64_t i = 0; i < s.n; i++) posoff[i + 1] = posoff[i] + len[i];
   const int64_t total_pos = posoff[s.n], total_slots = total_pos * (int64_t)P.slots_per_pos;
-  KL_REQUIRE(total_slots <= ((int64_t)1 << 27), "gapped alphabet: input too large for the sort-based GPU path");
+  KL_REQUIRE(total_slots <= ((int64_t)1 << 30), "input too large for the sort-based extraction path (2^30 k-mer instances per call)");
 
   auto out = std::make_shared<Matrix>();
   out->n = s.n; out->vt = cfg.binarize ? VAL_ONE : VAL_U32;
@@ -218,11 +216,10 @@ std::shared_ptr<Matrix> extract_gapped(const kmerlr_config &cfg, std::shared_ptr
     sync_stream();
   } else {
     if (nu > 0) KL_LAUNCH(gapped_mark, (unsigned)((nu + 255) / 256), 256, 0, ukeys.p, nu, bitmap.p);
-    if (sharded) {
-      DevBuf<uint8_t> bytes((size_t)nbits);
-      KL_LAUNCH(gap_bitmap_to_bytes, (unsigned)((nbits + 255) / 256), 256, 0, bitmap.p, nbits, bytes.p);
-      comm_allreduce_max_u8(bytes.p, nbits);
-      KL_LAUNCH(gap_bytes_to_bitmap, (unsigned)((nw + 255) / 256), 256, 0, bytes.p, nbits, bitmap.p, nw);
+    if (sharded && nw > 0) {
+      DevBuf<uint32_t> all((size_t)(nw * ctx().world));
+      comm_allgather_bytes(bitmap.p, all.p, nw * 4);
+      KL_LAUNCH(gap_or_ranks, (unsigned)((nw + 255) / 256), 256, 0, all.p, ctx().world, nw, bitmap.p);
     }
   }
   DevBuf<uint32_t> pc((size_t)(nw ? nw : 1)), rank((size_t)nw + 1);

@@ -203,9 +203,42 @@ def test_unsupported_configurations_fail_loudly(K):
         K.compile_test_data(None, K.NewKmerCounter(4, 12, revcomp=True, alphabet="gapped-nucleotide"), None, None, True,
                             False, ["ACGTACGTACGTACGT"])
     with pytest.raises(K.KmerLrError):
-        K.compile_test_data(None, K.NewKmerCounter(1, 14), None, None, True, False, ["ACGTACGTACGTACGT"])
-    with pytest.raises(K.KmerLrError):
-        K.compile_test_data(None, K.NewKmerCounter(6, 9, revcomp=True), None, None, True, False, ["ACGT" * 2000])
+        K.compile_test_data(None, K.NewKmerCounter(1, 15), None, None, True, False, ["ACGTACGTACGTACGT"])
+
+
+@pytest.mark.parametrize("M,N,flags,L", [
+    (1, 6, dict(complement=True, reverse=True), 300),                      # two strand flags, not closed under composition
+    (2, 8, dict(complement=True, reverse=True, revcomp=True), 250),         # all three: orbits of the Klein four-group
+    (3, 9, dict(reverse=True, revcomp=True, binarize=True), 120),
+    (1, 14, dict(revcomp=True), 90),                                        # k-mers of 14 bases
+    (12, 14, dict(), 200),
+    (6, 9, dict(revcomp=True), 8000),                                       # k > 8 on rows beyond the register sort
+    (1, 10, dict(revcomp=True, binarize=True), 2600),
+    (4, 7, dict(revcomp=True), 70000),                                      # rows beyond the 16-bit count tables
+])
+def test_sort_based_path_lifts_the_cliffs(K, oracle, M, N, flags, L):
+    """what the warp-per-row kernel does not take goes through the sort-based path (gapped.cu): several strand flags
+    at once (kmerLr_learn.go:94 passes them independently; class = min over every enabled image), k = 14, long rows
+    with k > 8.  Bit exact against the oracle, frozen subsets and gradient included."""
+    from kmerlr_b200 import synth
+    nrow = 6 if L >= 2600 else 40
+    buf, off, y = synth.training_set(nrow // 2, nrow // 2, L)
+    buf = buf.copy()
+    buf[off[1] + 7] = ord("N")
+    buf[off[2]:off[2] + L // 3] = ord("A")
+    binz = flags.get("binarize", False)
+    kc, oc = cfg_pair(K, oracle, M, N, **flags)
+    d = K.compile_test_data(None, kc, None, None, True, binz, (buf, off))
+    ref = oracle.extract(oc, (buf, off))
+    same_matrix(d, ref)
+    k, code = d.Kmers()
+    sub = (k[::3], code[::3])
+    same_matrix(K.compile_test_data(None, kc, sub, None, True, binz, (buf, off)), oracle.extract(oc, (buf, off), frozen=sub))
+    d2 = K.compile_test_data(None, kc, None, None, True, binz, (buf, off))
+    d2.SetLabels(y)
+    theta = np.random.default_rng(4).normal(scale=0.01, size=d2.m + 1)
+    g, og = K.logisticRegression(theta).Gradient(None, d2), oracle.gradient(ref, y, theta)
+    assert np.max(np.abs(g - og)) <= 1e-10 * np.max(np.abs(og))
 
 
 def test_full_size_properties(K):

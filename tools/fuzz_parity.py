@@ -22,15 +22,17 @@ def run(n_cases, seed, verbose=True):
         if gapped:
             M = int(rng.integers(1, 6)); N = int(rng.integers(M, min(M + 3, 7) + 1))
         else:
-            M = int(rng.integers(1, 10)); N = int(rng.integers(M, min(M + int(rng.integers(0, 8)), 13) + 1))
+            M = int(rng.integers(1, 10)); N = int(rng.integers(M, min(M + int(rng.integers(0, 8)), 14) + 1))
         op = rng.choice(["none", "revcomp", "complement", "reverse"])
         flags = {} if op == "none" else {op: True}
+        if not gapped and rng.random() < 0.12:                           # several strand flags at once (sort-based path)
+            for extra in rng.choice(["revcomp", "complement", "reverse"], size=2, replace=False):
+                flags[str(extra)] = True
+            op = "+".join(sorted(flags))
         binz = bool(rng.random() < 0.3)
         if gapped:
             flags["alphabet"] = "gapped-nucleotide"
         maxL = 150 if gapped else int(rng.choice([40, 200, 600, 1500, 2300]))
-        if N > 8:
-            maxL = min(maxL, 1900)
         nseq = int(rng.integers(1, 40 if not gapped else 8))
         seqs = []
         for _ in range(nseq):
