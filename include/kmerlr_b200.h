@@ -70,6 +70,7 @@ int         kmerlr_profile_dump(char *buf, int64_t buflen);
  *   "super_len" = length S of the super k-mer tables of that pass (S - N + 1 positions share one table
  *                entry; -1 = automatic: 10 for N <= 8, else 11; 0 = off);
  *   "hot_cols" = number of columns of that stored-row pass that accumulate in shared memory (default 6144);
+ *   "fused_ticket" = rows a warp of the stored-row pass takes per ticket (default 8; 0 = static grid of blocks);
  *   "p2p"      = 1 (default) lets sharded reduced-matrix iterations exchange the gradient over NVLink peer
  *                memory, 0 forces the NCCL collectives (set it identically on every rank);
  *   "persistent" = 1 (default) runs the reduced-matrix iterations of one GPU as one cooperative launch per

@@ -82,6 +82,8 @@ struct Ctx {
   bool implicit_ok = true;   // kmerlr_option("implicit")
   int super_len = -1;        // kmerlr_option("super_len"): length of the super k-mer tables (-1 = automatic, 0 = off)
   int hot_cols = 6144;       // kmerlr_option("hot_cols"): columns of the CSR pass that accumulate in shared memory
+  int fused_ticket = 8;      // kmerlr_option("fused_ticket"): rows per ticket of the CSR pass (0 = static grid); measured
+                             // at C3 / C2 per iteration: 8: 16.2 / 3.07 ms, 32: 16.7, 128: 19.8, static: 16.7 / 3.49 ms
   // communicator (NCCL via dlopen, see comm.cu)
   void *comm = nullptr;
   int rank = 0, world = 1;
@@ -160,7 +162,7 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) p = (T *)arena_alloc(count * sizeof(T));
+    if (count) p = (T *)arena_alloc(count * sizeof(T) + 32);   // + 32: kernels read whole aligned 16-byte groups
   }
   void release() {
     if (p) arena_free(p);
@@ -392,6 +394,34 @@ __device__ __forceinline__ double warp_sum_down(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   return v;
 }
+// ---- TMA bulk copy (cp.async.bulk, 1-D: no tensor map) global -> shared, completion on an mbarrier -------------
+// dst, src 16-byte aligned, bytes a multiple of 16.  One thread arms the barrier with the byte count and issues the
+// copy; every consumer waits on the barrier's phase.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "KL_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra KL_MBAR_DONE;\n"
+      "bra KL_MBAR_WAIT;\n"
+      "KL_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // log(1+exp(x)) with a = 0: LogAdd(0, x) of autodiff's logarithmetic package, restated as
 // max(0,x) + log1p(exp(-|x|))  (kmerLr_logistic_regression.go:138-145)
 __device__ __forceinline__ double log_add0(double x) {

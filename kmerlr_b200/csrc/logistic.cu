@@ -100,11 +100,18 @@ __global__ void reduce_stage2(const double *__restrict__ part, int np, double *_
   }
 }
 
-// the fused pass: persistent blocks, one warp per row
+// the fused pass over the stored rows: one warp per row
 //   G[0]    += round(w_i * S)                 (bias, Go index 0)
 //   G[c+1]  += round(w_i * v_ic * S)          for every entry of the row
-constexpr int FUSED_ROWS = 8;          // rows per ticket of the fused pass
-constexpr int HOT_COLS_MAX = 16384;   // at most this many columns accumulate in shared memory (8 B each)
+// Lane l reads the entries l, l + 32, ... of the row: one warp-level gather of theta then covers 32 CONSECUTIVE
+// entries of the sorted row, i.e. neighbouring columns that share cache lines.  (128-bit loads of four entries
+// per lane were measured slower, 15.3 vs 14.1 ms at C3: the gathers of one instruction then span 128 entries
+// and touch four times as many lines, and the gathers, not the streams, bound this kernel -- ncu: 44 % of the
+// stall samples on the theta gather, LSU wavefronts at 59 % of peak.)
+// Rows: ticket == nullptr: block b owns the rows [b rpb, (b+1) rpb) (fine static grid); else the warps take
+// `rpb` rows per atomic ticket.
+constexpr int FUSED_RPB = 256;         // rows per block (static grid)
+constexpr int HOT_COLS_MAX = 16384;    // at most this many columns accumulate in shared memory (8 B each)
 
 template <typename VT>
 __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t *__restrict__ col,
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
                                                     const uint8_t *__restrict__ labels, double cw0, double cw1,
                                                     double inv_n, double scale, unsigned long long *__restrict__ G,
                                                     double *__restrict__ lossterm, const PgState *st, int scatter,
-                                                    int hot_limit, unsigned long long *__restrict__ ticket) {
+                                                    int hot_limit, int rpb, unsigned long long *__restrict__ ticket) {
   if (st && st->done == 1) return;
   // 64-bit accumulators as two 32-bit words: shared memory has native 32-bit atomic adds only
   // (a 64-bit add would be a compare-and-swap loop); the carry out of the low word is added to
@@ -125,14 +132,7 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
   __syncthreads();
   const unsigned lane = lane_id();
   long long bias_acc = 0;
-  // rows are handed out FUSED_ROWS at a time through a ticket counter: warps on faster SMs take more
-  for (;;) {
-    unsigned long long t0 = 0;
-    if (lane == 0) t0 = atomicAdd(ticket, (unsigned long long)FUSED_ROWS);
-    const int64_t first = (int64_t)__shfl_sync(0xffffffffu, t0, 0);
-    if (first >= n) break;
-    const int64_t last = first + FUSED_ROWS < n ? first + FUSED_ROWS : n;
-   for (int64_t row = first; row < last; row++) {
+  auto do_row = [&](int64_t row) {
     int64_t a, b;
     R.range(row, a, b);
     double s = 0.0;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
       else             { w = inv_n * cw0 * exp(r);         lossterm[row] = cw0 * log_add0(z); }
       bias_acc += __double2ll_rn(w * scale);
     }
-    if (!scatter) continue;               // loss-only pass (the hook after the last iteration)
+    if (!scatter) return;                 // loss-only pass (the hook after the last iteration)
     w = __shfl_sync(0xffffffffu, w, 0);
     const double ws = w * scale;          // scale is a power of two: exact
     for (int64_t p = a + lane; p < b; p += 32) {
@@ -159,7 +159,19 @@ __global__ void __launch_bounds__(256) fused_kernel(const Rows R, const uint32_t
         if (add_hi) atomicAdd(&hot_hi[c], add_hi);
       } else atomicAdd(&G[c + 1], q);
     }
-   }
+  };
+  if (ticket) {
+    for (;;) {
+      unsigned long long t0 = 0;
+      if (lane == 0) t0 = atomicAdd(ticket, (unsigned long long)rpb);
+      const int64_t first = (int64_t)__shfl_sync(0xffffffffu, t0, 0);
+      if (first >= n) break;
+      const int64_t last = first + rpb < n ? first + rpb : n;
+      for (int64_t row = first; row < last; row++) do_row(row);
+    }
+  } else {
+    const int64_t first = (int64_t)blockIdx.x * rpb, last = first + rpb < n ? first + rpb : n;
+    for (int64_t row = first + (threadIdx.x >> 5); row < last; row += (blockDim.x >> 5)) do_row(row);
   }
   if (lane == 0 && bias_acc != 0) atomicAdd(&G[0], (unsigned long long)bias_acc);
   __syncthreads();
@@ -335,14 +347,20 @@ __global__ void __launch_bounds__(256) imp_pass(const ImpParams P, const ImpArgs
   if (A.st && A.st->done == 1) return;
   constexpr int CC = CACHE > 0 ? CACHE : 1;
   constexpr int RR = 8 * IMP_R;
-  extern __shared__ double s_low[];
+  extern __shared__ __align__(16) double s_low[];
   __shared__ double s_z[RR];
   __shared__ unsigned long long s_q[RR];
   __shared__ unsigned long long s_bias;
-  if (BIN)
-    for (int i = threadIdx.x; i < 128 * A.lwp; i += blockDim.x) s_low[i] = A.lowtab[i];
-  if (threadIdx.x == 0) s_bias = 0ull;
+  __shared__ __align__(8) unsigned long long s_bar;
+  if (threadIdx.x == 0) {
+    s_bias = 0ull;
+    if (BIN) mbar_init(&s_bar, 1);
+  }
   __syncthreads();
+  // binarized rows: the block's copy of lowtab (32 / 64 KB) arrives by ONE TMA bulk copy while the first round
+  // decodes and gathers; the warps wait on its mbarrier right before they first read the table
+  if (BIN && threadIdx.x == 0) bulk_copy_g2s(s_low, A.lowtab, (uint32_t)(128 * A.lwp * sizeof(double)), &s_bar);
+  bool low_ready = !BIN;
   const unsigned lane = lane_id();
   const int wib = threadIdx.x >> 5;
   const int c = P.c;
@@ -401,6 +419,7 @@ __global__ void __launch_bounds__(256) imp_pass(const ImpParams P, const ImpArgs
         }
       }
       if (BIN) {
+        if (!low_ready) { mbar_wait(&s_bar, 0); low_ready = true; }
         // table levels: 8 precomputed sums per word of the row's class bitmap
         for (int l = (int)lane; l < A.low_words; l += 32) {
           const uint32_t w = __ldcs(A.lowbits + row * A.low_words + l);
@@ -1208,9 +1227,8 @@ void launch_implicit(Matrix &M, Work &wk, const double cw[2], const PgState *st,
 // (the caller reduces over the ranks); scatter = 0: loss terms only (G is left untouched)
 template <typename VT>
 void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, int scatter = 1) {
-  // G: [0, m] gradient | [m+1, m+1+world) loss slots of the ranks | [m+1+PEER_MAX_WORLD] row ticket of fused_kernel
+  // G: [0, m] gradient | [m+1, m+1+world) loss slots of the ranks | [m+1+PEER_MAX_WORLD] row ticket (fused_kernel)
   if (scatter) KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 2 + PEER_MAX_WORLD) * sizeof(unsigned long long), ctx().stream));
-  else KL_CUDA(cudaMemsetAsync(wk.G.p + M.m + 1 + PEER_MAX_WORLD, 0, sizeof(unsigned long long), ctx().stream));
   if (M.n > 0) {
     if (use_implicit(M)) {
       launch_implicit(M, wk, cw, st, scatter);
@@ -1219,14 +1237,26 @@ void launch_fused(Matrix &M, Work &wk, const double cw[2], const PgState *st, in
       if (hot > M.m) hot = (int)M.m;
       const size_t smem = (size_t)hot * 8;
       KL_CUDA(cudaFuncSetAttribute(fused_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HOT_COLS_MAX * 8));
-      int per_sm = 0;
-      KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, smem));
-      if (per_sm < 1) per_sm = 1;
-      int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 7) / 8;
-      if (blocks > need) blocks = need;
-      KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, smem, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
-                M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter, hot,
-                wk.G.p + M.m + 1 + PEER_MAX_WORLD);
+      const int tk = ctx().fused_ticket;
+      if (tk > 0) {
+        // persistent blocks, `tk` rows per warp and ticket (the counter sits behind the loss slots of G)
+        unsigned long long *ticket = wk.G.p + M.m + 1 + PEER_MAX_WORLD;
+        KL_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), ctx().stream));
+        int per_sm = 0;
+        KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<VT>, 256, smem));
+        if (per_sm < 1) per_sm = 1;
+        int64_t blocks = (int64_t)ctx().sm_count * per_sm, need = (M.n + 8 * tk - 1) / (8 * tk);
+        if (blocks > need) blocks = need;
+        KL_LAUNCH((fused_kernel<VT>), (unsigned)blocks, 256, smem, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m, wk.theta.p,
+                  M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st, scatter, hot, tk,
+                  ticket);
+      } else {
+        int rpb = FUSED_RPB;
+        while ((M.n + rpb - 1) / rpb > 0x7fffffffLL) rpb *= 2;
+        KL_LAUNCH((fused_kernel<VT>), (unsigned)((M.n + rpb - 1) / rpb), 256, smem, M.rows(), M.col.p, csr_val<VT>(M), M.n,
+                  M.m, wk.theta.p, M.labels.p, cw[0], cw[1], 1.0 / (double)M.n_global, wk.scale, wk.G.p, wk.lossterm.p, st,
+                  scatter, hot, rpb, (unsigned long long *)nullptr);
+      }
     }
   }
 }
@@ -1236,7 +1266,7 @@ void alloc_work(const Matrix &M, int64_t ntheta, Work &wk) {
   wk.w.alloc((size_t)(M.n ? M.n : 1));
   wk.lossterm.alloc((size_t)(M.n ? M.n : 1));
   wk.g.alloc((size_t)ntheta);
-  wk.G.alloc((size_t)M.m + 2 + PEER_MAX_WORLD);      // + loss slots of the ranks + the row ticket of fused_kernel
+  wk.G.alloc((size_t)M.m + 2 + PEER_MAX_WORLD);      // + loss slots of the ranks
   wk.red.alloc(RED_BLOCKS);
   wk.scalars.alloc(8);
   wk.blockmax.alloc(4 * PROX_BLOCKS);    // max |theta|, max |delta|, NaN flag per block + the L1 partials of the hook

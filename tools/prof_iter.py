@@ -19,6 +19,8 @@ K.init(0)
 K.option("implicit", implicit)
 if len(sys.argv) > 5:
     K.option("super_len", int(sys.argv[5]))
+if len(sys.argv) > 6:
+    K.option("fused_ticket", int(sys.argv[6]))
 buf, off, y = synth.training_set(nf, nb, L)
 d = K.compile_test_data(None, K.NewKmerCounter(M, N, revcomp=True, binarize=binz), None, None, True, binz, (buf, off))
 print("extract: %.3f ms" % K.last_device_ms(), flush=True)
