@@ -174,16 +174,24 @@ def leg_c3(K, api, synth, shard, rank, world, dist, allmax, allsum, peak, iters=
     est.Theta = np.zeros(data.m + 1)
     est.estimate_proximal(data, 1e-3)
     est.MaxIterations = iters
+    its = []
+    for rep in range(4):                         # one more warm-up at this length (the arena settles), then 3 timed
+        est.Theta = np.zeros(data.m + 1)
+        if dist is not None:
+            dist.barrier()
+        est.estimate_proximal(data, 1e-3)
+        if rep > 0:
+            its.append(K.last_device_ms() / iters)
+    it_ms = float(np.median(its))                # timed without the per-kernel events
     est.Theta = np.zeros(data.m + 1)
     K.api.profile(True)
-    if dist is not None:
-        dist.barrier()
-    est.estimate_proximal(data, 1e-3)
-    it_ms = K.last_device_ms() / iters
+    est.estimate_proximal(data, 1e-3)            # the same iterations again for the per-kernel split
+    it_ms_prof = K.last_device_ms() / iters
     prof = K.api.profile_dump()
     K.api.profile(False)
-    ar_ms = sum(v[0] for k, v in prof.items() if k.startswith("nccl_")) / iters
+    ar_ms = sum(v[0] for k, v in prof.items() if k.startswith("nccl_") or "p2p_allreduce" in k) / iters
     pass_ms = sum(v[0] for k, v in prof.items() if "imp_pass" in k or "fused_kernel" in k or "low_accumulate" in k) / iters
+    other_ms = sum(v[0] for k, v in prof.items()) / iters - ar_ms - pass_ms
     n_loc, m, nnz_loc = data.n, data.m, data.nnz
     data.free(); seqs.free()
     ext_ms, it_ms, ar_ms, pass_ms = allmax(float(np.mean(ext))), allmax(it_ms), allmax(ar_ms), allmax(pass_ms)
@@ -197,15 +205,19 @@ def leg_c3(K, api, synth, shard, rank, world, dist, allmax, allsum, peak, iters=
             "extract_ms": ext_ms, "extract_sequences_per_sec": n / (ext_ms * 1e-3),
             "extract_frac_of_hbm_peak": ex_bytes / world / (ext_ms * 1e-3) / 1e9 / peak,
             "ms_per_iter": it_ms, "iters_per_sec": 1e3 / it_ms, "logistic_pass_ms": pass_ms,
+            "other_kernels_ms_per_iter": other_ms, "ms_per_iter_with_kernel_events": it_ms_prof,
             "allreduce_ms_per_iter": ar_ms, "allreduce_share_of_iter": ar_ms / it_ms if it_ms > 0 else None,
             "allreduce_bytes": 8 * (m + 1), "algorithmic_bytes_per_iter": it_bytes,
+            "allreduce_path": ("NVLink peer memory (two-shot, one cooperative launch)" if os.environ.get("KMERLR_P2P", "1") != "0" else "NCCL") if world > 1 else None,
             "iter_achieved_gbs_per_gpu": it_bytes / world / (it_ms * 1e-3) / 1e9,
             "iter_frac_of_hbm_peak": it_bytes / world / (it_ms * 1e-3) / 1e9 / peak}
 
 
 def leg_path(K, synth, targets=(10, 25, 50, 100)):
     """BASELINE configs[1] as it is worded: the proximal-gradient leapfrog path to 100 features on the C2 set
-    (1 GPU; EpsilonLoss = 1e-8 as the CLI default, `|g| desc, index asc` tie rule)"""
+    (1 GPU; EpsilonLoss = 1e-8 as the CLI default, `|g| desc, index asc` tie rule).  The last target alone needs
+    ~1.5 M iterations of the reference's fixed-step ISTA (minutes): the default bench stops at 50 features and
+    `--legs path100` runs the whole path (profiles/r02_path_to_100.json holds that run)."""
     n_fg, n_bg, L, M, N, _ = CONFIGS["c2"]
     buf, off, y = synth.training_set(n_fg, n_bg, L)
     t0 = time.perf_counter()
@@ -218,10 +230,11 @@ def leg_path(K, synth, targets=(10, 25, 50, 100)):
         t0 = time.perf_counter()
         epochs = est.estimate_loop(d, n_feat)
         out.append({"features": n_feat, "epochs": int(epochs), "iterations": int(sum(p[1] for p in est.path[-epochs:])),
-                    "lambda": float(est.path[-1][0]), "active": int(len(est.active_idx)), "s": time.perf_counter() - t0})
+                    "lambda": float(est.path[-1][0]), "active": int(len(est.active_idx)), "s": time.perf_counter() - t0,
+                    "reduced_nnz_last_epoch": int(est.path[-1][3])})
     total = time.perf_counter() - t_all
     d.free()
-    return {"path_to_100_features_s": total, "extract_s": t_extract, "iterations": int(sum(o["iterations"] for o in out)),
+    return {("path_to_%d_features_s" % targets[-1]): total, "extract_s": t_extract, "iterations": int(sum(o["iterations"] for o in out)),
             "epochs": int(sum(o["epochs"] for o in out)), "targets": out,
             "note": "wall clock through the C ABI, estimate_loop per target warm-started as Estimate does "
                     "(kmerLr_estimator.go:257-270); iteration counts are those of the reference's fixed-step ISTA"}
@@ -372,7 +385,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--score-mbp", type=float, default=96.0, help="genome size of the window-scoring leg (0 = skip)")
     ap.add_argument("--short", action="store_true", help="profiling runs only: allow fewer than 3 warm-up steps")
-    ap.add_argument("--legs", default="auto", help="extra legs on the same JSON line: comma list of c3,path,c4,c5; "
+    ap.add_argument("--legs", default="auto", help="extra legs on the same JSON line: comma list of c3,path,path100,c4,c5; "
                     "auto = all four on one GPU, c3,c5 on several; none = headline only")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.short:
@@ -481,10 +494,17 @@ def main():
     est.ClassWeights = cw
     est.estimate_proximal(data, lam)             # builds the CSC view, warms up
     est.MaxIterations = args.iters
+    its = []
+    for rep in range(4):                         # one more warm-up at this length (the arena settles), then 3 timed
+        barrier()
+        est.Theta = np.zeros(data.m + 1)
+        est.estimate_proximal(data, lam)
+        if rep > 0:
+            its.append(K.last_device_ms())
+    iter_ms = float(np.median(its))              # timed without the per-kernel events
     K.api.profile(True)
-    barrier()
-    est.estimate_proximal(data, lam)
-    iter_ms = K.last_device_ms()
+    est.Theta = np.zeros(data.m + 1)
+    est.estimate_proximal(data, lam)             # the same iterations again for the per-kernel split
     prof_it = K.api.profile_dump()
     K.api.profile(False)
     n_rows, m_cols, nnz = data.n, data.m, data.nnz
@@ -554,8 +574,15 @@ def main():
         c5["e2e_bases_per_sec"] *= world * c5["e2e_ms"] / ms5
         c5["e2e_ms"] = ms5
         extra["c5"] = c5
-    if rank == 0 and "path" in legs:
+    if rank == 0 and "path100" in legs:
         extra["c2_path"] = leg_path(K, synth)
+    elif rank == 0 and "path" in legs:
+        extra["c2_path"] = leg_path(K, synth, targets=(10, 25, 50))
+        extra["c2_path"]["path_to_100_features_s"] = None
+        try:
+            extra["c2_path"]["path_to_100_features_measured_separately"] = json.load(open(os.path.join(ROOT, "profiles", "r02_path_to_100.json")))
+        except Exception:
+            pass
     if rank == 0 and "c4" in legs:
         extra["c4"] = leg_c4(K, synth)
     barrier()

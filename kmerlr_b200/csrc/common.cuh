@@ -59,9 +59,15 @@ struct PeerMail {
   unsigned long long flag[2][PEER_MAX_WORLD];
   unsigned long long seq;                        // local: sequence number of the last exchange
   unsigned int senders_done;                     // local: sender blocks of the running exchange that are through
+  // all-reduce over peer memory (comm.cu: p2p_allreduce_kernel): two barriers per exchange
+  unsigned long long ar_flag[2][PEER_MAX_WORLD]; // ar_flag[b][s] = sequence number of sender s at barrier b
+  unsigned long long ar_seq;                     // local: sequence number of the last all-reduce
+  unsigned int ar_error;                         // local: a peer did not show up at a barrier
 };
+constexpr int64_t PEER_AR_CAP = (int64_t)4 << 20;   // 64-bit words per all-reduce over peer memory (32 MB in, 32 MB out)
 struct PeerBox {
   PeerMail *box[PEER_MAX_WORLD];                 // box[r] = rank r's mailbox as mapped into this process
+  unsigned long long *sym[PEER_MAX_WORLD];       // sym[r] = rank r's all-reduce buffer: IN[PEER_AR_CAP] then OUT[PEER_AR_CAP]
   int rank, world;
 };
 
@@ -90,6 +96,7 @@ struct Ctx {
   // peer-memory exchange over NVLink (comm.cu): every rank owns one mailbox, mapped into all ranks
   PeerBox *peer = nullptr;   // device copy of the mailbox table, nullptr = not available (NCCL is used)
   bool p2p_ok = true;        // kmerlr_option("p2p")
+  bool p2p_allreduce = false; // kmerlr_option("p2p_allreduce"): full-space gradient all-reduce over peer memory instead of NCCL
   bool coop_supported = true;
   bool coop_ok = true;       // kmerlr_option("persistent"); false when the device cannot launch cooperatively
 };
@@ -359,6 +366,8 @@ void comm_init(int rank, int world, const void *id128);
 void comm_destroy();
 void comm_allreduce_sum_f64(double *dev, int64_t count);
 void comm_allreduce_sum_i64(int64_t *dev, int64_t count);
+void comm_allreduce_sum_i64_fast(int64_t *dev, int64_t count);   // over NVLink peer memory when available, else NCCL
+void comm_check_peer_errors();                                   // throws when a peer-memory all-reduce timed out
 void comm_allreduce_max_f64(double *dev, int64_t count);
 void comm_allreduce_max_u8(uint8_t *dev, int64_t count);
 void comm_allgather_f64(const double *dev_in, double *dev_out, int64_t count_per_rank);

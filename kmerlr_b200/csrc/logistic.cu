@@ -1314,7 +1314,7 @@ void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2]
     using VT = typename std::remove_pointer<decltype(tag)>::type;
     if (!cooc) {
       launch_fused<VT>(M, wk, cw, nullptr);
-      if (M.sharded) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
+      if (M.sharded) comm_allreduce_sum_i64_fast((int64_t *)wk.G.p, M.m + 1);
     } else {
       // pair mode: z needs the pair terms, so the weights come from the general rows kernel; the
       // single-feature part still goes through the fixed-point pass with theta restricted to it
@@ -1343,6 +1343,7 @@ void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2]
     KL_LAUNCH(add_l1_sign, (unsigned)((ntheta + 255) / 256), 256, 0, wk.theta.p, wk.g.p, ntheta, lambda);
   if (g_host) wk.g.download(g_host, (size_t)ntheta);
   sync_stream();
+  if (M.sharded) comm_check_peer_errors();
   if (g_dev) *g_dev = std::move(wk.g);
 }
 
@@ -1492,8 +1493,8 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
           // ONE collective per iteration: gradient words + the loss sums of the ranks
           unsigned long long *slots = wk.G.p + M.m + 1;
           KL_LAUNCH(pack_loss_slots, 1, 32, 0, st.p, wk.scalars.p, slots, ctx().rank, ctx().world);
-          if (scatter) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1 + ctx().world);
-          else comm_allreduce_sum_i64((int64_t *)slots, ctx().world);
+          if (scatter) comm_allreduce_sum_i64_fast((int64_t *)wk.G.p, M.m + 1 + ctx().world);
+          else comm_allreduce_sum_i64_fast((int64_t *)slots, ctx().world);
           KL_LAUNCH(unpack_loss_slots, 1, 32, 0, st.p, slots, ctx().world, wk.scalars.p);
         }
         KL_LAUNCH(l1_partials, PROX_BLOCKS, 256, 0, st.p, wk.theta.p, M.m + 1, lambda, wk.blockmax.p + 3 * PROX_BLOCKS);
@@ -1506,6 +1507,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
     st.download(&h, 1);
     sync_stream();
     if (h.error) fail(KMERLR_ERR_CUDA, "proxgrad: a rank did not answer the gradient exchange over peer memory");
+    if (M.sharded) comm_check_peer_errors();
     if (h.done == 1) break;
   }
   wk.theta.download(theta, (size_t)ntheta);
