@@ -97,6 +97,7 @@ struct Ctx {
   PeerBox *peer = nullptr;   // device copy of the mailbox table, nullptr = not available (NCCL is used)
   bool p2p_ok = true;        // kmerlr_option("p2p")
   bool p2p_allreduce = false; // kmerlr_option("p2p_allreduce"): full-space gradient all-reduce over peer memory instead of NCCL
+  int persist_bps = 0;       // kmerlr_option("persist_bps"): blocks per SM of the persistent reduced-matrix solver (0 = all that fit)
   bool coop_supported = true;
   bool coop_ok = true;       // kmerlr_option("persistent"); false when the device cannot launch cooperatively
 };

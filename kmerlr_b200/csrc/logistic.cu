@@ -947,18 +947,29 @@ __global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_kernel(c
 // one launch are pass0, pass0 + 1, ...; pass number max_iter only evaluates the hook's loss.
 // (1024-thread blocks, one per SM -- fewer loss partials, a cheaper barrier -- measured no faster: 23 vs 21 us)
 constexpr int PERSIST_THREADS = 256;
-template <typename VT>
+// SHARDED: the rows are this rank's shard and the ranks are connected by NVLink peer memory.  After the grid
+// barrier block 0 exchanges the rank's payload (fixed-point gradient + loss partial) with all ranks through
+// the mailboxes -- stores into every rank's slot, a flag, a wait for the flags of the others, the sum in rank
+// order (integers: the same bits on every rank) -- and a second grid barrier releases the tail.  The
+// collective lives INSIDE the persistent kernel: no launch and no NCCL call per iteration.
+template <typename VT, bool SHARDED>
 __global__ void __launch_bounds__(PERSIST_THREADS, SMALL_BLOCKS_PER_SM) fused_small_persistent(
     const Rows R, const uint32_t *__restrict__ col, const VT *__restrict__ val, int64_t n, int64_t ntheta, double *theta,
     const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n, double scale, unsigned long long *G3,
     double *blockloss2, PgState *st, long long pass0, int npass, double inv_scale, double lambda, double eps_loss,
-    double step, double eps, long long max_iter) {
+    double step, double eps, long long max_iter, const PeerBox *pb, unsigned long long *Gx, double *scratch,
+    unsigned int *abort_flag) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ uint32_t acc_lo[SMALL_MAX_THETA], acc_hi[SMALL_MAX_THETA];
   __shared__ double sth[SMALL_MAX_THETA];
   __shared__ double red[256];
   __shared__ PgState ls;
-  if (threadIdx.x == 0) ls = *st;
+  __shared__ unsigned long long s_seq;
+  __shared__ int s_timeout;
+  if (threadIdx.x == 0) {
+    ls = *st;
+    if (SHARDED) s_seq = pb->box[pb->rank]->seq;
+  }
   for (int i = threadIdx.x; i < ntheta; i += blockDim.x) sth[i] = theta[i];
   __syncthreads();
   const int nblocks = (int)gridDim.x;
@@ -975,13 +986,75 @@ __global__ void __launch_bounds__(PERSIST_THREADS, SMALL_BLOCKS_PER_SM) fused_sm
     small_rows<VT, false>(R, col, val, n, ntheta, sth, labels, cw0, cw1, inv_n, scale,
                           G + (blockIdx.x % SMALL_REPLICAS) * ntheta, blockloss, scatter, acc_lo, acc_hi, sth, red);
     grid.sync();
-    small_tail<PERSIST_THREADS>(&ls, blockloss, nblocks, sth, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps,
-                                max_iter, false, SMALL_REPLICAS);
+    if (!SHARDED) {
+      small_tail<PERSIST_THREADS>(&ls, blockloss, nblocks, sth, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps,
+                                  max_iter, false, SMALL_REPLICAS);
+    } else {
+      if (blockIdx.x == 0) {
+        const int t = threadIdx.x, me = pb->rank, world = pb->world;
+        PeerMail *mine = pb->box[me];
+        const unsigned long long seq = s_seq + 1ull;
+        const int par = (int)(seq & 1ull);
+        // loss partial of this rank: block partials in a fixed order
+        double s = 0.0;
+        for (int i = t; i < nblocks; i += PERSIST_THREADS) s += __ldcg(blockloss + i);
+        red[t] = s;
+        if (t == 0) s_timeout = 0;
+        __syncthreads();
+        for (int o = PERSIST_THREADS / 2; o > 0; o >>= 1) {
+          if (t < o) red[t] += red[t + o];
+          __syncthreads();
+        }
+        // payload into every mailbox (NVLink stores), one system fence, then the flags
+        for (int64_t k = t; k < ntheta; k += PERSIST_THREADS) {
+          unsigned long long g = 0ull;
+          for (int r = 0; r < SMALL_REPLICAS; r++) g += __ldcg(G + r * ntheta + k);
+          for (int r = 0; r < world; r++) pb->box[r]->slot[par][me][k] = g;
+        }
+        if (t < world) pb->box[t]->slot[par][me][ntheta] = (unsigned long long)__double_as_longlong(red[0]);
+        __syncthreads();
+        if (t == 0) __threadfence_system();
+        __syncthreads();
+        if (t < world) {
+          *(volatile unsigned long long *)&pb->box[t]->flag[par][me] = seq;
+          volatile unsigned long long *f = &mine->flag[par][t];
+          const long long t0 = clock64();
+          while (*f < seq)
+            if (clock64() - t0 > 6000000000LL) { s_timeout = 1; break; }      // ~3 s: a peer is gone
+          __threadfence_system();
+        }
+        __syncthreads();
+        if (s_timeout) {
+          if (t == 0) *abort_flag = 1u;
+        } else {
+          for (int64_t k = t; k < ntheta; k += PERSIST_THREADS) {
+            unsigned long long g = 0ull;
+            for (int r = 0; r < world; r++) g += __ldcv(&mine->slot[par][r][k]);
+            Gx[k] = g;
+          }
+          if (t < world) scratch[t] = __longlong_as_double((long long)__ldcv(&mine->slot[par][t][ntheta]));
+        }
+        __threadfence();
+        if (t == 0) s_seq = seq;
+        __syncthreads();
+      }
+      grid.sync();
+      if (*(volatile unsigned int *)abort_flag) {
+        if (threadIdx.x == 0) { ls.error = 1; ls.done = 1; }
+        __syncthreads();
+        break;
+      }
+      small_tail<PERSIST_THREADS>(&ls, scratch, pb->world, sth, Gx, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps,
+                                  max_iter, false, 1);
+    }
     __syncthreads();
   }
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < ntheta; i += blockDim.x) theta[i] = sth[i];
-    if (threadIdx.x == 0) *st = ls;
+    if (threadIdx.x == 0) {
+      *st = ls;
+      if (SHARDED) pb->box[pb->rank]->seq = s_seq;
+    }
   }
 }
 
@@ -1142,7 +1215,7 @@ void set_scale(Matrix &M, Work &wk, const double cw[2]) {
 bool use_implicit(const Matrix &M) {
   static int env = -1;
   if (env < 0) { const char *e = getenv("KMERLR_IMPLICIT"); env = (e && *e == '0') ? 0 : 1; }
-  if (!(env == 1 && ctx().implicit_ok && M.imp && M.n > 0)) return false;
+  if (!(env == 1 && ctx().implicit_ok && M.imp)) return false;      // (rank invariant: no look at the local row count)
   return M.imp->binarized ? M.vt == VAL_ONE : M.vt == VAL_U32;
 }
 
@@ -1389,10 +1462,13 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   h.loss_old = hook ? hook[0] : NAN; h.loss_new = hook ? hook[1] : NAN; h.lossval = NAN; h.error = 0;
   st.upload(&h, 1);
   const double inv_n = 1.0 / (double)M.n_global;
-  // reduced matrices: two launches per iteration, long batches between host round trips
-  const bool small = ntheta <= SMALL_MAX_THETA && !use_implicit(M) && M.n > 0;
-  // one GPU: the passes of a batch are ONE cooperative launch (grid barriers instead of launches)
-  bool persistent = small && !M.sharded && ctx().coop_ok;
+  // reduced matrices: long batches between host round trips.  The choice of the path uses quantities that are
+  // the same on every rank (a rank with an empty shard must issue the same collectives as the others)
+  const bool small = ntheta <= SMALL_MAX_THETA && !use_implicit(M);
+  // the passes of a batch are ONE cooperative launch (grid barriers instead of launches); sharded matrices
+  // exchange the gradient inside that kernel over NVLink peer memory
+  const bool p2p = M.sharded && ctx().peer && ctx().p2p_ok;
+  bool persistent = small && ctx().coop_ok && (!M.sharded || p2p);
   const int64_t BATCH = persistent ? 4096 : (small ? 256 : 16);
   int small_blocks = 0;
   DevBuf<double> blockloss;
@@ -1405,12 +1481,15 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
       int per_sm = 0;
       dispatch_vt(M, [&](auto *tag) {
         using VT = typename std::remove_pointer<decltype(tag)>::type;
-        KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_persistent<VT>, PERSIST_THREADS, 0));
+        if (M.sharded) KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (fused_small_persistent<VT, true>), PERSIST_THREADS, 0));
+        else KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (fused_small_persistent<VT, false>), PERSIST_THREADS, 0));
       });
       KL_INVARIANT(per_sm >= 1);
+      if (ctx().persist_bps > 0 && ctx().persist_bps < per_sm) per_sm = ctx().persist_bps;
       nb = (int64_t)ctx().sm_count * per_sm;       // a cooperative grid must be resident as a whole
     }
     small_blocks = (int)(nb < need ? nb : need);
+    if (small_blocks < 1) small_blocks = 1;        // (an empty shard still takes part in the exchange)
     blockloss.alloc((size_t)small_blocks * (persistent ? 2 : 1));
     if (persistent) { G3.alloc((size_t)(3 * SMALL_REPLICAS * ntheta)); G3.zero(); }
     counter.alloc(1);
@@ -1440,16 +1519,21 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
         long long pass0 = (long long)(issued - nb), mi = (long long)max_iter;
         int npass = (int)nb;
         double lam = lambda, el = epsilon_loss, stp_size = step, eps = epsilon;
+        const PeerBox *pbp = ctx().peer;
+        unsigned long long *gx = wk.G.p;
+        double *scr = wk.gathered.p;
+        unsigned int *abortp = counter.p;
         void *args[] = {&rows, &colp, &valp, &n, &nt, &thp, &lab, &cw0, &cw1, &invn, &scale, &Gp, &bl, &stp, &pass0, &npass,
-                        &inv_scale, &lam, &el, &stp_size, &eps, &mi};
+                        &inv_scale, &lam, &el, &stp_size, &eps, &mi, &pbp, &gx, &scr, &abortp};
         if (ctx().profiling) profile_begin("fused_small_persistent");
-        const cudaError_t e = cudaLaunchCooperativeKernel((const void *)fused_small_persistent<VT>,
-                                                          dim3((unsigned)small_blocks), dim3(PERSIST_THREADS), args, 0,
-                                                          ctx().stream);
+        const cudaError_t e = cudaLaunchCooperativeKernel(
+            M.sharded ? (const void *)fused_small_persistent<VT, true> : (const void *)fused_small_persistent<VT, false>,
+            dim3((unsigned)small_blocks), dim3(PERSIST_THREADS), args, 0, ctx().stream);
         if (ctx().profiling) profile_end();
-        if (e == cudaErrorCooperativeLaunchTooLarge) {
+        if (e == cudaErrorCooperativeLaunchTooLarge && !M.sharded) {
           // the GPU is shared (MPS, another context): the grid cannot be resident as a whole right now.
-          // Nothing was launched; this call goes on with one launch per iteration.
+          // Nothing was launched; this call goes on with one launch per iteration.  (Not on a sharded matrix:
+          // the other ranks are inside their exchange by now, a rank that changes path would leave them waiting.)
           (void)cudaGetLastError();
           persistent = false;
         } else {
