@@ -12,7 +12,9 @@ namespace kl {
 namespace xk {
 
 #ifndef KL_X_OLDPOS
-#define KL_X_OLDPOS 0     // 1: position pass with one funnel-shift load per position (lane = positions lane, lane + 32, ...)
+#define KL_X_OLDPOS 1     // 1: position pass with one funnel-shift load per position (lane = positions lane, lane + 32, ...);
+                          // 0: a 64-bit window per 16 consecutive positions of a lane (no load / bit reversal per position:
+                          // fewer instructions, yet 2.57 vs 2.54 ms at C2 and 6.31 vs 6.37 ms at a quarter of C3)
 #endif
 #ifndef KL_X_WALK
 #define KL_X_WALK 1       // 1: bitmap levels emitted by a walk over the set bits; 0: a slot per position computed from
@@ -66,8 +68,10 @@ __device__ __forceinline__ uint32_t tab_off(int k) {  // sum_{j=1}^{k-1} 4^j
 // Index swizzle of the per-warp staging buffers: lanes that write runs of consecutive slots at a stride of
 // ~16 (the sorted level: E keys per lane) would all hit two banks; XOR-ing the row number into the bank bits
 // spreads them, and a read of 32 consecutive slots stays a permutation of one row (conflict free).
+// (Measured: the bank conflicts drop -- ncu counted 1 031 of 1 631 shared-memory wavefronts per C2 row as excess
+// before -- but the kernel is not bound by them: 2.60 ms with the swizzle, 2.58 ms without.  Off by default.)
 #ifndef KL_X_NOSWZ
-#define KL_X_NOSWZ 0
+#define KL_X_NOSWZ 1
 #endif
 __host__ __device__ __forceinline__ uint32_t sw(uint32_t j) { return KL_X_NOSWZ ? j : j ^ ((j >> 5) & 31u); }
 __host__ __device__ __forceinline__ int sw(int j) { return (int)sw((uint32_t)j); }

@@ -90,14 +90,14 @@ __global__ void reduce_stage1(const double *__restrict__ x, int64_t n, double *_
   }
   if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
 }
-// out[0] = sum(part) in index order
+// out[0] = sum(part): one warp, lane l adds part[l], part[l + 32], ... in index order, then a fixed shuffle tree
+// (deterministic; a single thread walking the 256 partials took 25 us of dependent loads)
 __global__ void reduce_stage2(const double *__restrict__ part, int np, double *__restrict__ out, const PgState *st) {
   if (st && st->done == 1) return;
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < np; i++) s += part[i];
-    out[0] = s;
-  }
+  double s = 0.0;
+  for (int i = threadIdx.x; i < np; i += 32) s += part[i];
+  s = warp_sum_down(s);
+  if (threadIdx.x == 0) out[0] = s;
 }
 
 // the fused pass over the stored rows: one warp per row
@@ -683,9 +683,10 @@ __global__ void l1_partials(const PgState *st, const double *__restrict__ theta,
 __global__ void hook_kernel(PgState *st, const double *__restrict__ losssum, const double *__restrict__ l1part, int nparts,
                             double inv_n, double eps_loss) {
   if (st->done == 1) return;
+  double l1 = 0.0;
+  for (int b = threadIdx.x; b < nparts; b += 32) l1 += l1part[b];
+  l1 = warp_sum_down(l1);
   if (threadIdx.x == 0) {
-    double l1 = 0.0;
-    for (int b = 0; b < nparts; b++) l1 += l1part[b];
     double l = losssum[0] * inv_n + l1;
     st->lossval = l;
     if (st->first) { st->first = 0; return; }   // loss at the start point: no hook call yet
@@ -1160,7 +1161,7 @@ __global__ void __launch_bounds__(256) small_p2p_tail_kernel(PgState *st, const 
   small_tail(st, scratch, world, theta, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps, max_iter);
 }
 
-constexpr int PROX_BLOCKS = 64;
+constexpr int PROX_BLOCKS = 256;
 
 struct Work {
   DevBuf<double> theta, w, lossterm, g, red, scalars, gathered, blockmax;
