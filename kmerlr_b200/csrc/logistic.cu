@@ -276,7 +276,9 @@ constexpr uint32_t IMP_NOIDX = 0xFFFFFFFFu, IMP_SINGLES = 0xFFFFFFFEu;
 struct ImpWindow {
   unsigned long long rev;
   uint32_t inv;
+  int left;                                     // bases of the row from the window's first base on (<= 0: none)
   __device__ __forceinline__ void load(const uint32_t *__restrict__ b2, const uint16_t *__restrict__ iv, int L, int p0) {
+    left = L - p0;
     if (p0 >= L) { rev = 0ull; inv = 0xFFFFFFFFu; return; }     // (and no load past the row)
     const int wi = p0 >> 4, sh = p0 & 15;
     const uint32_t w0 = __ldg(b2 + wi), w1 = __ldg(b2 + wi + 1), w2 = __ldg(b2 + wi + 2);
@@ -285,7 +287,6 @@ struct ImpWindow {
     const unsigned long long iw = (unsigned long long)__ldg(iv + wi) | ((unsigned long long)__ldg(iv + wi + 1) << 16) |
                                   ((unsigned long long)__ldg(iv + wi + 2) << 32);
     inv = (uint32_t)(iw >> sh);
-    const int left = L - p0;                    // bases of the row from p0 on
     if (left < 32) inv |= 0xFFFFFFFFu << left;
   }
   // the k bases starting at base x of the window (x + k <= 32)
@@ -297,6 +298,7 @@ struct ImpWindow {
 // group at base x of the window = c positions.  Table index of its super k-mer, IMP_SINGLES when the S bases
 // are not all usable, IMP_NOIDX when the group starts past the end of the row
 __device__ __forceinline__ uint32_t imp_group(const ImpParams &P, const ImpWindow &W, int x) {
+  if (x >= W.left) return IMP_NOIDX;            // the group starts past the end of the row: nothing to look at
   const uint32_t bits = (W.inv >> x) & ((1u << P.S) - 1u);
   return bits == 0u ? P.sup0 + W.code(x, P.S) : IMP_SINGLES;
 }
