@@ -211,7 +211,7 @@ def leg_c3(K, api, synth, shard, rank, world, dist, allmax, allsum, peak, iters=
             "other_kernels_ms_per_iter": other_ms, "ms_per_iter_with_kernel_events": it_ms_prof,
             "allreduce_ms_per_iter": ar_ms, "allreduce_share_of_iter": ar_ms / it_ms if it_ms > 0 else None,
             "allreduce_bytes": 8 * (m + 1), "algorithmic_bytes_per_iter": it_bytes,
-            "allreduce_path": ("NVLink peer memory (two-shot, one cooperative launch)" if os.environ.get("KMERLR_P2P", "1") != "0" else "NCCL") if world > 1 else None,
+            "allreduce_path": ("NVLink peer memory (two-shot, one cooperative launch)" if os.environ.get("KMERLR_OPT_P2P_ALLREDUCE", "0") not in ("", "0") else "NCCL int64 sum") if world > 1 else None,
             "iter_achieved_gbs_per_gpu": it_bytes / world / (it_ms * 1e-3) / 1e9,
             "iter_frac_of_hbm_peak": it_bytes / world / (it_ms * 1e-3) / 1e9 / peak}
 
