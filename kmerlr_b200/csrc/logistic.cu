@@ -596,37 +596,102 @@ __global__ void finalize_g(const unsigned long long *__restrict__ G, int64_t cou
   if (j < count) g[j] = (double)(long long)G[j] * inv_scale;
 }
 
-// pair coefficients (kmerLr_logistic_regression.go:183-195): g[Ind2Sub(a,b)] = sum_i w_i v_ia v_ib,
-// one warp per pair, intersecting the two CSC columns
+// pair coefficients (kmerLr_logistic_regression.go:183-195): g[Ind2Sub(a,b)] = sum_i (w_i v_ia) v_ib, a < b.
+// One block per pair of column tiles (32 x 32 pair accumulators in registers: warp = 4 columns a, lane = column
+// b).  The rows go by in chunks: the block spreads the B tile's entries of the chunk into a dense [row][b] array
+// in shared memory, then every warp walks the entries of its a columns IN ROW ORDER and adds (w_r v_ra) x the
+// dense row to its 32 accumulators -- a zero of the dense row adds +0.0, which changes nothing.  Every pair is
+// therefore summed in increasing sample order with the reference's product (w v1) v2, i.e. bit for bit what the
+// serial Go loop computes, without the per-element binary search of one warp per pair (227 ms at C4 before).
+constexpr int PAIR_T = 32;         // tile edge, columns
+constexpr int PAIR_CH = 256;       // rows per chunk: PAIR_CH x PAIR_T doubles = 64 KB of shared memory
 template <typename VT>
-__global__ void pairs_gradient(const int64_t *__restrict__ colptr, const uint32_t *__restrict__ crow,
-                               const VT *__restrict__ cval, int64_t m, const double *__restrict__ w,
-                               double *__restrict__ g) {
-  int64_t npairs = m * (m - 1) / 2;
-  int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  unsigned lane = lane_id();
-  for (int64_t pi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pi < npairs; pi += warps) {
-    // pair index -> (a, b), a < b, row-major over the strict upper triangle
-    int64_t a = (int64_t)floor(((double)(2 * m - 1) - sqrt((double)(2 * m - 1) * (double)(2 * m - 1) - 8.0 * (double)pi)) / 2.0);
-    while (a > 0 && a * (2 * m - a - 1) / 2 > pi) a--;
-    while ((a + 1) * (2 * m - a - 2) / 2 <= pi) a++;
-    int64_t b = pi - a * (2 * m - a - 1) / 2 + a + 1;
-    int64_t a0 = colptr[a], a1 = colptr[a + 1], b0 = colptr[b], b1 = colptr[b + 1];
-    // iterate the shorter column, binary search the longer one
-    bool swap = (a1 - a0) > (b1 - b0);
-    int64_t s0 = swap ? b0 : a0, s1 = swap ? b1 : a1, l0 = swap ? a0 : b0, l1 = swap ? a1 : b1;
-    double s = 0.0;
-    for (int64_t p = s0 + lane; p < s1; p += 32) {
-      uint32_t r = crow[p];
-      int64_t lo = l0, hi = l1;
-      while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (crow[mid] < r) lo = mid + 1; else hi = mid; }
-      if (lo < l1 && crow[lo] == r) {
-        double va = valf(cval, swap ? lo : p), vb = valf(cval, swap ? p : lo);
-        s += w[r] * va * vb;
+__global__ void __launch_bounds__(256) pairs_gradient(const int64_t *__restrict__ colptr, const uint32_t *__restrict__ crow,
+                                                      const VT *__restrict__ cval, int64_t m, int64_t n, int ntile,
+                                                      const double *__restrict__ w, double *__restrict__ g) {
+  extern __shared__ __align__(16) double Bd[];            // [PAIR_CH][PAIR_T], then the warps' staging areas
+  __shared__ int64_t pb[PAIR_T];
+  double *st_t = Bd + PAIR_CH * PAIR_T + (threadIdx.x >> 5) * PAIR_CH;                                       // w_r v_ra
+  unsigned short *st_r = reinterpret_cast<unsigned short *>(Bd + PAIR_CH * PAIR_T + 8 * PAIR_CH) + (threadIdx.x >> 5) * PAIR_CH;   // local row
+  // tile pair (ta <= tb) of this block: row-major over the upper triangle, diagonal included
+  int64_t rest = blockIdx.x;
+  int ta = 0;
+  while (rest >= ntile - ta) { rest -= ntile - ta; ta++; }
+  const int tb = ta + (int)rest;
+  const int64_t a0 = (int64_t)ta * PAIR_T, b0 = (int64_t)tb * PAIR_T;
+  const unsigned lane = lane_id();
+  const int wib = threadIdx.x >> 5;
+  int64_t pa[4], ea[4];
+  double acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int64_t a = a0 + wib * 4 + i;
+    pa[i] = a < m ? colptr[a] : 0; ea[i] = a < m ? colptr[a + 1] : 0;
+    acc[i] = 0.0;
+  }
+  if (threadIdx.x < PAIR_T) pb[threadIdx.x] = b0 + threadIdx.x < m ? colptr[b0 + threadIdx.x] : 0;
+  for (int64_t lo = 0; lo < n; lo += PAIR_CH) {
+    const int64_t hi = lo + PAIR_CH < n ? lo + PAIR_CH : n;
+    for (int i = threadIdx.x; i < PAIR_CH * PAIR_T / 2; i += blockDim.x) reinterpret_cast<double2 *>(Bd)[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    // the B tile's entries of this chunk -> dense rows (a warp takes 4 columns; the entries of a column are sorted by row)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int bc = wib * 4 + i;
+      const int64_t b = b0 + bc;
+      if (b >= m) continue;
+      int64_t p = pb[bc];
+      const int64_t end = colptr[b + 1];
+      for (;;) {
+        const int64_t q = p + lane;
+        const uint32_t r = q < end ? crow[q] : 0xFFFFFFFFu;
+        const bool in = q < end && (int64_t)r < hi;
+        if (in) Bd[(r - lo) * PAIR_T + bc] = valf(cval, q);
+        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+        p += cnt;
+        if (cnt < 32) break;
       }
+      __syncwarp();
+      if (lane == 0) pb[bc] = p;
     }
-    s = warp_sum_down(s);
-    if (lane == 0) g[ind2sub(m, a, b)] = s;
+    __syncthreads();
+    // the a columns of this warp, entries in row order: acc[a][b] += (w_r v_ra) v_rb.  The lanes stage the
+    // column's entries of the chunk (local row, w_r v_ra) in shared memory with coalesced loads; the serial
+    // walk then reads broadcasts whose addresses are known ahead, so only the chain of additions is left
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int64_t p = pa[i];
+      int cnt_tot = 0;
+      for (;;) {
+        const int64_t q = p + lane;
+        const uint32_t r = q < ea[i] ? crow[q] : 0xFFFFFFFFu;
+        const bool in = q < ea[i] && (int64_t)r < hi;
+        if (in) { st_r[cnt_tot + lane] = (unsigned short)(r - lo); st_t[cnt_tot + lane] = __ldg(w + r) * valf(cval, q); }
+        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+        p += cnt; cnt_tot += cnt;
+        if (cnt < 32) break;
+      }
+      pa[i] = p;
+      __syncwarp();
+      double a_ = acc[i];
+      int e = 0;
+      for (; e + 4 <= cnt_tot; e += 4) {
+        double d[4], t[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { t[q] = st_t[e + q]; d[q] = Bd[(int)st_r[e + q] * PAIR_T + lane]; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) a_ += t[q] * d[q];
+      }
+      for (; e < cnt_tot; e++) a_ += st_t[e] * Bd[(int)st_r[e] * PAIR_T + lane];
+      acc[i] = a_;
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int64_t a = a0 + wib * 4 + i, b = b0 + lane;
+    if (a < m && b < m && a < b) g[ind2sub(m, a, b)] = acc[i];
   }
 }
 
@@ -1404,8 +1469,11 @@ void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2]
                   wk.scale, wk.G.p);
       if (M.sharded) comm_allreduce_sum_i64((int64_t *)wk.G.p, M.m + 1);
       if (M.m > 1) {
-        KL_LAUNCH((pairs_gradient<VT>), (unsigned)(ctx().sm_count * 8), 256, 0, M.colptr.p, M.crow.p, csc_val<VT>(M),
-                  M.m, wk.w.p, wk.g.p);
+        const int ntile = (int)((M.m + PAIR_T - 1) / PAIR_T);
+        const size_t smem = (size_t)PAIR_CH * PAIR_T * sizeof(double) + (size_t)8 * PAIR_CH * (sizeof(double) + sizeof(unsigned short));
+        KL_CUDA(cudaFuncSetAttribute(pairs_gradient<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KL_LAUNCH((pairs_gradient<VT>), (unsigned)((int64_t)ntile * (ntile + 1) / 2), 256, smem, M.colptr.p, M.crow.p,
+                  csc_val<VT>(M), M.m, M.n, ntile, wk.w.p, wk.g.p);
         if (M.sharded) {
           // pair entries: every rank sums the per-rank values in rank order
           comm_allgather_f64(wk.g.p, wk.gathered.p, ntheta);

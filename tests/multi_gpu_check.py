@@ -58,6 +58,12 @@ def main():
         it_full, _ = est.estimate_proximal(rfull, 1e-3)
         thc_full = est.Theta.copy()
         rfull.free()
+        # a short leapfrog path with EpsilonLambda > 0 (the `ok` of Select then depends on L1Reg = lambda n: n must be
+        # the row count of the WHOLE set on every rank, or the ranks leave the epoch loop at different epochs)
+        full.SetLabels(np.concatenate([np.ones(n_fg, dtype=np.uint8), np.zeros(n_bg, dtype=np.uint8)]))
+        est = K.KmerLrEstimator(EpsilonLoss=1e-7, EpsilonLambda=1e-9, MaxIterations=20000, MaxEpochs=6, tie=K.TIE_INDEX)
+        est.estimate_loop(full, 4)
+        path_full, act_full, thp_full = [p[:3] for p in est.path], est.active_idx.copy(), est.Theta.copy()
         k_full, c_full = full.Kmers()
         full.free()
         # sharded
@@ -78,7 +84,17 @@ def main():
         est3.Theta = np.zeros(len(sel)); est3.ClassWeights = np.array(cw)
         it_s, _ = est3.estimate_proximal(rmine, 1e-3)
         rmine.free()
+        est4 = K.KmerLrEstimator(EpsilonLoss=1e-7, EpsilonLambda=1e-9, MaxIterations=20000, MaxEpochs=6, tie=K.TIE_INDEX)
+        est4.estimate_loop(mine, 4)
+        # the ABI from another host thread (cgo moves goroutines between OS threads): the library re-binds its device
+        import threading
+        box = {}
+        th = threading.Thread(target=lambda: box.update(l=lr.Loss(mine)))
+        th.start(); th.join()
         checks = {
+            "leapfrog path with EpsilonLambda > 0 (%d epochs)" % len(est4.path): [p[:3] for p in est4.path] == path_full
+                and np.array_equal(est4.active_idx, act_full) and np.array_equal(est4.Theta, thp_full),
+            "loss from a second host thread": box.get("l") == l_s,
             "reduced theta after 300 iterations": np.array_equal(est2.Theta, thr_full),
             "reduced converged (%d vs %d iterations)" % (it_s, it_full): abs(it_s - it_full) <= 2 and np.allclose(est3.Theta, thc_full, rtol=1e-6, atol=1e-12),
             "classes": mine.m == len(k_full) and np.array_equal(k_s, k_full) and np.array_equal(c_s, c_full),

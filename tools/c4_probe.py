@@ -22,10 +22,15 @@ print("extract: n=%d m=%d nnz=%d  %.1f ms" % (d.n, d.m, d.nnz, 1e3 * (time.perf_
 nt = K.CoeffIndex(d.m).Dim()
 theta = np.zeros(nt)
 lr = K.logisticRegression(theta, (1.0, 1.0), 0.0, Cooccurrence=True)
-for rep in range(2):
+for rep in range(3):
+    if rep == 2:
+        K.api.profile(True)
     t0 = time.perf_counter()
     g = lr.Gradient(None, d)
     print("pair gradient (%d coefficients): wall %.1f ms, device %.1f ms" % (nt, 1e3 * (time.perf_counter() - t0), K.last_device_ms()), flush=True)
+for k, v in sorted(K.api.profile_dump().items(), key=lambda kv: -kv[1][0])[:6]:
+    print("  %-60s %9.3f ms / %d launches" % (k[:60], v[0], v[1]))
+K.api.profile(False)
 s = K.featureSelector((1.0, 1.0), True, 20, d.m, tie=K.TIE_INDEX)
 t0 = time.perf_counter()
 sel, lam, ok = s.Select(d, 0.0, [], [], 0.0)
