@@ -39,12 +39,30 @@ __device__ __forceinline__ int64_t ind2sub(int64_t n, int64_t k1, int64_t k2) {
 template <typename VT>
 __device__ __forceinline__ double valf(const VT *val, int64_t p) { return val ? (double)val[p] : 1.0; }
 
-// rows pass: MODE 0 = z only, 1 = log sigma(z), 2 = w_i and loss term
+// a non-zero pair coefficient theta[Ind2Sub(a, b)], a < b (pair mode with a sparse theta)
+struct PairTerm {
+  uint32_t a, b;
+  double theta;
+};
+// value of column c in the row [a, b) (columns ascending), 0 when absent
+template <typename VT>
+__device__ __forceinline__ double row_value(const uint32_t *__restrict__ col, const VT *__restrict__ val, int64_t a, int64_t b,
+                                            uint32_t c) {
+  int64_t lo = a, hi = b;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (col[mid] < c) lo = mid + 1; else hi = mid; }
+  return (lo < b && col[lo] == c) ? valf(val, lo) : 0.0;
+}
+
+// rows pass: MODE 0 = z only, 1 = log sigma(z), 2 = w_i and loss term.
+// cooc = 1: pair terms over all pairs of entries of the row (O(q^2) gathers of theta); cooc = 2: over the list of
+// non-zero pair coefficients (`terms`, sorted by coefficient index): two lookups per term and row -- an L1-regularised
+// theta has a handful of them, and 3.84 M coefficients at C4
 template <typename VT, int MODE>
 __global__ void rows_kernel(const Rows R, const uint32_t *__restrict__ col,
                             const VT *__restrict__ val, int64_t n, int64_t m, const double *__restrict__ theta,
                             int cooc, const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n,
-                            double *__restrict__ out, double *__restrict__ lossterm, const PgState *st) {
+                            double *__restrict__ out, double *__restrict__ lossterm, const PgState *st,
+                            const PairTerm *__restrict__ terms, int nterms) {
   if (st && st->done == 1) return;
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
@@ -53,7 +71,13 @@ __global__ void rows_kernel(const Rows R, const uint32_t *__restrict__ col,
   R.range(row, a, b);
   double s = 0.0;
   for (int64_t p = a + lane; p < b; p += 32) s += valf(val, p) * __ldg(theta + col[p] + 1);
-  if (cooc) {
+  if (cooc == 2) {
+    for (int t = (int)lane; t < nterms; t += 32) {
+      const PairTerm pt = terms[t];
+      const double v1 = row_value(col, val, a, b, pt.a);
+      if (v1 != 0.0) s += v1 * row_value(col, val, a, b, pt.b) * pt.theta;
+    }
+  } else if (cooc) {
     // pair terms (kmerLr_logistic_regression.go:69-84)
     for (int64_t p1 = a; p1 < b; p1++) {
       double v1 = valf(val, p1);
@@ -1260,13 +1284,41 @@ void reduce_sum(const Matrix &M, const double *x, int64_t n, Work &wk, double *o
   }
 }
 
+// the non-zero pair coefficients of a host theta, in coefficient order; empty optional = too many (dense theta)
+constexpr int64_t PAIR_TERMS_MAX = 8192;
+struct PairTerms {
+  bool sparse = false;
+  DevBuf<PairTerm> dev;
+  int n = 0;
+};
+void collect_pair_terms(const Matrix &M, const double *theta_host, int64_t ntheta, int cooc, PairTerms &T) {
+  if (!cooc) return;
+  std::vector<PairTerm> h;
+  const uint64_t *bits = reinterpret_cast<const uint64_t *>(theta_host);
+  for (int64_t j = M.m + 1; j < ntheta; j++) {
+    // (blocks of eight zeros -- the normal case -- are skipped with integer ORs; the shift drops the sign of -0.0)
+    if (j + 8 <= ntheta && (((bits[j] | bits[j + 1] | bits[j + 2] | bits[j + 3] | bits[j + 4] | bits[j + 5] | bits[j + 6] | bits[j + 7]) << 1) == 0)) { j += 7; continue; }
+    if (theta_host[j] == 0.0) continue;
+    if ((int64_t)h.size() >= PAIR_TERMS_MAX) return;          // dense theta: the O(q^2) path
+    int64_t a, b;
+    kmerlr_coeff_sub2ind(M.m, j - 1, &a, &b);
+    h.push_back(PairTerm{(uint32_t)a, (uint32_t)b, theta_host[j]});
+  }
+  T.sparse = true; T.n = (int)h.size();
+  T.dev.alloc(h.size() ? h.size() : 1);
+  T.dev.upload(h.data(), h.size());
+  sync_stream();                                                // (h goes out of scope)
+}
+
 template <typename VT, int MODE>
 void launch_rows(const Matrix &M, const double *theta, int cooc, const double cw[2], double *out, double *lossterm,
-                 const PgState *st) {
+                 const PgState *st, const PairTerms *T = nullptr) {
   if (M.n == 0) return;
   double inv_n = 1.0 / (double)M.n_global;
+  const bool sparse = cooc && T && T->sparse;
   KL_LAUNCH((rows_kernel<VT, MODE>), warp_grid(M.n, 256), 256, 0, M.rows(), M.col.p, csr_val<VT>(M), M.n, M.m,
-            theta, cooc, M.labels.p, cw ? cw[0] : 1.0, cw ? cw[1] : 1.0, inv_n, out, lossterm, st);
+            theta, sparse ? 2 : cooc, M.labels.p, cw ? cw[0] : 1.0, cw ? cw[1] : 1.0, inv_n, out, lossterm, st,
+            sparse ? T->dev.p : (const PairTerm *)nullptr, sparse ? T->n : 0);
 }
 
 // fixed-point scale: sum_i |w_i v_ic| <= max(cw) * max|v|, kept below 2^60
@@ -1433,10 +1485,12 @@ void linear_pdf(Matrix &M, const double *theta, int64_t ntheta, int cooc, double
   check_theta(M, ntheta, cooc);
   DevBuf<double> dth((size_t)ntheta), out((size_t)(M.n ? M.n : 1));
   dth.upload(theta, (size_t)ntheta);
+  PairTerms terms;
+  collect_pair_terms(M, theta, ntheta, cooc, terms);
   dispatch_vt(M, [&](auto *tag) {
     using VT = typename std::remove_pointer<decltype(tag)>::type;
-    if (logpdf) launch_rows<VT, 1>(M, dth.p, cooc, nullptr, out.p, nullptr, nullptr);
-    else launch_rows<VT, 0>(M, dth.p, cooc, nullptr, out.p, nullptr, nullptr);
+    if (logpdf) launch_rows<VT, 1>(M, dth.p, cooc, nullptr, out.p, nullptr, nullptr, &terms);
+    else launch_rows<VT, 0>(M, dth.p, cooc, nullptr, out.p, nullptr, nullptr, &terms);
   });
   out.download(out_host, (size_t)M.n);
   sync_stream();
@@ -1461,7 +1515,9 @@ void gradient(Matrix &M, const double *theta, int64_t ntheta, const double cw[2]
       // single-feature part still goes through the fixed-point pass with theta restricted to it
       // being irrelevant: w is what matters.  Reuse the fused kernel's scatter by running the pair
       // aware rows kernel for w and the CSC kernels for the pairs.
-      launch_rows<VT, 2>(M, wk.theta.p, cooc, cw, wk.w.p, wk.lossterm.p, nullptr);
+      PairTerms terms;
+      collect_pair_terms(M, theta, ntheta, cooc, terms);
+      launch_rows<VT, 2>(M, wk.theta.p, cooc, cw, wk.w.p, wk.lossterm.p, nullptr, &terms);
       ensure_csc(M);
       KL_CUDA(cudaMemsetAsync(wk.G.p, 0, (size_t)(M.m + 1) * sizeof(unsigned long long), ctx().stream));
       if (M.n > 0)
@@ -1498,9 +1554,11 @@ double loss(Matrix &M, const double *theta, int64_t ntheta, const double cw[2], 
   if (M.n_global == 0) return 0.0;
   Work wk; alloc_work(M, ntheta, wk);
   wk.theta.upload(theta, (size_t)ntheta);
+  PairTerms terms;
+  collect_pair_terms(M, theta, ntheta, cooc, terms);
   dispatch_vt(M, [&](auto *tag) {
     using VT = typename std::remove_pointer<decltype(tag)>::type;
-    launch_rows<VT, 2>(M, wk.theta.p, cooc, cw, wk.w.p, wk.lossterm.p, nullptr);
+    launch_rows<VT, 2>(M, wk.theta.p, cooc, cw, wk.w.p, wk.lossterm.p, nullptr, &terms);
   });
   reduce_sum(M, wk.lossterm.p, M.n, wk, wk.scalars.p, nullptr);
   double s = 0.0;
