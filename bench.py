@@ -161,7 +161,7 @@ def leg_c3(K, api, synth, shard, rank, world, dist, allmax, allsum, peak, iters=
     counter = K.NewKmerCounter(M, N, revcomp=True, binarize=binarize)
     seqs = K.Sequences((buf, off))
     sharded = world > 1
-    for opt in ("persist_bps", "p2p_allreduce", "super_len", "fused_ticket"):       # experiments: KMERLR_OPT_<NAME>=value
+    for opt in ("persist_bps", "p2p_allreduce", "super_len", "fused_ticket", "small_long"):       # experiments: KMERLR_OPT_<NAME>=value
         if os.environ.get("KMERLR_OPT_" + opt.upper()):
             K.option(opt, int(os.environ["KMERLR_OPT_" + opt.upper()]))
     ext = []

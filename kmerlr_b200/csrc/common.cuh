@@ -97,6 +97,7 @@ struct Ctx {
   PeerBox *peer = nullptr;   // device copy of the mailbox table, nullptr = not available (NCCL is used)
   bool p2p_ok = true;        // kmerlr_option("p2p")
   bool p2p_allreduce = false; // kmerlr_option("p2p_allreduce"): full-space gradient all-reduce over peer memory instead of NCCL
+  int small_long = -1;       // kmerlr_option("small_long"): reduced-matrix solver on the sliced + column-major layouts (1), on the rows (0), by row length (-1)
   int persist_bps = 0;       // kmerlr_option("persist_bps"): blocks per SM of the persistent reduced-matrix solver (0 = all that fit)
   bool coop_supported = true;
   bool coop_ok = true;       // kmerlr_option("persistent"); false when the device cannot launch cooperatively
@@ -268,6 +269,18 @@ struct Matrix : Object {
   DevBuf<uint32_t> crow;     // nnz
   DevBuf<uint32_t> cval_u32;
   DevBuf<double> cval_f64;
+  // sliced view (built on first use by ensure_sliced): slices of 32 rows, entry k of the 32 rows side by side
+  // (entry k of row r at slice_off[r / 32] + 32 k + r % 32), so that one thread per row reads coalesced
+  bool has_sliced = false;
+  DevBuf<int64_t> slice_off;   // n/32 + 1
+  DevBuf<uint32_t> scol;
+  DevBuf<uint32_t> sval_u32;
+  DevBuf<double> sval_f64;
+  // both views with the count packed beside the index, one 32-bit word per entry (ensure_packed; counts and at
+  // most 1 024 columns only): sliced = column | count << 10, column-major = row | count << pack_row_bits
+  bool has_packed = false, packable = false;
+  int pack_row_bits = 0;
+  DevBuf<uint32_t> spack, cpack;
   // labels
   bool has_labels = false;
   DevBuf<uint8_t> labels;    // n
@@ -337,6 +350,8 @@ void matrix_pair_moments(Matrix &M, double *sum, double *sumsq, double *absmax, 
 std::shared_ptr<Matrix> matrix_transform(Matrix &M, const double *offset, const double *scale, int64_t len);
 void matrix_compact(Matrix &M);      // padded rows -> compact CSR (no-op for compact matrices)
 void ensure_csc(Matrix &M);
+void ensure_sliced(Matrix &M);
+bool ensure_packed(Matrix &M);      // false: the entries do not fit (real values, large counts, > 1 024 columns)
 std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel);
 double matrix_maxsq(Matrix &M);
 double matrix_vmax(Matrix &M);

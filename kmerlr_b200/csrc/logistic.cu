@@ -1000,6 +1000,145 @@ __device__ __forceinline__ void small_rows(const Rows &R, const uint32_t *__rest
     }
 }
 
+// Reduced matrices with LONG rows (late epochs of a leapfrog path: the classes of the short k-mers are in every
+// row -- 47 entries per row at 100 features of C2).  One thread per row over the compact rows then costs one L1
+// wavefront PER LANE and load (the rows of a warp are 200 bytes apart), and the rows of a warp add to the same
+// shared-memory accumulator at the same time (every row starts with the same columns): 138 us per iteration at
+// 9.4 M entries.  Two more views of the same matrix remove both: the forward sum reads the SLICED view (entry k of
+// 32 consecutive rows side by side: one wavefront per warp and load; the sum of a row still runs in entry order,
+// so z has the same bits as on the compact rows), leaves the scaled weights in wbuf, and after a grid barrier
+// the gradient is a segmented sum over the COLUMN-MAJOR view (contiguous entries, weights gathered by row, a
+// thread's entries of one column summed in a register): exact integers -- the same G as the row-wise scatter.
+template <typename VT>
+struct LongView {
+  const int64_t *slice_off; const uint32_t *scol; const VT *sval;     // sliced view (Matrix::ensure_sliced)
+  const int64_t *colptr; const uint32_t *crow; const VT *cval;        // column-major view (ensure_csc)
+  const uint32_t *spack, *cpack;                                      // both with the count packed in (ensure_packed), or null
+  int row_bits;
+  double *wbuf;                                                       // n scaled row weights
+  int64_t nnz;
+};
+
+__device__ __forceinline__ void small_acc_add(uint32_t *acc_lo, uint32_t *acc_hi, uint32_t c, unsigned long long q) {
+  const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
+  const uint32_t old = atomicAdd(&acc_lo[c], lo);
+  const uint32_t add_hi = hi + ((old + lo) < old ? 1u : 0u);
+  if (add_hi) atomicAdd(&acc_hi[c], add_hi);
+}
+
+template <typename VT>
+__device__ __forceinline__ void long_forward(const Rows &R, const LongView<VT> &V, int64_t n, int64_t ntheta,
+                                             const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n,
+                                             double scale, double *blockloss, int scatter, uint32_t *acc_lo,
+                                             uint32_t *acc_hi, const double *sth, double *red) {
+  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) { acc_lo[i] = 0u; acc_hi[i] = 0u; }
+  __syncthreads();
+  double lacc = 0.0;
+  long long bias = 0;
+  const int64_t row_lo = n * blockIdx.x / gridDim.x, row_hi = n * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t row = row_lo + threadIdx.x; row < row_hi; row += blockDim.x) {
+    int64_t a, b;
+    R.range(row, a, b);
+    const int64_t base = 32 * V.slice_off[row >> 5] + (row & 31);
+    const int len = (int)(b - a);
+    double s = 0.0;
+    if (V.spack) {
+      // four loads in flight, the sum in entry order
+      const uint32_t *sp = V.spack + base;
+      int k = 0;
+      for (; k + 4 <= len; k += 4) {
+        const uint32_t e0 = __ldg(sp + 32 * k), e1 = __ldg(sp + 32 * k + 32), e2 = __ldg(sp + 32 * k + 64), e3 = __ldg(sp + 32 * k + 96);
+        s += (double)(e0 >> 10) * sth[(e0 & 1023u) + 1];
+        s += (double)(e1 >> 10) * sth[(e1 & 1023u) + 1];
+        s += (double)(e2 >> 10) * sth[(e2 & 1023u) + 1];
+        s += (double)(e3 >> 10) * sth[(e3 & 1023u) + 1];
+      }
+      for (; k < len; k++) { const uint32_t e = __ldg(sp + 32 * k); s += (double)(e >> 10) * sth[(e & 1023u) + 1]; }
+    } else {
+      for (int k = 0; k < len; k++) s += valf(V.sval, base + 32 * k) * sth[V.scol[base + 32 * k] + 1];
+    }
+    double z = sth[0] + s, r = -log_add0(-z), w;
+    if (labels[row]) { w = inv_n * cw1 * (exp(r) - 1.0); lacc += -cw1 * r; }
+    else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
+    if (!scatter) continue;
+    const double ws = w * scale;
+    V.wbuf[row] = ws;
+    bias += __double2ll_rn(ws);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lacc += __shfl_down_sync(0xffffffffu, lacc, o); bias += __shfl_down_sync(0xffffffffu, bias, o); }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = lacc;
+    if (bias) small_acc_add(acc_lo, acc_hi, 0u, (unsigned long long)bias);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) l += red[w];
+    blockloss[blockIdx.x] = l;
+  }
+}
+
+// gradient of the block's share of the column-major entries into the block's accumulators, then into G
+template <typename VT>
+__device__ __forceinline__ void long_columns(const LongView<VT> &V, int64_t ntheta, unsigned long long *G, uint32_t *acc_lo,
+                                             uint32_t *acc_hi, const long long *scp, int c_first) {
+  const int64_t lo = V.nnz * blockIdx.x / gridDim.x, hi = V.nnz * (blockIdx.x + 1) / gridDim.x;
+  int64_t p = lo + threadIdx.x;
+  long long acc = 0;
+  int c = -1;
+  if (p < hi) {
+    c = c_first;
+    long long cend = scp[c + 1];
+    auto boundary = [&](int64_t q) {
+      if (q >= cend) {
+        if (acc) small_acc_add(acc_lo, acc_hi, (uint32_t)c + 1u, (unsigned long long)acc);
+        acc = 0;
+        do { c++; cend = scp[c + 1]; } while (q >= cend);
+      }
+    };
+    if (V.cpack) {
+      const uint32_t rmask = (1u << V.row_bits) - 1u;
+      const int64_t bd = blockDim.x;
+      for (; p < hi; p += 4 * bd) {
+        uint32_t e[4];
+        double ws[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) e[j] = p + j * bd < hi ? __ldg(V.cpack + p + j * bd) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) ws[j] = __ldcg(V.wbuf + (e[j] & rmask));     // (written by other blocks before the barrier)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (p + j * bd < hi) {
+            boundary(p + j * bd);
+            acc += __double2ll_rn(ws[j] * (double)(e[j] >> V.row_bits));
+          }
+        }
+      }
+    } else {
+      for (; p < hi; p += blockDim.x) {
+        boundary(p);
+        const double ws = __ldcg(V.wbuf + V.crow[p]);
+        acc += __double2ll_rn(ws * valf(V.cval, p));
+      }
+    }
+  }
+  // the threads of a warp mostly end in the same column: one add per warp
+  const int c0 = __shfl_sync(0xffffffffu, c, 0);
+  if (__all_sync(0xffffffffu, c == c0)) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && c >= 0 && acc) small_acc_add(acc_lo, acc_hi, (uint32_t)c + 1u, (unsigned long long)acc);
+  } else if (c >= 0 && acc) {
+    small_acc_add(acc_lo, acc_hi, (uint32_t)c + 1u, (unsigned long long)acc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) {
+    unsigned long long v = ((unsigned long long)acc_hi[i] << 32) | acc_lo[i];
+    if (v) atomicAdd(&G[i], v);
+  }
+}
+
 template <typename VT>
 __global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
                                                           const VT *__restrict__ val, int64_t n, int64_t ntheta,
@@ -1044,13 +1183,13 @@ constexpr int PERSIST_THREADS = 256;
 // the mailboxes -- stores into every rank's slot, a flag, a wait for the flags of the others, the sum in rank
 // order (integers: the same bits on every rank) -- and a second grid barrier releases the tail.  The
 // collective lives INSIDE the persistent kernel: no launch and no NCCL call per iteration.
-template <typename VT, bool SHARDED>
+template <typename VT, bool SHARDED, bool LONG>
 __global__ void __launch_bounds__(PERSIST_THREADS, SMALL_BLOCKS_PER_SM) fused_small_persistent(
     const Rows R, const uint32_t *__restrict__ col, const VT *__restrict__ val, int64_t n, int64_t ntheta, double *theta,
     const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n, double scale, unsigned long long *G3,
     double *blockloss2, PgState *st, long long pass0, int npass, double inv_scale, double lambda, double eps_loss,
     double step, double eps, long long max_iter, const PeerBox *pb, unsigned long long *Gx, double *scratch,
-    unsigned int *abort_flag) {
+    unsigned int *abort_flag, const LongView<VT> LV) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ uint32_t acc_lo[SMALL_MAX_THETA], acc_hi[SMALL_MAX_THETA];
   __shared__ double sth[SMALL_MAX_THETA];
@@ -1063,6 +1202,17 @@ __global__ void __launch_bounds__(PERSIST_THREADS, SMALL_BLOCKS_PER_SM) fused_sm
     if (SHARDED) s_seq = pb->box[pb->rank]->seq;
   }
   for (int i = threadIdx.x; i < ntheta; i += blockDim.x) sth[i] = theta[i];
+  // LONG: the column offsets stay in shared memory; c_first = the column of this thread's first column-major entry
+  __shared__ long long scp[LONG ? SMALL_MAX_THETA + 1 : 1];
+  int c_first = 0;
+  if constexpr (LONG) {
+    for (int i = threadIdx.x; i < ntheta; i += blockDim.x) scp[i] = LV.colptr[i];        // m + 1 = ntheta offsets
+    __syncthreads();
+    const int64_t p = LV.nnz * blockIdx.x / gridDim.x + threadIdx.x;
+    int a = 0, b = (int)ntheta - 1;                 // scp[a] <= p < scp[b] (empty columns skipped)
+    while (b - a > 1) { const int mid = (a + b) >> 1; if (scp[mid] <= p) a = mid; else b = mid; }
+    c_first = a;
+  }
   __syncthreads();
   const int nblocks = (int)gridDim.x;
   for (int it = 0; it < npass; it++) {
@@ -1075,8 +1225,16 @@ __global__ void __launch_bounds__(PERSIST_THREADS, SMALL_BLOCKS_PER_SM) fused_sm
     double *blockloss = blockloss2 + (pass & 1) * nblocks;
     if (blockIdx.x == 0)
       for (int i = threadIdx.x; i < SMALL_REPLICAS * ntheta; i += blockDim.x) Gnext[i] = 0ull;
-    small_rows<VT, false>(R, col, val, n, ntheta, sth, labels, cw0, cw1, inv_n, scale,
-                          G + (blockIdx.x % SMALL_REPLICAS) * ntheta, blockloss, scatter, acc_lo, acc_hi, sth, red);
+    if constexpr (LONG) {
+      long_forward<VT>(R, LV, n, ntheta, labels, cw0, cw1, inv_n, scale, blockloss, scatter, acc_lo, acc_hi, sth, red);
+      if (scatter) {
+        grid.sync();
+        long_columns<VT>(LV, ntheta, G + (blockIdx.x % SMALL_REPLICAS) * ntheta, acc_lo, acc_hi, scp, c_first);
+      }
+    } else {
+      small_rows<VT, false>(R, col, val, n, ntheta, sth, labels, cw0, cw1, inv_n, scale,
+                            G + (blockIdx.x % SMALL_REPLICAS) * ntheta, blockloss, scatter, acc_lo, acc_hi, sth, red);
+    }
     grid.sync();
     if (!SHARDED) {
       small_tail<PERSIST_THREADS>(&ls, blockloss, nblocks, sth, G, inv_scale, ntheta, inv_n, lambda, eps_loss, step, eps,
@@ -1266,6 +1424,15 @@ template <typename VT>
 const VT *csr_val(const Matrix &M);
 template <> const uint32_t *csr_val<uint32_t>(const Matrix &M) { return M.vt == VAL_U32 ? M.val_u32.p : nullptr; }
 template <> const double *csr_val<double>(const Matrix &M) { return M.val_f64.p; }
+template <typename VT>
+const VT *sliced_val(const Matrix &M);
+template <> const uint32_t *sliced_val<uint32_t>(const Matrix &M) { return M.vt == VAL_U32 ? M.sval_u32.p : nullptr; }
+template <> const double *sliced_val<double>(const Matrix &M) { return M.sval_f64.p; }
+template <typename VT>
+const void *persistent_kernel(bool sharded, bool long_rows) {
+  if (sharded) return long_rows ? (const void *)fused_small_persistent<VT, true, true> : (const void *)fused_small_persistent<VT, true, false>;
+  return long_rows ? (const void *)fused_small_persistent<VT, false, true> : (const void *)fused_small_persistent<VT, false, false>;
+}
 template <typename VT>
 const VT *csc_val(const Matrix &M);
 template <> const uint32_t *csc_val<uint32_t>(const Matrix &M) { return M.vt == VAL_U32 ? M.cval_u32.p : nullptr; }
@@ -1598,6 +1765,12 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   // exchange the gradient inside that kernel over NVLink peer memory
   const bool p2p = M.sharded && ctx().peer && ctx().p2p_ok;
   bool persistent = small && ctx().coop_ok && (!M.sharded || p2p);
+  // long rows: sliced + column-major views (the iterates are the same bits on either path, so a rank may choose by
+  // its own shard)
+  const bool long_rows = persistent && M.nnz > 0 && (ctx().small_long == 1 || (ctx().small_long < 0 && M.nnz >= 8 * M.n));
+  DevBuf<double> wbuf;
+  bool packed = false;
+  if (long_rows) { ensure_sliced(M); ensure_csc(M); packed = ensure_packed(M); wbuf.alloc((size_t)M.n); }
   const int64_t BATCH = persistent ? 4096 : (small ? 256 : 16);
   int small_blocks = 0;
   DevBuf<double> blockloss;
@@ -1610,8 +1783,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
       int per_sm = 0;
       dispatch_vt(M, [&](auto *tag) {
         using VT = typename std::remove_pointer<decltype(tag)>::type;
-        if (M.sharded) KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (fused_small_persistent<VT, true>), PERSIST_THREADS, 0));
-        else KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (fused_small_persistent<VT, false>), PERSIST_THREADS, 0));
+        KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel<VT>(M.sharded, long_rows), PERSIST_THREADS, 0));
       });
       KL_INVARIANT(per_sm >= 1);
       if (ctx().persist_bps > 0 && ctx().persist_bps < per_sm) per_sm = ctx().persist_bps;
@@ -1652,11 +1824,18 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
         unsigned long long *gx = wk.G.p;
         double *scr = wk.gathered.p;
         unsigned int *abortp = counter.p;
+        LongView<VT> lv{};
+        if (long_rows) {
+          lv.slice_off = M.slice_off.p; lv.scol = M.scol.p; lv.sval = sliced_val<VT>(M);
+          lv.colptr = M.colptr.p; lv.crow = M.crow.p; lv.cval = csc_val<VT>(M);
+          if (packed) { lv.spack = M.spack.p; lv.cpack = M.cpack.p; lv.row_bits = M.pack_row_bits; }
+          lv.wbuf = wbuf.p; lv.nnz = M.nnz;
+        }
         void *args[] = {&rows, &colp, &valp, &n, &nt, &thp, &lab, &cw0, &cw1, &invn, &scale, &Gp, &bl, &stp, &pass0, &npass,
-                        &inv_scale, &lam, &el, &stp_size, &eps, &mi, &pbp, &gx, &scr, &abortp};
+                        &inv_scale, &lam, &el, &stp_size, &eps, &mi, &pbp, &gx, &scr, &abortp, &lv};
         if (ctx().profiling) profile_begin("fused_small_persistent");
         const cudaError_t e = cudaLaunchCooperativeKernel(
-            M.sharded ? (const void *)fused_small_persistent<VT, true> : (const void *)fused_small_persistent<VT, false>,
+            persistent_kernel<VT>(M.sharded, long_rows),
             dim3((unsigned)small_blocks), dim3(PERSIST_THREADS), args, 0, ctx().stream);
         if (ctx().profiling) profile_end();
         if (e == cudaErrorCooperativeLaunchTooLarge && !M.sharded) {

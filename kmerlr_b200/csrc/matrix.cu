@@ -606,6 +606,111 @@ void ensure_csc(Matrix &M) {
   M.has_csc = true;
 }
 
+// ---- sliced view: slices of 32 rows, column-major inside a slice -----------------------------------------------
+__global__ void slice_widths(const int64_t *__restrict__ rowptr, int64_t n, int64_t nslices, uint32_t *__restrict__ width32) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslices) return;
+  int64_t w = 0;
+  for (int64_t r = 32 * s; r < 32 * s + 32 && r < n; r++) w = max(w, rowptr[r + 1] - rowptr[r]);
+  width32[s] = (uint32_t)w;                  // slots of the slice = 32 w
+}
+
+template <typename VT>
+__global__ void slice_fill(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ col, const VT *__restrict__ val,
+                           int64_t n, const int64_t *__restrict__ slice_off, uint32_t *__restrict__ scol, VT *__restrict__ sval) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const int64_t a = rowptr[row], b = rowptr[row + 1], base = 32 * slice_off[row >> 5] + (row & 31);
+  for (int64_t p = a; p < b; p++) {
+    scol[base + 32 * (p - a)] = col[p];
+    if (val) sval[base + 32 * (p - a)] = val[p];
+  }
+}
+
+void ensure_sliced(Matrix &M) {
+  if (M.has_sliced) return;
+  matrix_compact(M);
+  const int64_t ns = (M.n + 31) / 32;
+  M.slice_off.alloc((size_t)ns + 1);
+  if (ns == 0) { M.slice_off.zero(); M.has_sliced = true; return; }
+  DevBuf<uint32_t> w((size_t)ns);
+  KL_LAUNCH(slice_widths, (unsigned)((ns + 255) / 256), 256, 0, M.rowptr.p, M.n, ns, w.p);
+  exclusive_scan_u32_to_i64(w.p, M.slice_off.p, ns);            // in units of 32 slots
+  int64_t total = 0;
+  KL_CUDA(cudaMemcpyAsync(&total, M.slice_off.p + ns, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
+  sync_stream();
+  const size_t slots = (size_t)(32 * total > 0 ? 32 * total : 1);
+  M.scol.alloc(slots);
+  const unsigned blocks = (unsigned)((M.n + 255) / 256);
+  if (M.vt == VAL_U32) {
+    M.sval_u32.alloc(slots);
+    KL_LAUNCH((slice_fill<uint32_t>), blocks, 256, 0, M.rowptr.p, M.col.p, M.val_u32.p, M.n, M.slice_off.p, M.scol.p, M.sval_u32.p);
+  } else if (M.vt == VAL_F64) {
+    M.sval_f64.alloc(slots);
+    KL_LAUNCH((slice_fill<double>), blocks, 256, 0, M.rowptr.p, M.col.p, M.val_f64.p, M.n, M.slice_off.p, M.scol.p, M.sval_f64.p);
+  } else {
+    KL_LAUNCH((slice_fill<uint32_t>), blocks, 256, 0, M.rowptr.p, M.col.p, (const uint32_t *)nullptr, M.n, M.slice_off.p, M.scol.p,
+              (uint32_t *)nullptr);
+  }
+  M.has_sliced = true;
+}
+
+template <typename VT>
+__global__ void pack_entries(const uint32_t *__restrict__ idx, const VT *__restrict__ val, int64_t count, int shift,
+                             uint32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = idx[i] | ((val ? (uint32_t)val[i] : 1u) << shift);
+}
+
+// real values that are all small counts (what a reduced count matrix holds)?
+__global__ void count_non_counts(const double *__restrict__ val, int64_t count, double limit, unsigned int *__restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double v = val[i];
+  if (!(v >= 0.0 && v < limit && v == floor(v))) atomicAdd(bad, 1u);
+}
+
+bool ensure_packed(Matrix &M) {
+  if (M.has_packed) return M.packable;
+  M.has_packed = true;
+  M.packable = false;
+  if (M.m > 1024 || M.n < 1 || M.nnz < 1) return false;
+  int rb = 1;
+  while (((int64_t)1 << rb) < M.n) rb++;
+  if (rb > 24) return false;
+  const double limit = (double)(1u << (32 - rb < 22 ? 32 - rb : 22));
+  matrix_compact(M);
+  if (M.vt == VAL_U32) {
+    if (matrix_vmax(M) >= limit) return false;                       // (cached by the callers: no collective here)
+  } else if (M.vt == VAL_F64) {
+    DevBuf<unsigned int> bad(1);
+    bad.zero();
+    KL_LAUNCH(count_non_counts, (unsigned)((M.nnz + 255) / 256), 256, 0, M.val_f64.p, M.nnz, limit, bad.p);
+    unsigned int nbad = 0;
+    bad.download(&nbad, 1);
+    sync_stream();
+    if (nbad) return false;
+  }
+  ensure_sliced(M);
+  ensure_csc(M);
+  M.pack_row_bits = rb;
+  const int64_t slots = (int64_t)M.scol.n;
+  M.spack.alloc((size_t)slots);
+  M.cpack.alloc((size_t)M.nnz);
+  // (padding slots of the sliced view hold whatever the allocation held; nobody reads them)
+  const unsigned sb = (unsigned)((slots + 255) / 256), cb = (unsigned)((M.nnz + 255) / 256);
+  if (M.vt == VAL_F64) {
+    KL_LAUNCH((pack_entries<double>), sb, 256, 0, M.scol.p, M.sval_f64.p, slots, 10, M.spack.p);
+    KL_LAUNCH((pack_entries<double>), cb, 256, 0, M.crow.p, M.cval_f64.p, M.nnz, rb, M.cpack.p);
+  } else {
+    const uint32_t *sval = M.vt == VAL_U32 ? M.sval_u32.p : nullptr, *cval = M.vt == VAL_U32 ? M.cval_u32.p : nullptr;
+    KL_LAUNCH((pack_entries<uint32_t>), sb, 256, 0, M.scol.p, sval, slots, 10, M.spack.p);
+    KL_LAUNCH((pack_entries<uint32_t>), cb, 256, 0, M.crow.p, cval, M.nnz, rb, M.cpack.p);
+  }
+  M.packable = true;
+  return true;
+}
+
 std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel) {
   require_ready();
   KL_REQUIRE(nsel >= 1 && sel[0] == 0, "reduce: sel[0] must be the bias (0)");
