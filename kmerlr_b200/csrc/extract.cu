@@ -260,9 +260,11 @@ const uint2 *table_classes(int op, int t_lo, int t_hi, const uint32_t *level_off
           else r |= d << (2 * (k - 1 - i));
         }
       }
-      // table positions in u16 units with the word index swizzled as the kernel does (xk::sw)
-      auto pos = [](uint32_t i) { return (sw(i >> 1) << 1) | (i & 1u); };
-      if (u <= r) list.push_back(make_uint2(pos(toff + u) | (pos(toff + r) << 16), level_off[k] + u));
+      // BYTE offsets of the two 16-bit counters inside the warp's table (word index swizzled as the kernel does,
+      // xk::sw); a code that is its own image gets a counter of the padding (always 0) as its second one
+      auto pos = [](uint32_t i) { return (sw(i >> 1) << 2) | ((i & 1u) << 1); };
+      const uint32_t zero_slot = 2u * TAB_WORDS - 2u;
+      if (u <= r) list.push_back(make_uint2(pos(toff + u) | (pos(u == r ? zero_slot : toff + r) << 16), level_off[k] + u));
     }
   }
   auto e = std::make_unique<Entry>();
@@ -506,11 +508,12 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   // the block's bitmap of observed classes covers the levels up to OBS_MAX_LEVEL
   {
     int top = cfg.N < OBS_MAX_LEVEL ? cfg.N : OBS_MAX_LEVEL;
-    P.obs_words = top >= cfg.M ? (int)(P.level_off[top + 1] / 32) : 0;
-    P.obs_words = (P.obs_words + 3) / 4 * 4;
+    P.obs_id_words = top >= cfg.M ? (int)(P.level_off[top + 1] / 32) : 0;
+    P.obs_id_words = (P.obs_id_words + 3) / 4 * 4;
   }
-  // classes of the table levels
+  // classes of the table levels (their marks sit behind the marks by class id, one bit per list entry)
   if (P.t_lo <= P.t_hi) P.tl = table_classes(P.op, P.t_lo, P.t_hi, P.level_off, &P.tl_cnt);
+  P.obs_words = P.obs_id_words + (P.t_lo <= P.t_hi ? (int)((P.tl_cnt + 127) / 128 * 4) : 0);
   Trace tr("extract");
   auto out = std::make_shared<Matrix>();
   out->n = s.n; out->vt = P.binarize ? VAL_ONE : VAL_U32;

@@ -42,12 +42,13 @@ struct XParams {
   uint32_t tl_cnt;                 // classes of the table levels (flat list tl, in (k, code) order)
   int bm_words, pf_words, ts_words;// per-warp shared memory areas, in 32-bit words
   int warp_words;                  // total per-warp shared memory, in 32-bit words
-  int obs_words;                   // per-block bitmap of observed classes (levels <= OBS_MAX_LEVEL)
+  int obs_words;                   // per-block marks of observed classes: obs_id_words by class id (levels <= OBS_MAX_LEVEL),
+  int obs_id_words;                // then one bit per entry of the table-level class list tl
   int64_t stride, n, row0, ovf_stride;   // the launch covers the rows [row0, n)
   const int64_t *len, *blk;
   const uint32_t *bits2;
   const uint16_t *inv16;
-  const uint2 *tl;                 // x = (swizzled) table index of the code | table index of its image << 16, y = class id
+  const uint2 *tl;                 // x = byte offset of the code's 16-bit counter in the warp's table | that of its image << 16, y = class id
   uint32_t *st_id, *st_cnt, *rowcnt, *bitmap, *ovf;
   const uint2 *nbx;                // numbering set (all classes of the configuration, or the frozen list)
   int filter;                      // drop ids outside the numbering set
@@ -162,6 +163,7 @@ struct Emitter {
     vm = max(vm, cnt);
   }
   // ballot-compacted emission (coalesced stores); col_known >= 0: the column when no class is dropped
+  template <bool MARK = true>
   __device__ __forceinline__ unsigned emit(bool flag, uint32_t id, uint32_t cnt, int64_t col_known = -1) {
     uint32_t col = (uint32_t)col_known;
     if (flag && (filter || col_known < 0)) { const bool member = column(id, col); if (filter) flag = member; }
@@ -170,7 +172,7 @@ struct Emitter {
       uint32_t pos = cursor + __popc(em & lanemask_lt());
       sid[pos] = col;
       if (!binarize) scnt[pos] = cnt;
-      mark_id(id);
+      if (MARK) mark_id(id);
       stat(binarize ? 1u : cnt);
     }
     cursor += __popc(em);
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
 #endif
     Emitter em;
     em.sid = P.st_id + row * P.stride; em.scnt = P.st_cnt + (P.binarize ? 0 : row * P.stride);
-    em.obs = obs; em.bitmap = P.bitmap; em.obs_bits = (uint32_t)P.obs_words * 32u;
+    em.obs = obs; em.bitmap = P.bitmap; em.obs_bits = (uint32_t)P.obs_id_words * 32u;
     em.nbx = P.nbx; em.filter = P.filter;
     em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
     em.sq = 0; em.vm = 0;
@@ -568,6 +570,16 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
       // a k-mer count is the sum of its 4 extensions plus the suffixes that end right after it
       for (int k = P.t_hi - 1; k >= P.t_lo; k--) {
         const uint32_t nk = 1u << (2 * k), toff = tab_off(k), coff = tab_off(k + 1);
+#if KL_X_NOSWZ
+        // a lane takes the two parents that share a word: their 8 children are four consecutive words
+        for (uint32_t u2 = lane; u2 < nk / 2; u2 += 32) {
+          const uint2 a = *reinterpret_cast<const uint2 *>(tab + (coff >> 1) + 4 * u2);
+          const uint2 b = *reinterpret_cast<const uint2 *>(tab + (coff >> 1) + 4 * u2 + 2);
+          const uint32_t s0 = (a.x & 0xFFFFu) + (a.x >> 16) + (a.y & 0xFFFFu) + (a.y >> 16);
+          const uint32_t s1 = (b.x & 0xFFFFu) + (b.x >> 16) + (b.y & 0xFFFFu) + (b.y >> 16);
+          tab[(toff >> 1) + u2] += s0 | (s1 << 16);
+        }
+#else
         for (uint32_t u = lane; u < nk; u += 32) {
           uint32_t c0 = coff + 4 * u;                 // 4 children = two aligned words
           uint32_t w0 = tab[sw(c0 >> 1)], w1 = tab[sw(c0 >> 1) ^ 1u];   // (the swizzle keeps an even / odd pair together)
@@ -575,6 +587,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
           uint32_t idx = toff + u;
           if (sum) atomicAdd(tab + sw(idx >> 1), sum << (16 * (idx & 1)));
         }
+#endif
         __syncwarp();
       }
       // walk the classes of the table levels in (k, code) order: count = code + image
@@ -583,13 +596,15 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         uint32_t id = 0, cnt = 0;
         if (j < P.tl_cnt) {
           const uint2 e = __ldg(P.tl + j);
-          const uint32_t i1 = e.x & 0xFFFFu, i2 = e.x >> 16;
-          cnt = (tab[i1 >> 1] >> (16 * (i1 & 1))) & 0xFFFFu;
-          if (i2 != i1) cnt += (tab[i2 >> 1] >> (16 * (i2 & 1))) & 0xFFFFu;
+          const unsigned char *tb = reinterpret_cast<const unsigned char *>(tab);
+          cnt = (uint32_t)*reinterpret_cast<const unsigned short *>(tb + (e.x & 0xFFFFu)) +
+                (uint32_t)*reinterpret_cast<const unsigned short *>(tb + (e.x >> 16));
           id = e.y;
         }
         // without a frozen list the numbering set is ALL classes: the j-th class of the list is column j
-        const unsigned kept = em.emit(cnt > 0, id, cnt, P.filter ? -1 : (int64_t)j);
+        const unsigned kept = em.emit<false>(cnt > 0, id, cnt, P.filter ? -1 : (int64_t)j);
+        // marks of the table levels: one word per 32 list entries (translated to class ids when the block ends)
+        if (P.mark && lane == 0 && (kept & ~obs[P.obs_id_words + (base >> 5)])) atomicOr(obs + P.obs_id_words + (base >> 5), kept);
         if (EV && P.lowbits && lane == 0 && active) P.lowbits[row * P.low_words + (base >> 5)] = kept;
       }
       __syncwarp();
@@ -845,11 +860,18 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
   }
   // flush the block's observed classes
   __syncthreads();
-  if (P.mark)
-    for (int i = threadIdx.x; i < P.obs_words; i += blockDim.x) {
+  if (P.mark) {
+    for (int i = threadIdx.x; i < P.obs_id_words; i += blockDim.x) {
       const uint32_t w = obs[i];
       if (w && (w & ~P.bitmap[i])) atomicOr(P.bitmap + i, w);
     }
+    if (P.t_lo <= P.t_hi)
+      for (uint32_t j = threadIdx.x; j < P.tl_cnt; j += blockDim.x)
+        if ((obs[P.obs_id_words + (j >> 5)] >> (j & 31)) & 1u) {
+          const uint32_t id = __ldg(P.tl + j).y;
+          if (!((P.bitmap[id >> 5] >> (id & 31)) & 1u)) atomicOr(P.bitmap + (id >> 5), 1u << (id & 31));
+        }
+  }
 }
 
 template <int E, int OPT, bool EV>

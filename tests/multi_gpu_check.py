@@ -53,6 +53,15 @@ def main():
         est.Theta = np.zeros(len(sel)); est.ClassWeights = np.array(cw)
         est.estimate_proximal(rfull, 1e-3)
         thr_full = est.Theta.copy()
+        # long rows (the classes of the short k-mers): the solver runs on the sliced + column-major views
+        sel_long = np.unique(np.concatenate([[0], np.arange(1, min(31, full.m)), np.linspace(1, full.m, 20).astype(np.int64)]))
+        rlong = K.select_data(full, sel_long)
+        rlong.SetLabels(np.concatenate([np.ones(n_fg, dtype=np.uint8), np.zeros(n_bg, dtype=np.uint8)]))
+        est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=200)
+        est.Theta = np.zeros(len(sel_long)); est.ClassWeights = np.array(cw)
+        est.estimate_proximal(rlong, 1e-3)
+        thl_full, long_density = est.Theta.copy(), rlong.nnz / max(rlong.n, 1)
+        rlong.free()
         est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=1e-9, MaxIterations=100000)
         est.Theta = np.zeros(len(sel)); est.ClassWeights = np.array(cw)
         it_full, _ = est.estimate_proximal(rfull, 1e-3)
@@ -84,6 +93,12 @@ def main():
         est3.Theta = np.zeros(len(sel)); est3.ClassWeights = np.array(cw)
         it_s, _ = est3.estimate_proximal(rmine, 1e-3)
         rmine.free()
+        rlmine = K.select_data(mine, sel_long)
+        rlmine.SetLabels(labels)
+        est5 = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=200)
+        est5.Theta = np.zeros(len(sel_long)); est5.ClassWeights = np.array(cw)
+        est5.estimate_proximal(rlmine, 1e-3)
+        rlmine.free()
         est4 = K.KmerLrEstimator(EpsilonLoss=1e-7, EpsilonLambda=1e-9, MaxIterations=20000, MaxEpochs=6, tie=K.TIE_INDEX)
         est4.estimate_loop(mine, 4)
         # the ABI from another host thread (cgo moves goroutines between OS threads): the library re-binds its device
@@ -96,6 +111,7 @@ def main():
                 and np.array_equal(est4.active_idx, act_full) and np.array_equal(est4.Theta, thp_full),
             "loss from a second host thread": box.get("l") == l_s,
             "reduced theta after 300 iterations": np.array_equal(est2.Theta, thr_full),
+            "long-row reduced theta after 200 iterations (%.0f entries per row)" % long_density: np.array_equal(est5.Theta, thl_full),
             "reduced converged (%d vs %d iterations)" % (it_s, it_full): abs(it_s - it_full) <= 2 and np.allclose(est3.Theta, thc_full, rtol=1e-6, atol=1e-12),
             "classes": mine.m == len(k_full) and np.array_equal(k_s, k_full) and np.array_equal(c_s, c_full),
             "gradient bit-identical": np.array_equal(g_s, g_full),

@@ -469,6 +469,45 @@ def test_persistent_reduced_iterations_equal_per_launch(K, oracle):
         rd.free(); d.free()
 
 
+def test_reduced_solver_long_rows_same_bits(K, oracle):
+    """reduced matrices with long rows run on the sliced + column-major views (packed counts; real values unpacked):
+    the iterates must be those of the row-wise solver bit for bit, and those of the oracle to rounding"""
+    from kmerlr_b200 import synth
+    O = oracle
+    buf, off, y = synth.training_set(900, 833, 180)
+    kc, oc = K.NewKmerCounter(1, 6, revcomp=True), O.make_config(1, 6, revcomp=True)
+    d = K.compile_test_data(None, kc, None, None, True, False, (buf, off))
+    ref = O.extract(oc, (buf, off))
+    # the classes of k <= 3 are in (almost) every row: 44 dense columns + 30 spread ones
+    sel = np.unique(np.concatenate([[0], np.arange(1, 45), np.linspace(50, d.m, 30).astype(np.int64)]))
+    rd = K.select_data(d, sel)
+    rd.SetLabels(y)
+    assert rd.nnz >= 30 * rd.n
+    scaled = K.Transform(Scale=np.concatenate([[1.0], 1.0 / (1.0 + np.arange(len(sel) - 1) % 7)])).Apply(rd)   # real values
+    scaled.SetLabels(y)
+    cw = np.array([0.8, 1.3])
+    try:
+        for data in (rd, scaled):
+            for eps, eps_loss, lam, cap in [(0.0, 0.0, 1e-3, 61), (1e-6, 0.0, 1e-3, 100000), (0.0, 1e-9, 2e-3, 100000), (0.0, 0.0, 1e-3, 0)]:
+                res = []
+                for mode in (0, 1):
+                    K.option("small_long", mode)
+                    est = K.KmerLrEstimator(Epsilon=eps, EpsilonLoss=eps_loss, MaxIterations=cap)
+                    est.Theta = np.zeros(len(sel)); est.ClassWeights = cw
+                    it, delta = est.estimate_proximal(data, lam)
+                    res.append((it, delta, est.Theta.copy()))
+                assert res[0][0] == res[1][0], (cap, res[0][0], res[1][0])
+                assert res[0][1] == res[1][1] or (np.isnan(res[0][1]) and np.isnan(res[1][1]))
+                assert np.array_equal(res[0][2], res[1][2])
+                if data is rd and cap == 61:
+                    rm = O.reduce(ref, sel)
+                    oth, oit, _ = O.proxgrad(rm, y, np.zeros(len(sel)), tuple(cw), lam, epsilon=eps, epsilon_loss=eps_loss, max_iter=cap)
+                    assert oit == res[1][0] and np.max(np.abs(res[1][2] - oth)) <= 1e-9
+    finally:
+        K.option("small_long", -1)
+        scaled.free(); rd.free(); d.free()
+
+
 def test_coordinate_estimator_matches_restatement(K, oracle):
     """estimate_coordinate (kmerLr_estimator_coordinate.go:31-139, slices de-aliased) on reduced matrices: the
     CUDA path (fixed-point Gram matrix, one-block sweeps) against the numpy restatement -- same number of
