@@ -549,6 +549,9 @@ static std::shared_ptr<Matrix> extract_impl(const kmerlr_config &cfg, std::share
   KL_LAUNCH(popc_words, (unsigned)((nw + 255) / 256), 256, 0, nb.p, nw, pc.p);
   exclusive_scan_u32(pc.p, nbrank.p, nw);
   bitmap.zero();
+  DevBuf<uint32_t> full(1);                 // "every class has been observed" (set by the kernel, ends the marks)
+  full.zero();
+  P.full = full.p; P.nb_words = nw;
   DevBuf<unsigned long long> stats(2);
   stats.zero();
   P.st_id = out->col.p; P.st_cnt = P.binarize ? dummy_cnt.p : out->val_u32.p; P.rowcnt = out->rowcnt.p;

@@ -21,6 +21,9 @@ namespace xk {
                           // prefix popcounts (measured slower: 2.90 vs 2.55 ms at C2 -- a numbering gather, three
                           // shared-memory reads and a scattered store per position cost more than the bit loops)
 #endif
+#ifndef KL_X_MARKSKIP
+#define KL_X_MARKSKIP 1   // 1: the marks of observed classes stop once the device-wide bitmap covers the numbering set
+#endif
 constexpr uint32_t SENT = 0xFFFFFFFFu;    // sort key of a position without a valid k-mer (sorts last)
 constexpr uint32_t NOKEY = 0xFFFFFFFEu;   // "no previous key" in front of the sorted array
 constexpr int KT_MAX = 5;          // levels <= KT_MAX use direct count tables
@@ -54,6 +57,8 @@ struct XParams {
   int filter;                      // drop ids outside the numbering set
   unsigned long long *stats;       // [0] max_i sum_j v_ij^2, [1] max v_ij
   uint32_t *ticket;                // rows are handed out to the blocks in groups of one row per warp
+  int64_t nb_words;                // words of the numbering set / of the bitmap of observed classes
+  uint32_t *full;                  // set once every class of the numbering set has been observed: the marks stop
   // binarized rows, for the matrix-free logistic pass (see Implicit in common.cuh)
   uint32_t *lowbits;               // per row: bitmap over the classes of the table levels (nullptr: not wanted)
   int low_words;
@@ -411,6 +416,25 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
   // Groups of rows (one row per warp) are handed out through a ticket counter: the blocks that run
   // faster take more groups.
   uint32_t *s_ticket = smem + P.obs_words + P.bm_words + P.pf_words + P.ts_words + 1;   // warp 0's spare word
+  // Marks of the observed classes: on real inputs every class of the configuration has shown up after the first few
+  // thousand rows of the launch, and from then on a mark is a shared-memory (levels > OBS_MAX_LEVEL: L2) read per
+  // emitted entry that never changes anything.  After 4, 8, 16, ... groups of rows a block therefore flushes its
+  // marks and looks whether the device-wide bitmap covers the numbering set; once it does (P.full) nobody marks.
+  auto flush_marks = [&]() {
+    for (int i = threadIdx.x; i < P.obs_id_words; i += blockDim.x) {
+      const uint32_t w = obs[i];
+      if (w && (w & ~P.bitmap[i])) atomicOr(P.bitmap + i, w);
+    }
+    if (P.t_lo <= P.t_hi)
+      for (uint32_t j = threadIdx.x; j < P.tl_cnt; j += blockDim.x)
+        if ((obs[P.obs_id_words + (j >> 5)] >> (j & 31)) & 1u) {
+          const uint32_t id = __ldg(P.tl + j).y;
+          if (!((P.bitmap[id >> 5] >> (id & 31)) & 1u)) atomicOr(P.bitmap + (id >> 5), 1u << (id & 31));
+        }
+  };
+  int mk = P.mark;
+  uint32_t groups = 0, next_check = KL_X_MARKSKIP ? 4u : 0xFFFFFFFFu;
+  if (mk) mk = __syncthreads_or(threadIdx.x == 0 && *(volatile uint32_t *)P.full == 0u) ? 1 : 0;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) *s_ticket = atomicAdd(P.ticket, 1u);
@@ -561,7 +585,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
     em.sid = P.st_id + row * P.stride; em.scnt = P.st_cnt + (P.binarize ? 0 : row * P.stride);
     em.obs = obs; em.bitmap = P.bitmap; em.obs_bits = (uint32_t)P.obs_id_words * 32u;
     em.nbx = P.nbx; em.filter = P.filter;
-    em.cursor = 0; em.binarize = P.binarize; em.mark = P.mark;
+    em.cursor = 0; em.binarize = P.binarize; em.mark = mk;
     em.sq = 0; em.vm = 0;
     em.ev = 0;
 
@@ -604,7 +628,7 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         // without a frozen list the numbering set is ALL classes: the j-th class of the list is column j
         const unsigned kept = em.emit<false>(cnt > 0, id, cnt, P.filter ? -1 : (int64_t)j);
         // marks of the table levels: one word per 32 list entries (translated to class ids when the block ends)
-        if (P.mark && lane == 0 && (kept & ~obs[P.obs_id_words + (base >> 5)])) atomicOr(obs + P.obs_id_words + (base >> 5), kept);
+        if (mk && lane == 0 && (kept & ~obs[P.obs_id_words + (base >> 5)])) atomicOr(obs + P.obs_id_words + (base >> 5), kept);
         if (EV && P.lowbits && lane == 0 && active) P.lowbits[row * P.low_words + (base >> 5)] = kept;
       }
       __syncwarp();
@@ -857,21 +881,26 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         if ((unsigned long long)vm > P.stats[1]) atomicMax(P.stats + 1, (unsigned long long)vm);
       }
     }
+    if (mk && ++groups == next_check) {
+      next_check *= 2;
+      __syncthreads();
+      flush_marks();
+      __threadfence();
+      __syncthreads();
+      int missing = 0;
+      for (int64_t i = threadIdx.x; i < P.nb_words; i += blockDim.x)
+        missing |= (__ldg(P.nbx + i).x & ~*(volatile const uint32_t *)(P.bitmap + i)) != 0u;
+      if (!__syncthreads_or(missing)) {
+        mk = 0;
+        if (threadIdx.x == 0) *(volatile uint32_t *)P.full = 1u;
+      } else if (__syncthreads_or(threadIdx.x == 0 && *(volatile uint32_t *)P.full != 0u)) {
+        mk = 0;
+      }
+    }
   }
   // flush the block's observed classes
   __syncthreads();
-  if (P.mark) {
-    for (int i = threadIdx.x; i < P.obs_id_words; i += blockDim.x) {
-      const uint32_t w = obs[i];
-      if (w && (w & ~P.bitmap[i])) atomicOr(P.bitmap + i, w);
-    }
-    if (P.t_lo <= P.t_hi)
-      for (uint32_t j = threadIdx.x; j < P.tl_cnt; j += blockDim.x)
-        if ((obs[P.obs_id_words + (j >> 5)] >> (j & 31)) & 1u) {
-          const uint32_t id = __ldg(P.tl + j).y;
-          if (!((P.bitmap[id >> 5] >> (id & 31)) & 1u)) atomicOr(P.bitmap + (id >> 5), 1u << (id & 31));
-        }
-  }
+  if (mk) flush_marks();
 }
 
 template <int E, int OPT, bool EV>
