@@ -211,6 +211,34 @@ int kmerlr_score_windows_resident(const kmerlr_model *models, int n_models, kmer
                                   int64_t W, int64_t step, double *out_host_or_null,
                                   kmerlr_handle *out_dev_or_null);
 
+/* ---- on-disk formats either side of the path ------------------------------------
+ * The bytes the reference's fmt verbs produce; filename "" = standard output where the reference allows it.
+ *
+ * saveWindowPredictionsWiggle (kmerLr_predict_genomic.go:37-60): "track type=wiggle_0 name=<track>", per region
+ * "fixedStep chrom=<name> start=<from + W/2> step=<step> span=<step>" and one "%0.15f" of exp(prediction) per slot.
+ * The records are formatted on the device: exp of a log-probability lies in [0, 1] and prints as 18 bytes, so record j
+ * sits at byte 18 j (exact decimal expansion, round half to even; exp = Go's portable math.Exp, see formats.cu).
+ * Predictions of region i = pred[slot_off[i], slot_off[i+1]) (kmerlr_window_slots per region); pred is a host array,
+ * or NULL with `scores` = the device handle kmerlr_score_windows_resident returned. */
+#define KMERLR_WIGGLE_RECORD 18
+int kmerlr_wiggle_records(const double *pred, int64_t n, char *out_18n, int64_t *n_irregular_out);
+int kmerlr_save_wiggle(const char *filename, const char *track_name, int64_t n_regions, const char *const *seqnames,
+                       const int64_t *from, const int64_t *slot_off, const double *pred_or_null, kmerlr_handle scores,
+                       int64_t window_size, int64_t window_step);
+/* export_kmers (kmerLr_data.go:127-174): the class names ("aaaatt|aatttt") joined by ',', then every row dense:
+ * "%d" of the counts, or "%e" when as_float != 0 (data that went through kmerlr_matrix_transform, as
+ * kmerLr_export.go:45-56 does before it exports).  kmerlr_class_name: the printed name of one class. */
+int kmerlr_export_kmers(kmerlr_handle data, const kmerlr_config *cfg, const char *filename, int as_float);
+int kmerlr_class_name(const kmerlr_config *cfg, int32_t k, uint64_t code, char *buf, int64_t buflen);
+/* KmerRegularizationPath.Export (kmerLr_estimator_path.go:41-73); estimator may be NULL (no such column);
+ * theta of entry i = theta[theta_off[i], theta_off[i+1]) */
+int kmerlr_export_path(const char *filename, int64_t n, const int64_t *estimator_or_null, const double *lambda,
+                       const double *norm, const int64_t *theta_off, const double *theta);
+/* Trace.Export (kmerLr_estimator_trace.go:28-80); durations in nanoseconds (time.Duration); lambda / loss may be NULL */
+int kmerlr_export_trace(const char *filename, int64_t n, const int64_t *duration_ns, const int64_t *iteration,
+                        const double *change, const int64_t *nonzero, const double *lambda_or_null,
+                        const double *loss_or_null);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,5 +6,6 @@ from .api import (  # noqa: F401
     CoeffIndex, KmerDataSet, KmerLrEstimator, NewKmerCounter, Sequences, Transform, TransformFull, comm_destroy, comm_init,
     comm_init_torch, comm_unique_id, compile_test_data, compile_data, compile_training_data, compute_class_weights,
     featureSelector, flatten, from_csr, from_dense, genomicKmerLr, init, last_device_ms, launch_count,
-    logisticRegression, option, select_data, shutdown,
+    logisticRegression, option, select_data, shutdown, wiggle_records, saveWindowPredictionsWiggle, class_name, export_kmers,
+    KmerRegularizationPath, Trace,
 )

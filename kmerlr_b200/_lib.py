@@ -23,7 +23,8 @@ SYMBOLS = [
     "kmerlr_free", "kmerlr_coeff_dim", "kmerlr_coeff_ind2sub", "kmerlr_coeff_sub2ind", "kmerlr_linear_pdf",
     "kmerlr_logpdf", "kmerlr_gradient", "kmerlr_loss", "kmerlr_class_weights", "kmerlr_select", "kmerlr_select_from_gradient", "kmerlr_reduce",
     "kmerlr_step_size", "kmerlr_proxgrad", "kmerlr_coordinate", "kmerlr_window_slots", "kmerlr_score_windows", "kmerlr_predict_windows",
-    "kmerlr_score_windows_resident",
+    "kmerlr_score_windows_resident", "kmerlr_wiggle_records", "kmerlr_save_wiggle", "kmerlr_export_kmers", "kmerlr_class_name",
+    "kmerlr_export_path", "kmerlr_export_trace",
 ]
 
 
@@ -106,6 +107,13 @@ def lib():
     L.kmerlr_score_windows.argtypes = [C.POINTER(Model), C.c_int, vp, vp, i64, i64, i64, vp]
     L.kmerlr_predict_windows.argtypes = [C.POINTER(Model), vp, vp, i64, i64, i64, vp]
     L.kmerlr_score_windows_resident.argtypes = [C.POINTER(Model), C.c_int, h, i64, i64, vp, ph]
+    ppc = C.POINTER(C.c_char_p)
+    L.kmerlr_wiggle_records.argtypes = [vp, i64, vp, pi64]
+    L.kmerlr_save_wiggle.argtypes = [C.c_char_p, C.c_char_p, i64, ppc, vp, vp, vp, h, i64, i64]
+    L.kmerlr_export_kmers.argtypes = [h, C.POINTER(Config), C.c_char_p, C.c_int]
+    L.kmerlr_class_name.argtypes = [C.POINTER(Config), i32, C.c_uint64, C.c_char_p, i64]
+    L.kmerlr_export_path.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp]
+    L.kmerlr_export_trace.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -674,3 +674,78 @@ class genomicKmerLr:
         check(lib().kmerlr_score_windows_resident(self._arr, len(self.classifiers), sequences.h, window_size,
                                                   window_step, _p(out), None))
         return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# on-disk formats either side of the path
+# ---------------------------------------------------------------------------------------------------
+def wiggle_records(predictions):
+    """the "%0.15f\n" records of exp(prediction), formatted on the device: (bytes, number of irregular records)"""
+    pred = np.ascontiguousarray(predictions, dtype=np.float64)
+    out = np.zeros(max(18 * len(pred), 1), dtype=np.uint8)
+    irr = C.c_int64(0)
+    check(lib().kmerlr_wiggle_records(_p(pred), len(pred), _p(out), C.byref(irr)))
+    return out[:18 * len(pred)].tobytes(), irr.value
+
+
+def saveWindowPredictionsWiggle(filename, regions, predictions, track_name, window_size, window_step, scores=None):
+    """saveWindowPredictionsWiggle (kmerLr_predict_genomic.go:37-60).  regions = [(seqname, from), ...];
+    predictions = one array per region (what predict_window_genomic returns), or None with `scores` = the handle
+    of device-resident scores and predictions replaced by the number of slots per region."""
+    names = (C.c_char_p * max(len(regions), 1))(*[r[0].encode() for r in regions])
+    frm = np.array([r[1] for r in regions], dtype=np.int64)
+    if scores is None:
+        lens = [len(p) for p in predictions]
+        pred = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64) for p in predictions])
+                                    if len(predictions) else np.zeros(0))
+    else:
+        lens, pred = list(predictions), None
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    if scores is None:
+        parg = _p(pred) if len(pred) else _p(np.zeros(1))
+    else:
+        parg = None
+    check(lib().kmerlr_save_wiggle(filename.encode(), track_name.encode(), len(regions), names, _p(frm), _p(off), parg,
+                                   0 if scores is None else scores, window_size, window_step))
+
+
+def class_name(counter, k, code):
+    """printed name of a class (gonetics KmerClass.String): "aaaatt|aatttt" """
+    buf = C.create_string_buffer(256)
+    check(lib().kmerlr_class_name(C.byref(counter), int(k), int(code), buf, 256))
+    return buf.value.decode()
+
+
+def export_kmers(counter, filename, data, transformed=False):
+    """export_kmers (kmerLr_data.go:127-174); transformed = the data went through Transform.Apply ("%e" rows)"""
+    check(lib().kmerlr_export_kmers(data.h, C.byref(counter), filename.encode(), 1 if transformed else 0))
+
+
+class KmerRegularizationPath:
+    """the table of KmerRegularizationPath.Export (kmerLr_estimator_path.go:29-73)"""
+
+    def __init__(self):
+        self.Estimator, self.Lambda, self.Norm, self.Theta = [], [], [], []
+
+    def Export(self, filename):
+        off = np.concatenate([[0], np.cumsum([len(t) for t in self.Theta])]).astype(np.int64)
+        th = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64) for t in self.Theta])
+                                  if len(self.Theta) else np.zeros(0))
+        est = np.asarray(self.Estimator, dtype=np.int64) if len(self.Estimator) else None
+        check(lib().kmerlr_export_path(filename.encode(), len(self.Lambda), _p(est), _p(np.asarray(self.Lambda, dtype=np.float64)),
+                                       _p(np.asarray(self.Norm, dtype=np.float64)), _p(off), _p(th) if len(th) else _p(np.zeros(1))))
+
+
+class Trace:
+    """the table of Trace.Export (kmerLr_estimator_trace.go:39-80); Duration in nanoseconds"""
+
+    def __init__(self):
+        self.Iteration, self.Nonzero, self.Change, self.Lambda, self.Loss, self.Duration = [], [], [], [], [], []
+
+    def Export(self, filename):
+        i64 = lambda v: np.asarray(v, dtype=np.int64)
+        f64 = lambda v: np.asarray(v, dtype=np.float64)
+        check(lib().kmerlr_export_trace(filename.encode(), len(self.Iteration), _p(i64(self.Duration)), _p(i64(self.Iteration)),
+                                        _p(f64(self.Change)), _p(i64(self.Nonzero)),
+                                        _p(f64(self.Lambda)) if len(self.Lambda) else None,
+                                        _p(f64(self.Loss)) if len(self.Loss) else None))

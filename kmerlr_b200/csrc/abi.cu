@@ -472,4 +472,51 @@ int kmerlr_score_windows_resident(const kmerlr_model *models, int n_models, kmer
   });
 }
 
+// ---- on-disk formats (formats.cu) -----------------------------------------------------------------------------
+int kmerlr_wiggle_records(const double *pred, int64_t n, char *out, int64_t *n_irregular_out) {
+  return guarded([&] {
+    const int64_t irr = wiggle_records(pred, false, n, out);
+    if (n_irregular_out) *n_irregular_out = irr;
+  });
+}
+
+int kmerlr_save_wiggle(const char *filename, const char *track_name, int64_t n_regions, const char *const *seqnames,
+                       const int64_t *from, const int64_t *slot_off, const double *pred_or_null, kmerlr_handle scores,
+                       int64_t window_size, int64_t window_step) {
+  return guarded([&] {
+    require_ready();
+    if (pred_or_null) { save_wiggle(filename, track_name, n_regions, seqnames, from, slot_off, pred_or_null, false, window_size, window_step); return; }
+    auto S = lookup<Matrix>(scores, "scores");
+    KL_REQUIRE(n_regions == 0 || (slot_off && (size_t)slot_off[n_regions] <= S->val_f64.n), "save_wiggle: more slots than scores");
+    save_wiggle(filename, track_name, n_regions, seqnames, from, slot_off, S->val_f64.p, true, window_size, window_step);
+  });
+}
+
+int kmerlr_export_kmers(kmerlr_handle data, const kmerlr_config *cfg, const char *filename, int as_float) {
+  return guarded([&] {
+    KL_REQUIRE(cfg, "null configuration");
+    export_kmers(*lookup<Matrix>(data, "matrix"), *cfg, filename, as_float != 0);
+  });
+}
+
+int kmerlr_class_name(const kmerlr_config *cfg, int32_t k, uint64_t code, char *buf, int64_t buflen) {
+  return guarded([&] {
+    KL_REQUIRE(cfg && buf && buflen > 0, "null argument");
+    const std::string s = class_name(*cfg, k, code);
+    KL_REQUIRE((int64_t)s.size() < buflen, "class_name: buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
+  }, false);
+}
+
+int kmerlr_export_path(const char *filename, int64_t n, const int64_t *estimator_or_null, const double *lambda,
+                       const double *norm, const int64_t *theta_off, const double *theta) {
+  return guarded([&] { export_path(filename, n, estimator_or_null, lambda, norm, theta_off, theta); }, false);
+}
+
+int kmerlr_export_trace(const char *filename, int64_t n, const int64_t *duration_ns, const int64_t *iteration,
+                        const double *change, const int64_t *nonzero, const double *lambda_or_null,
+                        const double *loss_or_null) {
+  return guarded([&] { export_trace(filename, n, duration_ns, iteration, change, nonzero, lambda_or_null, loss_or_null); }, false);
+}
+
 }  // extern "C"

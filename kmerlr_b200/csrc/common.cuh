@@ -376,6 +376,18 @@ void select_from_gradient(const double *g, int64_t ntheta, int64_t N, const int6
 // score.cu
 void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, int64_t W, int64_t step,
                    double *out_host, std::shared_ptr<Object> *out_dev, int layout = 0);
+// formats.cu: the on-disk formats either side of the path
+int64_t wiggle_records(const double *pred, bool pred_on_device, int64_t n, char *out);
+void save_wiggle(const char *filename, const char *track_name, int64_t n_regions, const char *const *seqnames,
+                 const int64_t *from, const int64_t *slot_off, const double *pred, bool pred_on_device, int64_t window_size,
+                 int64_t window_step);
+std::string class_name(const kmerlr_config &cfg, int k, uint64_t code);
+void export_kmers(Matrix &M, const kmerlr_config &cfg, const char *filename, bool as_float);
+void export_path(const char *filename, int64_t n, const int64_t *estimator, const double *lambda, const double *norm,
+                 const int64_t *theta_off, const double *theta);
+void export_trace(const char *filename, int64_t n, const int64_t *duration_ns, const int64_t *iteration, const double *change,
+                  const int64_t *nonzero, const double *lambda, const double *loss);
+
 // comm.cu
 void comm_unique_id(void *id128);
 void comm_init(int rank, int world, const void *id128);

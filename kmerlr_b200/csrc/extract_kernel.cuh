@@ -21,6 +21,13 @@ namespace xk {
                           // prefix popcounts (measured slower: 2.90 vs 2.55 ms at C2 -- a numbering gather, three
                           // shared-memory reads and a scattered store per position cost more than the bit loops)
 #endif
+#ifndef KL_X_TKPRE
+#define KL_X_TKPRE 0      // 1: the ticket of the next row group is drawn one group ahead (measured: the register it holds costs more than
+                          // the round trip it hides -- 2.275 vs 2.251 ms at C2)
+#endif
+#ifndef KL_X_TLPIPE
+#define KL_X_TLPIPE 1     // the class list of the table levels is read one iteration ahead
+#endif
 #ifndef KL_X_MARKSKIP
 #define KL_X_MARKSKIP 1   // 1: the marks of observed classes stop once the device-wide bitmap covers the numbering set
 #endif
@@ -273,12 +280,21 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
   };
   if (!em.filter) {
     // no class is dropped: slot i of the buffer is entry i of the level
-    for (int i = lane; i < total; i += 32) {
-      const uint32_t id = sbuf[sw(i)];
-      uint32_t col;
-      em.column(id, col);
-      em.sid[em.cursor + i] = col;
-      em.mark_id(id);
+    // four numbering gathers in flight per lane (each is an L2 round trip)
+    for (int i0 = lane; i0 < total; i0 += 128) {
+      uint32_t id[4];
+      uint2 e[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) id[j] = i0 + 32 * j < total ? sbuf[sw(i0 + 32 * j)] : idbase;
+#pragma unroll
+      for (int j = 0; j < 4; j++) e[j] = __ldg(em.nbx + (id[j] >> 5));
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (i0 + 32 * j < total) {
+          em.sid[em.cursor + i0 + 32 * j] = e[j].y + __popc(e[j].x & ((1u << (id[j] & 31)) - 1u));
+          em.mark_id(id[j]);
+        }
+      }
     }
     __syncwarp();
     if (!em.binarize) {
@@ -435,12 +451,23 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
   int mk = P.mark;
   uint32_t groups = 0, next_check = KL_X_MARKSKIP ? 4u : 0xFFFFFFFFu;
   if (mk) mk = __syncthreads_or(threadIdx.x == 0 && *(volatile uint32_t *)P.full == 0u) ? 1 : 0;
+  // (the ticket of the NEXT group is drawn while this one is worked on: the atomic's round trip is off the path)
+#if KL_X_TKPRE
+  uint32_t tk = threadIdx.x == 0 ? atomicAdd(P.ticket, 1u) : 0u;
+#endif
   for (;;) {
     __syncthreads();
+#if KL_X_TKPRE
+    if (threadIdx.x == 0) *s_ticket = tk;
+#else
     if (threadIdx.x == 0) *s_ticket = atomicAdd(P.ticket, 1u);
+#endif
     __syncthreads();
     const int64_t row0 = P.row0 + (int64_t)*s_ticket * wpb;
     if (row0 >= P.n) break;
+#if KL_X_TKPRE
+    if (threadIdx.x == 0) tk = atomicAdd(P.ticket, 1u);
+#endif
     const int64_t row = row0 + warp_in_block;
     const bool active = row < P.n;
     const int L = active ? (int)P.len[row] : 0;
@@ -615,11 +642,18 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         __syncwarp();
       }
       // walk the classes of the table levels in (k, code) order: count = code + image
+      uint32_t mylow = 0, mylow2 = 0;                      // lane w: words w and w + 32 of the row's table-level class bitmap
+      uint2 e_next = lane < P.tl_cnt ? __ldg(P.tl + lane) : make_uint2(0u, 0u);
       for (uint32_t base = 0; base < P.tl_cnt; base += 32) {
         const uint32_t j = base + lane;
         uint32_t id = 0, cnt = 0;
+#if KL_X_TLPIPE
+        const uint2 e = e_next;
+        if (j + 32 < P.tl_cnt) e_next = __ldg(P.tl + j + 32);
+#else
+        const uint2 e = j < P.tl_cnt ? __ldg(P.tl + j) : e_next;
+#endif
         if (j < P.tl_cnt) {
-          const uint2 e = __ldg(P.tl + j);
           const unsigned char *tb = reinterpret_cast<const unsigned char *>(tab);
           cnt = (uint32_t)*reinterpret_cast<const unsigned short *>(tb + (e.x & 0xFFFFu)) +
                 (uint32_t)*reinterpret_cast<const unsigned short *>(tb + (e.x >> 16));
@@ -629,7 +663,11 @@ __global__ void __launch_bounds__(ext_threads(E), 2) extract_kernel(const XParam
         const unsigned kept = em.emit<false>(cnt > 0, id, cnt, P.filter ? -1 : (int64_t)j);
         // marks of the table levels: one word per 32 list entries (translated to class ids when the block ends)
         if (mk && lane == 0 && (kept & ~obs[P.obs_id_words + (base >> 5)])) atomicOr(obs + P.obs_id_words + (base >> 5), kept);
-        if (EV && P.lowbits && lane == 0 && active) P.lowbits[row * P.low_words + (base >> 5)] = kept;
+        if (EV && lane == ((base >> 5) & 31u)) { if (base < 1024u) mylow = kept; else mylow2 = kept; }
+      }
+      if (EV && P.lowbits && active) {
+        if ((int)lane < P.low_words) P.lowbits[row * P.low_words + lane] = mylow;
+        if ((int)lane + 32 < P.low_words) P.lowbits[row * P.low_words + lane + 32] = mylow2;
       }
       __syncwarp();
     }

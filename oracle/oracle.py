@@ -598,3 +598,118 @@ def coordinate(rmat, labels, theta, cw_hook=(1.0, 1.0), l1reg=0.0, l2reg=0.0, ep
     if np.any(np.isnan(theta1)):
         theta1[:] = np.nan
     return theta1, sweeps, delta
+
+
+# ---------------------------------------------------------------------------------------------------
+# on-disk formats (test infrastructure, like everything in this file): the reference's fmt verbs restated with
+# Python's % operator -- C's printf and Go's fmt print the same digits for %e / %f / %d (both round the exact
+# binary value half to even); only the names of the non-finite values differ (Go: NaN, +Inf, -Inf)
+# ---------------------------------------------------------------------------------------------------
+def go_exp(x):
+    """Go's portable math.Exp (src/math/exp.go: exp + expmulti, the FreeBSD e_exp.c algorithm); Python floats are
+    IEEE doubles and never fused, as the algorithm is written"""
+    import math
+    Ln2Hi, Ln2Lo, Log2e = 6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00
+    if x != x or x == math.inf:
+        return x
+    if x == -math.inf:
+        return 0.0
+    if x > 7.09782712893383973096e+02:
+        return math.inf
+    if x < -7.45133219101941108420e+02:
+        return 0.0
+    if -1.0 / (1 << 28) < x < 1.0 / (1 << 28):
+        return 1.0 + x
+    k = 0
+    if x < 0:
+        k = int(Log2e * x - 0.5)
+    elif x > 0:
+        k = int(Log2e * x + 0.5)
+    hi = x - float(k) * Ln2Hi
+    lo = float(k) * Ln2Lo
+    P1, P2, P3 = 1.66666666666666657415e-01, -2.77777777770155933842e-03, 6.61375632143793436117e-05
+    P4, P5 = -1.65339022054652515390e-06, 4.13813679705723846039e-08
+    r = hi - lo
+    t = r * r
+    c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))))
+    y = 1 - ((lo - (r * c) / (2 - c)) - hi)
+    return math.ldexp(y, k)
+
+
+def go_fmt(fmt, v):
+    """one float64 through a Go verb like %e, %13e, %0.15f"""
+    import math
+    import re
+    if v != v or math.isinf(v):
+        w = re.match(r"%0?(\d*)", fmt).group(1)
+        name = "NaN" if v != v else ("+Inf" if v > 0 else "-Inf")
+        return name.rjust(int(w)) if w else name
+    return fmt % v
+
+
+def wiggle_text(regions, predictions, track_name, window_size, window_step):
+    """saveWindowPredictionsWiggle (kmerLr_predict_genomic.go:37-60); regions = [(seqname, from), ...]"""
+    out = ["track type=wiggle_0 name=%s\n" % track_name]
+    for (name, frm), pred in zip(regions, predictions):
+        out.append("fixedStep chrom=%s start=%d step=%d span=%d\n" % (name, frm + window_size // 2, window_step, window_step))
+        for p in pred:
+            out.append(go_fmt("%0.15f", go_exp(float(p))) + "\n")
+    return "".join(out)
+
+
+def export_kmers_text(names, dense_rows, transformed):
+    """export_kmers (kmerLr_data.go:127-174): names joined by ',', then every row dense"""
+    out = [",".join(names) + "\n"]
+    for row in dense_rows:
+        out.append(",".join(go_fmt("%e", float(v)) if transformed else "%d" % int(v) for v in row) + "\n")
+    return "".join(out)
+
+
+def path_text(estimator, lam, norm, theta):
+    """KmerRegularizationPath.Export (kmerLr_estimator_path.go:41-73)"""
+    out = []
+    head = ""
+    if len(estimator) > 0:
+        head += "%9s " % "estimator"
+    head += "%13s %13s %s\n" % ("lambda", "norm", "theta")
+    out.append(head)
+    for i in range(len(lam)):
+        line = ""
+        if len(estimator) > 0:
+            line += "%9d " % estimator[i]
+        line += "%s %s" % (go_fmt("%13e", lam[i]), go_fmt("%13e", norm[i]))
+        for j, t in enumerate(theta[i]):
+            line += (" " if j == 0 else ",") + go_fmt("%e", float(t))
+        out.append(line + "\n")
+    return "".join(out)
+
+
+def format_duration(ns):
+    """format_duration (kmerLr_estimator_trace.go:28-35) with the float64 arithmetic of time.Duration.Hours etc."""
+    import math
+    ns = int(ns)
+
+    def split(unit):          # Duration.Hours(): integer part + remainder / unit (durations are not negative)
+        return float(ns // unit) + float(ns % unit) / float(unit)
+    hours, minutes, seconds = split(3600 * 10 ** 9), split(60 * 10 ** 9), split(10 ** 9)
+    millis = float(ns // 10 ** 6)
+    return "%02d:%02d:%02d:%02d.%03d" % (int(hours / 24), int(math.fmod(hours, 24)), int(math.fmod(minutes, 60)),
+                                         int(math.fmod(seconds, 60)), int(math.fmod(millis, 1000)))
+
+
+def trace_text(duration_ns, iteration, change, nonzero, lam, loss):
+    """Trace.Export (kmerLr_estimator_trace.go:49-80)"""
+    head = "%15s %9s %12s %8s" % ("duration", "iteration", "change", "nonzero")
+    if len(lam) > 0:
+        head += " %12s" % "lambda"
+    if len(loss) > 0:
+        head += " %12s" % "loss"
+    out = [head + "\n"]
+    for i in range(len(iteration)):
+        line = "%15s %9d %s %8d" % (format_duration(duration_ns[i]), iteration[i], go_fmt("%12e", change[i]), nonzero[i])
+        if len(lam) > 0:
+            line += " " + go_fmt("%12e", lam[i])
+        if len(loss) > 0:
+            line += " " + go_fmt("%12e", loss[i])
+        out.append(line + "\n")
+    return "".join(out)

@@ -11,7 +11,7 @@ while [ $# -ge 2 ]; do
   done
   wait
   objs=""
-  for f in abi comm coordinate gapped logistic matrix scan score select; do objs="$objs build/$f.o"; done
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/lib$name.so /tmp/vb_$name/*.o $objs -lcudart -ldl
-  echo built variants/lib$name.so
+  for f in abi comm coordinate formats gapped logistic matrix scan score select; do objs="$objs build/$f.o"; done
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libv_$name.so /tmp/vb_$name/*.o $objs -lcudart -ldl
+  echo built kmerlr_b200/libv_$name.so
 done
