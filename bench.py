@@ -324,7 +324,20 @@ def leg_c5(K, lib, torch, rank, world, mbp=384.0):
         if i > 0:
             times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
-    return {"workload": "C5 slice: %.0f Mbp per GPU in %d contigs, W=%d, step=%d, 100-feature k=1..8 model" % (mbp, ncontig, W, step),
+    # the wiggle track of those scores (saveWindowPredictionsWiggle): records formatted on the device, host buffers on
+    # both sides -- H2D of the scores (8 B per slot), D2H of the text (18 B per slot)
+    text = torch.empty(18 * slots, dtype=torch.uint8).pin_memory()
+    irr = C.c_int64(0)
+    wt = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        _lib.check(lib.kmerlr_wiggle_records(C.c_void_p(out.data_ptr()), slots, C.c_void_p(text.data_ptr()), C.byref(irr)))
+        if i > 0:
+            wt.append(time.perf_counter() - t0)
+    tw = float(np.mean(wt))
+    wig = {"records": int(slots), "e2e_ms": 1e3 * tw, "e2e_records_per_sec": slots / tw, "text_bytes": int(18 * slots),
+           "irregular_records": int(irr.value), "first_record": bytes(text.numpy()[:17]).decode()}
+    return {"wiggle": wig, "workload": "C5 slice: %.0f Mbp per GPU in %d contigs, W=%d, step=%d, 100-feature k=1..8 model" % (mbp, ncontig, W, step),
             "e2e_windows_per_sec": windows / t, "e2e_bases_per_sec": total / t, "e2e_ms": 1e3 * t, "windows": int(windows),
             "h2d_bytes": int(total + off.nbytes), "d2h_bytes": int(8 * slots), "device_ms_last_call": K.last_device_ms(),
             "checksum": float(out.numpy()[:1000].sum())}
