@@ -243,7 +243,7 @@ def leg_path(K, synth, targets=(10, 25, 50, 100)):
                     "(kmerLr_estimator.go:257-270); iteration counts are those of the reference's fixed-step ISTA"}
 
 
-def leg_c4(K, synth, n=20000, folds=5, n_feat=20, max_epochs=12):
+def leg_c4(K, synth, n=20000, folds=5, n_feat=20, max_epochs=12, only=None):
     """BASELINE configs[3]: pair features over k = 1..6 (CoeffIndex.Dim = 3.84 M coefficients), leapfrog path to N = 20,
     5-fold cross-validation with fold = i mod 5 over fg||bg (no shuffle).  Per fold: extraction of the training rows,
     the pair gradient / Select of every epoch, the reduced solves, loss on the held-out fold."""
@@ -254,6 +254,8 @@ def leg_c4(K, synth, n=20000, folds=5, n_feat=20, max_epochs=12):
     out = []
     lens = np.diff(off)
     for f in range(folds):
+        if only is not None and f not in only:           # several GPUs: the folds are independent replicas, rank r takes f = r mod N
+            continue
         t_fold = time.perf_counter()
         tr, te = np.nonzero(fold != f)[0], np.nonzero(fold == f)[0]
 
@@ -290,10 +292,21 @@ def leg_c4(K, synth, n=20000, folds=5, n_feat=20, max_epochs=12):
                     "iterations": int(sum(p[1] for p in est.path)), "path_s": t_path, "lambda": float(est.path[-1][0]),
                     "active": int(len(est.active_idx)), "test_loss": float(loss), "wall_s": time.perf_counter() - t_fold})
     return {"workload": "C4: %d sequences x 500 bp, k=1..6 revcomp, pair features (%d coefficients), N=%d, %d folds (fold = i mod %d)"
-                        % (n, K.CoeffIndex(2772).Dim(), n_feat, folds, folds),
-            "pair_gradient_ms": float(np.mean([o["pair_gradient_ms"] for o in out])),
-            "select_wall_ms": float(np.mean([o["select_wall_ms"] for o in out])),
-            "fold_wall_s": float(np.mean([o["wall_s"] for o in out])), "folds": out}
+                        % (n, K.CoeffIndex(2772).Dim(), n_feat, folds, folds), "folds": out}
+
+
+def c4_summary(c4, world):
+    import numpy as np
+    out = sorted(c4["folds"], key=lambda o: o["fold"])
+    per_rank = {}
+    for o in out:
+        per_rank[o["fold"] % world] = per_rank.get(o["fold"] % world, 0.0) + o["wall_s"]
+    c4.update({"folds": out, "pair_gradient_ms": float(np.mean([o["pair_gradient_ms"] for o in out])),
+               "select_wall_ms": float(np.mean([o["select_wall_ms"] for o in out])),
+               "fold_wall_s": float(np.mean([o["wall_s"] for o in out])),
+               "cross_validation_wall_s": float(max(per_rank.values())),
+               "replicas": "fold f on GPU f mod %d, no collective" % world if world > 1 else "one GPU, folds one after the other"})
+    return c4
 
 
 def leg_c5(K, lib, torch, rank, world, mbp=384.0):
@@ -575,7 +588,7 @@ def main():
 
     legs = args.legs
     if legs == "auto":
-        legs = ("c3,path,c4,c5" if world == 1 else "c3,c5") if args.config == "c2" else "none"
+        legs = ("c3,path,c4,c5" if world == 1 else "c3,c4,c5") if args.config == "c2" else "none"
     legs = [x for x in legs.split(",") if x and x != "none"]
     seqs.free()
     extra = {}
@@ -599,8 +612,15 @@ def main():
             extra["c2_path"]["path_to_100_features_measured_separately"] = json.load(open(os.path.join(ROOT, "profiles", "r02_path_to_100.json")))
         except Exception:
             pass
-    if rank == 0 and "c4" in legs:
-        extra["c4"] = leg_c4(K, synth)
+    if "c4" in legs:
+        # the folds of a cross-validation are independent (kmerLr_crossvalidation.go:167-211): replicas over the GPUs
+        c4 = leg_c4(K, synth, only=[f for f in range(5) if f % world == rank])
+        if dist is not None:
+            parts = [None] * world
+            dist.all_gather_object(parts, c4["folds"])
+            c4["folds"] = [o for p in parts for o in p]
+        if rank == 0:
+            extra["c4"] = c4_summary(c4, world)
     barrier()
 
     ms_step = allmax(float(np.mean(dev_ms)))

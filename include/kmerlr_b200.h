@@ -73,6 +73,8 @@ int         kmerlr_profile_dump(char *buf, int64_t buflen);
  *   "fused_ticket" = rows a warp of the stored-row pass takes per ticket (default 8; 0 = static grid of blocks);
  *   "p2p"      = 1 (default) lets sharded reduced-matrix iterations exchange the gradient over NVLink peer
  *                memory, 0 forces the NCCL collectives (set it identically on every rank);
+ *   "feed_growth" = growth of the chunk sizes of a pipelined host feed in per cent (default 135; measured at C2:
+ *                100 .. 135 give the same 3.15 ms per extraction from host buffers);
  *   "small_long" = 1 runs the reduced-matrix solver on the sliced + column-major views of the matrix (long rows), 0 on
  *                the compact rows, -1 (default) chooses by the row length (8 entries per row and more); same bits;
  *   "persist_bps" = blocks per SM of the persistent reduced-matrix solver (0 = as many as fit, the default);

@@ -97,6 +97,7 @@ struct Ctx {
   PeerBox *peer = nullptr;   // device copy of the mailbox table, nullptr = not available (NCCL is used)
   bool p2p_ok = true;        // kmerlr_option("p2p")
   bool p2p_allreduce = false; // kmerlr_option("p2p_allreduce"): full-space gradient all-reduce over peer memory instead of NCCL
+  int feed_growth = 135;     // kmerlr_option("feed_growth"): growth of the chunk sizes of a host feed, per cent
   int small_long = -1;       // kmerlr_option("small_long"): reduced-matrix solver on the sliced + column-major layouts (1), on the rows (0), by row length (-1)
   int persist_bps = 0;       // kmerlr_option("persist_bps"): blocks per SM of the persistent reduced-matrix solver (0 = all that fit)
   bool coop_supported = true;

@@ -304,7 +304,8 @@ struct HostFeed {
   static int64_t cut(int64_t n, int c, int nchunks) {
     if (c <= 0) return 0;
     if (c >= nchunks) return n;
-    const double g = 1.35;
+    const double g = 0.01 * (double)ctx().feed_growth;      // kmerlr_option("feed_growth"), per cent
+    if (g <= 1.0001) return n * c / nchunks;
     return (int64_t)((double)n * (pow(g, c) - 1.0) / (pow(g, nchunks) - 1.0));
   }
   DevBuf<uint8_t> raw;            // bytes [byte[0], byte[nchunks])

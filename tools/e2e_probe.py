@@ -7,6 +7,8 @@ import kmerlr_b200 as K
 from kmerlr_b200 import api, synth
 
 K.init(0)
+if len(sys.argv) > 1:
+    K.option("feed_growth", int(sys.argv[1]))
 n_fg = n_bg = 100000
 buf, off, labels = synth.training_set(n_fg, n_bg, 500)
 pin = torch.empty(len(buf), dtype=torch.uint8).pin_memory(); pin.numpy()[:] = buf
