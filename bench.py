@@ -557,6 +557,7 @@ def main():
                    "exchange": ("peer memory (NVLink mailboxes)" if os.environ.get("KMERLR_P2P", "1") != "0" else "NCCL") if world > 1 else None}
     except K.KmerLrError as e:           # a failed peer exchange must not take the headline numbers down
         reduced = {"error": str(e)}
+        print("bench.py: reduced-matrix leg FAILED on rank %d: %s" % (rank, e), file=sys.stderr, flush=True)
     rd.free()
     data.free()
 
