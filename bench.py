@@ -713,6 +713,41 @@ def main():
             dtc = time.perf_counter() - t0
             genomic["cpu_baseline"] = {"windows_per_sec": ((nb - 200 + 9) // 10) / dtc, "cores": cores, "kind": "port",
                                        "sample": "%d bp of the same genome, all host threads" % nb}
+        # the other legs: the same oracle port on a bounded sample of each leg's own shape (seconds each)
+        if "c3" in extra:
+            s3 = 3000
+            b3, o3, l3 = synth.training_set(s3, s3, 200)
+            t0 = time.perf_counter()
+            m3 = O.extract(O.make_config(1, 10, revcomp=True, binarize=True), (b3, o3), threads=cores, faithful=True)
+            t_e = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            O.proxgrad(m3, l3, np.zeros(m3.m + 1), (1.0, 1.0), lam=lam, epsilon=0.0, epsilon_loss=1e-300, max_iter=1)
+            t_i = time.perf_counter() - t0
+            extra["c3"]["cpu_baseline"] = {"extract_sequences_per_sec": 2 * s3 / t_e, "iteration_rows_per_sec": 2 * s3 / t_i,
+                                           "cores": cores, "kind": "port",
+                                           "sample": "%d + %d sequences x 200 bp, k=1..10 binarized: extraction on all host threads, one "
+                                                     "prox-grad iteration (serial over the samples, as the reference's Gradient is)" % (s3, s3)}
+            extra["c3"]["iteration_rows_per_sec"] = extra["c3"]["n_total"] * extra["c3"]["iters_per_sec"]
+        if "c4" in extra:
+            s4 = 150
+            b4, o4, l4 = synth.training_set(s4, s4, 500)
+            m4 = O.extract(O.make_config(1, 6, revcomp=True), (b4, o4), threads=cores)
+            t0 = time.perf_counter()
+            O.gradient(m4, l4, np.zeros(O.ntheta(m4, True)), (1.0, 1.0), 0.0, cooccurrence=True)
+            t_g = time.perf_counter() - t0
+            extra["c4"]["cpu_baseline"] = {"pair_gradient_rows_per_sec": 2 * s4 / t_g, "cores": 1, "kind": "port",
+                                           "sample": "%d + %d sequences x 500 bp, k=1..6 revcomp, every pair product of every row "
+                                                     "(kmerLr_logistic_regression.go:200-216), serial over the samples" % (s4, s4)}
+            extra["c4"]["pair_gradient_rows_per_sec"] = 16000 / (extra["c4"]["pair_gradient_ms"] * 1e-3)
+        if "c5" in extra and "wiggle" in extra["c5"]:
+            rng = np.random.default_rng(4)
+            vals = -rng.random(20000) * 5
+            t0 = time.perf_counter()
+            for v in vals:
+                O.go_fmt("%0.15f", O.go_exp(float(v)))
+            extra["c5"]["wiggle"]["cpu_baseline"] = {"records_per_sec": len(vals) / (time.perf_counter() - t0), "cores": 1,
+                                                     "kind": "port", "sample": "20 000 records through the Python restatement of "
+                                                     "math.Exp + Fprintf (not Go's speed: a reference point for the checker only)"}
         s_half = max(1, min(n_fg, args.ref_sample // 2))
         sb, so, sl = synth.training_set(s_half, s_half, L)
         t0 = time.perf_counter()
