@@ -176,7 +176,9 @@ int kmerlr_proxgrad(kmerlr_handle h, double *theta_inout, int64_t ntheta, const 
  * (ntheta <= 1024: it keeps the dense Gram matrix, as the reference does), one GPU.  The reference never
  * calls it and its theta slices alias (:89-91); built with the slices de-aliased, like kmerlr_proxgrad.
  * The IRLS weights use compute_class_weights(labels) (:88), the hook's loss class_w_hook (the estimator's
- * ClassWeights, kmerLr_estimator_hook.go:36-42) and lambda = l1reg / n.  sweeps_out = coordinate sweeps done. */
+ * ClassWeights, kmerLr_estimator_hook.go:36-42) and lambda = l1reg / n.  sweeps_out = coordinate sweeps done.
+ * PARITY UNPINNED IN THE REFERENCE ITSELF: no test, no golden and no caller there; the numpy restatement it is
+ * checked against (oracle/oracle.py:coordinate) is pinned by optimality properties only. */
 int kmerlr_coordinate(kmerlr_handle h, double *theta_inout, int64_t ntheta, const double class_w_hook[2],
                       double l1reg, double l2reg, double epsilon, double epsilon_loss, int64_t max_iter,
                       double hook_state[2], int64_t *sweeps_out, double *delta_out);
