@@ -351,3 +351,26 @@ def test_generate_features_off_with_empty_feature_list_gives_bias_only_rows(K):
     lr = K.logisticRegression(np.array([0.37]), (1.0, 1.0), 0.0)
     assert np.array_equal(lr.LinearPdf(d), np.full(30, 0.37))
     d.free(); full.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,flags,L", [
+    (1, 4, dict(revcomp=True), 60), (1, 6, dict(), 40), (2, 9, dict(revcomp=True, binarize=True), 48), (5, 8, dict(revcomp=True), 64),
+])
+def test_marks_of_observed_classes_end_only_when_all_are_seen(K, oracle, M, N, flags, L):
+    """Many row groups per block: the kernel stops marking observed classes once the device-wide bitmap covers the
+    numbering set.  (a) random rows: every class of a small configuration is seen early, the marks end, nothing may
+    change; (b) a class that shows up only in the LAST rows (homopolymer rows before them) must still get its column;
+    (c) a configuration whose classes are never all seen keeps marking (columns = ranks among the observed classes)."""
+    from kmerlr_b200 import synth
+    kc, oc = cfg_pair(K, oracle, M, N, **flags)
+    n = 40000
+    buf, off, _ = synth.training_set(n // 2, n // 2, L)
+    d = K.compile_test_data(None, kc, None, None, True, flags.get("binarize", False), (buf, off))
+    same_matrix(d, oracle.extract(oc, (buf, off), threads=8))
+    d.free()
+    late = buf.copy()
+    late[:off[n - 40]] = ord("A")                                  # only the last 40 rows carry anything but poly-A
+    d = K.compile_test_data(None, kc, None, None, True, flags.get("binarize", False), (late, off))
+    same_matrix(d, oracle.extract(oc, (late, off), threads=8))
+    d.free()
