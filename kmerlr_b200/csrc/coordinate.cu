@@ -1,7 +1,7 @@
 // coordinate.cu -- the IRLS + coordinate-descent estimator of the reference
 // (kmerLr_estimator_coordinate.go:31-139), for reduced matrices (<= 1023 columns).
 // PARITY UNPINNED IN THE REFERENCE ITSELF: the function has no caller, no test and no golden there; the numpy
-// restatement this kernel is compared with (oracle/oracle.py:coordinate) is pinned by optimality properties only.
+// restatement the tests compare this kernel with is pinned by optimality properties only.
 //
 //   outer iteration: r_i = x_i theta, p_i = sigma(r_i), w_i = p_i (1 - p_i), z_i = r_i + (y_i - p_i) / w_i,
 //                    w_i *= class weight of y_i                                          (:97-111)
