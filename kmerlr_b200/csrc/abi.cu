@@ -448,8 +448,10 @@ int64_t kmerlr_window_slots(int64_t len, int64_t W, int64_t step) {
 int kmerlr_score_windows(const kmerlr_model *models, int n_models, const uint8_t *seq, const int64_t *region_off,
                          int64_t n_regions, int64_t W, int64_t step, double *out) {
   return guarded([&] {
-    auto s = sequences_create(seq, region_off, n_regions);
-    score_windows(models, n_models, *s, W, step, out, nullptr);
+    // the contigs arrive in chunks: copies in both directions overlap the scoring (score.cu)
+    std::unique_ptr<SeqFeed> feed;
+    auto s = sequences_begin_chunked(seq, region_off, n_regions, feed);
+    score_windows(models, n_models, *s, W, step, out, nullptr, 0, feed.get());
   });
 }
 

@@ -330,6 +330,15 @@ void exclusive_scan_u32_to_i64(const uint32_t *in, int64_t *out, int64_t n);    
 void exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n);          // out[n] = total
 // extract.cu
 std::shared_ptr<SeqSet> sequences_create(const uint8_t *seq, const int64_t *off, int64_t n);
+// host sequences that arrive in chunks of whole rows: feed(c) copies chunk c on the copy stream and packs it on the
+// main stream (asynchronously; c < 0: everything); rows [first_row(c), first_row(c + 1))
+struct SeqFeed {
+  virtual ~SeqFeed() {}
+  virtual int chunks() const = 0;
+  virtual int64_t first_row(int c) const = 0;
+  virtual void feed(int c) = 0;
+};
+std::shared_ptr<SeqSet> sequences_begin_chunked(const uint8_t *seq, const int64_t *off, int64_t n, std::unique_ptr<SeqFeed> &feed);
 std::shared_ptr<Matrix> extract(const kmerlr_config &cfg, std::shared_ptr<SeqSet> seqs, const int32_t *frozen_k,
                                 const uint64_t *frozen_code, int64_t n_frozen, const int32_t *features,
                                 int64_t n_features, int flags);
@@ -376,7 +385,7 @@ void select_from_gradient(const double *g, int64_t ntheta, int64_t N, const int6
                           double *lambda_out, int64_t *c_out, int *ok_out);
 // score.cu
 void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, int64_t W, int64_t step,
-                   double *out_host, std::shared_ptr<Object> *out_dev, int layout = 0);
+                   double *out_host, std::shared_ptr<Object> *out_dev, int layout = 0, SeqFeed *feed = nullptr);
 // formats.cu: the on-disk formats either side of the path
 int64_t wiggle_records(const double *pred, bool pred_on_device, int64_t n, char *out);
 void save_wiggle(const char *filename, const char *track_name, int64_t n_regions, const char *const *seqnames,

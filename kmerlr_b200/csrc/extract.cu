@@ -328,18 +328,35 @@ struct HostFeed {
   }
 };
 
-static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t *off, int64_t n, HostFeed &hf) {
+// by_bytes: few long sequences (the contigs of a genome on their way to the window scoring) -- chunks of whole
+// rows of about equal size in bytes instead of the growing row counts of a training set
+static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t *off, int64_t n, HostFeed &hf,
+                                               bool by_bytes = false) {
   require_ready();
   KL_REQUIRE(n >= 0 && off != nullptr, "sequences: bad arguments");
   auto s = std::make_shared<SeqSet>();
   s->n = n;
   hf.seq = seq;
-  hf.nchunks = (int)(n / 8192 < 1 ? 1 : (n / 8192 > CTX_COPY_EVENTS - 1 ? CTX_COPY_EVENTS - 1 : n / 8192));
+  int64_t cutrow[CTX_COPY_EVENTS + 1];
+  if (by_bytes) {
+    const int64_t total = off[n] - off[0], per = (int64_t)8 << 20;
+    hf.nchunks = (int)(total / per < 1 ? 1 : (total / per > CTX_COPY_EVENTS - 1 ? CTX_COPY_EVENTS - 1 : total / per));
+    if (hf.nchunks > n) hf.nchunks = n > 0 ? (int)n : 1;
+    int64_t i = 0;
+    for (int c = 0; c <= hf.nchunks; c++) {
+      const int64_t want = c == hf.nchunks ? total : total / hf.nchunks * c;
+      while (i < n && off[i] - off[0] < want) i++;
+      cutrow[c] = c == hf.nchunks ? n : i;
+    }
+  } else {
+    hf.nchunks = (int)(n / 8192 < 1 ? 1 : (n / 8192 > CTX_COPY_EVENTS - 1 ? CTX_COPY_EVENTS - 1 : n / 8192));
+    for (int c = 0; c <= hf.nchunks; c++) cutrow[c] = HostFeed::cut(n, c, hf.nchunks);
+  }
   Trace tr("feed");
   // one pass over the offsets: validation, longest sequence, block counts at the chunk boundaries
   int64_t blocks = 0, max_len = 0, min_len = 0;
   for (int c = 0; c < hf.nchunks; c++) {
-    const int64_t r0 = HostFeed::cut(n, c, hf.nchunks), r1 = HostFeed::cut(n, c + 1, hf.nchunks);
+    const int64_t r0 = cutrow[c], r1 = cutrow[c + 1];
     hf.row[c] = r0; hf.blk[c] = blocks; hf.byte[c] = off[r0];
     for (int64_t i = r0; i < r1; i++) {
       const int64_t l = off[i + 1] - off[i];
@@ -375,6 +392,25 @@ static std::shared_ptr<SeqSet> sequences_begin(const uint8_t *seq, const int64_t
   KL_CUDA(cudaEventRecord(ctx().copy_ev[CTX_COPY_EVENTS - 1], ctx().stream));
   KL_CUDA(cudaStreamWaitEvent(ctx().copy_stream, ctx().copy_ev[CTX_COPY_EVENTS - 1], 0));
   tr.mark("offsets, metadata");
+  return s;
+}
+
+// host sequences arriving in chunks of whole rows, for a consumer that works chunk by chunk (score.cu)
+namespace {
+struct FeedImpl : SeqFeed {
+  HostFeed hf;
+  std::shared_ptr<SeqSet> s;
+  int chunks() const override { return hf.nchunks; }
+  int64_t first_row(int c) const override { return hf.row[c]; }
+  void feed(int c) override { if (s->n > 0) hf.feed(*s, c); }
+};
+}  // namespace
+
+std::shared_ptr<SeqSet> sequences_begin_chunked(const uint8_t *seq, const int64_t *off, int64_t n, std::unique_ptr<SeqFeed> &feed) {
+  auto f = std::make_unique<FeedImpl>();
+  f->s = sequences_begin(seq, off, n, f->hf, true);
+  auto s = f->s;
+  feed = std::move(f);
   return s;
 }
 

@@ -23,7 +23,7 @@ namespace {
 
 constexpr int WIG_REC = 18;          // "d.ddddddddddddddd\n"
 constexpr int WIG_THREADS = 256;     // 256 records = 4 608 bytes = 288 16-byte words per block
-constexpr int64_t WIG_CHUNK = (int64_t)1 << 24;   // records per device round trip (288 MB of text)
+constexpr int64_t WIG_CHUNK = (int64_t)1 << 21;   // records per chunk of the pipeline (36 MB of text)
 
 __host__ __device__ inline double go_ldexp(double y, int k) {
 #ifdef __CUDA_ARCH__
@@ -134,31 +134,55 @@ struct File {
 
 }  // namespace
 
-// records of n predictions (host or device pointer), 18 n bytes into out (host); returns the irregular ones
+// records of n predictions (host or device pointer), 18 n bytes into out (host); returns the irregular ones.
+// Chunks of 2^21 records through two sets of device buffers: the copy of chunk i + 1 to the device (copy stream), the
+// formatting of chunk i (main stream) and the copy of the text of chunk i - 1 to the host (third stream) overlap.
 int64_t wiggle_records(const double *pred, bool pred_on_device, int64_t n, char *out) {
   require_ready();
   KL_REQUIRE(n >= 0 && (n == 0 || (pred && out)), "wiggle_records: null argument");
-  int64_t irregular = 0;
   if (n == 0) return 0;
   const int64_t cap = n < WIG_CHUNK ? n : WIG_CHUNK;
-  DevBuf<double> dp;
-  if (!pred_on_device) dp.alloc((size_t)cap);
-  DevBuf<char> drec((size_t)cap * WIG_REC);
+  DevBuf<double> dp[2];
+  DevBuf<char> drec[2];
+  for (int b = 0; b < 2; b++) {
+    if (!pred_on_device) dp[b].alloc((size_t)cap);
+    drec[b].alloc((size_t)cap * WIG_REC);
+  }
   DevBuf<unsigned long long> dirr(1);
   dirr.zero();
-  for (int64_t j0 = 0; j0 < n; j0 += cap) {
+  cudaEvent_t up[2], done[2], home[2];
+  for (int b = 0; b < 2; b++) {
+    KL_CUDA(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
+    KL_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    KL_CUDA(cudaEventCreateWithFlags(&home[b], cudaEventDisableTiming));
+    KL_CUDA(cudaEventRecord(home[b], ctx().stream));          // (the buffers exist, the counter is zero)
+  }
+  int64_t i = 0;
+  for (int64_t j0 = 0; j0 < n; j0 += cap, i++) {
+    const int b = (int)(i & 1);
     const int64_t c = n - j0 < cap ? n - j0 : cap;
     const double *src = pred + j0;
-    if (!pred_on_device) { dp.upload(pred + j0, (size_t)c); src = dp.p; }
-    KL_LAUNCH(wiggle_kernel, (unsigned)((c + WIG_THREADS - 1) / WIG_THREADS), WIG_THREADS, 0, src, c, drec.p, dirr.p);
-    KL_CUDA(cudaMemcpyAsync(out + j0 * WIG_REC, drec.p, (size_t)c * WIG_REC, cudaMemcpyDeviceToHost, ctx().stream));
-    sync_stream();
+    if (!pred_on_device) {
+      KL_CUDA(cudaStreamWaitEvent(ctx().copy_stream, home[b], 0));      // the buffers of chunk i - 2 are free again
+      KL_CUDA(cudaMemcpyAsync(dp[b].p, pred + j0, (size_t)c * sizeof(double), cudaMemcpyHostToDevice, ctx().copy_stream));
+      KL_CUDA(cudaEventRecord(up[b], ctx().copy_stream));
+      KL_CUDA(cudaStreamWaitEvent(ctx().stream, up[b], 0));
+      src = dp[b].p;
+    } else {
+      KL_CUDA(cudaStreamWaitEvent(ctx().stream, home[b], 0));
+    }
+    KL_LAUNCH(wiggle_kernel, (unsigned)((c + WIG_THREADS - 1) / WIG_THREADS), WIG_THREADS, 0, src, c, drec[b].p, dirr.p);
+    KL_CUDA(cudaEventRecord(done[b], ctx().stream));
+    KL_CUDA(cudaStreamWaitEvent(ctx().alt_stream, done[b], 0));
+    KL_CUDA(cudaMemcpyAsync(out + j0 * WIG_REC, drec[b].p, (size_t)c * WIG_REC, cudaMemcpyDeviceToHost, ctx().alt_stream));
+    KL_CUDA(cudaEventRecord(home[b], ctx().alt_stream));
   }
+  KL_CUDA(cudaStreamSynchronize(ctx().alt_stream));
   unsigned long long h = 0;
   dirr.download(&h, 1);
   sync_stream();
-  irregular = (int64_t)h;
-  return irregular;
+  for (int b = 0; b < 2; b++) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(home[b]); }
+  return (int64_t)h;
 }
 
 // saveWindowPredictionsWiggle (kmerLr_predict_genomic.go:37-60); predictions of region i = pred[slot_off[i], slot_off[i+1])

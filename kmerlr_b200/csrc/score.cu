@@ -279,8 +279,11 @@ struct HostModel {
 
 // layout 0: predict_window_genomic -- n/step + 1 slots per region, window j*step in slot j
 // layout 1: predict_window (kmerLr_predict.go:89-124) -- n = len - W slots, window starting at j in slot j
+// feed: the sequences are still on the host and arrive in chunks of whole rows (kmerlr_score_windows with host
+// buffers).  Count models without pair features then work chunk by chunk: the copy of chunk c + 1 (copy stream)
+// and the copy of the scores of chunk c - 1 back to the host (third stream) overlap the scoring of chunk c.
 void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, int64_t W, int64_t step,
-                   double *out_host, std::shared_ptr<Object> *out_dev, int layout) {
+                   double *out_host, std::shared_ptr<Object> *out_dev, int layout, SeqFeed *feed) {
   require_ready();
   KL_REQUIRE(n_models >= 1 && W >= 1 && step >= 1, "score_windows: bad arguments");
   std::vector<std::unique_ptr<HostModel>> hm;
@@ -359,6 +362,7 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
   DevBuf<int64_t> dslot((size_t)s.n + 1), dwin((size_t)s.n + 1);
   dslot.upload(slot_off.data(), (size_t)s.n + 1);
   dwin.upload(win_off.data(), (size_t)s.n + 1);
+  bool copied_home = false;       // the scores went to out_host chunk by chunk
   if (total_windows > 0) {
     if (all_linear) {
       for (int mi = 0; mi < n_models; mi++) {
@@ -383,11 +387,36 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
         dt.upload(tiles.data(), tiles.size());
         size_t smem = (size_t)nlev * (size_t)(TP + 1) * sizeof(double) + (size_t)hs_smem * 8 + (size_t)wt_bytes;
         KL_CUDA(cudaFuncSetAttribute(score_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        KL_LAUNCH(score_linear, (unsigned)tiles.size(), SCORE_THREADS, smem, dmodels.p, n_models, 0, mi > 0 ? 1 : 0, s.len.p,
-                  s.blk.p, s.bits2.p, s.inv16.p, dt.p, dslot.p, W, step, (int)TP, mi, hs_smem, layout == 1 ? step : (int64_t)1, outbuf->val_f64.p);
+        // chunk by chunk (one chunk when the sequences are resident): the tiles are sorted by region
+        const int nch = feed ? feed->chunks() : 1;
+        size_t t0 = 0;
+        for (int c = 0; c < nch; c++) {
+          const int64_t r0 = feed ? feed->first_row(c) : 0, r1 = feed ? feed->first_row(c + 1) : s.n;
+          if (feed && mi == 0) feed->feed(c);
+          size_t t1 = t0;
+          while (t1 < tiles.size() && tiles[t1].region < r1) t1++;
+          if (t1 > t0)
+            KL_LAUNCH(score_linear, (unsigned)(t1 - t0), SCORE_THREADS, smem, dmodels.p, n_models, 0, mi > 0 ? 1 : 0, s.len.p,
+                      s.blk.p, s.bits2.p, s.inv16.p, dt.p + t0, dslot.p, W, step, (int)TP, mi, hs_smem,
+                      layout == 1 ? step : (int64_t)1, outbuf->val_f64.p);
+          t0 = t1;
+          // the scores of the chunk go home while the next chunk is scored (last model only: the models add up)
+          if (feed && out_host && mi == n_models - 1 && slot_off[r1] > slot_off[r0]) {
+            cudaEvent_t ev;
+            KL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            KL_CUDA(cudaEventRecord(ev, ctx().stream));
+            KL_CUDA(cudaStreamWaitEvent(ctx().alt_stream, ev, 0));
+            KL_CUDA(cudaMemcpyAsync(out_host + slot_off[r0], outbuf->val_f64.p + slot_off[r0],
+                                    (size_t)(slot_off[r1] - slot_off[r0]) * sizeof(double), cudaMemcpyDeviceToHost, ctx().alt_stream));
+            KL_CUDA(cudaEventDestroy(ev));            // (released once the event has completed)
+            copied_home = true;
+          }
+        }
         sync_stream();
       }
+      if (copied_home) KL_CUDA(cudaStreamSynchronize(ctx().alt_stream));
     } else {
+      if (feed) feed->feed(-1);
       size_t smem = (size_t)4 * (size_t)max_classes * sizeof(uint32_t);
       KL_CUDA(cudaFuncSetAttribute(score_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int64_t blocks = (total_windows + 3) / 4, cap = (int64_t)ctx().sm_count * 16;
@@ -397,7 +426,8 @@ void score_windows(const kmerlr_model *models, int n_models, const SeqSet &s, in
                 outbuf->val_f64.p);
     }
   }
-  if (out_host) outbuf->val_f64.download(out_host, (size_t)total_slots);
+  else if (feed) feed->feed(-1);
+  if (out_host && !copied_home) outbuf->val_f64.download(out_host, (size_t)total_slots);
   sync_stream();
   if (out_dev) *out_dev = outbuf;
 }
