@@ -200,3 +200,21 @@ def test_export_kmers_tables(K, oracle, fixtures, tmp_path):
         offset, scale = oracle.fit_transform(om, "standardizer")
         dense = (om.dense() - offset[1:]) * scale[1:]
         assert open(f).read() == oracle.export_kmers_text(om.class_names(), dense, True)
+
+
+@pytest.mark.gpu
+def test_wiggle_records_at_scale_round_trip(K):
+    """size-independent property at the size of a chromosome's track (8 M records, several pipeline chunks): every
+    record is well formed and, read back as a number, is exp(prediction) to within the last printed digit"""
+    rng = np.random.default_rng(12)
+    n = 8_000_003
+    pred = np.concatenate([-rng.random(n // 2) * 3.0, np.log(rng.random(n - n // 2))])
+    rec, irr = K.wiggle_records(pred)
+    assert irr == 0 and len(rec) == 18 * n
+    b = np.frombuffer(rec, dtype=np.uint8).reshape(n, 18)
+    assert np.all(b[:, 1] == ord(".")) and np.all(b[:, 17] == ord("\n"))
+    digits = np.delete(b[:, :17], 1, axis=1).astype(np.int64) - 48
+    assert digits.min() >= 0 and digits.max() <= 9
+    value = (digits * (10 ** np.arange(15, -1, -1, dtype=np.int64))).sum(axis=1)          # x 10^15, exact
+    want = np.exp(pred) * 1e15
+    assert np.max(np.abs(value - want)) <= 1.0 + 1e15 * 2.3e-16       # half a unit of the last digit + one ulp of exp near 1
