@@ -368,8 +368,18 @@ constexpr int IMP_R = 2;           // rows per warp and round
 // packed bases (digit-reversed once) serves all of them.
 // CACHE > 0: the lane's groups fit one window and their table indices stay in registers between gather and
 // scatter (rows of up to 32 CACHE groups); CACHE = 0: window after window, decoded twice (rows of any length).
+#ifndef KL_IMP_MINB
+#define KL_IMP_MINB 0      // resident blocks per SM the compiler has to make room for (0: its own choice, 62-64 registers,
+                           // 4 blocks; measured with 5 blocks / 48 registers: the same at C2, 3 % faster at C3; with 6 / 40: 25 % slower)
+#endif
 template <int CACHE, bool BIN>
-__global__ void __launch_bounds__(256) imp_pass(const ImpParams P, const ImpArgs A) {
+__global__ void
+#if KL_IMP_MINB > 0
+__launch_bounds__(256, KL_IMP_MINB)
+#else
+__launch_bounds__(256)
+#endif
+imp_pass(const ImpParams P, const ImpArgs A) {
   if (A.st && A.st->done == 1) return;
   constexpr int CC = CACHE > 0 ? CACHE : 1;
   constexpr int RR = 8 * IMP_R;
