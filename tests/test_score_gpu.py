@@ -102,3 +102,30 @@ def test_ensemble_without_summary_fails(K, oracle):
     km, _ = make_model(K, oracle, seqs, 2, 4, 10, members=2, summary="")
     with pytest.raises(K.KmerLrError):
         K.genomicKmerLr([km]).predict_window_genomic(seqs, 100, 10)
+
+
+def test_host_buffers_arrive_in_chunks(K, oracle):
+    """kmerlr_score_windows with host buffers above 16 MB works chunk by chunk (copies in both directions overlap the
+    scoring): ragged regions -- empty, shorter than the window, one as long as several chunks -- and two summed
+    models; the result equals the resident path bit for bit and the oracle on the regions it finishes in seconds"""
+    from kmerlr_b200 import synth
+    lens = [300_000, 0, 150, 5_000_000, 17, 11_000_000, 201, 2_500_000, 64, 9_000_000, 123_457, 3_000_000, 1_000]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    buf = synth.random_bases(int(off[-1]), 7)
+    buf[1000:1040] = ord("N")
+    small = [bytes(buf[off[i]:off[i + 1]]).decode() for i in (0, 2)]
+    km, om = make_model(K, oracle, small[:1], 1, 8, 100, seed=1, revcomp=True)
+    km2, om2 = make_model(K, oracle, small[:1], 2, 6, 30, seed=2)
+    g = K.genomicKmerLr([km, km2])
+    W, step = 200, 10
+    out = g.predict_window_genomic((buf, off), W, step)
+    slots = [oracle.window_slots(int(L), W, step) for L in lens]
+    assert [len(o) for o in out] == slots
+    seqs = K.Sequences((buf, off))
+    res = g.predict_resident(seqs, W, step, fetch=True, total_slots=sum(slots))
+    seqs.free()
+    assert np.array_equal(np.concatenate(out), res[:sum(slots)])
+    for i in (0, 2, 4, 6, 8, 10, 12):
+        s = bytes(buf[off[i]:off[i + 1]]).decode()
+        ref = oracle.score_windows([om, om2], [s], W, step)
+        assert np.allclose(out[i], ref, rtol=1e-12, atol=1e-12), i
