@@ -219,6 +219,9 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
     if (lane >= (unsigned)o) { incl += y; mx = max(mx, z); }
   }
   const int base = incl - c, total = __shfl_sync(0xffffffffu, incl, 31);
+  // the last run of the sorted array is the run of SENT keys (a level has fewer valid keys than sort slots): its start
+  // is the number of valid keys, and valid keys - classes = repeats of the level
+  const int nvalid = __shfl_sync(0xffffffffu, mx, 31);
   int start0 = __shfl_up_sync(0xffffffffu, mx, 1);   // last boundary before this lane's keys
   if (lane == 0) start0 = 0;
   // round 1: ids
@@ -315,7 +318,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
       __syncwarp();
     } else {
       em.sq += (unsigned long long)c; if (c) em.vm = max(em.vm, 1u);
-      if (events) { repeat_events(); __syncwarp(); }
+      if (events && nvalid > total) { repeat_events(); __syncwarp(); }
     }
     em.cursor += (uint32_t)total;
     return;
@@ -365,7 +368,7 @@ __device__ __forceinline__ void emit_sorted(const uint32_t (&K)[E], unsigned lan
     __syncwarp();
   } else {
     em.sq += __popcll(keepbits); if (keepbits) em.vm = max(em.vm, 1u);
-    if (events) { repeat_events(); __syncwarp(); }
+    if (events && nvalid > total) { repeat_events(); __syncwarp(); }
   }
   em.cursor += kept;
 }
