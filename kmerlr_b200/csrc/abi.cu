@@ -184,7 +184,7 @@ int kmerlr_option(const char *name, int64_t value) {
     else if (!strcmp(name, "super_len")) g_ctx.super_len = (int)(value < 0 ? -1 : (value > IMP_SUPER_MAX ? IMP_SUPER_MAX : value));
     else if (!strcmp(name, "p2p")) g_ctx.p2p_ok = value != 0;
     else if (!strcmp(name, "feed_growth")) g_ctx.feed_growth = (int)(value < 100 ? 100 : (value > 400 ? 400 : value));
-    else if (!strcmp(name, "small_long")) g_ctx.small_long = (int)(value < 0 ? -1 : (value ? 1 : 0));
+    else if (!strcmp(name, "small_long")) g_ctx.small_long = (int)(value < 0 ? -1 : (value > 2 ? 2 : value));
     else if (!strcmp(name, "persist_bps")) g_ctx.persist_bps = (int)(value < 0 ? 0 : value);
     else if (!strcmp(name, "p2p_allreduce")) g_ctx.p2p_allreduce = value != 0;
     else if (!strcmp(name, "persistent")) g_ctx.coop_ok = value != 0 && g_ctx.coop_supported;

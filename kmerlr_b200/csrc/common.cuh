@@ -282,6 +282,15 @@ struct Matrix : Object {
   bool has_packed = false, packable = false;
   int pack_row_bits = 0;
   DevBuf<uint32_t> spack, cpack;
+  // block-local column-major view for the persistent reduced-matrix solver (ensure_blockview): block b of a grid of
+  // bv_grid blocks owns the rows [n b / bv_grid, n (b+1) / bv_grid); its entries, sorted by (column, row), are dealt
+  // to the 256 threads of the block in contiguous shares of width_b entries and stored share-interleaved (entry j of
+  // thread t at 256 (bv_off[b] + j) + t), one word each: local row | column << bv_row_bits | count << (bv_row_bits
+  // + 10); 0xFFFFFFFF pads the last shares
+  int bv_grid = 0, bv_row_bits = 0, bv_rows = 0;
+  bool bv_ok = false;
+  DevBuf<int64_t> bv_off;
+  DevBuf<uint32_t> bv_pack;
   // labels
   bool has_labels = false;
   DevBuf<uint8_t> labels;    // n
@@ -362,6 +371,7 @@ void matrix_compact(Matrix &M);      // padded rows -> compact CSR (no-op for co
 void ensure_csc(Matrix &M);
 void ensure_sliced(Matrix &M);
 bool ensure_packed(Matrix &M);      // false: the entries do not fit (real values, large counts, > 1 024 columns)
+bool ensure_blockview(Matrix &M, int grid);   // false: rows per block / counts do not fit the packed word
 std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel);
 double matrix_maxsq(Matrix &M);
 double matrix_vmax(Matrix &M);

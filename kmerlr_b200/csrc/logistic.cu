@@ -1027,6 +1027,9 @@ struct LongView {
   int row_bits;
   double *wbuf;                                                       // n scaled row weights
   int64_t nnz;
+  // block-local column-major view (Matrix::bv_*, LONG == 2): the weights of the block's rows stay in shared memory and
+  // the gradient of the block's rows is summed by the block itself -- one grid barrier per iteration instead of two
+  const int64_t *bv_off; const uint32_t *bv_pack; int bv_row_bits;
 };
 
 __device__ __forceinline__ void small_acc_add(uint32_t *acc_lo, uint32_t *acc_hi, uint32_t c, unsigned long long q) {
@@ -1040,7 +1043,7 @@ template <typename VT>
 __device__ __forceinline__ void long_forward(const Rows &R, const LongView<VT> &V, int64_t n, int64_t ntheta,
                                              const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n,
                                              double scale, double *blockloss, int scatter, uint32_t *acc_lo,
-                                             uint32_t *acc_hi, const double *sth, double *red) {
+                                             uint32_t *acc_hi, const double *sth, double *red, double *w_local = nullptr) {
   for (int i = threadIdx.x; i < ntheta; i += blockDim.x) { acc_lo[i] = 0u; acc_hi[i] = 0u; }
   __syncthreads();
   double lacc = 0.0;
@@ -1072,7 +1075,7 @@ __device__ __forceinline__ void long_forward(const Rows &R, const LongView<VT> &
     else             { w = inv_n * cw0 * exp(r);         lacc += cw0 * log_add0(z); }
     if (!scatter) continue;
     const double ws = w * scale;
-    V.wbuf[row] = ws;
+    if (w_local) w_local[row - row_lo] = ws; else V.wbuf[row] = ws;
     bias += __double2ll_rn(ws);
   }
 #pragma unroll
@@ -1149,6 +1152,41 @@ __device__ __forceinline__ void long_columns(const LongView<VT> &V, int64_t nthe
   }
 }
 
+// LONG == 2: gradient of the block's OWN rows from the block-local view (thread t sums its contiguous share of the
+// block's entries, which are sorted by column: a register run per column, a shared-memory add when the column
+// changes), the weights read from shared memory; then into G.  The same integer terms as long_columns.
+template <typename VT>
+__device__ __forceinline__ void block_columns(const LongView<VT> &V, int64_t ntheta, unsigned long long *G, uint32_t *acc_lo,
+                                              uint32_t *acc_hi, const double *w_s) {
+  const int64_t o0 = V.bv_off[blockIdx.x], wdt = V.bv_off[blockIdx.x + 1] - o0;
+  const uint32_t *bp = V.bv_pack + 256 * o0 + threadIdx.x;
+  const uint32_t rmask = (1u << V.bv_row_bits) - 1u;
+  const int cs = V.bv_row_bits, vs = V.bv_row_bits + 10;
+  long long acc = 0;
+  int cur = -1;
+  for (int64_t j = 0; j < wdt; j += 4) {
+    uint32_t e[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) e[i] = j + i < wdt ? __ldg(bp + 256 * (j + i)) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (e[i] == 0xFFFFFFFFu) continue;
+      const int c = (int)((e[i] >> cs) & 1023u);
+      if (c != cur) {
+        if (acc) small_acc_add(acc_lo, acc_hi, (uint32_t)cur + 1u, (unsigned long long)acc);
+        acc = 0; cur = c;
+      }
+      acc += __double2ll_rn(w_s[e[i] & rmask] * (double)(e[i] >> vs));
+    }
+  }
+  if (acc) small_acc_add(acc_lo, acc_hi, (uint32_t)cur + 1u, (unsigned long long)acc);
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntheta; i += blockDim.x) {
+    unsigned long long v = ((unsigned long long)acc_hi[i] << 32) | acc_lo[i];
+    if (v) atomicAdd(&G[i], v);
+  }
+}
+
 template <typename VT>
 __global__ void __launch_bounds__(256, SMALL_BLOCKS_PER_SM) fused_small_kernel(const Rows R, const uint32_t *__restrict__ col,
                                                           const VT *__restrict__ val, int64_t n, int64_t ntheta,
@@ -1193,7 +1231,7 @@ constexpr int PERSIST_THREADS = 256;
 // the mailboxes -- stores into every rank's slot, a flag, a wait for the flags of the others, the sum in rank
 // order (integers: the same bits on every rank) -- and a second grid barrier releases the tail.  The
 // collective lives INSIDE the persistent kernel: no launch and no NCCL call per iteration.
-template <typename VT, bool SHARDED, bool LONG>
+template <typename VT, bool SHARDED, int LONG>
 __global__ void __launch_bounds__(PERSIST_THREADS, SMALL_BLOCKS_PER_SM) fused_small_persistent(
     const Rows R, const uint32_t *__restrict__ col, const VT *__restrict__ val, int64_t n, int64_t ntheta, double *theta,
     const uint8_t *__restrict__ labels, double cw0, double cw1, double inv_n, double scale, unsigned long long *G3,
@@ -1213,9 +1251,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, SMALL_BLOCKS_PER_SM) fused_sm
   }
   for (int i = threadIdx.x; i < ntheta; i += blockDim.x) sth[i] = theta[i];
   // LONG: the column offsets stay in shared memory; c_first = the column of this thread's first column-major entry
-  __shared__ long long scp[LONG ? SMALL_MAX_THETA + 1 : 1];
+  __shared__ long long scp[LONG == 1 ? SMALL_MAX_THETA + 1 : 1];
+  extern __shared__ __align__(16) double w_s[];          // LONG == 2: the scaled weights of the block's rows
   int c_first = 0;
-  if constexpr (LONG) {
+  if constexpr (LONG == 1) {
     for (int i = threadIdx.x; i < ntheta; i += blockDim.x) scp[i] = LV.colptr[i];        // m + 1 = ntheta offsets
     __syncthreads();
     const int64_t p = LV.nnz * blockIdx.x / gridDim.x + threadIdx.x;
@@ -1235,12 +1274,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, SMALL_BLOCKS_PER_SM) fused_sm
     double *blockloss = blockloss2 + (pass & 1) * nblocks;
     if (blockIdx.x == 0)
       for (int i = threadIdx.x; i < SMALL_REPLICAS * ntheta; i += blockDim.x) Gnext[i] = 0ull;
-    if constexpr (LONG) {
+    if constexpr (LONG == 1) {
       long_forward<VT>(R, LV, n, ntheta, labels, cw0, cw1, inv_n, scale, blockloss, scatter, acc_lo, acc_hi, sth, red);
       if (scatter) {
         grid.sync();
         long_columns<VT>(LV, ntheta, G + (blockIdx.x % SMALL_REPLICAS) * ntheta, acc_lo, acc_hi, scp, c_first);
       }
+    } else if constexpr (LONG == 2) {
+      long_forward<VT>(R, LV, n, ntheta, labels, cw0, cw1, inv_n, scale, blockloss, scatter, acc_lo, acc_hi, sth, red, w_s);
+      if (scatter) block_columns<VT>(LV, ntheta, G + (blockIdx.x % SMALL_REPLICAS) * ntheta, acc_lo, acc_hi, w_s);
     } else {
       small_rows<VT, false>(R, col, val, n, ntheta, sth, labels, cw0, cw1, inv_n, scale,
                             G + (blockIdx.x % SMALL_REPLICAS) * ntheta, blockloss, scatter, acc_lo, acc_hi, sth, red);
@@ -1439,9 +1481,11 @@ const VT *sliced_val(const Matrix &M);
 template <> const uint32_t *sliced_val<uint32_t>(const Matrix &M) { return M.vt == VAL_U32 ? M.sval_u32.p : nullptr; }
 template <> const double *sliced_val<double>(const Matrix &M) { return M.sval_f64.p; }
 template <typename VT>
-const void *persistent_kernel(bool sharded, bool long_rows) {
-  if (sharded) return long_rows ? (const void *)fused_small_persistent<VT, true, true> : (const void *)fused_small_persistent<VT, true, false>;
-  return long_rows ? (const void *)fused_small_persistent<VT, false, true> : (const void *)fused_small_persistent<VT, false, false>;
+const void *persistent_kernel(bool sharded, int long_mode) {
+  if (sharded) return long_mode == 2 ? (const void *)fused_small_persistent<VT, true, 2>
+                    : long_mode == 1 ? (const void *)fused_small_persistent<VT, true, 1> : (const void *)fused_small_persistent<VT, true, 0>;
+  return long_mode == 2 ? (const void *)fused_small_persistent<VT, false, 2>
+       : long_mode == 1 ? (const void *)fused_small_persistent<VT, false, 1> : (const void *)fused_small_persistent<VT, false, 0>;
 }
 template <typename VT>
 const VT *csc_val(const Matrix &M);
@@ -1777,10 +1821,16 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   bool persistent = small && ctx().coop_ok && (!M.sharded || p2p);
   // long rows: sliced + column-major views (the iterates are the same bits on either path, so a rank may choose by
   // its own shard)
-  const bool long_rows = persistent && M.nnz > 0 && (ctx().small_long == 1 || (ctx().small_long < 0 && M.nnz >= 8 * M.n));
+  const bool long_rows = persistent && M.nnz > 0 && (ctx().small_long >= 1 || (ctx().small_long < 0 && M.nnz >= 8 * M.n));
   DevBuf<double> wbuf;
   bool packed = false;
   if (long_rows) { ensure_sliced(M); ensure_csc(M); packed = ensure_packed(M); wbuf.alloc((size_t)M.n); }
+  // long_mode 2: the block-local view (one grid barrier per iteration); it is built for the grid of this launch
+  int long_mode = long_rows ? 1 : 0;
+  size_t dyn_smem = 0;
+  // (measured at C2 rows, 100 columns: 19.4 / 24.8 / 28.8 us against 23.6 / 28.1 / 32.2 us on the two views at 5 / 14 / 24
+  // entries per row, the same 41 us at 50, 139 against 132 us at 249: chosen below 40 entries per row)
+  const bool want_block = long_rows && packed && (ctx().small_long == 2 || (ctx().small_long < 0 && M.nnz < 40 * M.n));
   const int64_t BATCH = persistent ? 4096 : (small ? 256 : 16);
   int small_blocks = 0;
   DevBuf<double> blockloss;
@@ -1790,14 +1840,40 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
     // one wave: as many blocks as are resident at once (a second, partly filled wave costs a whole round)
     int64_t nb = (int64_t)ctx().sm_count * SMALL_BLOCKS_PER_SM, need = (M.n + 63) / 64;   // >= 64 rows per block
     if (persistent) {
-      int per_sm = 0;
-      dispatch_vt(M, [&](auto *tag) {
-        using VT = typename std::remove_pointer<decltype(tag)>::type;
-        KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel<VT>(M.sharded, long_rows), PERSIST_THREADS, 0));
-      });
-      KL_INVARIANT(per_sm >= 1);
-      if (ctx().persist_bps > 0 && ctx().persist_bps < per_sm) per_sm = ctx().persist_bps;
-      nb = (int64_t)ctx().sm_count * per_sm;       // a cooperative grid must be resident as a whole
+      auto resident = [&](int mode, size_t smem) {
+        int per_sm = 0;
+        dispatch_vt(M, [&](auto *tag) {
+          using VT = typename std::remove_pointer<decltype(tag)>::type;
+          if (smem > 16 * 1024)
+            KL_CUDA(cudaFuncSetAttribute(persistent_kernel<VT>(M.sharded, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+          KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel<VT>(M.sharded, mode), PERSIST_THREADS, smem));
+        });
+        if (ctx().persist_bps > 0 && ctx().persist_bps < per_sm) per_sm = ctx().persist_bps;
+        return per_sm;
+      };
+      if (want_block) {
+        // the grid fixes the rows per block, the rows per block fix the shared memory, the shared memory the grid
+        int per_sm = resident(2, 0);
+        for (int round = 0; round < 4 && per_sm >= 1; round++) {
+          int64_t g = (int64_t)ctx().sm_count * per_sm;
+          if (g > need) g = need;
+          const size_t smem = (size_t)((M.n + g - 1) / g + 1) * sizeof(double);
+          const int p2 = smem <= 32 * 1024 ? resident(2, smem) : 0;
+          if (p2 >= per_sm) { dyn_smem = smem; break; }
+          per_sm = p2;
+        }
+        if (per_sm >= 1 && dyn_smem > 0) {
+          int64_t g = (int64_t)ctx().sm_count * per_sm;
+          if (g > need) g = need;
+          if (ensure_blockview(M, (int)g)) { long_mode = 2; nb = (int64_t)ctx().sm_count * per_sm; }
+          else dyn_smem = 0;
+        } else dyn_smem = 0;
+      }
+      if (long_mode != 2) {
+        const int per_sm = resident(long_mode, 0);
+        KL_INVARIANT(per_sm >= 1);
+        nb = (int64_t)ctx().sm_count * per_sm;       // a cooperative grid must be resident as a whole
+      }
     }
     small_blocks = (int)(nb < need ? nb : need);
     if (small_blocks < 1) small_blocks = 1;        // (an empty shard still takes part in the exchange)
@@ -1840,13 +1916,14 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
           lv.colptr = M.colptr.p; lv.crow = M.crow.p; lv.cval = csc_val<VT>(M);
           if (packed) { lv.spack = M.spack.p; lv.cpack = M.cpack.p; lv.row_bits = M.pack_row_bits; }
           lv.wbuf = wbuf.p; lv.nnz = M.nnz;
+          if (long_mode == 2) { lv.bv_off = M.bv_off.p; lv.bv_pack = M.bv_pack.p; lv.bv_row_bits = M.bv_row_bits; }
         }
         void *args[] = {&rows, &colp, &valp, &n, &nt, &thp, &lab, &cw0, &cw1, &invn, &scale, &Gp, &bl, &stp, &pass0, &npass,
                         &inv_scale, &lam, &el, &stp_size, &eps, &mi, &pbp, &gx, &scr, &abortp, &lv};
         if (ctx().profiling) profile_begin("fused_small_persistent");
         const cudaError_t e = cudaLaunchCooperativeKernel(
-            persistent_kernel<VT>(M.sharded, long_rows),
-            dim3((unsigned)small_blocks), dim3(PERSIST_THREADS), args, 0, ctx().stream);
+            persistent_kernel<VT>(M.sharded, long_mode),
+            dim3((unsigned)small_blocks), dim3(PERSIST_THREADS), args, dyn_smem, ctx().stream);
         if (ctx().profiling) profile_end();
         if (e == cudaErrorCooperativeLaunchTooLarge && !M.sharded) {
           // the GPU is shared (MPS, another context): the grid cannot be resident as a whole right now.

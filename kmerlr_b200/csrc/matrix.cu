@@ -711,6 +711,78 @@ bool ensure_packed(Matrix &M) {
   return true;
 }
 
+// ---- block-local column-major view (see Matrix::bv_*) ---------------------------------------------------------------
+// first entry of column c with row >= n b / grid, for b = 0 .. grid (b = grid: the end of the column)
+__global__ void bv_bounds(const int64_t *__restrict__ colptr, const uint32_t *__restrict__ cpack, uint32_t rmask, int64_t n,
+                          int64_t m, int grid, int64_t *__restrict__ lb) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)(grid + 1) * m) return;
+  const int64_t b = idx / m, c = idx % m;
+  const int64_t row_lo = n * b / grid;
+  int64_t lo = colptr[c], hi = colptr[c + 1];
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)(cpack[mid] & rmask) < row_lo) lo = mid + 1; else hi = mid; }
+  lb[idx] = lo;
+}
+// per block: position of its first entry of every column in the block's list, number of entries, share width
+__global__ void bv_starts(const int64_t *__restrict__ lb, int64_t m, int grid, int64_t *__restrict__ start,
+                          uint32_t *__restrict__ width) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= grid) return;
+  int64_t run = 0;
+  for (int64_t c = 0; c < m; c++) { start[b * m + c] = run; run += lb[(b + 1) * m + c] - lb[b * m + c]; }
+  width[b] = (uint32_t)((run + 255) / 256);
+}
+__global__ void bv_fill(const int64_t *__restrict__ lb, const int64_t *__restrict__ start, const uint32_t *__restrict__ width,
+                        const int64_t *__restrict__ off, const uint32_t *__restrict__ cpack, int crow_bits, int64_t n, int64_t m,
+                        int grid, int row_bits, uint32_t *__restrict__ out, unsigned int *__restrict__ bad) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)grid * m) return;
+  const int64_t b = idx / m, c = idx % m;
+  const int64_t p0 = lb[b * m + c], p1 = lb[(b + 1) * m + c], row_lo = n * b / grid;
+  const int64_t w = width[b];
+  const uint32_t rmask = (1u << crow_bits) - 1u;
+  for (int64_t p = p0; p < p1; p++) {
+    const uint32_t e = cpack[p], cnt = e >> crow_bits;
+    const int64_t lr = (int64_t)(e & rmask) - row_lo;
+    if (lr < 0 || lr >= ((int64_t)1 << row_bits) || (row_bits + 10 < 32 && (cnt >> (32 - row_bits - 10)) != 0u)) { atomicAdd(bad, 1u); continue; }
+    const int64_t q = start[b * m + c] + (p - p0), t = q / w, j = q % w;
+    out[256 * (off[b] + j) + t] = (uint32_t)lr | ((uint32_t)c << row_bits) | (cnt << (row_bits + 10));
+  }
+}
+
+bool ensure_blockview(Matrix &M, int grid) {
+  if (M.bv_grid == grid) return M.bv_ok;
+  M.bv_grid = grid; M.bv_ok = false;
+  if (!ensure_packed(M) || grid < 1 || M.m < 1 || M.m > 1024) return false;
+  const int64_t rows = (M.n + grid - 1) / grid + 1;             // upper bound of the rows of one block
+  int rb = 1;
+  while (((int64_t)1 << rb) < rows) rb++;
+  if (rb + 10 > 28 || rows * 8 > 32 * 1024) return false;       // (at least 4 bits of count; the block's weights live in 32 KB)
+  DevBuf<int64_t> lb((size_t)(grid + 1) * M.m), start((size_t)grid * M.m);
+  DevBuf<uint32_t> width((size_t)grid);
+  const uint32_t rmask = (1u << M.pack_row_bits) - 1u;
+  KL_LAUNCH(bv_bounds, (unsigned)(((int64_t)(grid + 1) * M.m + 255) / 256), 256, 0, M.colptr.p, M.cpack.p, rmask, M.n, M.m, grid, lb.p);
+  KL_LAUNCH(bv_starts, (unsigned)((grid + 127) / 128), 128, 0, lb.p, M.m, grid, start.p, width.p);
+  M.bv_off.alloc((size_t)grid + 1);
+  exclusive_scan_u32_to_i64(width.p, M.bv_off.p, grid);
+  int64_t total = 0;
+  KL_CUDA(cudaMemcpyAsync(&total, M.bv_off.p + grid, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx().stream));
+  sync_stream();
+  M.bv_pack.alloc((size_t)(total > 0 ? 256 * total : 1));
+  KL_CUDA(cudaMemsetAsync(M.bv_pack.p, 0xFF, (size_t)(total > 0 ? 256 * total : 1) * sizeof(uint32_t), ctx().stream));
+  DevBuf<unsigned int> bad(1);
+  bad.zero();
+  KL_LAUNCH(bv_fill, (unsigned)(((int64_t)grid * M.m + 255) / 256), 256, 0, lb.p, start.p, width.p, M.bv_off.p, M.cpack.p,
+            M.pack_row_bits, M.n, M.m, grid, rb, M.bv_pack.p, bad.p);
+  unsigned int nbad = 0;
+  bad.download(&nbad, 1);
+  sync_stream();
+  if (nbad) return false;                                       // a count does not fit beside the row and the column
+  M.bv_row_bits = rb; M.bv_rows = (int)rows;
+  M.bv_ok = true;
+  return true;
+}
+
 std::shared_ptr<Matrix> matrix_reduce(Matrix &M, const int64_t *sel, int64_t nsel) {
   require_ready();
   KL_REQUIRE(nsel >= 1 && sel[0] == 0, "reduce: sel[0] must be the bias (0)");

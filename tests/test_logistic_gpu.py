@@ -470,7 +470,8 @@ def test_persistent_reduced_iterations_equal_per_launch(K, oracle):
 
 
 def test_reduced_solver_long_rows_same_bits(K, oracle):
-    """reduced matrices with long rows run on the sliced + column-major views (packed counts; real values unpacked):
+    """reduced matrices with long rows run on the sliced + column-major views (packed counts; real values unpacked) or on
+    the block-local view (one grid barrier per iteration; counts only, real values fall back to the views):
     the iterates must be those of the row-wise solver bit for bit, and those of the oracle to rounding"""
     from kmerlr_b200 import synth
     O = oracle
@@ -490,15 +491,16 @@ def test_reduced_solver_long_rows_same_bits(K, oracle):
         for data in (rd, scaled):
             for eps, eps_loss, lam, cap in [(0.0, 0.0, 1e-3, 61), (1e-6, 0.0, 1e-3, 100000), (0.0, 1e-9, 2e-3, 100000), (0.0, 0.0, 1e-3, 0)]:
                 res = []
-                for mode in (0, 1):
+                for mode in (0, 1, 2):              # rows; sliced + column-major views; block-local view (counts only)
                     K.option("small_long", mode)
                     est = K.KmerLrEstimator(Epsilon=eps, EpsilonLoss=eps_loss, MaxIterations=cap)
                     est.Theta = np.zeros(len(sel)); est.ClassWeights = cw
                     it, delta = est.estimate_proximal(data, lam)
                     res.append((it, delta, est.Theta.copy()))
-                assert res[0][0] == res[1][0], (cap, res[0][0], res[1][0])
-                assert res[0][1] == res[1][1] or (np.isnan(res[0][1]) and np.isnan(res[1][1]))
-                assert np.array_equal(res[0][2], res[1][2])
+                for other in (1, 2):
+                    assert res[0][0] == res[other][0], (cap, res[0][0], res[other][0])
+                    assert res[0][1] == res[other][1] or (np.isnan(res[0][1]) and np.isnan(res[other][1]))
+                    assert np.array_equal(res[0][2], res[other][2])
                 if data is rd and cap == 61:
                     rm = O.reduce(ref, sel)
                     oth, oit, _ = O.proxgrad(rm, y, np.zeros(len(sel)), tuple(cw), lam, epsilon=eps, epsilon_loss=eps_loss, max_iter=cap)

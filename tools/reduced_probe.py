@@ -35,7 +35,7 @@ for name, cols in cases.items():
     rd = K.select_data(d, sel)
     rd.SetLabels(y)
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         K.option("small_long", mode)
         est = K.KmerLrEstimator(Epsilon=0.0, EpsilonLoss=0.0, MaxIterations=50)
         est.Theta = np.zeros(len(sel)); est.ClassWeights = np.array([1.0, 1.0])
@@ -44,8 +44,8 @@ for name, cols in cases.items():
         est.Theta = np.zeros(len(sel))
         n_it, _ = est.estimate_proximal(rd, 1e-6)
         out[mode] = (K.last_device_ms() / max(n_it, 1), est.Theta.copy())
-    same = np.array_equal(out[0][1], out[1][1])
-    print("%-22s nnz %9d (%5.1f per row): rows %7.2f us  sliced+columns %7.2f us  same bits: %s" % (
-        name, rd.nnz, rd.nnz / rd.n, 1e3 * out[0][0], 1e3 * out[1][0], same), flush=True)
+    same = np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][1], out[2][1])
+    print("%-22s nnz %9d (%5.1f per row): rows %7.2f us  sliced+columns %7.2f us  block-local %7.2f us  same bits: %s" % (
+        name, rd.nnz, rd.nnz / rd.n, 1e3 * out[0][0], 1e3 * out[1][0], 1e3 * out[2][0], same), flush=True)
     rd.free()
 K.option("small_long", -1)
