@@ -77,7 +77,8 @@ int         kmerlr_profile_dump(char *buf, int64_t buflen);
  *                100 .. 135 give the same 3.15 ms per extraction from host buffers);
  *   "small_long" = 1 runs the reduced-matrix solver on the sliced + column-major views of the matrix (long rows), 2 on
  *                the sliced view + a block-local column-major view (one grid barrier per iteration), 0 on the compact
- *                rows, -1 (default) chooses by the row length (8 entries per row and more: 2 below 40, else 1); same bits;
+ *                rows, -1 (default) chooses by the row length (8 entries per row and more: 2 when the counts fit its packed
+ *                word, else 1); same bits;
  *   "persist_bps" = blocks per SM of the persistent reduced-matrix solver (0 = as many as fit, the default);
  *   "p2p_allreduce" = 1 runs the int64 all-reduce of the full-space gradient as a two-shot exchange over NVLink peer
  *                memory in one cooperative launch instead of NCCL (default 0: NCCL is faster at these sizes; same bits);

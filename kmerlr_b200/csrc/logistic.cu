@@ -1010,6 +1010,11 @@ __device__ __forceinline__ void small_rows(const Rows &R, const uint32_t *__rest
     }
 }
 
+#ifndef KL_LONG_U
+#define KL_LONG_U 8
+#endif
+constexpr int LONG_U = KL_LONG_U;     // loads in flight per thread in the long-row passes (8 against 4, block-local view:
+                                      // 40.6 vs 41.8 us at 50 entries per row, 62.4 vs 67.7 at 98, 137 vs 148 at 249)
 // Reduced matrices with LONG rows (late epochs of a leapfrog path: the classes of the short k-mers are in every
 // row -- 47 entries per row at 100 features of C2).  One thread per row over the compact rows then costs one L1
 // wavefront PER LANE and load (the rows of a warp are 200 bytes apart), and the rows of a warp add to the same
@@ -1059,12 +1064,12 @@ __device__ __forceinline__ void long_forward(const Rows &R, const LongView<VT> &
       // four loads in flight, the sum in entry order
       const uint32_t *sp = V.spack + base;
       int k = 0;
-      for (; k + 4 <= len; k += 4) {
-        const uint32_t e0 = __ldg(sp + 32 * k), e1 = __ldg(sp + 32 * k + 32), e2 = __ldg(sp + 32 * k + 64), e3 = __ldg(sp + 32 * k + 96);
-        s += (double)(e0 >> 10) * sth[(e0 & 1023u) + 1];
-        s += (double)(e1 >> 10) * sth[(e1 & 1023u) + 1];
-        s += (double)(e2 >> 10) * sth[(e2 & 1023u) + 1];
-        s += (double)(e3 >> 10) * sth[(e3 & 1023u) + 1];
+      for (; k + LONG_U <= len; k += LONG_U) {
+        uint32_t e[LONG_U];
+#pragma unroll
+        for (int j = 0; j < LONG_U; j++) e[j] = __ldg(sp + 32 * (k + j));
+#pragma unroll
+        for (int j = 0; j < LONG_U; j++) s += (double)(e[j] >> 10) * sth[(e[j] & 1023u) + 1];
       }
       for (; k < len; k++) { const uint32_t e = __ldg(sp + 32 * k); s += (double)(e >> 10) * sth[(e & 1023u) + 1]; }
     } else {
@@ -1113,15 +1118,15 @@ __device__ __forceinline__ void long_columns(const LongView<VT> &V, int64_t nthe
     if (V.cpack) {
       const uint32_t rmask = (1u << V.row_bits) - 1u;
       const int64_t bd = blockDim.x;
-      for (; p < hi; p += 4 * bd) {
-        uint32_t e[4];
-        double ws[4];
+      for (; p < hi; p += LONG_U * bd) {
+        uint32_t e[LONG_U];
+        double ws[LONG_U];
 #pragma unroll
-        for (int j = 0; j < 4; j++) e[j] = p + j * bd < hi ? __ldg(V.cpack + p + j * bd) : 0u;
+        for (int j = 0; j < LONG_U; j++) e[j] = p + j * bd < hi ? __ldg(V.cpack + p + j * bd) : 0u;
 #pragma unroll
-        for (int j = 0; j < 4; j++) ws[j] = __ldcg(V.wbuf + (e[j] & rmask));     // (written by other blocks before the barrier)
+        for (int j = 0; j < LONG_U; j++) ws[j] = __ldcg(V.wbuf + (e[j] & rmask));     // (written by other blocks before the barrier)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < LONG_U; j++) {
           if (p + j * bd < hi) {
             boundary(p + j * bd);
             acc += __double2ll_rn(ws[j] * (double)(e[j] >> V.row_bits));
@@ -1164,12 +1169,12 @@ __device__ __forceinline__ void block_columns(const LongView<VT> &V, int64_t nth
   const int cs = V.bv_row_bits, vs = V.bv_row_bits + 10;
   long long acc = 0;
   int cur = -1;
-  for (int64_t j = 0; j < wdt; j += 4) {
-    uint32_t e[4];
+  for (int64_t j = 0; j < wdt; j += LONG_U) {
+    uint32_t e[LONG_U];
 #pragma unroll
-    for (int i = 0; i < 4; i++) e[i] = j + i < wdt ? __ldg(bp + 256 * (j + i)) : 0xFFFFFFFFu;
+    for (int i = 0; i < LONG_U; i++) e[i] = j + i < wdt ? __ldg(bp + 256 * (j + i)) : 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < LONG_U; i++) {
       if (e[i] == 0xFFFFFFFFu) continue;
       const int c = (int)((e[i] >> cs) & 1023u);
       if (c != cur) {
@@ -1821,16 +1826,17 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
   bool persistent = small && ctx().coop_ok && (!M.sharded || p2p);
   // long rows: sliced + column-major views (the iterates are the same bits on either path, so a rank may choose by
   // its own shard)
-  const bool long_rows = persistent && M.nnz > 0 && (ctx().small_long >= 1 || (ctx().small_long < 0 && M.nnz >= 8 * M.n));
+  // (by row length: the block-local view from 4 entries per row, the two global views from 8)
+  bool long_rows = persistent && M.nnz > 0 && (ctx().small_long >= 1 || (ctx().small_long < 0 && M.nnz >= 4 * M.n));
   DevBuf<double> wbuf;
   bool packed = false;
   if (long_rows) { ensure_sliced(M); ensure_csc(M); packed = ensure_packed(M); wbuf.alloc((size_t)M.n); }
   // long_mode 2: the block-local view (one grid barrier per iteration); it is built for the grid of this launch
   int long_mode = long_rows ? 1 : 0;
   size_t dyn_smem = 0;
-  // (measured at C2 rows, 100 columns: 19.4 / 24.8 / 28.8 us against 23.6 / 28.1 / 32.2 us on the two views at 5 / 14 / 24
-  // entries per row, the same 41 us at 50, 139 against 132 us at 249: chosen below 40 entries per row)
-  const bool want_block = long_rows && packed && (ctx().small_long == 2 || (ctx().small_long < 0 && M.nnz < 40 * M.n));
+  // (measured at C2 rows, 100 columns, 5 / 14 / 24 / 50 / 98 / 249 entries per row: 19.0 / 23.5 / 28.2 / 40.6 / 62.4 / 137 us
+  // against 23.2 / 27.4 / 32.5 / 42.5 / 67.0 / 141 us on the sliced + column-major views: chosen whenever it fits)
+  const bool want_block = long_rows && packed && (ctx().small_long == 2 || ctx().small_long < 0);
   const int64_t BATCH = persistent ? 4096 : (small ? 256 : 16);
   int small_blocks = 0;
   DevBuf<double> blockloss;
@@ -1869,6 +1875,7 @@ void proxgrad(Matrix &M, double *theta, int64_t ntheta, const double cw[2], doub
           else dyn_smem = 0;
         } else dyn_smem = 0;
       }
+      if (long_mode != 2 && long_rows && ctx().small_long < 0 && M.nnz < 8 * M.n) { long_rows = false; long_mode = 0; }
       if (long_mode != 2) {
         const int per_sm = resident(long_mode, 0);
         KL_INVARIANT(per_sm >= 1);
