@@ -139,7 +139,26 @@ def bench_scoring(K, mbp, rank, reps=3):
             ms.append(K.last_device_ms())
     seqs.free()
     t = float(np.mean(ms)) * 1e-3
-    return {"windows_per_sec": windows / t, "bases_per_sec": clen * ncontig / t, "ms": 1e3 * t, "genome_mbp": mbp,
+    # the general kernel (binarized counts or pair features: a warp recounts every window) on a sixteenth of the slice
+    glen = max(clen // 16, 4 * W)
+    gmodel = dict(model, counter=K.NewKmerCounter(1, 8, revcomp=True, binarize=True),
+                  features=[(i, i) for i in range(len(ck))] + [(0, 1), (2, 5), (3, 4)],
+                  theta=rng.normal(scale=0.05, size=(1, len(ck) + 4)))
+    gg = K.genomicKmerLr([gmodel])
+    goff = np.arange(ncontig + 1, dtype=np.int64) * glen
+    gseqs = K.Sequences((buf[:glen * ncontig], goff))
+    gms = []
+    for i in range(3):
+        gg.predict_resident(gseqs, W, step)
+        if i > 0:
+            gms.append(K.last_device_ms())
+    gseqs.free()
+    gt = float(np.mean(gms)) * 1e-3
+    gwin = ncontig * ((glen - W + step - 1) // step)
+    generic = {"what": "score_generic: binarized model with 3 pair features, %d bp per contig" % glen, "ms": 1e3 * gt,
+               "windows_per_sec": gwin / gt, "bases_per_sec": glen * ncontig / gt}
+    return {"generic_kernel": generic,
+            "windows_per_sec": windows / t, "bases_per_sec": clen * ncontig / t, "ms": 1e3 * t, "genome_mbp": mbp,
             "window": W, "step": step, "model_features": int(len(ck)), "algorithmic_bytes_per_window": step / 4 + 8,
             "achieved_gbs": windows * (step / 4 + 8) / t / 1e9,
             # the honest bound of this stage is integer throughput: one class-table probe per base and level
