@@ -701,8 +701,9 @@ def saveWindowPredictionsWiggle(filename, regions, predictions, track_name, wind
     else:
         lens, pred = list(predictions), None
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    dummy = np.zeros(1)                       # (kept alive over the call; never read when there are no slots)
     if scores is None:
-        parg = _p(pred) if len(pred) else _p(np.zeros(1))
+        parg = _p(pred) if len(pred) else _p(dummy)
     else:
         parg = None
     check(lib().kmerlr_save_wiggle(filename.encode(), track_name.encode(), len(regions), names, _p(frm), _p(off), parg,

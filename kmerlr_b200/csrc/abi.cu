@@ -488,6 +488,7 @@ int kmerlr_save_wiggle(const char *filename, const char *track_name, int64_t n_r
                        int64_t window_size, int64_t window_step) {
   return guarded([&] {
     require_ready();
+    if (n_regions == 0) { save_wiggle(filename, track_name, 0, nullptr, nullptr, nullptr, nullptr, false, window_size, window_step); return; }
     if (pred_or_null) { save_wiggle(filename, track_name, n_regions, seqnames, from, slot_off, pred_or_null, false, window_size, window_step); return; }
     auto S = lookup<Matrix>(scores, "scores");
     KL_REQUIRE(n_regions == 0 || (slot_off && (size_t)slot_off[n_regions] <= S->val_f64.n), "save_wiggle: more slots than scores");

@@ -176,6 +176,10 @@ def test_save_wiggle_file(K, oracle, fixtures, tmp_path):
     f3 = str(tmp_path / "c.wig")
     K.saveWindowPredictionsWiggle(f3, regions, odd, "t", 201, 7)
     assert open(f3).read() == oracle.wiggle_text(regions, odd, "t", 201, 7)
+    # no regions at all: the track line only
+    f4 = str(tmp_path / "d.wig")
+    K.saveWindowPredictionsWiggle(f4, [], [], "empty", 200, 10)
+    assert open(f4).read() == "track type=wiggle_0 name=empty\n"
 
 
 @pytest.mark.gpu
